@@ -1,0 +1,185 @@
+"""Seeded synthetic Qwen3-TTS checkpoint (random-init weights of the real architecture).
+
+There is no network and no HF checkpoint in the build/bench environment, so every
+parity test and benchmark runs on random-init weights of the reference's exact shapes
+(reference layout: qwen_megakernel/model_tts.py:98-146 of the upstream repo).
+
+The recipe is a *named, versioned, platform-independent* function: values come from
+numpy's counter-based Philox bit generator and pure integer arithmetic (an Irwin-Hall(4)
+approximation of a normal built from four 16-bit uniforms), followed by one float32
+multiply and a round-to-nearest-even cast to bf16.  No libm call is involved, so the
+tensors are bit-identical on every machine (the golden fixtures in tests/golden were
+produced on a different host than the GPU box that replays them).
+
+Returned dict has exactly the keys of ``load_tts_weights`` (model_tts.py:153-171).
+"""
+
+from __future__ import annotations
+
+import math
+import zlib
+
+import numpy as np
+import torch
+
+RECIPE_VERSION = "synth-v2"
+
+# Model dims (model_tts.py:19-34 upstream)
+_L, _LCP = 28, 5
+_H, _I, _Q, _KV, _HD = 1024, 3072, 2048, 1024, 128
+_VOCAB, _VOCAB_CP, _GROUPS = 3072, 2048, 15
+_TEXT_HIDDEN = 2048
+ROPE_THETA = 1000000.0
+
+_IH_STD = 65536.0 * math.sqrt(1.0 / 3.0)  # std of the sum of four U{0..65535}
+
+
+def _normal_bf16(shape, std: float, seed: int, stream: int, mean: float = 0.0) -> torch.Tensor:
+    """Approximately N(mean, std^2) bf16 tensor; deterministic across platforms."""
+    n = int(np.prod(shape))
+    bitgen = np.random.Philox(key=np.array([seed, stream], dtype=np.uint64))
+    raw = bitgen.random_raw(n)  # uint64
+    s = (raw & 0xFFFF).astype(np.int32)
+    s += ((raw >> 16) & 0xFFFF).astype(np.int32)
+    s += ((raw >> 32) & 0xFFFF).astype(np.int32)
+    s += ((raw >> 48) & 0xFFFF).astype(np.int32)
+    s -= 131070
+    x = s.astype(np.float32) * np.float32(std / _IH_STD)
+    if mean != 0.0:
+        x += np.float32(mean)
+    return torch.from_numpy(x.reshape(shape)).to(torch.bfloat16)
+
+
+def rope_tables(max_seq: int, device="cpu"):
+    """bf16 cos/sin tables [max_seq, 128], halves duplicated (model_tts.py:90-96 upstream)."""
+    inv_freq = 1.0 / (ROPE_THETA ** (torch.arange(0, _HD, 2, dtype=torch.float32) / _HD))
+    pos = torch.arange(max_seq, dtype=torch.float32)
+    freqs = torch.outer(pos, inv_freq)
+    cos = torch.cos(freqs).repeat(1, 2).to(torch.bfloat16).to(device).contiguous()
+    sin = torch.sin(freqs).repeat(1, 2).to(torch.bfloat16).to(device).contiguous()
+    return cos, sin
+
+
+def _layer(seed: int, base_stream: int, residual_gain: float) -> list[torch.Tensor]:
+    """11 tensors in LDGLayerWeights order (kernel.cu:78-90 upstream)."""
+    s = base_stream
+    return [
+        _normal_bf16((_H,), 0.1, seed, s + 0, mean=1.0),                          # input_layernorm
+        _normal_bf16((_Q, _H), 1.0 / math.sqrt(_H), seed, s + 1),                  # q_proj
+        _normal_bf16((_KV, _H), 1.0 / math.sqrt(_H), seed, s + 2),                 # k_proj
+        _normal_bf16((_KV, _H), 1.0 / math.sqrt(_H), seed, s + 3),                 # v_proj
+        _normal_bf16((_HD,), 0.1, seed, s + 4, mean=1.0),                          # q_norm
+        _normal_bf16((_HD,), 0.1, seed, s + 5, mean=1.0),                          # k_norm
+        _normal_bf16((_H, _Q), residual_gain / math.sqrt(_Q), seed, s + 6),        # o_proj
+        _normal_bf16((_H,), 0.1, seed, s + 7, mean=1.0),                           # post_attention_layernorm
+        _normal_bf16((_I, _H), 1.0 / math.sqrt(_H), seed, s + 8),                  # gate_proj
+        _normal_bf16((_I, _H), 1.0 / math.sqrt(_H), seed, s + 9),                  # up_proj
+        _normal_bf16((_H, _I), residual_gain / math.sqrt(_I), seed, s + 10),       # down_proj
+    ]
+
+
+_LAYER_KEYS = [
+    "input_layernorm.weight", "self_attn.q_proj.weight", "self_attn.k_proj.weight",
+    "self_attn.v_proj.weight", "self_attn.q_norm.weight", "self_attn.k_norm.weight",
+    "self_attn.o_proj.weight", "post_attention_layernorm.weight", "mlp.gate_proj.weight",
+    "mlp.up_proj.weight", "mlp.down_proj.weight",
+]
+
+
+def synthetic_tts_weights(
+    seed: int = 1234,
+    device: str = "cpu",
+    max_seq_len: int = 8192,
+    text_vocab: int = 16,
+    num_layers: int = _L,
+    residual_gain: float | None = None,
+    head_gain: float = 0.5,
+    include_talker: bool = True,
+    include_code_predictor: bool = True,
+) -> dict:
+    """Build the weights dict of ``load_tts_weights`` from the seeded recipe.
+
+    ``text_vocab`` defaults to a tiny table: the text side (TextProjection) is outside the
+    accelerated path and the full [151936, 2048] table is 622 MB.
+    ``num_layers`` < 28 builds a truncated talker for fast CPU tests (streams of layer i are
+    independent of num_layers, so layer i is identical in every truncation).
+    """
+    w: dict = {}
+    layer_weights: list[torch.Tensor] = []
+    # GPT-2 / Megatron "scaled init": residual-branch output projections are scaled by
+    # 1/sqrt(2 * num_layers) so the residual stream keeps O(1) gain per layer.
+    gain_talker = residual_gain if residual_gain is not None else 1.0 / math.sqrt(2 * _L)
+    gain_cp = residual_gain if residual_gain is not None else 1.0 / math.sqrt(2 * _LCP)
+    if include_talker:
+        for i in range(num_layers):
+            layer_weights.extend(_layer(seed, 1000 + 16 * i, gain_talker))
+        w["embed_weight"] = _normal_bf16((_VOCAB, _H), 1.0, seed, 1)
+        # head_gain 0.5 keeps the top logits below 2.0, where one bf16 ulp (0.0078) is smaller than
+        # the 1e-2 margin rule of the parity contract; with unit gain the top logits sit in [2, 4)
+        # where a ONE-ulp margin (0.0156) already exceeds 1e-2 and flips with summation order.
+        w["lm_head_weight"] = _normal_bf16((_VOCAB, _H), head_gain / math.sqrt(_H), seed, 2)
+        w["final_norm_weight"] = _normal_bf16((_H,), 0.1, seed, 3, mean=1.0)
+    w["layer_weights"] = layer_weights
+    cos, sin = rope_tables(max_seq_len)
+    w["cos_table"], w["sin_table"] = cos, sin
+
+    w["text_embedding"] = _normal_bf16((text_vocab, _TEXT_HIDDEN), 1.0, seed, 10)
+    w["text_proj_fc1_w"] = _normal_bf16((_TEXT_HIDDEN, _TEXT_HIDDEN), 1.0 / math.sqrt(_TEXT_HIDDEN), seed, 11)
+    w["text_proj_fc1_b"] = _normal_bf16((_TEXT_HIDDEN,), 0.02, seed, 12)
+    w["text_proj_fc2_w"] = _normal_bf16((_H, _TEXT_HIDDEN), 1.0 / math.sqrt(_TEXT_HIDDEN), seed, 13)
+    w["text_proj_fc2_b"] = _normal_bf16((_H,), 0.02, seed, 14)
+
+    cp: dict = {}
+    if include_code_predictor:
+        for i in range(_LCP):
+            tensors = _layer(seed, 5000 + 16 * i, gain_cp)
+            for key, t in zip(_LAYER_KEYS, tensors):
+                cp[f"layers.{i}.{key}"] = t
+        cp["norm.weight"] = _normal_bf16((_H,), 0.1, seed, 4, mean=1.0)
+        for g in range(_GROUPS):
+            cp[f"lm_head.{g}.weight"] = _normal_bf16((_VOCAB_CP, _H), head_gain / math.sqrt(_H), seed, 6000 + g)
+            cp[f"codec_embedding.{g}.weight"] = _normal_bf16((_VOCAB_CP, _H), 1.0, seed, 7000 + g)
+    w["code_predictor"] = cp
+    w["speaker_encoder"] = {}
+
+    if device != "cpu":
+        w = weights_to(w, device)
+    return w
+
+
+def weights_to(w: dict, device: str) -> dict:
+    """Move every tensor of a weights dict to ``device`` (contiguous)."""
+    out = {}
+    for k, v in w.items():
+        if isinstance(v, torch.Tensor):
+            out[k] = v.to(device).contiguous()
+        elif isinstance(v, list):
+            out[k] = [t.to(device).contiguous() for t in v]
+        elif isinstance(v, dict):
+            out[k] = {kk: vv.to(device).contiguous() for kk, vv in v.items()}
+        else:
+            out[k] = v
+    return out
+
+
+def weights_fingerprint(w: dict) -> str:
+    """CRC32 over a few tensors — lets a test prove the GPU box regenerated identical weights."""
+    crc = 0
+    probes = []
+    if w.get("layer_weights"):
+        probes += [w["layer_weights"][1], w["layer_weights"][-1]]
+    for k in ("embed_weight", "lm_head_weight"):
+        if k in w:
+            probes.append(w[k])
+    cp = w.get("code_predictor", {})
+    for k in ("layers.0.mlp.gate_proj.weight", "lm_head.14.weight", "codec_embedding.0.weight"):
+        if k in cp:
+            probes.append(cp[k])
+    for t in probes:
+        crc = zlib.crc32(t.detach().cpu().contiguous().view(torch.int16).numpy().tobytes(), crc)
+    return f"{RECIPE_VERSION}:{crc:08x}"
+
+
+def synthetic_inputs(seed: int, n: int, dim: int = _H) -> torch.Tensor:
+    """``n`` seeded N(0,1) bf16 vectors (prefill embeddings / trailing text embeddings)."""
+    return _normal_bf16((n, dim), 1.0, seed, 424242)
