@@ -1,0 +1,145 @@
+/*
+ * qmk_b200.h — C ABI of the B200 (sm_100a) decode engine for the Qwen3-TTS talker and code predictor.
+ *
+ * This is the drop-in boundary for ONE path of jayanth-kumar-morem/qwen-megakernel-tts: the fused
+ * decode step behind torch.ops.qwen_megakernel_C.decode.  Plain pointers and sizes only (no torch
+ * types).  All pointers are DEVICE pointers unless stated; `stream` is a cudaStream_t passed as void*.
+ *
+ * Upstream interfaces replaced (paths relative to the upstream repo root):
+ *   launch_ldg_decode_direct      csrc/kernel.cu:1485-1513   (declared csrc/torch_bindings.cpp:45-53)
+ *   struct LDGLayerWeights        csrc/kernel.cu:78-90       (mirrored csrc/torch_bindings.cpp:21-33)
+ *   op decode(...)                csrc/torch_bindings.cpp:55-81, schema :130-141
+ *   CodePredictorKernel.predict   qwen_megakernel/model_tts.py:729-773  -> qmk_cp_predict (one launch)
+ *
+ * Return convention: 0 = success, negative = error (text via qmk_last_error()).  The upstream C entry
+ * returns void and checks nothing; the drop-in symbol keeps the void signature and records its status
+ * for qmk_legacy_status().
+ */
+#ifndef QMK_B200_H
+#define QMK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QMK_ABI_VERSION 1
+
+/* Model constants (upstream kernel.cu:21-28, model_tts.py:19-34); compile-time in the kernel. */
+#define QMK_HIDDEN 1024
+#define QMK_INTER 3072
+#define QMK_Q_SIZE 2048
+#define QMK_KV_SIZE 1024
+#define QMK_HEAD_DIM 128
+#define QMK_NUM_Q_HEADS 16
+#define QMK_NUM_KV_HEADS 8
+#define QMK_CP_GROUPS 15
+
+/* Error codes */
+#define QMK_OK 0
+#define QMK_ERR_ARG (-1)      /* invalid argument (null pointer, position out of range, ...) */
+#define QMK_ERR_CUDA (-2)     /* CUDA runtime error */
+#define QMK_ERR_KERNEL (-3)   /* device-side watchdog fired (a wait inside the persistent kernel timed out) */
+#define QMK_ERR_UNSUPPORTED (-4)
+
+/* Per-layer weight pointers, bf16 row-major [out, in]; same field order as upstream LDGLayerWeights
+ * (kernel.cu:78-90) so the caller's packed blob (model_tts.py:182-193) is consumed unchanged. */
+typedef struct LDGLayerWeights {
+  const void* input_layernorm_weight;     /* [1024]        */
+  const void* q_proj_weight;              /* [2048, 1024]  */
+  const void* k_proj_weight;              /* [1024, 1024]  */
+  const void* v_proj_weight;              /* [1024, 1024]  */
+  const void* q_norm_weight;              /* [128]         */
+  const void* k_norm_weight;              /* [128]         */
+  const void* o_proj_weight;              /* [1024, 2048]  */
+  const void* post_attn_layernorm_weight; /* [1024]        */
+  const void* gate_proj_weight;           /* [3072, 1024]  */
+  const void* up_proj_weight;             /* [3072, 1024]  */
+  const void* down_proj_weight;           /* [1024, 3072]  */
+} LDGLayerWeights;
+
+typedef struct qmk_engine qmk_engine; /* per-device context: exchange buffers, watchdog word, epoch */
+typedef struct qmk_model qmk_model;   /* a layer stack re-packed into per-SM weight streams */
+
+int qmk_abi_version(void);
+const char* qmk_last_error(void);
+
+/* ---- engine ------------------------------------------------------------------------------------ */
+/* num_ctas = 0 -> one persistent CTA per SM of `device` (148 on B200). */
+int qmk_engine_create(int device, int num_ctas, qmk_engine** out);
+void qmk_engine_destroy(qmk_engine* e);
+int qmk_engine_num_ctas(const qmk_engine* e);
+/* Synchronise `stream` and return the device-side status of all launches since the last call
+ * (QMK_OK or QMK_ERR_KERNEL); detail[0..3] (optional, host) receives the watchdog record. */
+int qmk_engine_sync_status(qmk_engine* e, void* stream, int32_t* detail);
+
+/* ---- model (weight re-packing; replaces upstream _pack_layer_weights as the packing layer) ------ */
+/* `layers` is the caller's DEVICE blob of num_layers LDGLayerWeights structs.  The weights are copied
+ * into the engine's own per-CTA stream layout; the originals are not referenced afterwards.
+ * residual_fp32: 1 = fp32 residual stream across layers (upstream talker PyTorch path,
+ * validate_kernel.py:123-188), 0 = bf16 residual (upstream CodePredictor, model_tts.py:567-619). */
+int qmk_model_create(qmk_engine* e, const LDGLayerWeights* layers, int num_layers,
+                     const void* final_norm_weight, int residual_fp32, void* stream, qmk_model** out);
+/* Register an LM head [rows, 1024] bf16 (talker codec head: 3072 rows; code-predictor group heads:
+ * 2048 rows).  Returns the head index (>= 0) or a negative error. */
+int qmk_model_add_head(qmk_model* m, const void* lm_head_weight, int rows, void* stream);
+/* Register the code-predictor embedding table of group g (bf16 [2048,1024]); used by qmk_cp_predict. */
+int qmk_model_set_group_embedding(qmk_model* m, int group, const void* embedding_weight);
+void qmk_model_destroy(qmk_model* m);
+int64_t qmk_model_packed_bytes(const qmk_model* m);
+
+/* ---- one decode step (replaces launch_ldg_decode_direct) ----------------------------------------- */
+/* Semantics of upstream decode (torch_bindings.cpp:55-81 / kernel.cu:1317-1432):
+ *   input_token_id >= 0 : layer-0 input = embed_weight[input_token_id]        (kernel.cu:1364-1367)
+ *   input_token_id <  0 : layer-0 input = hidden_buffer (bf16[1024], caller-written sentinel path)
+ *   KV row `position` of every layer is written into k_cache/v_cache ([L][8][max_seq_len][128] bf16)
+ *   normalized_out (f32[1024])  = post-final-RMSNorm hidden (bf16-rounded values)
+ *   hidden_buffer  (bf16[1024]) = last layer output (clobbered)
+ *   out_token (int32[1])        = argmax of head `head_index` (lowest index on ties); head_index < 0
+ *                                 skips the LM head (code-predictor steps).
+ * mode: 0 = fused persistent kernel (one cooperative launch), 1 = staged (one launch per phase; a
+ * debugging/bisect mode that runs the same device code without inter-CTA waits).
+ * Asynchronous on `stream`. */
+int qmk_decode_step(qmk_model* m, int head_index, int input_token_id, const void* embed_weight,
+                    const void* cos_table, const void* sin_table, void* k_cache, void* v_cache,
+                    void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
+                    int max_seq_len, float attn_scale, int mode, void* stream);
+
+/* ---- one code-predictor frame in ONE launch (replaces the 16-step loop of
+ *      CodePredictorKernel.predict, model_tts.py:729-773) ------------------------------------------ */
+/* talker_hidden: f32[1024]; talker_embed_weight: bf16[3072,1024]; out_codes: int64[16] =
+ * [first_token, g0..g14].  do_sample=0 -> argmax on bf16 logits; else temperature / top-k (ties kept)
+ * / softmax / inverse-CDF draw from a counter-based generator keyed by (seed, frame_counter).
+ * k_cache/v_cache: [5][8][max_seq_len][128] bf16 scratch owned by the caller (max_seq_len >= 16).
+ * logits_out (optional, f32[15*2048]) and hidden_out (optional, f32[15*1024]) receive the per-group
+ * bf16 logits / post-norm hidden for teacher-forced parity checks; forced_tokens (optional, int32[15],
+ * device) overrides the fed-back tokens. */
+int qmk_cp_predict(qmk_model* m, const float* talker_hidden, int first_codebook_token,
+                   const void* talker_embed_weight, const void* cos_table, const void* sin_table,
+                   void* k_cache, void* v_cache, int max_seq_len, int do_sample, float temperature,
+                   int top_k, uint64_t seed, uint64_t frame_counter, const int32_t* forced_tokens,
+                   int64_t* out_codes, float* logits_out, float* hidden_out, void* stream);
+
+/* ---- upstream-compatible entry point (same symbol, same argument list) ---------------------------- */
+/* The scratch arguments (g_activations .. g_mlp_intermediate, block_max_*) are accepted and ignored:
+ * the engine keeps its own exchange buffers.  The first call for a given `layer_weights` blob re-packs
+ * the weights (one-time, synchronous); qmk_legacy_configure() sets how that blob is interpreted. */
+void launch_ldg_decode_direct(int input_token_id, int* output_token_id, const void* embed_weight,
+                              const LDGLayerWeights* layer_weights, const void* final_norm_weight,
+                              const void* lm_head_weight, const void* cos_table, const void* sin_table,
+                              void* k_cache, void* v_cache, void* hidden_buffer, void* g_activations,
+                              void* g_residual, void* g_q, void* g_k, void* g_v, void* g_attn_out,
+                              void* g_mlp_intermediate, void* g_normalized, void* block_max_vals,
+                              void* block_max_idxs, int num_layers, int position, int max_seq_len,
+                              float attn_scale, void* stream);
+/* residual_fp32: see qmk_model_create.  lm_head_rows: 3072 (upstream compile-time LDG_VOCAB_SIZE) or 0
+ * to skip the head (the code predictor passes an all-zero dummy table, model_tts.py:657-659). */
+int qmk_legacy_configure(const LDGLayerWeights* layer_weights, int residual_fp32, int lm_head_rows);
+int qmk_legacy_status(void);        /* status of the last launch_ldg_decode_direct call */
+void qmk_legacy_release(void);      /* drop cached engines / re-packed models */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QMK_B200_H */

@@ -1,0 +1,425 @@
+// qmk_engine.cu — host side of the C ABI declared in include/qmk_b200.h.
+//
+// Per-device engine context (exchange buffers, watchdog word, epoch counter), weight re-packing into
+// per-CTA streams, launch of the persistent decode kernel, and the upstream-compatible symbol
+// launch_ldg_decode_direct (upstream csrc/kernel.cu:1485-1513).  No torch types anywhere.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "qmk_b200.h"
+#include "qmk_device.cuh"
+
+using namespace qmk;
+
+static thread_local std::string g_last_error;
+
+static int set_error(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define QMK_CUDA(expr)                                                                           \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return set_error(QMK_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+struct qmk_head {
+  uint8_t* packed = nullptr;
+  int rows = 0;
+  int segs_max = 0;
+};
+
+struct qmk_engine {
+  int device = 0;
+  int G = 0;
+  u64* xbuf = nullptr;
+  int* status_dev = nullptr;
+  uint32_t epoch = 0;
+  long long timeout_cycles = 4000000000LL;  // ~2 s at 1.9 GHz
+  std::mutex mu;
+};
+
+struct qmk_model {
+  qmk_engine* e = nullptr;
+  Layout lay{};
+  uint8_t* packed_layers = nullptr;
+  __nv_bfloat16* qk_norm = nullptr;
+  uint8_t* norm_seg = nullptr;  // 2 KB: final RMSNorm weight (aux segment of a head-less final phase)
+  int residual_fp32 = 1;
+  int64_t packed_bytes = 0;
+  std::vector<qmk_head> heads;
+  const void* group_embed[QMK_CP_GROUPS] = {nullptr};
+};
+
+extern "C" int qmk_abi_version(void) { return QMK_ABI_VERSION; }
+extern "C" const char* qmk_last_error(void) { return g_last_error.c_str(); }
+
+static Layout make_layout(int G, int L) {
+  Layout y;
+  y.G = G;
+  y.L = L;
+  y.qkv_max = (QKV_ROWS + G - 1) / G;
+  y.o_max = (H + G - 1) / G;
+  y.gu_max = (INTER + G - 1) / G;
+  y.off_o = 1 + y.qkv_max;
+  y.off_gu = y.off_o + 2 * y.o_max;
+  y.off_down = y.off_gu + 1 + 2 * y.gu_max;
+  y.layer_segs = y.off_down + 3 * y.o_max;
+  return y;
+}
+
+extern "C" int qmk_engine_create(int device, int num_ctas, qmk_engine** out) {
+  if (!out) return set_error(QMK_ERR_ARG, "qmk_engine_create: out is null");
+  *out = nullptr;
+  int ndev = 0;
+  QMK_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return set_error(QMK_ERR_ARG, "qmk_engine_create: bad device %d", device);
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  QMK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 9)
+    return set_error(QMK_ERR_UNSUPPORTED, "device %d is sm_%d%d; this engine needs TMA bulk copies (built for sm_100a)",
+                     device, prop.major, prop.minor);
+  int coop = 0;
+  QMK_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+  if (!coop) return set_error(QMK_ERR_UNSUPPORTED, "device %d lacks cooperative launch", device);
+  if (const char* env = getenv("QMK_NUM_CTAS")) {
+    if (num_ctas <= 0) num_ctas = atoi(env);
+  }
+  int G = num_ctas > 0 ? num_ctas : prop.multiProcessorCount;
+  if (G > prop.multiProcessorCount) G = prop.multiProcessorCount;
+  // every CTA must own >=1 row in every phase; per-phase item tables hold 128 entries
+  if (G < 64 || G > 1024) return set_error(QMK_ERR_UNSUPPORTED, "unsupported CTA count %d (need 64..1024)", G);
+  QMK_CUDA(cudaFuncSetAttribute(qmk_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  int occ = 0;
+  QMK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qmk_decode_kernel, NTHREADS, SMEM_BYTES));
+  if (occ < 1) return set_error(QMK_ERR_UNSUPPORTED, "decode kernel does not fit on an SM (smem %d B)", SMEM_BYTES);
+
+  qmk_engine* e = new qmk_engine();
+  e->device = device;
+  e->G = G;
+  if (const char* env = getenv("QMK_TIMEOUT_CYCLES")) e->timeout_cycles = atoll(env);
+  cudaError_t err = cudaMalloc(&e->xbuf, sizeof(u64) * XW_TOTAL);
+  if (err == cudaSuccess) err = cudaMemset(e->xbuf, 0, sizeof(u64) * XW_TOTAL);
+  if (err == cudaSuccess) err = cudaMalloc(&e->status_dev, 4 * sizeof(int));
+  if (err == cudaSuccess) err = cudaMemset(e->status_dev, 0, 4 * sizeof(int));
+  if (err != cudaSuccess) {
+    if (e->xbuf) cudaFree(e->xbuf);
+    if (e->status_dev) cudaFree(e->status_dev);
+    delete e;
+    return set_error(QMK_ERR_CUDA, "engine allocation failed: %s", cudaGetErrorString(err));
+  }
+  *out = e;
+  return QMK_OK;
+}
+
+extern "C" void qmk_engine_destroy(qmk_engine* e) {
+  if (!e) return;
+  DeviceGuard guard(e->device);
+  cudaDeviceSynchronize();
+  cudaFree(e->xbuf);
+  cudaFree(e->status_dev);
+  delete e;
+}
+
+extern "C" int qmk_engine_num_ctas(const qmk_engine* e) { return e ? e->G : 0; }
+
+extern "C" int qmk_engine_sync_status(qmk_engine* e, void* stream, int32_t* detail) {
+  if (!e) return set_error(QMK_ERR_ARG, "qmk_engine_sync_status: engine is null");
+  DeviceGuard guard(e->device);
+  QMK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  int st[4] = {0, 0, 0, 0};
+  QMK_CUDA(cudaMemcpy(st, e->status_dev, sizeof(st), cudaMemcpyDeviceToHost));
+  if (detail) memcpy(detail, st, sizeof(st));
+  if (st[0] != 0) {
+    cudaMemset(e->status_dev, 0, sizeof(st));
+    return set_error(QMK_ERR_KERNEL, "device watchdog fired: code %d (1=exchange wait 2=ring full wait 3=ring empty wait) cta %d phase %d aux %d",
+                     st[0], st[1], st[2], st[3]);
+  }
+  return QMK_OK;
+}
+
+extern "C" int qmk_model_create(qmk_engine* e, const LDGLayerWeights* layers, int num_layers,
+                                const void* final_norm_weight, int residual_fp32, void* stream, qmk_model** out) {
+  if (!e || !layers || !final_norm_weight || !out) return set_error(QMK_ERR_ARG, "qmk_model_create: null argument");
+  if (num_layers < 1 || num_layers > 1024) return set_error(QMK_ERR_ARG, "qmk_model_create: bad num_layers %d", num_layers);
+  static_assert(sizeof(LDGLayerWeights) == sizeof(LayerPtrs), "layer pointer struct mismatch");
+  *out = nullptr;
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  qmk_model* m = new qmk_model();
+  m->e = e;
+  m->lay = make_layout(e->G, num_layers);
+  m->residual_fp32 = residual_fp32 ? 1 : 0;
+  const size_t bytes = (size_t)e->G * num_layers * m->lay.layer_segs * SEG_BYTES;
+  cudaError_t err = cudaMalloc(&m->packed_layers, bytes);
+  if (err == cudaSuccess) err = cudaMalloc(&m->qk_norm, (size_t)num_layers * 2 * HD * sizeof(__nv_bfloat16));
+  if (err == cudaSuccess) err = cudaMalloc(&m->norm_seg, SEG_BYTES);
+  if (err == cudaSuccess) {
+    qmk_pack_layers_kernel<<<dim3(e->G, num_layers), 128, 0, st>>>(reinterpret_cast<const LayerPtrs*>(layers), m->lay,
+                                                                  m->packed_layers, m->qk_norm);
+    err = cudaGetLastError();
+  }
+  if (err == cudaSuccess) err = cudaMemcpyAsync(m->norm_seg, final_norm_weight, SEG_BYTES, cudaMemcpyDeviceToDevice, st);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+  if (err != cudaSuccess) {
+    qmk_model_destroy(m);
+    return set_error(QMK_ERR_CUDA, "qmk_model_create: %s", cudaGetErrorString(err));
+  }
+  m->packed_bytes = (int64_t)bytes;
+  *out = m;
+  return QMK_OK;
+}
+
+extern "C" int qmk_model_add_head(qmk_model* m, const void* lm_head_weight, int rows, void* stream) {
+  if (!m || !lm_head_weight) return set_error(QMK_ERR_ARG, "qmk_model_add_head: null argument");
+  if (rows < m->e->G || rows > MAX_HEAD_ROWS) return set_error(QMK_ERR_ARG, "qmk_model_add_head: rows %d out of range", rows);
+  DeviceGuard guard(m->e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  qmk_head h;
+  h.rows = rows;
+  h.segs_max = (rows + m->e->G - 1) / m->e->G + 1;
+  const size_t bytes = (size_t)m->e->G * h.segs_max * SEG_BYTES;
+  QMK_CUDA(cudaMalloc(&h.packed, bytes));
+  qmk_pack_head_kernel<<<m->e->G, 128, 0, st>>>(reinterpret_cast<const uint4*>(lm_head_weight),
+                                                reinterpret_cast<const uint4*>(m->norm_seg), rows, m->e->G, h.segs_max,
+                                                h.packed);
+  cudaError_t err = cudaGetLastError();
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+  if (err != cudaSuccess) {
+    cudaFree(h.packed);
+    return set_error(QMK_ERR_CUDA, "qmk_model_add_head: %s", cudaGetErrorString(err));
+  }
+  m->packed_bytes += (int64_t)bytes;
+  m->heads.push_back(h);
+  return (int)m->heads.size() - 1;
+}
+
+extern "C" int qmk_model_set_group_embedding(qmk_model* m, int group, const void* embedding_weight) {
+  if (!m || group < 0 || group >= QMK_CP_GROUPS) return set_error(QMK_ERR_ARG, "qmk_model_set_group_embedding: bad argument");
+  m->group_embed[group] = embedding_weight;
+  return QMK_OK;
+}
+
+extern "C" void qmk_model_destroy(qmk_model* m) {
+  if (!m) return;
+  DeviceGuard guard(m->e->device);
+  cudaDeviceSynchronize();
+  if (m->packed_layers) cudaFree(m->packed_layers);
+  if (m->qk_norm) cudaFree(m->qk_norm);
+  if (m->norm_seg) cudaFree(m->norm_seg);
+  for (auto& h : m->heads) cudaFree(h.packed);
+  delete m;
+}
+
+extern "C" int64_t qmk_model_packed_bytes(const qmk_model* m) { return m ? m->packed_bytes : 0; }
+
+static int launch_slice(qmk_engine* e, Params& p, int begin, int end, cudaStream_t st) {
+  p.phase_begin = begin;
+  p.phase_end = end;
+  void* args[] = {&p};
+  QMK_CUDA(cudaLaunchCooperativeKernel((const void*)qmk_decode_kernel, dim3(e->G), dim3(NTHREADS), args, SMEM_BYTES, st));
+  return QMK_OK;
+}
+
+extern "C" int qmk_decode_step(qmk_model* m, int head_index, int input_token_id, const void* embed_weight,
+                               const void* cos_table, const void* sin_table, void* k_cache, void* v_cache,
+                               void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
+                               int max_seq_len, float attn_scale, int mode, void* stream) {
+  if (!m) return set_error(QMK_ERR_ARG, "qmk_decode_step: model is null");
+  if (!cos_table || !sin_table || !k_cache || !v_cache || !hidden_buffer)
+    return set_error(QMK_ERR_ARG, "qmk_decode_step: null table / cache / hidden_buffer pointer");
+  if (max_seq_len < 1 || position < 0 || position >= max_seq_len)
+    return set_error(QMK_ERR_ARG, "qmk_decode_step: position %d outside [0, max_seq_len=%d)", position, max_seq_len);
+  if (input_token_id >= 0 && !embed_weight) return set_error(QMK_ERR_ARG, "qmk_decode_step: token given but embed_weight is null");
+  if (head_index >= (int)m->heads.size()) return set_error(QMK_ERR_ARG, "qmk_decode_step: head index %d not registered", head_index);
+  if (head_index >= 0 && !out_token) return set_error(QMK_ERR_ARG, "qmk_decode_step: out_token is null");
+  qmk_engine* e = m->e;
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> lock(e->mu);
+
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.lay = m->lay;
+  p.packed_layers = m->packed_layers;
+  p.qk_norm = m->qk_norm;
+  if (head_index >= 0) {
+    p.head.packed = m->heads[head_index].packed;
+    p.head.rows = m->heads[head_index].rows;
+    p.head.segs_max = m->heads[head_index].segs_max;
+  } else {
+    p.head.packed = m->norm_seg;
+    p.head.rows = 0;
+    p.head.segs_max = 1;
+  }
+  p.embed = reinterpret_cast<const __nv_bfloat16*>(embed_weight);
+  p.in_vec = reinterpret_cast<const __nv_bfloat16*>(hidden_buffer);
+  p.cos_t = reinterpret_cast<const __nv_bfloat16*>(cos_table);
+  p.sin_t = reinterpret_cast<const __nv_bfloat16*>(sin_table);
+  p.k_cache = reinterpret_cast<__nv_bfloat16*>(k_cache);
+  p.v_cache = reinterpret_cast<__nv_bfloat16*>(v_cache);
+  p.max_seq = max_seq_len;
+  p.xbuf = e->xbuf;
+  p.token = input_token_id;
+  p.position = position;
+  p.out_token = out_token;
+  p.out_norm = normalized_out;
+  p.hidden_out = reinterpret_cast<__nv_bfloat16*>(hidden_buffer);
+  p.attn_scale = attn_scale;
+  p.residual_fp32 = m->residual_fp32;
+  p.status = e->status_dev;
+  p.timeout_cycles = e->timeout_cycles;
+
+  const uint32_t need = (uint32_t)m->lay.L + 2u;
+  if (e->epoch > 0xfff00000u) {  // wrap: clear the exchange words (stream-ordered) and restart the epochs
+    QMK_CUDA(cudaMemsetAsync(e->xbuf, 0, sizeof(u64) * XW_TOTAL, st));
+    e->epoch = 0;
+  }
+  p.epoch_base = e->epoch;
+  e->epoch += need;
+
+  const int n_idx = m->lay.L * PH_PER_LAYER + 2;
+  if (mode == 0) return launch_slice(e, p, 0, n_idx, st);
+  for (int idx = 0; idx < n_idx; ++idx) {
+    int rc = launch_slice(e, p, idx, idx + 1, st);
+    if (rc != QMK_OK) return rc;
+  }
+  return QMK_OK;
+}
+
+extern "C" int qmk_cp_predict(qmk_model*, const float*, int, const void*, const void*, const void*, void*, void*, int,
+                              int, float, int, uint64_t, uint64_t, const int32_t*, int64_t*, float*, float*, void*) {
+  return set_error(QMK_ERR_UNSUPPORTED, "qmk_cp_predict: fused frame kernel not built in this revision");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// upstream-compatible entry (kernel.cu:1485-1513).  Process-wide cache: device -> engine,
+// (device, blob pointer, num_layers) -> re-packed model.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct LegacyCfg {
+  int residual_fp32 = 1;
+  int lm_head_rows = 3072;
+};
+struct LegacyModel {
+  qmk_model* m = nullptr;
+  const void* final_norm = nullptr;
+  std::map<const void*, int> heads;
+};
+std::mutex g_legacy_mu;
+std::map<int, qmk_engine*> g_engines;
+std::map<std::tuple<int, const void*, int>, LegacyModel> g_models;
+std::map<const void*, LegacyCfg> g_cfg;
+int g_legacy_status = QMK_OK;
+}  // namespace
+
+extern "C" int qmk_legacy_configure(const LDGLayerWeights* layer_weights, int residual_fp32, int lm_head_rows) {
+  if (!layer_weights) return set_error(QMK_ERR_ARG, "qmk_legacy_configure: null blob");
+  if (lm_head_rows != 0 && (lm_head_rows < 64 || lm_head_rows > MAX_HEAD_ROWS))
+    return set_error(QMK_ERR_ARG, "qmk_legacy_configure: lm_head_rows %d", lm_head_rows);
+  std::lock_guard<std::mutex> lock(g_legacy_mu);
+  LegacyCfg c;
+  c.residual_fp32 = residual_fp32 ? 1 : 0;
+  c.lm_head_rows = lm_head_rows;
+  g_cfg[layer_weights] = c;
+  return QMK_OK;
+}
+
+extern "C" int qmk_legacy_status(void) { return g_legacy_status; }
+
+extern "C" void qmk_legacy_release(void) {
+  std::lock_guard<std::mutex> lock(g_legacy_mu);
+  for (auto& kv : g_models) qmk_model_destroy(kv.second.m);
+  g_models.clear();
+  for (auto& kv : g_engines) qmk_engine_destroy(kv.second);
+  g_engines.clear();
+  g_cfg.clear();
+}
+
+extern "C" void launch_ldg_decode_direct(int input_token_id, int* output_token_id, const void* embed_weight,
+                                         const LDGLayerWeights* layer_weights, const void* final_norm_weight,
+                                         const void* lm_head_weight, const void* cos_table, const void* sin_table,
+                                         void* k_cache, void* v_cache, void* hidden_buffer, void* /*g_activations*/,
+                                         void* /*g_residual*/, void* /*g_q*/, void* /*g_k*/, void* /*g_v*/,
+                                         void* /*g_attn_out*/, void* /*g_mlp_intermediate*/, void* g_normalized,
+                                         void* /*block_max_vals*/, void* /*block_max_idxs*/, int num_layers,
+                                         int position, int max_seq_len, float attn_scale, void* stream) {
+  std::lock_guard<std::mutex> lock(g_legacy_mu);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    g_legacy_status = set_error(QMK_ERR_CUDA, "launch_ldg_decode_direct: no CUDA device");
+    return;
+  }
+  qmk_engine*& e = g_engines[dev];
+  if (!e) {
+    int rc = qmk_engine_create(dev, 0, &e);
+    if (rc != QMK_OK) {
+      g_engines.erase(dev);
+      g_legacy_status = rc;
+      fprintf(stderr, "[qmk] %s\n", qmk_last_error());
+      return;
+    }
+  }
+  LegacyCfg cfg;
+  auto ci = g_cfg.find(layer_weights);
+  if (ci != g_cfg.end()) cfg = ci->second;
+  LegacyModel& lm = g_models[std::make_tuple(dev, (const void*)layer_weights, num_layers)];
+  if (!lm.m || lm.final_norm != final_norm_weight) {
+    if (lm.m) qmk_model_destroy(lm.m);
+    lm = LegacyModel();
+    int rc = qmk_model_create(e, layer_weights, num_layers, final_norm_weight, cfg.residual_fp32, stream, &lm.m);
+    if (rc != QMK_OK) {
+      g_legacy_status = rc;
+      fprintf(stderr, "[qmk] %s\n", qmk_last_error());
+      return;
+    }
+    lm.final_norm = final_norm_weight;
+  }
+  int head = -1;
+  if (cfg.lm_head_rows > 0) {
+    auto hi = lm.heads.find(lm_head_weight);
+    if (hi == lm.heads.end()) {
+      int rc = qmk_model_add_head(lm.m, lm_head_weight, cfg.lm_head_rows, stream);
+      if (rc < 0) {
+        g_legacy_status = rc;
+        fprintf(stderr, "[qmk] %s\n", qmk_last_error());
+        return;
+      }
+      hi = lm.heads.emplace(lm_head_weight, rc).first;
+    }
+    head = hi->second;
+  }
+  g_legacy_status = qmk_decode_step(lm.m, head, input_token_id, embed_weight, cos_table, sin_table, k_cache, v_cache,
+                                    hidden_buffer, reinterpret_cast<float*>(g_normalized), output_token_id, position,
+                                    max_seq_len, attn_scale, 0, stream);
+  if (g_legacy_status != QMK_OK) fprintf(stderr, "[qmk] %s\n", qmk_last_error());
+}

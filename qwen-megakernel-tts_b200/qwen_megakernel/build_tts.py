@@ -1,0 +1,189 @@
+"""Build / load the native engine and register ``torch.ops.qwen_megakernel_C.decode``.
+
+Replaces upstream qwen_megakernel/build_tts.py (JIT ``cpp_extension.load`` with ``-arch=sm_120a``,
+build_tts.py:45-71).  Here the kernel is compiled ahead of time for sm_100a with plain nvcc into an
+in-tree shared library (``libqmk_b200.so``, the C ABI of include/qmk_b200.h) so that it travels with the
+source tree; ``get_extension()`` compiles it only if the library is missing and nvcc is available.
+
+There is deliberately NO CPU or PyTorch fallback: if the library cannot be loaded, every entry point
+raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+import threading
+
+import torch
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_DIR)
+_CSRC = os.path.join(_ROOT, "csrc")
+_INCLUDE = os.path.join(os.path.dirname(_ROOT), "include")
+LIB_PATH = os.path.join(_DIR, "libqmk_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "--expt-relaxed-constexpr", "--extended-lambda",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+_lock = threading.Lock()
+_lib = None
+_op_lib = None
+
+
+def _nvcc() -> str | None:
+    cand = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
+    return cand if os.path.exists(cand) else shutil.which("nvcc")
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/qmk_engine.cu -> libqmk_b200.so (cross-compiles without a GPU)."""
+    srcs = [os.path.join(_CSRC, "qmk_engine.cu")]
+    deps = srcs + [os.path.join(_CSRC, "qmk_device.cuh"), os.path.join(_INCLUDE, "qmk_b200.h")]
+    if not force and os.path.exists(LIB_PATH):
+        if all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps if os.path.exists(d)):
+            return LIB_PATH
+    nvcc = _nvcc()
+    if nvcc is None:
+        raise RuntimeError("qwen_megakernel: libqmk_b200.so is missing/stale and nvcc was not found")
+    cmd = [nvcc] + NVCC_FLAGS + ["-Xptxas", "-v"] * int(verbose) + [f"-I{_INCLUDE}", f"-I{_CSRC}", "-o", LIB_PATH] + srcs
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_vp, _i32, _f32, _u64, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_uint64, ctypes.c_int64
+
+# symbol -> (restype, argtypes); must list every function declared in include/qmk_b200.h
+SIGNATURES = {
+    "qmk_abi_version": (_i32, []),
+    "qmk_last_error": (ctypes.c_char_p, []),
+    "qmk_engine_create": (_i32, [_i32, _i32, ctypes.POINTER(_vp)]),
+    "qmk_engine_destroy": (None, [_vp]),
+    "qmk_engine_num_ctas": (_i32, [_vp]),
+    "qmk_engine_sync_status": (_i32, [_vp, _vp, ctypes.POINTER(ctypes.c_int32)]),
+    "qmk_model_create": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, ctypes.POINTER(_vp)]),
+    "qmk_model_add_head": (_i32, [_vp, _vp, _i32, _vp]),
+    "qmk_model_set_group_embedding": (_i32, [_vp, _i32, _vp]),
+    "qmk_model_destroy": (None, [_vp]),
+    "qmk_model_packed_bytes": (_i64, [_vp]),
+    "qmk_decode_step": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _vp]),
+    "qmk_cp_predict": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _u64, _u64, _vp,
+                              _vp, _vp, _vp, _vp]),
+    "launch_ldg_decode_direct": (None, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
+    "qmk_legacy_configure": (_i32, [_vp, _i32, _i32]),
+    "qmk_legacy_status": (_i32, []),
+    "qmk_legacy_release": (None, []),
+}
+
+
+def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
+    """dlopen the C-ABI library and type its entry points.  No GPU work happens here."""
+    if not os.path.exists(path):
+        raise RuntimeError(f"qwen_megakernel: native library {path} not found (run build_tts.build())")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def check(lib, rc: int, what: str):
+    if rc < 0:
+        raise NativeError(f"{what}: {lib.qmk_last_error().decode()} (code {rc})")
+    return rc
+
+
+DECODE_SCHEMA = (
+    "decode(Tensor output_token, int input_token_id, "
+    "Tensor embed_weight, Tensor layer_weights_packed, "
+    "Tensor final_norm_weight, Tensor lm_head_weight, "
+    "Tensor cos_table, Tensor sin_table, "
+    "Tensor k_cache, Tensor v_cache, "
+    "Tensor hidden_buffer, Tensor activations, Tensor residual, "
+    "Tensor q, Tensor k, Tensor v, Tensor attn_out, "
+    "Tensor mlp_intermediate, Tensor normalized, "
+    "Tensor block_max_vals, Tensor block_max_idxs, "
+    "int num_layers, int position, int max_seq_len, "
+    "float attn_scale) -> ()"
+)
+
+
+def _decode_op(output_token, input_token_id, embed_weight, layer_weights_packed, final_norm_weight, lm_head_weight,
+               cos_table, sin_table, k_cache, v_cache, hidden_buffer, activations, residual, q, k, v, attn_out,
+               mlp_intermediate, normalized, block_max_vals, block_max_idxs, num_layers, position, max_seq_len,
+               attn_scale):
+    """Same schema and semantics as upstream torch_bindings.cpp:55-81 / :130-141, with the argument
+    validation upstream lacks (upstream performs no checks at all)."""
+    lib = _lib
+    for name, t, dt in (("output_token", output_token, torch.int32), ("embed_weight", embed_weight, torch.bfloat16),
+                        ("final_norm_weight", final_norm_weight, torch.bfloat16),
+                        ("lm_head_weight", lm_head_weight, torch.bfloat16), ("cos_table", cos_table, torch.bfloat16),
+                        ("sin_table", sin_table, torch.bfloat16), ("k_cache", k_cache, torch.bfloat16),
+                        ("v_cache", v_cache, torch.bfloat16), ("hidden_buffer", hidden_buffer, torch.bfloat16),
+                        ("normalized", normalized, torch.float32),
+                        ("layer_weights_packed", layer_weights_packed, torch.uint8)):
+        if not t.is_cuda or t.dtype != dt or not t.is_contiguous():
+            raise ValueError(f"decode: {name} must be a contiguous CUDA tensor of dtype {dt}")
+    if layer_weights_packed.numel() != int(num_layers) * 88:
+        raise ValueError("decode: layer_weights_packed must hold num_layers * 88 bytes (11 pointers per layer)")
+    if hidden_buffer.numel() != 1024 or normalized.numel() != 1024:
+        raise ValueError("decode: hidden_buffer / normalized must have 1024 elements")
+    if not (0 <= int(position) < int(max_seq_len)):
+        raise ValueError(f"decode: position {position} outside [0, {max_seq_len})")
+    with torch.cuda.device(hidden_buffer.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        lib.launch_ldg_decode_direct(
+            int(input_token_id), output_token.data_ptr(), embed_weight.data_ptr(), layer_weights_packed.data_ptr(),
+            final_norm_weight.data_ptr(), lm_head_weight.data_ptr(), cos_table.data_ptr(), sin_table.data_ptr(),
+            k_cache.data_ptr(), v_cache.data_ptr(), hidden_buffer.data_ptr(), activations.data_ptr(),
+            residual.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(), attn_out.data_ptr(),
+            mlp_intermediate.data_ptr(), normalized.data_ptr(), block_max_vals.data_ptr(), block_max_idxs.data_ptr(),
+            int(num_layers), int(position), int(max_seq_len), float(attn_scale), stream)
+    rc = lib.qmk_legacy_status()
+    if rc < 0:
+        raise NativeError(f"decode: {lib.qmk_last_error().decode()} (code {rc})")
+
+
+class _Extension:
+    """What ``get_extension()`` returns: the loaded C-ABI library plus the registered torch op."""
+
+    def __init__(self, lib):
+        self.lib = lib
+        self.decode = torch.ops.qwen_megakernel_C.decode
+        self.path = LIB_PATH
+
+
+_ext = None
+
+
+def get_extension():
+    """Build (if needed), load, and register ``torch.ops.qwen_megakernel_C.decode`` (upstream build_tts.py:55-71)."""
+    global _lib, _op_lib, _ext
+    with _lock:
+        if _ext is not None:
+            return _ext
+        path = build()
+        _lib = load_library(path)
+        if _lib.qmk_abi_version() != 1:
+            raise RuntimeError("qwen_megakernel: ABI version mismatch between Python layer and libqmk_b200.so")
+        _op_lib = torch.library.Library("qwen_megakernel_C", "DEF")
+        _op_lib.define(DECODE_SCHEMA)
+        _op_lib.impl("decode", _decode_op, "CUDA")
+        _ext = _Extension(_lib)
+        return _ext

@@ -1,0 +1,547 @@
+"""Model layer of the B200 decode engine — same public surface as upstream qwen_megakernel/model_tts.py.
+
+Replaced (new code, B200-native): ``load_tts_weights``, ``_pack_layer_weights``, ``TTSDecoder``,
+``CodePredictorKernel``.  Kept for callers that import them from here (``tts_engine.py:19-34`` upstream):
+``TextProjection``, ``CodePredictor``, ``build_prefill_embeddings`` — plain PyTorch helpers that sit
+outside the accelerated path.
+
+Differences a caller can observe (all additive):
+  * constructors accept an optional ``device=`` keyword (upstream hard-wires ``"cuda"``,
+    model_tts.py:227-247) so eight replicas can live on eight GPUs;
+  * ``reset()`` is O(1): attention reads rows ``0..position`` only, so the 939 MB KV memset upstream
+    performs per utterance (model_tts.py:332-336) is not needed;
+  * argument validation: bad token ids / positions raise instead of writing out of bounds;
+  * numerics follow the upstream *PyTorch* talker / code-predictor path (bf16 rounding points, fp32 vs
+    bf16 residual), which is what parity is judged against — not upstream kernel.cu's rounding.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+import struct
+from typing import Optional
+
+import torch
+
+# ─── Talker decoder constants (upstream model_tts.py:19-29) ─────────────────────────────────────────
+NUM_LAYERS = 28
+NUM_KV_HEADS = 8
+NUM_Q_HEADS = 16
+HEAD_DIM = 128
+HIDDEN_SIZE = 1024
+INTERMEDIATE_SIZE = 3072
+Q_SIZE = NUM_Q_HEADS * HEAD_DIM
+KV_SIZE = NUM_KV_HEADS * HEAD_DIM
+VOCAB_SIZE = 3072
+MAX_SEQ_LEN = 8192
+ROPE_THETA = 1000000.0
+
+# ─── Code predictor constants (upstream model_tts.py:31-34) ─────────────────────────────────────────
+NUM_CODE_GROUPS = 16
+CODE_PREDICTOR_LAYERS = 5
+CODE_PREDICTOR_VOCAB = 2048
+
+# ─── Special token ids (upstream model_tts.py:36-53) ────────────────────────────────────────────────
+CODEC_BOS = 2149
+CODEC_EOS = 2150
+CODEC_PAD = 2148
+CODEC_NOTHINK = 2155
+CODEC_THINK_BOS = 2156
+CODEC_THINK_EOS = 2157
+TTS_BOS = 151672
+TTS_EOS = 151673
+TTS_PAD = 151671
+EMBED_FROM_BUFFER = -1
+
+_LAYER_FIELDS = (
+    "input_layernorm.weight", "self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.v_proj.weight",
+    "self_attn.q_norm.weight", "self_attn.k_norm.weight", "self_attn.o_proj.weight",
+    "post_attention_layernorm.weight", "mlp.gate_proj.weight", "mlp.up_proj.weight", "mlp.down_proj.weight",
+)
+_LAYER_SHAPES = (
+    (HIDDEN_SIZE,), (Q_SIZE, HIDDEN_SIZE), (KV_SIZE, HIDDEN_SIZE), (KV_SIZE, HIDDEN_SIZE), (HEAD_DIM,), (HEAD_DIM,),
+    (HIDDEN_SIZE, Q_SIZE), (HIDDEN_SIZE,), (INTERMEDIATE_SIZE, HIDDEN_SIZE), (INTERMEDIATE_SIZE, HIDDEN_SIZE),
+    (HIDDEN_SIZE, INTERMEDIATE_SIZE),
+)
+
+
+def _rope_tables(max_seq: int, device) -> tuple[torch.Tensor, torch.Tensor]:
+    inv_freq = 1.0 / (ROPE_THETA ** (torch.arange(0, HEAD_DIM, 2, dtype=torch.float32) / HEAD_DIM))
+    freqs = torch.outer(torch.arange(max_seq, dtype=torch.float32), inv_freq)
+    cos = torch.cos(freqs).repeat(1, 2).to(torch.bfloat16).to(device).contiguous()
+    sin = torch.sin(freqs).repeat(1, 2).to(torch.bfloat16).to(device).contiguous()
+    return cos, sin
+
+
+def load_tts_weights(model_path: str = "Qwen/Qwen3-TTS-12Hz-0.6B-Base", device: str = "cuda",
+                     verbose: bool = True) -> dict:
+    """safetensors checkpoint -> the weights dict every other class consumes.
+
+    Same keys, layouts and dtypes as upstream ``load_tts_weights`` (model_tts.py:56-179): ordinary torch
+    tensors in the original ``[out, in]`` layout (kept code such as ``TextProjection`` and the frame loop
+    of tts_engine.py index this dict directly); the engine re-packs its own copy at construction time.
+    """
+    if verbose:
+        print(f"Loading TTS weights from {model_path}...")
+    if os.path.isdir(model_path):
+        path = os.path.join(model_path, "model.safetensors")
+    else:
+        from huggingface_hub import hf_hub_download
+        path = hf_hub_download(model_path, "model.safetensors")
+    from safetensors.torch import load_file
+    state = load_file(path, device=device)
+
+    def take(key):
+        return state[key].contiguous()
+
+    layer_weights = [take(f"talker.model.layers.{i}.{f}") for i in range(NUM_LAYERS) for f in _LAYER_FIELDS]
+    cos_table, sin_table = _rope_tables(MAX_SEQ_LEN, device)
+    cp = {}
+    for i in range(CODE_PREDICTOR_LAYERS):
+        for f in _LAYER_FIELDS:
+            cp[f"layers.{i}.{f}"] = state[f"talker.code_predictor.model.layers.{i}.{f}"]
+    cp["norm.weight"] = state["talker.code_predictor.model.norm.weight"]
+    for g in range(NUM_CODE_GROUPS - 1):
+        cp[f"lm_head.{g}.weight"] = state[f"talker.code_predictor.lm_head.{g}.weight"]
+        cp[f"codec_embedding.{g}.weight"] = state[f"talker.code_predictor.model.codec_embedding.{g}.weight"]
+    weights = dict(
+        embed_weight=take("talker.model.codec_embedding.weight"),
+        lm_head_weight=take("talker.codec_head.weight"),
+        final_norm_weight=take("talker.model.norm.weight"),
+        layer_weights=layer_weights,
+        cos_table=cos_table,
+        sin_table=sin_table,
+        text_embedding=take("talker.model.text_embedding.weight"),
+        text_proj_fc1_w=take("talker.text_projection.linear_fc1.weight"),
+        text_proj_fc1_b=take("talker.text_projection.linear_fc1.bias"),
+        text_proj_fc2_w=take("talker.text_projection.linear_fc2.weight"),
+        text_proj_fc2_b=take("talker.text_projection.linear_fc2.bias"),
+        code_predictor=cp,
+        speaker_encoder={k: v for k, v in state.items() if k.startswith("speaker_encoder.")},
+    )
+    if verbose:
+        print(f"Loaded {len(state)} tensors ({sum(v.numel() for v in state.values()) / 1e6:.1f}M params)")
+    del state
+    if torch.cuda.is_available():
+        torch.cuda.empty_cache()
+    return weights
+
+
+def _check_layer_tensors(layer_weights, num_layers: int, device) -> None:
+    if len(layer_weights) != 11 * num_layers:
+        raise ValueError(f"expected {11 * num_layers} layer tensors, got {len(layer_weights)}")
+    for i, t in enumerate(layer_weights):
+        want = _LAYER_SHAPES[i % 11]
+        if tuple(t.shape) != want or t.dtype != torch.bfloat16 or not t.is_contiguous():
+            raise ValueError(f"layer tensor {i} ({_LAYER_FIELDS[i % 11]}): need contiguous bf16 {want}, "
+                             f"got {t.dtype} {tuple(t.shape)}")
+        if device is not None and t.device != device:
+            raise ValueError(f"layer tensor {i} is on {t.device}, expected {device}")
+
+
+def _pack_layer_weights(layer_weights: list[torch.Tensor], num_layers: int = NUM_LAYERS,
+                        device=None) -> torch.Tensor:
+    """11 data pointers per layer -> uint8[num_layers * 88] blob of ``LDGLayerWeights`` structs
+    (include/qmk_b200.h; upstream model_tts.py:182-193).  The caller keeps the tensors alive."""
+    buf = bytearray(num_layers * 88)
+    for i in range(num_layers * 11):
+        struct.pack_into("Q", buf, i * 8, layer_weights[i].data_ptr())
+    blob = torch.frombuffer(buf, dtype=torch.uint8)
+    dev = device if device is not None else (layer_weights[0].device if layer_weights[0].is_cuda else "cuda")
+    return blob.to(dev)
+
+
+def _require_cuda_bf16(t: torch.Tensor, n: int, what: str) -> None:
+    if not (t.is_cuda and t.dtype == torch.bfloat16 and t.numel() == n and t.is_contiguous()):
+        raise ValueError(f"{what}: need a contiguous CUDA bf16 tensor with {n} elements, got "
+                         f"{t.dtype} {tuple(t.shape)} on {t.device}")
+
+
+class _Native:
+    """Process-wide handle on libqmk_b200.so plus one engine per CUDA device."""
+
+    _engines: dict = {}
+
+    @classmethod
+    def lib(cls):
+        from .build_tts import get_extension
+        return get_extension().lib
+
+    @classmethod
+    def engine(cls, device: torch.device):
+        from .build_tts import check
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if idx not in cls._engines:
+            lib = cls.lib()
+            h = ctypes.c_void_p()
+            check(lib, lib.qmk_engine_create(idx, 0, ctypes.byref(h)), "qmk_engine_create")
+            cls._engines[idx] = h
+        return cls._engines[idx]
+
+    @classmethod
+    def raise_kernel_status(cls, device: torch.device, what: str):
+        from .build_tts import NativeError, check
+        lib = cls.lib()
+        detail = (ctypes.c_int32 * 4)()
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib, lib.qmk_engine_sync_status(cls.engine(device), stream, detail), what)
+        raise NativeError(f"{what}: kernel reported failure but the status word is clear")
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class TTSDecoder:
+    """Stateful talker decoder (28 layers) on the fused sm_100a kernel.
+
+    Same contract as upstream ``TTSDecoder`` (model_tts.py:196-345): ``step(token_id)`` /
+    ``step_with_embed(embed_bf16)`` return ``(next_token:int, hidden:float32[1024])`` where ``hidden`` is the
+    post-final-RMSNorm state the code predictor consumes; ``position`` is host state.
+    """
+
+    def __init__(self, weights: Optional[dict] = None, model_path: str = "Qwen/Qwen3-TTS-12Hz-0.6B-Base",
+                 verbose: bool = True, *, device=None, max_seq_len: int = MAX_SEQ_LEN, mode: int = 0,
+                 num_layers: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("TTSDecoder needs a CUDA device (sm_100a); there is no CPU fallback")
+        dev = torch.device(device if device is not None else "cuda")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if weights is None:
+            weights = load_tts_weights(model_path, device=str(dev), verbose=verbose)
+        self.device = dev
+        self._weights = weights
+        self._position = 0
+        self._mode = mode
+        self._max_seq = int(max_seq_len)
+        # num_layers is a runtime parameter of the kernel (upstream passes 28 or 5, model_tts.py:278,724)
+        self._num_layers = int(num_layers) if num_layers is not None else len(weights["layer_weights"]) // 11
+        self._embed_weight = weights["embed_weight"]
+        self._final_norm_weight = weights["final_norm_weight"]
+        self._lm_head_weight = weights["lm_head_weight"]
+        self._cos_table = weights["cos_table"]
+        self._sin_table = weights["sin_table"]
+        if self._cos_table.shape[0] < self._max_seq:
+            raise ValueError("RoPE tables are shorter than max_seq_len")
+        _check_layer_tensors(weights["layer_weights"][:11 * self._num_layers], self._num_layers, dev)
+        for name, t, shape in (("embed_weight", self._embed_weight, (VOCAB_SIZE, HIDDEN_SIZE)),
+                               ("lm_head_weight", self._lm_head_weight, (VOCAB_SIZE, HIDDEN_SIZE)),
+                               ("final_norm_weight", self._final_norm_weight, (HIDDEN_SIZE,))):
+            if tuple(t.shape) != shape or t.dtype != torch.bfloat16 or t.device != dev:
+                raise ValueError(f"{name}: need bf16 {shape} on {dev}")
+        self._attn_scale = 1.0 / math.sqrt(HEAD_DIM)
+
+        from .build_tts import check
+        self._lib = _Native.lib()
+        self._engine = _Native.engine(dev)
+        with torch.cuda.device(dev):
+            self._layer_weights_packed = _pack_layer_weights(weights["layer_weights"], self._num_layers, dev)
+            h = ctypes.c_void_p()
+            check(self._lib, self._lib.qmk_model_create(
+                self._engine, self._layer_weights_packed.data_ptr(), self._num_layers, self._final_norm_weight.data_ptr(),
+                1, _stream_ptr(dev), ctypes.byref(h)), "qmk_model_create")
+            self._model = h
+            self._head = check(self._lib, self._lib.qmk_model_add_head(
+                self._model, self._lm_head_weight.data_ptr(), VOCAB_SIZE, _stream_ptr(dev)), "qmk_model_add_head")
+            self._k_cache = torch.zeros(self._num_layers, NUM_KV_HEADS, self._max_seq, HEAD_DIM,
+                                        dtype=torch.bfloat16, device=dev)
+            self._v_cache = torch.zeros_like(self._k_cache)
+            self._hidden = torch.zeros(HIDDEN_SIZE, dtype=torch.bfloat16, device=dev)
+            self._norm_out = torch.zeros(HIDDEN_SIZE, dtype=torch.float32, device=dev)
+            self._out_token = torch.zeros(1, dtype=torch.int32, device=dev)
+        if verbose:
+            mb = self._lib.qmk_model_packed_bytes(self._model) / 1e6
+            print(f"TTSDecoder: {self._lib.qmk_engine_num_ctas(self._engine)} persistent CTAs, "
+                  f"{mb:.0f} MB re-packed weights on {dev}")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_model", None):
+                self._lib.qmk_model_destroy(self._model)
+                self._model = None
+        except Exception:
+            pass
+
+    def _launch(self, token_id: int, input_ptr: int) -> None:
+        from .build_tts import check
+        if self._position >= self._max_seq:
+            raise IndexError(f"KV cache is full (position {self._position} == max_seq_len)")
+        check(self._lib, self._lib.qmk_decode_step(
+            self._model, self._head, token_id, self._embed_weight.data_ptr(), self._cos_table.data_ptr(),
+            self._sin_table.data_ptr(), self._k_cache.data_ptr(), self._v_cache.data_ptr(), input_ptr,
+            self._norm_out.data_ptr(), self._out_token.data_ptr(), self._position, self._max_seq,
+            self._attn_scale, self._mode, _stream_ptr(self.device)), "qmk_decode_step")
+        self._position += 1
+
+    def _finish(self) -> tuple[int, torch.Tensor]:
+        hidden = self._norm_out.clone()
+        token = int(self._out_token.item())          # the one host sync per step the upstream API implies
+        if token < 0:
+            _Native.raise_kernel_status(self.device, "TTSDecoder.step")
+        return token, hidden
+
+    def step(self, token_id: int) -> tuple[int, torch.Tensor]:
+        """Decode one token via embedding lookup. Returns (next_token, hidden_state_f32)."""
+        token_id = int(token_id)
+        if not 0 <= token_id < VOCAB_SIZE:
+            raise ValueError(f"token id {token_id} outside [0, {VOCAB_SIZE})")
+        self._launch(token_id, self._hidden.data_ptr())
+        return self._finish()
+
+    def step_with_embed(self, embed_bf16: torch.Tensor) -> tuple[int, torch.Tensor]:
+        """Decode from a precomputed bf16[1024] embedding (upstream sentinel path, token_id = -1)."""
+        if embed_bf16.dtype != torch.bfloat16:
+            embed_bf16 = embed_bf16.to(torch.bfloat16)
+        embed_bf16 = embed_bf16.reshape(-1)
+        if embed_bf16.device != self.device:
+            embed_bf16 = embed_bf16.to(self.device)
+        _require_cuda_bf16(embed_bf16.contiguous(), HIDDEN_SIZE, "step_with_embed(embed_bf16)")
+        self._hidden.copy_(embed_bf16)
+        self._launch(EMBED_FROM_BUFFER, self._hidden.data_ptr())
+        return self._finish()
+
+    def reset(self):
+        """New utterance.  O(1): rows beyond ``position`` are never read."""
+        self._position = 0
+
+    @property
+    def position(self) -> int:
+        return self._position
+
+    @property
+    def embed_weight(self) -> torch.Tensor:
+        """Codec embedding table [3072, 1024] bf16."""
+        return self._embed_weight
+
+
+class TextProjection:
+    """text ids -> talker hidden size: embedding(151936 -> 2048) -> fc1 + SiLU -> fc2 (-> 1024).
+
+    Outside the accelerated path (once per utterance); same interface as upstream model_tts.py:348-374.
+    """
+
+    def __init__(self, weights: dict, device: str = "cuda"):
+        self.text_embedding = weights["text_embedding"]
+        self.fc1_w, self.fc1_b = weights["text_proj_fc1_w"], weights["text_proj_fc1_b"]
+        self.fc2_w, self.fc2_b = weights["text_proj_fc2_w"], weights["text_proj_fc2_b"]
+
+    @torch.no_grad()
+    def embed_text_ids(self, token_ids: torch.Tensor) -> torch.Tensor:
+        F = torch.nn.functional
+        x = F.embedding(token_ids, self.text_embedding)
+        return F.linear(F.silu(F.linear(x, self.fc1_w, self.fc1_b)), self.fc2_w, self.fc2_b)
+
+
+class CodePredictorKernel:
+    """Code predictor (5 layers, 15 group heads) on the same kernel as the talker (``num_layers=5``).
+
+    Same contract as upstream ``CodePredictorKernel`` (model_tts.py:622-773).  Group LM heads are registered
+    with the engine, so greedy prediction never leaves the kernel; the sampling path applies the upstream
+    temperature / top-k / multinomial rule on the kernel's hidden state.
+    """
+
+    def __init__(self, weights: dict, device: str = "cuda", *, mode: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("CodePredictorKernel needs a CUDA device (sm_100a); there is no CPU fallback")
+        dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self._mode = mode
+        cp = weights["code_predictor"]
+        self.num_groups = NUM_CODE_GROUPS - 1
+        self._layer_weights = [cp[f"layers.{i}.{f}"].contiguous() for i in range(CODE_PREDICTOR_LAYERS)
+                               for f in _LAYER_FIELDS]
+        _check_layer_tensors(self._layer_weights, CODE_PREDICTOR_LAYERS, dev)
+        self._final_norm_weight = cp["norm.weight"].contiguous()
+        self.codec_embeddings = [cp[f"codec_embedding.{g}.weight"].contiguous() for g in range(self.num_groups)]
+        self.lm_heads = [cp[f"lm_head.{g}.weight"].contiguous() for g in range(self.num_groups)]
+        self._max_seq = 64
+        self._cos_table, self._sin_table = _rope_tables(self._max_seq, dev)
+        self._attn_scale = 1.0 / math.sqrt(HEAD_DIM)
+        self._position = 0
+
+        from .build_tts import check
+        self._lib = _Native.lib()
+        self._engine = _Native.engine(dev)
+        with torch.cuda.device(dev):
+            self._layer_weights_packed = _pack_layer_weights(self._layer_weights, CODE_PREDICTOR_LAYERS, dev)
+            h = ctypes.c_void_p()
+            check(self._lib, self._lib.qmk_model_create(
+                self._engine, self._layer_weights_packed.data_ptr(), CODE_PREDICTOR_LAYERS,
+                self._final_norm_weight.data_ptr(), 0, _stream_ptr(dev), ctypes.byref(h)), "qmk_model_create")
+            self._model = h
+            self._heads = []
+            for g in range(self.num_groups):
+                self._heads.append(check(self._lib, self._lib.qmk_model_add_head(
+                    self._model, self.lm_heads[g].data_ptr(), CODE_PREDICTOR_VOCAB, _stream_ptr(dev)),
+                    "qmk_model_add_head"))
+                check(self._lib, self._lib.qmk_model_set_group_embedding(
+                    self._model, g, self.codec_embeddings[g].data_ptr()), "qmk_model_set_group_embedding")
+            self._k_cache = torch.zeros(CODE_PREDICTOR_LAYERS, NUM_KV_HEADS, self._max_seq, HEAD_DIM,
+                                        dtype=torch.bfloat16, device=dev)
+            self._v_cache = torch.zeros_like(self._k_cache)
+            self._hidden = torch.zeros(HIDDEN_SIZE, dtype=torch.bfloat16, device=dev)
+            self._norm_out = torch.zeros(HIDDEN_SIZE, dtype=torch.float32, device=dev)
+            self._out_token = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._token_buf = torch.zeros(1, dtype=torch.long, device=dev)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_model", None):
+                self._lib.qmk_model_destroy(self._model)
+                self._model = None
+        except Exception:
+            pass
+
+    def reset(self):
+        self._position = 0
+
+    def _step_with_embed(self, embed_bf16: torch.Tensor, head: int = -1):
+        """One 5-layer decode step; afterwards ``_norm_out`` holds the hidden state and, if ``head`` >= 0,
+        ``_out_token`` the argmax of that group head."""
+        from .build_tts import check
+        if self._position >= self._max_seq:
+            raise IndexError("code-predictor KV cache is full")
+        self._hidden.copy_(embed_bf16.reshape(-1))
+        check(self._lib, self._lib.qmk_decode_step(
+            self._model, head, EMBED_FROM_BUFFER, None, self._cos_table.data_ptr(), self._sin_table.data_ptr(),
+            self._k_cache.data_ptr(), self._v_cache.data_ptr(), self._hidden.data_ptr(),
+            self._norm_out.data_ptr(), self._out_token.data_ptr(), self._position, self._max_seq,
+            self._attn_scale, self._mode, _stream_ptr(self.device)), "qmk_decode_step")
+        self._position += 1
+
+    @torch.no_grad()
+    def predict(self, talker_hidden: torch.Tensor, first_codebook_token: int, talker_embed_weight: torch.Tensor,
+                do_sample: bool = True, temperature: float = 0.9, top_k: int = 50) -> torch.Tensor:
+        """All 16 codebook groups of one frame: int64[16] on device = [first_token, g0..g14]."""
+        F = torch.nn.functional
+        first_codebook_token = int(first_codebook_token)
+        if not 0 <= first_codebook_token < talker_embed_weight.shape[0]:
+            raise ValueError(f"first_codebook_token {first_codebook_token} out of range")
+        sample = bool(do_sample) and temperature > 0
+        with torch.cuda.device(self.device):
+            self.reset()
+            self._step_with_embed(talker_hidden.to(self.device).to(torch.bfloat16))
+            self._token_buf[0] = first_codebook_token
+            out = [self._token_buf.clone()]
+            embed = F.embedding(self._token_buf, talker_embed_weight).squeeze(0)
+            for g in range(self.num_groups):
+                self._step_with_embed(embed, head=-1 if sample else self._heads[g])
+                if sample:
+                    logits = F.linear(self._norm_out.to(torch.bfloat16).unsqueeze(0), self.lm_heads[g]).squeeze(0)
+                    z = logits.float() / temperature
+                    if top_k > 0:
+                        kth = torch.topk(z, min(top_k, z.numel())).values[-1]
+                        z = z.masked_fill(z < kth, float("-inf"))
+                    tok = torch.multinomial(F.softmax(z, dim=-1), 1)
+                else:
+                    tok = self._out_token.long()
+                out.append(tok)
+                if g < self.num_groups - 1:
+                    embed = F.embedding(tok, self.codec_embeddings[g]).squeeze(0)
+            return torch.cat(out)
+
+
+class CodePredictor:
+    """Pure-PyTorch code predictor with the upstream interface (model_tts.py:377-504).
+
+    Upstream keeps this class as the slow reference implementation; it is not on the accelerated path.
+    It is provided so that ``from .model_tts import CodePredictor`` keeps working; it evaluates the same
+    decode-step arithmetic with ordinary torch ops on whatever device the weights live on.
+    """
+
+    def __init__(self, weights: dict, device: str = "cuda"):
+        self.device = device
+        cp = weights["code_predictor"]
+        self.num_groups = NUM_CODE_GROUPS - 1
+        self.codec_embeddings = [cp[f"codec_embedding.{g}.weight"] for g in range(self.num_groups)]
+        self.lm_heads = [cp[f"lm_head.{g}.weight"] for g in range(self.num_groups)]
+        self.layers = [[cp[f"layers.{i}.{f}"] for f in _LAYER_FIELDS] for i in range(CODE_PREDICTOR_LAYERS)]
+        self.final_norm = cp["norm.weight"]
+        self._max_seq = 20
+        self._cos, self._sin = _rope_tables(64, device)
+        self._k = torch.zeros(CODE_PREDICTOR_LAYERS, NUM_KV_HEADS, self._max_seq, HEAD_DIM, dtype=torch.bfloat16,
+                              device=device)
+        self._v = torch.zeros_like(self._k)
+
+    @staticmethod
+    def _norm(x, w, eps=1e-6):
+        xf = x.float()
+        return (xf / torch.sqrt(xf.pow(2).mean(-1, keepdim=True) + eps) * w.float()).to(x.dtype)
+
+    def _rope(self, t, pos):
+        half = HEAD_DIM // 2
+        c, s = self._cos[pos, :half], self._sin[pos, :half]
+        t1, t2 = t[..., :half], t[..., half:]
+        return torch.cat([t1 * c - t2 * s, t2 * c + t1 * s], dim=-1)
+
+    def _token_step(self, x, pos):
+        F = torch.nn.functional
+        h = x.to(torch.bfloat16)
+        for li, (w_in, wq, wk, wv, w_qn, w_kn, wo, w_post, wg, wu, wd) in enumerate(self.layers):
+            n = self._norm(h, w_in)
+            q = self._rope(self._norm(F.linear(n, wq).view(NUM_Q_HEADS, HEAD_DIM), w_qn), pos)
+            k = self._rope(self._norm(F.linear(n, wk).view(NUM_KV_HEADS, HEAD_DIM), w_kn), pos)
+            self._k[li, :, pos] = k
+            self._v[li, :, pos] = F.linear(n, wv).view(NUM_KV_HEADS, HEAD_DIM)
+            kf = self._k[li, :, :pos + 1].float().repeat_interleave(2, dim=0)
+            vf = self._v[li, :, :pos + 1].float().repeat_interleave(2, dim=0)
+            p = torch.softmax(torch.einsum("hd,hsd->hs", q.float(), kf) / math.sqrt(HEAD_DIM), dim=-1)
+            a = torch.einsum("hs,hsd->hd", p, vf).to(torch.bfloat16).reshape(-1)
+            h = h + F.linear(a, wo)
+            n2 = self._norm(h, w_post)
+            h = h + F.linear(F.silu(F.linear(n2, wg)) * F.linear(n2, wu), wd)
+        return self._norm(h, self.final_norm)
+
+    @torch.no_grad()
+    def predict(self, talker_hidden, first_codebook_token, talker_embed_weight, do_sample=True, temperature=0.9,
+                top_k=50):
+        F = torch.nn.functional
+        self._token_step(talker_hidden, 0)
+        hn = self._token_step(talker_embed_weight[int(first_codebook_token)], 1)
+        out = [int(first_codebook_token)]
+        for g in range(self.num_groups):
+            z = F.linear(hn, self.lm_heads[g]).float()
+            if do_sample and temperature > 0:
+                z = z / temperature
+                if top_k > 0:
+                    z = z.masked_fill(z < torch.topk(z, min(top_k, z.numel())).values[-1], float("-inf"))
+                tok = int(torch.multinomial(F.softmax(z, dim=-1), 1))
+            else:
+                tok = int(z.argmax())
+            out.append(tok)
+            if g < self.num_groups - 1:
+                hn = self._token_step(self.codec_embeddings[g][tok], 2 + g)
+        return torch.tensor(out, dtype=torch.int64, device=self.device)
+
+
+def build_prefill_embeddings(text_token_ids: torch.Tensor, text_projection: TextProjection,
+                             codec_embed_weight: torch.Tensor, language: str = "Auto", device: str = "cuda",
+                             cached_tts_embeds: Optional[dict] = None) -> tuple[torch.Tensor, torch.Tensor]:
+    """Prefill sequence of the talker (upstream model_tts.py:776-864), outside the accelerated path.
+
+    Returns ``(prefill[8, 1024], trailing_text[T, 1024])``: 3 role tokens, 4 codec tags fused with
+    tts_pad/tts_bos, first text token fused with codec_bos; the remaining text (minus the 5 closing
+    format tokens) plus tts_eos is fed one embedding per decode step.
+    """
+    F = torch.nn.functional
+    ids = text_token_ids.to(device)
+    if cached_tts_embeds is None:
+        special = torch.tensor([TTS_PAD, TTS_BOS, TTS_EOS], device=device)
+        emb = text_projection.embed_text_ids(torch.cat([ids, special]))
+        text, (pad, bos, eos) = emb[:-3], (emb[-3:-2], emb[-2:-1], emb[-1:])
+    else:
+        text = text_projection.embed_text_ids(ids)
+        pad, bos, eos = cached_tts_embeds["pad"], cached_tts_embeds["bos"], cached_tts_embeds["eos"]
+    role, content = text[:3], text[3:]
+    tags = F.embedding(torch.tensor([CODEC_NOTHINK, CODEC_THINK_BOS, CODEC_THINK_EOS, CODEC_PAD, CODEC_BOS],
+                                    device=device), codec_embed_weight)
+    fused = torch.cat([pad.expand(3, -1), bos], dim=0) + tags[:4]
+    prefill = torch.cat([role, fused, content[:1] + tags[4:5]], dim=0)
+    trailing = torch.cat([content[1:-5], eos], dim=0)
+    return prefill, trailing
