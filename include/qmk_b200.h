@@ -74,6 +74,12 @@ int qmk_engine_num_ctas(const qmk_engine* e);
  * (QMK_OK or QMK_ERR_KERNEL); detail[0..3] (optional, host) receives the watchdog record. */
 int qmk_engine_sync_status(qmk_engine* e, void* stream, int32_t* detail);
 
+/* Optional phase trace (debug/profiling): with stride > 0 every CTA records clock64() at the start of each
+ * phase of the next launches into a [num_ctas][stride] device array; stride 0 disables it.
+ * qmk_engine_trace_read synchronises `stream`, copies the array to host_out and returns the stride. */
+int qmk_engine_trace_enable(qmk_engine* e, int stride);
+int qmk_engine_trace_read(qmk_engine* e, void* stream, long long* host_out, int64_t max_elems);
+
 /* ---- model (weight re-packing; replaces upstream _pack_layer_weights as the packing layer) ------ */
 /* `layers` is the caller's DEVICE blob of num_layers LDGLayerWeights structs.  The weights are copied
  * into the engine's own per-CTA stream layout; the originals are not referenced afterwards.

@@ -91,6 +91,10 @@ struct Params {
   int* status;                     // int[4]: code, cta, phase index, aux
   int phase_begin, phase_end;      // half-open range in the linear phase index space
   long long timeout_cycles;
+  int replicas;                    // R copies of every exchange buffer; CTA c polls copy c % R
+  int probe;                       // 1: one warp probes a sample of words before the CTA-wide gather
+  long long* trace;                // optional [G][trace_stride] clock64 stamps at phase starts
+  int trace_stride;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -157,6 +161,10 @@ __device__ __forceinline__ uint2 ld_cg_u2(const void* p) {
   asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
   return v;
 }
+// Publish one exchange word into every replica (stride XW_TOTAL words).
+__device__ __forceinline__ void ll_pub(u64* p, uint32_t payload, uint32_t epoch, int replicas, int stride_words) {
+  for (int r = 0; r < replicas; ++r) ll_st(p + (size_t)r * stride_words, payload, epoch);
+}
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------
@@ -183,6 +191,7 @@ struct Ctx {
   u64* empty;
   volatile int* s_abort;
   float* s_red;
+  const u64* xrd;  // exchange replica this CTA reads
   int tid, warp, lane, cta;
   uint32_t k;     // stage counter (same sequence in producer and consumers)
   long long t0;
@@ -246,10 +255,27 @@ __device__ __forceinline__ uint32_t ll_wait(Ctx& c, const u64* p, uint32_t epoch
   return (uint32_t)w;
 }
 
+// Debug trace: trace[cta][(idx - phase_begin) * 8 + sub] = clock64() (thread 0 of the CTA only).
+__device__ __forceinline__ void trace_sub(const Ctx& c, int sub) {
+  if (c.p.trace != nullptr && c.tid == 0) {
+    const int slot = (c.cur_idx - c.p.phase_begin) * 8 + sub;
+    if (slot < c.p.trace_stride) c.p.trace[(size_t)c.cta * c.p.trace_stride + slot] = clock64();
+  }
+}
+
 // Gather N exchange words (all loads issued before the first check) and hand each payload to `store`.
+// With p.probe, warp 0 first polls a 32-word sample while the other warps sleep at a barrier: thousands
+// of threads spinning on the same few L2 lines delay the very stores they are waiting for.
 template <int N, typename F>
 __device__ __forceinline__ void gather_words(Ctx& c, const u64* buf, uint32_t epoch, F store, int n = N) {
   constexpr int PER = (N + NCT - 1) / NCT;
+  if (c.p.probe) {
+    if (c.warp == 0) {
+      const int idx = (int)(((long long)c.lane * n) >> 5) + (n >> 6);
+      (void)ll_wait(c, buf + (idx < n ? idx : n - 1), epoch);
+    }
+    consumer_bar();
+  }
   u64 w[PER];
 #pragma unroll
   for (int u = 0; u < PER; ++u) {
@@ -471,10 +497,11 @@ __device__ __forceinline__ void attn_prefetch(const Ctx& c, int l, const AttnIte
 
 __device__ void phase_attn(Ctx& c, int l, uint32_t epoch, const AttnItem& it, KvRegs& kv, bool prefetched) {
   const Params& p = c.p;
-  u64* x_qkv = p.xbuf + XW_RES;
-  u64* x_a = x_qkv + XW_QKV;
-  u64* x_part = p.xbuf + (XW_TOTAL - XW_PART);
+  const u64* x_qkv = c.xrd + XW_RES;                  // this CTA's replica
+  u64* x_a = p.xbuf + XW_RES + XW_QKV;                // writers publish into every replica
+  u64* x_part = p.xbuf + (XW_TOTAL - XW_PART);        // split partials: replica 0 only (few readers)
   float* s_small = c.s_small;
+  const int R = p.replicas;
   if (!prefetched) attn_prefetch(c, l, it, 0, kv);
 
   // 1) raw q (2 heads), k, v of this kv group
@@ -489,6 +516,7 @@ __device__ void phase_attn(Ctx& c, int l, uint32_t epoch, const AttnItem& it, Kv
     }
   }
   consumer_bar();
+  trace_sub(c, 1);
 
   // 2) per-head RMSNorm + rotate-half RoPE in bf16 steps (warp 0,1: q heads; warp 2: k)
   if (c.warp < 2 || (c.warp == 2 && it.owner)) {
@@ -516,6 +544,7 @@ __device__ void phase_attn(Ctx& c, int l, uint32_t epoch, const AttnItem& it, Kv
     }
   }
   consumer_bar();
+  trace_sub(c, 2);
 
   // 3) scores / online softmax / PV over this item's positions; lane owns dims 4*lane..4*lane+3
   float q0[4], q1[4], acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
@@ -588,6 +617,7 @@ __device__ void phase_attn(Ctx& c, int l, uint32_t epoch, const AttnItem& it, Kv
       m0 = mx0; m1 = mx1;
     }
   }
+  trace_sub(c, 3);
   // 4) cross-warp merge through shared memory (s_vec region is free during attention)
   float* s_acc = c.s_vec;  // [12][2][128]
 #pragma unroll
@@ -600,6 +630,7 @@ __device__ void phase_attn(Ctx& c, int l, uint32_t epoch, const AttnItem& it, Kv
     s_small[SS_ML + (c.warp * 2 + 1) * 2 + 0] = m1; s_small[SS_ML + (c.warp * 2 + 1) * 2 + 1] = l1;
   }
   consumer_bar();
+  trace_sub(c, 4);
   if (c.tid < 128) {
     const int h = c.tid >> 6, dp = c.tid & 63;
     float M = -INFINITY;
@@ -617,7 +648,7 @@ __device__ void phase_attn(Ctx& c, int l, uint32_t epoch, const AttnItem& it, Kv
     const int hq = 2 * it.g + h;
     if (it.S == 1) {
       const uint32_t pk = bf16_bits(A0 / Lsum) | (bf16_bits(A1 / Lsum) << 16);
-      ll_st(x_a + hq * 64 + dp, pk, epoch);
+      ll_pub(x_a + hq * 64 + dp, pk, epoch, R, XW_TOTAL);
     } else {
       u64* part = x_part + ((size_t)hq * S_MAX + it.s) * PART_STRIDE;
       ll_st(part + 2 + 2 * dp, __float_as_uint(A0), epoch);
@@ -641,10 +672,11 @@ __device__ void phase_attn(Ctx& c, int l, uint32_t epoch, const AttnItem& it, Kv
           B1 = fmaf(__uint_as_float(ll_wait(c, ps + 3 + 2 * dp, epoch)), f, B1);
         }
         const uint32_t pk = bf16_bits(B0 / Lt) | (bf16_bits(B1 / Lt) << 16);
-        ll_st(x_a + hq * 64 + dp, pk, epoch);
+        ll_pub(x_a + hq * 64 + dp, pk, epoch, R, XW_TOTAL);
       }
     }
   }
+  trace_sub(c, 5);
   // 5) append the new K/V row (off the critical path: after `a` has been published)
   if (it.owner && c.tid < 128) {
     const size_t off = ((size_t)(l * NKVH + it.g) * p.max_seq + p.position) * HD + c.tid;
@@ -653,6 +685,7 @@ __device__ void phase_attn(Ctx& c, int l, uint32_t epoch, const AttnItem& it, Kv
     __threadfence();
   }
   consumer_bar();  // s_small / s_acc are reused by the next phase
+  trace_sub(c, 6);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -662,12 +695,18 @@ __device__ void consumer_loop(Ctx& c) {
   const Params& p = c.p;
   const Layout& y = p.lay;
   const int nlayer_idx = y.L * PH_PER_LAYER;
-  u64* x_res = p.xbuf;
-  u64* x_qkv = x_res + XW_RES;
-  u64* x_a = x_qkv + XW_QKV;
-  u64* x_res2 = x_a + XW_A;
-  u64* x_m = x_res2 + XW_RES2;
-  u64* x_logits = x_m + XW_M;
+  // writer views (replica 0; ll_pub fans out) and reader views (replica cta % R)
+  u64* w_res = p.xbuf;
+  u64* w_qkv = w_res + XW_RES;
+  u64* w_res2 = w_qkv + XW_QKV + XW_A;
+  u64* w_m = w_res2 + XW_RES2;
+  u64* w_logits = w_m + XW_M;
+  const u64* x_res = c.xrd;
+  const u64* x_a = x_res + XW_RES + XW_QKV;
+  const u64* x_res2 = x_a + XW_A;
+  const u64* x_m = x_res2 + XW_RES2;
+  const u64* x_logits = x_m + XW_M;
+  const int R = p.replicas;
   float xr[32];
   KvRegs kv;
   AttnItem item;
@@ -678,6 +717,7 @@ __device__ void consumer_loop(Ctx& c) {
 
   for (int idx = p.phase_begin; idx < p.phase_end; ++idx) {
     c.cur_idx = idx;
+    trace_sub(c, 0);
     if (idx < nlayer_idx) {
       const int l = idx / PH_PER_LAYER, ph = idx % PH_PER_LAYER;
       const uint32_t epoch = p.epoch_base + 1u + (uint32_t)l;
@@ -694,13 +734,18 @@ __device__ void consumer_loop(Ctx& c) {
           gather_words<XW_RES>(c, x_res, epoch - 1u, [&](int i, uint32_t v) { c.s_vec[i] = __uint_as_float(v); });
         }
         consumer_bar();
+        trace_sub(c, 1);
         wait_full(c, c.k);
+        trace_sub(c, 2);
         rmsnorm_regs(c.s_vec, reinterpret_cast<const uint4*>(c.ring + (size_t)(c.k % NSTAGES) * STAGE_BYTES), c.lane, xr);
+        trace_sub(c, 3);
         run_stages(c, d, xr);
+        trace_sub(c, 4);
         consumer_bar();
+        trace_sub(c, 5);
         if (c.tid < d.n_items) {
           const int row = row_begin(c.cta, QKV_ROWS, y.G) + c.tid;
-          ll_st(x_qkv + row, __float_as_uint(bf16_round(c.s_part[c.tid])), epoch);
+          ll_pub(w_qkv + row, __float_as_uint(bf16_round(c.s_part[c.tid])), epoch, R, XW_TOTAL);
         }
       } else if (ph == PH_ATTN) {
         if (has_item) phase_attn(c, l, epoch, item, kv, prefetched_layer == l);
@@ -716,28 +761,36 @@ __device__ void consumer_loop(Ctx& c) {
           c.s_vec[2 * i + 1] = bf16_hi(v);
         });
         consumer_bar();
+        trace_sub(c, 1);
         load_xr(c.s_vec + (c.warp % 2) * SEG_ELEMS, c.lane, xr);
         run_stages(c, d, xr);
+        trace_sub(c, 4);
         consumer_bar();
+        trace_sub(c, 5);
         if (c.tid < o_rows) {
           const float o = bf16_round(c.s_part[2 * c.tid] + c.s_part[2 * c.tid + 1]);
           const float res = p.residual_fp32 ? res_old + o : bf16_round(res_old + o);
-          ll_st(x_res2 + o_row0 + c.tid, __float_as_uint(res), epoch);
+          ll_pub(w_res2 + o_row0 + c.tid, __float_as_uint(res), epoch, R, XW_TOTAL);
         }
       } else if (ph == PH_GU) {
         const PhaseDesc d = layer_phase_desc(p, l, PH_GU, c.cta);
         gather_words<XW_RES2>(c, x_res2, epoch, [&](int i, uint32_t v) { c.s_vec[i] = __uint_as_float(v); });
         consumer_bar();
+        trace_sub(c, 1);
         wait_full(c, c.k);
+        trace_sub(c, 2);
         rmsnorm_regs(c.s_vec, reinterpret_cast<const uint4*>(c.ring + (size_t)(c.k % NSTAGES) * STAGE_BYTES), c.lane, xr);
+        trace_sub(c, 3);
         run_stages(c, d, xr);
+        trace_sub(c, 4);
         consumer_bar();
+        trace_sub(c, 5);
         if (c.tid < d.n_items / 2) {
           const float g = bf16_round(c.s_part[2 * c.tid]);
           const float u = bf16_round(c.s_part[2 * c.tid + 1]);
           const float sg = bf16_round(g / (1.0f + expf(-g)));
           const int pair = row_begin(c.cta, INTER, y.G) + c.tid;
-          ll_st(x_m + pair, __float_as_uint(bf16_round(sg * u)), epoch);
+          ll_pub(w_m + pair, __float_as_uint(bf16_round(sg * u)), epoch, R, XW_TOTAL);
         }
       } else {  // PH_DOWN
         const PhaseDesc d = layer_phase_desc(p, l, PH_DOWN, c.cta);
@@ -745,13 +798,16 @@ __device__ void consumer_loop(Ctx& c) {
         if (c.tid < o_rows) res_old = __uint_as_float(ll_wait(c, x_res2 + o_row0 + c.tid, epoch));
         gather_words<XW_M>(c, x_m, epoch, [&](int i, uint32_t v) { c.s_vec[i] = __uint_as_float(v); });
         consumer_bar();
+        trace_sub(c, 1);
         load_xr(c.s_vec + (c.warp % 3) * SEG_ELEMS, c.lane, xr);
         run_stages(c, d, xr);
+        trace_sub(c, 4);
         consumer_bar();
+        trace_sub(c, 5);
         if (c.tid < o_rows) {
           const float dn = bf16_round((c.s_part[3 * c.tid] + c.s_part[3 * c.tid + 1]) + c.s_part[3 * c.tid + 2]);
           const float res = p.residual_fp32 ? res_old + dn : bf16_round(res_old + dn);
-          ll_st(x_res + o_row0 + c.tid, __float_as_uint(res), epoch);
+          ll_pub(w_res + o_row0 + c.tid, __float_as_uint(res), epoch, R, XW_TOTAL);
         }
       }
     } else if (idx == nlayer_idx) {
@@ -775,7 +831,7 @@ __device__ void consumer_loop(Ctx& c) {
       consumer_bar();
       if (c.tid < d.n_items) {
         const int row = row_begin(c.cta, p.head.rows, y.G) + c.tid;
-        ll_st(x_logits + row, __float_as_uint(bf16_round(c.s_part[c.tid])), epoch_last + 1u);
+        ll_pub(w_logits + row, __float_as_uint(bf16_round(c.s_part[c.tid])), epoch_last + 1u, R, XW_TOTAL);
       }
     } else {
       // argmax over the bf16 logits, lowest index wins ties (CTA 0)
@@ -834,6 +890,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) qmk_decode_kernel(const __grid_co
   c.k = 0;
   c.t0 = clock64();
   c.cur_idx = p.phase_begin;
+  c.xrd = p.xbuf + (size_t)(blockIdx.x % p.replicas) * XW_TOTAL;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGES; ++i) {
@@ -851,6 +908,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) qmk_decode_kernel(const __grid_co
     consumer_loop(c);
   }
   __syncthreads();
+  c.cur_idx = p.phase_end;
+  trace_sub(c, 0);
   if (*c.s_abort && threadIdx.x == 0) {
     // failure path only: give in-flight bulk copies time to land before the CTA's shared memory is released
     const long long t = clock64();

@@ -61,6 +61,10 @@ struct qmk_engine {
   int device = 0;
   int G = 0;
   u64* xbuf = nullptr;
+  int replicas = 8;
+  int probe = 1;
+  long long* trace_dev = nullptr;
+  int trace_stride = 0;
   int* status_dev = nullptr;
   uint32_t epoch = 0;
   long long timeout_cycles = 4000000000LL;  // ~2 s at 1.9 GHz
@@ -127,8 +131,12 @@ extern "C" int qmk_engine_create(int device, int num_ctas, qmk_engine** out) {
   e->device = device;
   e->G = G;
   if (const char* env = getenv("QMK_TIMEOUT_CYCLES")) e->timeout_cycles = atoll(env);
-  cudaError_t err = cudaMalloc(&e->xbuf, sizeof(u64) * XW_TOTAL);
-  if (err == cudaSuccess) err = cudaMemset(e->xbuf, 0, sizeof(u64) * XW_TOTAL);
+  if (const char* env = getenv("QMK_REPLICAS")) e->replicas = atoi(env);
+  if (const char* env = getenv("QMK_PROBE")) e->probe = atoi(env);
+  if (e->replicas < 1) e->replicas = 1;
+  if (e->replicas > G) e->replicas = G;
+  cudaError_t err = cudaMalloc(&e->xbuf, sizeof(u64) * XW_TOTAL * e->replicas);
+  if (err == cudaSuccess) err = cudaMemset(e->xbuf, 0, sizeof(u64) * XW_TOTAL * e->replicas);
   if (err == cudaSuccess) err = cudaMalloc(&e->status_dev, 4 * sizeof(int));
   if (err == cudaSuccess) err = cudaMemset(e->status_dev, 0, 4 * sizeof(int));
   if (err != cudaSuccess) {
@@ -147,7 +155,33 @@ extern "C" void qmk_engine_destroy(qmk_engine* e) {
   cudaDeviceSynchronize();
   cudaFree(e->xbuf);
   cudaFree(e->status_dev);
+  if (e->trace_dev) cudaFree(e->trace_dev);
   delete e;
+}
+
+extern "C" int qmk_engine_trace_enable(qmk_engine* e, int stride) {
+  if (!e || stride < 0) return set_error(QMK_ERR_ARG, "qmk_engine_trace_enable: bad argument");
+  DeviceGuard guard(e->device);
+  cudaDeviceSynchronize();
+  if (e->trace_dev) cudaFree(e->trace_dev);
+  e->trace_dev = nullptr;
+  e->trace_stride = 0;
+  if (stride == 0) return QMK_OK;
+  QMK_CUDA(cudaMalloc(&e->trace_dev, sizeof(long long) * (size_t)e->G * stride));
+  QMK_CUDA(cudaMemset(e->trace_dev, 0, sizeof(long long) * (size_t)e->G * stride));
+  e->trace_stride = stride;
+  return QMK_OK;
+}
+
+extern "C" int qmk_engine_trace_read(qmk_engine* e, void* stream, long long* host_out, int64_t max_elems) {
+  if (!e || !host_out) return set_error(QMK_ERR_ARG, "qmk_engine_trace_read: null argument");
+  if (!e->trace_dev) return set_error(QMK_ERR_ARG, "qmk_engine_trace_read: tracing is not enabled");
+  DeviceGuard guard(e->device);
+  QMK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  int64_t n = (int64_t)e->G * e->trace_stride;
+  if (n > max_elems) n = max_elems;
+  QMK_CUDA(cudaMemcpy(host_out, e->trace_dev, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+  return e->trace_stride;
 }
 
 extern "C" int qmk_engine_num_ctas(const qmk_engine* e) { return e ? e->G : 0; }
@@ -298,10 +332,14 @@ extern "C" int qmk_decode_step(qmk_model* m, int head_index, int input_token_id,
   p.residual_fp32 = m->residual_fp32;
   p.status = e->status_dev;
   p.timeout_cycles = e->timeout_cycles;
+  p.replicas = e->replicas;
+  p.probe = e->probe;
+  p.trace = e->trace_dev;
+  p.trace_stride = e->trace_stride;
 
   const uint32_t need = (uint32_t)m->lay.L + 2u;
   if (e->epoch > 0xfff00000u) {  // wrap: clear the exchange words (stream-ordered) and restart the epochs
-    QMK_CUDA(cudaMemsetAsync(e->xbuf, 0, sizeof(u64) * XW_TOTAL, st));
+    QMK_CUDA(cudaMemsetAsync(e->xbuf, 0, sizeof(u64) * XW_TOTAL * e->replicas, st));
     e->epoch = 0;
   }
   p.epoch_base = e->epoch;

@@ -1,0 +1,127 @@
+#!/usr/bin/env python3
+"""GPU perf probe: talker / code-predictor step time under engine settings, plus a per-phase trace.
+
+    python scripts/perf_probe.py [--configs "R,probe;R,probe;..."] [--trace]
+"""
+import argparse
+import ctypes
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "qwen-megakernel-tts_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from qwen_megakernel import model_tts  # noqa: E402
+from qwen_megakernel.synthetic import synthetic_inputs, synthetic_tts_weights, weights_to  # noqa: E402
+
+
+def time_steps(dec, x, n=50, warm=10):
+    dec.reset()
+    for i in range(8):
+        dec.step_with_embed(x[i])
+    dec._hidden.copy_(x[0])
+    for _ in range(warm):
+        dec._launch(-1, dec._hidden.data_ptr())
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        dec._launch(-1, dec._hidden.data_ptr())
+    b.record()
+    torch.cuda.synchronize()
+    assert int(dec._out_token.item()) >= 0
+    return a.elapsed_time(b) / n * 1e3
+
+
+def time_cp_steps(cp, x, n=64, warm=16):
+    cp.reset()
+    for _ in range(warm // 16):
+        cp.reset()
+        for i in range(16):
+            cp._step_with_embed(x[i])
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for r in range(n // 16):
+        cp.reset()
+        for i in range(16):
+            cp._step_with_embed(x[i], head=cp._heads[i % 15])
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n * 1e3
+
+
+def trace(dec, x, lib, engine, L):
+    n_idx = L * 5 + 2
+    stride = (n_idx + 1) * 8
+    assert lib.qmk_engine_trace_enable(engine, stride) == 0
+    dec.reset()
+    for i in range(12):
+        dec.step_with_embed(x[i % 8])
+    G = lib.qmk_engine_num_ctas(engine)
+    buf = (ctypes.c_longlong * (G * stride))()
+    lib.qmk_engine_trace_read(engine, torch.cuda.current_stream().cuda_stream, buf, G * stride)
+    lib.qmk_engine_trace_enable(engine, 0)
+    t = np.frombuffer(buf, dtype=np.int64).reshape(G, n_idx + 1, 8).astype(np.float64)
+    start = t[:, :, 0]
+    d = np.diff(start, axis=1)
+    names = ["qkv", "attn", "o", "gu", "down"]
+    labels = {0: ["gather+bar", "wait_full", "norm", "stages", "bar", "publish->next"],
+              1: ["qkv wait+bar", "norm/rope+bar", "scores", "merge bar", "combine+publish", "kv store+fence+bar"],
+              2: ["gather+bar", None, None, "xr+stages", "bar", "publish->next"],
+              3: ["gather+bar", "wait_full", "norm", "stages", "bar", "publish->next"],
+              4: ["gather+bar", None, None, "xr+stages", "bar", "publish->next"]}
+    layers = list(range(2, L))
+    for grp_name, sl in (("attention CTAs 0-7", slice(0, 8)), ("other CTAs", slice(8, G))):
+        print(f"--- {grp_name}: mean cycles per sub-step over layers 2..{L-1}")
+        for ph in range(5):
+            idxs = [l * 5 + ph for l in layers]
+            tot = d[sl][:, idxs].mean()
+            parts = []
+            prev = 0
+            for sub in range(1, 7):
+                lab = labels[ph][sub - 1]
+                if lab is None:
+                    continue
+                cur = t[sl][:, idxs, sub]
+                if not np.any(cur):
+                    continue
+                ref = t[sl][:, idxs, prev]
+                parts.append(f"{lab}={np.mean(cur - ref):.0f}")
+                prev = sub
+            last = t[sl][:, idxs, prev]
+            nxt = start[sl][:, [i + 1 for i in idxs]]
+            parts.append(f"tail={np.mean(nxt - last):.0f}")
+            print(f"  {names[ph]:5s} total {tot:7.0f} : " + "  ".join(parts))
+    print(f"  per-layer total (cta 0): {d[0, :L*5].sum() / L:9.0f} cycles;  kernel total cta0 {start[0, n_idx] - start[0, 0]:.0f} cycles")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,0")
+    ap.add_argument("--trace", action="store_true")
+    ap.add_argument("--layers", type=int, default=28)
+    args = ap.parse_args()
+    torch.cuda.set_device(0)
+    w = weights_to(synthetic_tts_weights(max_seq_len=256, num_layers=args.layers), "cuda")
+    x = synthetic_inputs(99, 16).cuda()
+    for cfg in args.configs.split(";"):
+        R, probe = cfg.split(",")
+        os.environ["QMK_REPLICAS"], os.environ["QMK_PROBE"] = R, probe
+        model_tts._Native._engines.clear()
+        dec = model_tts.TTSDecoder(weights=w, verbose=False, max_seq_len=256)
+        cp = model_tts.CodePredictorKernel(w, device="cuda")
+        us = time_steps(dec, x)
+        us_cp = time_cp_steps(cp, x)
+        print(f"replicas={R:>3s} probe={probe}: talker {us:8.1f} us/step ({args.layers} layers)   cp step {us_cp:7.1f} us", flush=True)
+        if args.trace:
+            trace(dec, x, dec._lib, dec._engine, args.layers)
+        del dec, cp
+
+
+if __name__ == "__main__":
+    main()
