@@ -1,16 +1,21 @@
 // qmk_device.cuh — device side of the B200 decode engine (sm_100a).
 //
-// One persistent cooperative kernel, one CTA per SM.  Inside a CTA:
-//   * warp 12 (one elected lane) is the PRODUCER: it streams this CTA's slice of the re-packed weights
-//     with 1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) into an 8-slot x 24 KB
-//     shared-memory ring.  Weight addresses do not depend on activations, so the producer runs ahead
-//     through every data dependency of the layer and HBM stays busy while consumers synchronise.
-//   * warps 0-11 are CONSUMERS: one 1024-element row segment (2 KB) per warp per stage, activations in
-//     registers, 128-bit conflict-free shared loads, fp32 FMA, warp-shuffle reduction.
-// CTAs exchange activations through "LL" words in global memory: a 64-bit store carries a 32-bit payload
-// and a 32-bit epoch, so data and flag arrive in one single-copy-atomic access and a consumer simply
-// re-reads a word until its epoch matches.  There is no grid barrier, no fence on the critical path and
-// no separate flag: one store->L2->load hop per dependency.
+// One persistent cooperative kernel, one CTA per SM, 15 warps per CTA:
+//   * warp 14 (one elected lane) is the PRODUCER: it streams this CTA's slice of the re-packed weights with
+//     1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) into a 6-slot x 30.5 KB shared-memory
+//     ring.  Weight addresses do not depend on activations, so the producer runs ahead through every data
+//     dependency of the layer and HBM stays busy while the consumers wait on each other.
+//   * warps 0-13 are CONSUMERS: one 1024-element row segment (2 KB) per warp per stage, activations in
+//     registers, 128-bit conflict-free shared loads, fp32 FMA, one transposed warp-shuffle reduction per
+//     phase (6 shuffles for up to 4 row segments).
+// CTAs exchange activations through "LL" words in global memory: every exchanged vector is bf16-valued
+// (the reference rounds to bf16 at exactly these points), so a 32-bit word carries {bf16 payload, 16-bit
+// epoch}.  Data and flag arrive in one single-copy-atomic access: there is no grid barrier, no fence and no
+// separate flag on the critical path, and a consumer gathers a whole vector with 16-byte loads (4 words).
+// Measured on B200 (scripts/ubench/xchg*.cu): polling a line before it is written more than doubles the
+// exchange latency (4500 vs 1700 cycles for 148 CTAs x 1024 words), so each CTA waits an ADAPTIVE delay
+// after its own publish before the first poll; the delay grows when a poll had to be repeated and decays
+// otherwise, and the wait window is used to test the weight-ring barriers of the next phase.
 //
 // Numerics follow the upstream *PyTorch* path, not upstream kernel.cu (see oracle/tts_oracle.py for the
 // rounding points and the upstream file:line of each): bf16 rounding after every projection / norm /
@@ -28,30 +33,37 @@ typedef unsigned long long u64;
 constexpr int H = 1024, INTER = 3072, QSZ = 2048, KVSZ = 1024, HD = 128, NQH = 16, NKVH = 8;
 constexpr int QKV_ROWS = QSZ + 2 * KVSZ;  // 4096
 constexpr int SEG_ELEMS = 1024, SEG_BYTES = 2048;
-constexpr int NCW = 12;              // consumer warps
-constexpr int NCT = NCW * 32;        // 384 consumer threads
+constexpr int NCW = 14;              // consumer warps
+constexpr int NCT = NCW * 32;        // 448 consumer threads
 constexpr int NTHREADS = NCT + 32;   // + producer warp
-constexpr int STAGE_SEGS = 12;
-constexpr int STAGE_BYTES = STAGE_SEGS * SEG_BYTES;  // 24576
-constexpr int NSTAGES = 8;
+constexpr int AUX_BYTES = 2560;      // norm weights (2048) + q_norm / k_norm (2 x 256)
+constexpr int SLOT_BYTES = AUX_BYTES + NCW * SEG_BYTES;  // 31232: [aux][one segment per consumer warp]
+constexpr int NSLOTS = 6;
+constexpr int MAX_ST = 4;            // stages per phase (42 gate/up segments on 148 CTAs = 3 stages)
+constexpr int MAX_ITEMS = MAX_ST * NCW;
 constexpr int ATT_PER_WARP = 5;
-constexpr int ATT_ROUND = NCW * ATT_PER_WARP;  // 60 cached positions per round per item
+constexpr int ATT_ROUND = NCW * ATT_PER_WARP;  // 70 cached positions per round per item
 constexpr int S_MAX = 18;                      // max KV splits per kv head (8 * 18 = 144 CTAs)
-constexpr int PART_STRIDE = 132;               // words per (q head, split) partial: m, l, acc[128], pad
+constexpr int PART_STRIDE = 132;               // u64 words per (q head, split) partial: m, l, acc[128], pad
 constexpr int MAX_HEAD_ROWS = 3072;
+constexpr int MAX_STEPS = 16;
 constexpr float EPS = 1e-6f;
 
 enum Phase { PH_QKV = 0, PH_ATTN = 1, PH_O = 2, PH_GU = 3, PH_DOWN = 4, PH_PER_LAYER = 5 };
+enum DelaySlot { DL_QKV = 0, DL_ATTN = 1, DL_O = 2, DL_GU = 3, DL_DOWN = 4, DL_HEAD = 5, DL_ARGMAX = 6, DL_TOKEN = 7, DL_N = 8 };
 enum Status { ST_OK = 0, ST_TIMEOUT_LL = 1, ST_TIMEOUT_FULL = 2, ST_TIMEOUT_EMPTY = 3, ST_BAD_CONFIG = 4 };
 
-// Exchange-buffer word counts
-constexpr int XW_RES = H, XW_QKV = QKV_ROWS, XW_A = QSZ / 2, XW_RES2 = H, XW_M = INTER,
-              XW_LOGITS = MAX_HEAD_ROWS, XW_PART = NQH * S_MAX * PART_STRIDE;
-constexpr int XW_TOTAL = XW_RES + XW_QKV + XW_A + XW_RES2 + XW_M + XW_LOGITS + XW_PART;
+// Exchange buffer: 32-bit LL words first, then the 64-bit LL words of the split-attention partials.
+constexpr int XW_RES = 0, XW_QKV = XW_RES + H, XW_A = XW_QKV + QKV_ROWS, XW_RES2 = XW_A + QSZ, XW_M = XW_RES2 + H,
+              XW_LOGITS = XW_M + INTER, XW_TOKEN = XW_LOGITS + MAX_HEAD_ROWS, XW_END32 = XW_TOKEN + 32;
+constexpr int XW_PART64 = NQH * S_MAX * PART_STRIDE;
+constexpr size_t XBUF_BYTES = (size_t)XW_END32 * 4 + (size_t)XW_PART64 * 8;
+static_assert((XW_END32 * 4) % 16 == 0, "64-bit region must stay aligned");
 
 // Segment layout of one (cta, layer) block of the packed weight stream, in 2 KB segments:
-//   [aux: input_layernorm][qkv rows] | [o items (row,kb) kb<2] | [aux: post_ln][gate_j, up_j pairs] |
-//   [down items (row,kb) kb<3]
+//   [qkv rows] | [o items (row,kb) kb<2] | [gate_j, up_j pairs] | [down items (row,kb) kb<3]
+// The norm weights live once per layer in `aux_layers` ([L][2][AUX_BYTES]) and are fetched into the aux
+// part of the first stage of the QKV / gate-up phases.
 struct Layout {
   int G;        // CTAs (= SMs)
   int L;        // layers
@@ -62,39 +74,47 @@ struct Layout {
 };
 
 struct HeadDesc {
-  const uint8_t* packed;  // [G][segs_max][2048]: per CTA [aux: final norm][rows]; rows==0 -> single aux segment
+  const uint8_t* packed;  // [G][segs_max][2048]: rows of this CTA; rows==0 -> no LM head
+  const uint8_t* aux;     // AUX_BYTES: final RMSNorm weight
   int rows;
   int segs_max;
+};
+
+struct StepDesc {
+  const __nv_bfloat16* in_table;  // in_mode 0: row `token` of this table
+  const void* in_vec;             // in_mode 1: bf16[1024]
+  int in_mode;
+  int token;
+  int position;
+  HeadDesc head;
+  int* out_token;                 // int32[1] (head.rows > 0)
+  float* out_norm;                // f32[1024] post-final-norm hidden (bf16-rounded values) or null
+  __nv_bfloat16* hidden_out;      // bf16[1024] last-layer output or null
 };
 
 struct Params {
   Layout lay;
   const uint8_t* packed_layers;    // [G][L][layer_segs][2048]
-  const __nv_bfloat16* qk_norm;    // [L][2][128]
-  HeadDesc head;
-  const __nv_bfloat16* embed;      // [vocab][1024] (token >= 0)
-  const __nv_bfloat16* in_vec;     // bf16[1024]     (token < 0: upstream sentinel path)
+  const uint8_t* aux_layers;       // [L][2][AUX_BYTES]
   const __nv_bfloat16* cos_t;      // [max_seq][128]
   const __nv_bfloat16* sin_t;
   __nv_bfloat16* k_cache;          // [L][8][max_seq][128]
   __nv_bfloat16* v_cache;
   int max_seq;
-  u64* xbuf;                       // exchange words, XW_TOTAL
-  int token;
-  int position;
-  int* out_token;
-  float* out_norm;                 // f32[1024]
-  __nv_bfloat16* hidden_out;       // bf16[1024]
   float attn_scale;
   int residual_fp32;
-  uint32_t epoch_base;
+  uint8_t* xbuf;                   // exchange words (XBUF_BYTES)
+  float* res_spill;                // f32[1024]: fp32 residual of every row (read back only by staged launches)
+  int* delays;                     // [G][2][DL_N]: poll delays (cycles after own publish; in) and repeated-poll counts (in/out)
+  int delay_o_idle;                // O-phase delay of CTAs without an attention item (they wait for the attention CTAs)
+  uint32_t epoch_base;             // epochs base+1 .. base+n_steps*(L+2) are used by this launch (16-bit, never 0)
   int* status;                     // int[4]: code, cta, phase index, aux
-  int phase_begin, phase_end;      // half-open range in the linear phase index space
+  int phase_begin, phase_end;      // half-open range in the linear phase index space of step 0 (staged mode)
   long long timeout_cycles;
-  int replicas;                    // R copies of every exchange buffer; CTA c polls copy c % R
-  int probe;                       // 1: one warp probes a sample of words before the CTA-wide gather
-  long long* trace;                // optional [G][trace_stride] clock64 stamps at phase starts
+  long long* trace;                // optional [G][trace_stride] clock64 stamps
   int trace_stride;
+  int n_steps;
+  StepDesc steps[MAX_STEPS];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -113,6 +133,18 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+// Transposed reduction of four per-lane partial sums: afterwards every lane of the 8-lane group q holds
+// the warp-wide total of v[q].  6 shuffles instead of 20.
+__device__ __forceinline__ float warp_sum4(const float (&v)[4], int lane) {
+  const bool hi = (lane & 16) != 0, mid = (lane & 8) != 0;
+  const float u0 = (hi ? v[2] : v[0]) + __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[2], 16);
+  const float u1 = (hi ? v[3] : v[1]) + __shfl_xor_sync(0xffffffffu, hi ? v[1] : v[3], 16);
+  float w = (mid ? u1 : u0) + __shfl_xor_sync(0xffffffffu, mid ? u0 : u1, 8);
+  w += __shfl_xor_sync(0xffffffffu, w, 4);
+  w += __shfl_xor_sync(0xffffffffu, w, 2);
+  w += __shfl_xor_sync(0xffffffffu, w, 1);
+  return w;
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -138,6 +170,17 @@ __device__ __forceinline__ bool mbar_try_wait(u64* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(u64* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, u64* bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -146,12 +189,29 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
       : "memory");
 }
 
-// LL words: {payload (low 32), epoch (high 32)} moved with one 64-bit relaxed gpu-scope access.
-__device__ __forceinline__ void ll_st(u64* p, uint32_t payload, uint32_t epoch) {
+// LL4 words: {epoch (high 16), bf16 payload (low 16)} in one 32-bit relaxed gpu-scope access.
+__device__ __forceinline__ void ll4_st(uint32_t* p, float value_bf16, uint32_t epoch) {
+  const uint32_t v = (epoch << 16) | (__float_as_uint(value_bf16) >> 16);
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ll4_ld4(const uint32_t* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ bool ll4_ok(const uint4& w, uint32_t epoch) {
+  return ((w.x >> 16) == epoch) & ((w.y >> 16) == epoch) & ((w.z >> 16) == epoch) & ((w.w >> 16) == epoch);
+}
+__device__ __forceinline__ float ll4_val(uint32_t w) { return __uint_as_float(w << 16); }
+// LL8 words: {epoch (high 32), payload (low 32)}; used for the fp32 split-attention partials and the token.
+__device__ __forceinline__ void ll8_st(u64* p, uint32_t payload, uint32_t epoch) {
   u64 v = ((u64)epoch << 32) | payload;
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ u64 ll_ld(const u64* p) {
+__device__ __forceinline__ u64 ll8_ld(const u64* p) {
   u64 v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
@@ -161,25 +221,39 @@ __device__ __forceinline__ uint2 ld_cg_u2(const void* p) {
   asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
   return v;
 }
-// Publish one exchange word into every replica (stride XW_TOTAL words).
-__device__ __forceinline__ void ll_pub(u64* p, uint32_t payload, uint32_t epoch, int replicas, int stride_words) {
-  for (int r = 0; r < replicas; ++r) ll_st(p + (size_t)r * stride_words, payload, epoch);
-}
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
+// Barrier over the consumer warps that also ORs a predicate across them.
+__device__ __forceinline__ bool consumer_bar_or(bool pred) {
+  uint32_t out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 p, %1, 0;\n\t"
+      "bar.red.or.pred q, 1, %2, p;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t}"
+      : "=r"(out)
+      : "r"((uint32_t)pred), "n"(NCT)
+      : "memory");
+  return out != 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // shared-memory carve-up
 // ------------------------------------------------------------------------------------------------
 constexpr int SM_RING = 0;
-constexpr int SM_VEC = SM_RING + NSTAGES * STAGE_BYTES;   // float[3072]  (aliased: attention merge acc [12][2][128])
-constexpr int SM_SMALL = SM_VEC + INTER * 4;              // float[1024]  attention scratch
-constexpr int SM_PART = SM_SMALL + 1024 * 4;              // float[128]   per-item partial dot products
-constexpr int SM_BAR = SM_PART + 128 * 4;                 // u64 full[8], empty[8]
-constexpr int SM_MISC = SM_BAR + 2 * NSTAGES * 8;         // int abort; int pad[3]; float red[..]
+constexpr int SM_VEC = SM_RING + NSLOTS * SLOT_BYTES;     // float[3584]: activation vector (<= 3072) / attention merge acc [14][2][128]
+constexpr int SM_VEC_FLOATS = NCW * 2 * HD;
+static_assert(SM_VEC_FLOATS >= INTER, "s_vec holds the widest activation vector");
+constexpr int SM_SMALL = SM_VEC + SM_VEC_FLOATS * 4;              // float[1024]  attention scratch
+constexpr int SM_PART = SM_SMALL + 1024 * 4;              // float[64]    per-item partial dot products
+constexpr int SM_RED = SM_PART + 64 * 4;                  // float[64]    cross-warp reductions
+constexpr int SM_BAR = SM_RED + 64 * 4;                   // u64 full[NSLOTS], empty[NSLOTS]
+constexpr int SM_MISC = SM_BAR + 2 * 8 * 8;               // int abort; int delays[DL_N]; ...
 constexpr int SMEM_BYTES = SM_MISC + 256;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(MAX_ITEMS <= 64, "s_part size");
 
 // s_small sub-offsets (floats)
-constexpr int SS_QRAW = 0, SS_KRAW = 256, SS_V = 384, SS_QN = 512, SS_KN = 768, SS_ML = 896;  // ML: [12][2][2]
+constexpr int SS_V = 0, SS_QN = 128, SS_KN = 384, SS_M = 512, SS_L = 544, SS_CS = 576;  // CS: cos[64], sin[64]
 
 struct Ctx {
   const Params& p;
@@ -187,14 +261,16 @@ struct Ctx {
   float* s_vec;
   float* s_small;
   float* s_part;
+  float* s_red;
   u64* full;
   u64* empty;
   volatile int* s_abort;
-  float* s_red;
-  const u64* xrd;  // exchange replica this CTA reads
+  int* s_delay;
+  uint32_t* x32;
   int tid, warp, lane, cta;
   uint32_t k;     // stage counter (same sequence in producer and consumers)
   long long t0;
+  long long t_pub;  // clock64 at this CTA's latest publish
   int cur_idx;
   __device__ Ctx(const Params& pp) : p(pp) {}
 };
@@ -224,8 +300,8 @@ __device__ __forceinline__ bool check_abort(Ctx& c, int code, int aux) {
 }
 
 __device__ __forceinline__ void wait_full(Ctx& c, uint32_t k) {
-  u64* bar = &c.full[k % NSTAGES];
-  uint32_t parity = (k / NSTAGES) & 1u;
+  u64* bar = &c.full[k % NSLOTS];
+  uint32_t parity = (k / NSLOTS) & 1u;
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -233,25 +309,38 @@ __device__ __forceinline__ void wait_full(Ctx& c, uint32_t k) {
   }
 }
 __device__ __forceinline__ void wait_empty(Ctx& c, uint32_t k) {
-  u64* bar = &c.empty[k % NSTAGES];
-  uint32_t parity = ((k / NSTAGES) & 1u) ^ 1u;
+  u64* bar = &c.empty[k % NSLOTS];
+  uint32_t parity = ((k / NSLOTS) & 1u) ^ 1u;
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 63u) == 0 && check_abort(c, ST_TIMEOUT_EMPTY, (int)k)) return;
   }
 }
-__device__ __forceinline__ u64 ll_wait_slow(Ctx& c, const u64* p, uint32_t epoch) {
+__device__ __noinline__ uint4 ll4_wait_slow(int* status, volatile int* s_abort, long long t0, long long timeout, int cta,
+                                            int cur_idx, const uint32_t* p, uint32_t epoch, int aux) {
   uint32_t spins = 0;
   for (;;) {
-    u64 w = ll_ld(p);
-    if ((uint32_t)(w >> 32) == epoch) return w;
-    if ((++spins & 127u) == 0 && check_abort(c, ST_TIMEOUT_LL, (int)(p - c.p.xbuf))) return w;
+    uint4 w = ll4_ld4(p);
+    if (ll4_ok(w, epoch)) return w;
+    if ((++spins & 127u) == 0 && check_abort_slow(status, s_abort, t0, timeout, cta, cur_idx, ST_TIMEOUT_LL, aux)) return w;
   }
 }
-__device__ __forceinline__ uint32_t ll_wait(Ctx& c, const u64* p, uint32_t epoch) {
-  u64 w = ll_ld(p);
-  if ((uint32_t)(w >> 32) != epoch) w = ll_wait_slow(c, p, epoch);
+__device__ __forceinline__ uint4 ll4_wait(Ctx& c, const uint32_t* p, uint32_t epoch, bool& retried) {
+  uint4 w = ll4_ld4(p);
+  if (!ll4_ok(w, epoch)) {
+    retried = true;
+    w = ll4_wait_slow(c.p.status, c.s_abort, c.t0, c.p.timeout_cycles, c.cta, c.cur_idx, p, epoch, (int)(p - c.x32));
+  }
+  return w;
+}
+__device__ __forceinline__ uint32_t ll8_wait(Ctx& c, const u64* p, uint32_t epoch) {
+  u64 w = ll8_ld(p);
+  uint32_t spins = 0;
+  while ((uint32_t)(w >> 32) != epoch) {
+    if ((++spins & 127u) == 0 && check_abort(c, ST_TIMEOUT_LL, -1)) break;
+    w = ll8_ld(p);
+  }
   return (uint32_t)w;
 }
 
@@ -259,36 +348,7 @@ __device__ __forceinline__ uint32_t ll_wait(Ctx& c, const u64* p, uint32_t epoch
 __device__ __forceinline__ void trace_sub(const Ctx& c, int sub) {
   if (c.p.trace != nullptr && c.tid == 0) {
     const int slot = (c.cur_idx - c.p.phase_begin) * 8 + sub;
-    if (slot < c.p.trace_stride) c.p.trace[(size_t)c.cta * c.p.trace_stride + slot] = clock64();
-  }
-}
-
-// Gather N exchange words (all loads issued before the first check) and hand each payload to `store`.
-// With p.probe, warp 0 first polls a 32-word sample while the other warps sleep at a barrier: thousands
-// of threads spinning on the same few L2 lines delay the very stores they are waiting for.
-template <int N, typename F>
-__device__ __forceinline__ void gather_words(Ctx& c, const u64* buf, uint32_t epoch, F store, int n = N) {
-  constexpr int PER = (N + NCT - 1) / NCT;
-  if (c.p.probe) {
-    if (c.warp == 0) {
-      const int idx = (int)(((long long)c.lane * n) >> 5) + (n >> 6);
-      (void)ll_wait(c, buf + (idx < n ? idx : n - 1), epoch);
-    }
-    consumer_bar();
-  }
-  u64 w[PER];
-#pragma unroll
-  for (int u = 0; u < PER; ++u) {
-    int idx = u * NCT + c.tid;
-    if (idx < n) w[u] = ll_ld(buf + idx);
-  }
-#pragma unroll
-  for (int u = 0; u < PER; ++u) {
-    int idx = u * NCT + c.tid;
-    if (idx < n) {
-      if ((uint32_t)(w[u] >> 32) != epoch) w[u] = ll_wait_slow(c, buf + idx, epoch);
-      store(idx, (uint32_t)w[u]);
-    }
+    if (slot >= 0 && slot < c.p.trace_stride) c.p.trace[(size_t)c.cta * c.p.trace_stride + slot] = clock64();
   }
 }
 
@@ -296,82 +356,99 @@ __device__ __forceinline__ void gather_words(Ctx& c, const u64* buf, uint32_t ep
 // phase descriptors (identical arithmetic in producer and consumers)
 // ------------------------------------------------------------------------------------------------
 struct PhaseDesc {
-  const uint8_t* src;
-  int total_segs;  // aux + items
-  int has_aux;
+  const uint8_t* src;   // this CTA's items of the phase (contiguous 2 KB segments)
+  const uint8_t* aux;   // AUX_BYTES block fetched with the first stage, or null
   int n_items;
 };
-
-__device__ __forceinline__ PhaseDesc layer_phase_desc(const Params& p, int l, int ph, int cta) {
+struct CtaRows {  // per-CTA row ranges, computed once per kernel
+  int q_row0, q_rows, o_row0, o_rows, gu_row0, gu_rows;
+};
+__device__ __forceinline__ CtaRows cta_rows(const Layout& y, int cta) {
+  CtaRows r;
+  r.q_row0 = row_begin(cta, QKV_ROWS, y.G);
+  r.q_rows = row_begin(cta + 1, QKV_ROWS, y.G) - r.q_row0;
+  r.o_row0 = row_begin(cta, H, y.G);
+  r.o_rows = row_begin(cta + 1, H, y.G) - r.o_row0;
+  r.gu_row0 = row_begin(cta, INTER, y.G);
+  r.gu_rows = row_begin(cta + 1, INTER, y.G) - r.gu_row0;
+  return r;
+}
+__device__ __forceinline__ PhaseDesc layer_phase_desc(const Params& p, const CtaRows& r, int l, int ph, int cta) {
   const Layout& y = p.lay;
   PhaseDesc d;
   const uint8_t* base = p.packed_layers + ((size_t)((size_t)cta * y.L + l) * y.layer_segs) * SEG_BYTES;
+  d.aux = nullptr;
   if (ph == PH_QKV) {
-    d.n_items = row_begin(cta + 1, QKV_ROWS, y.G) - row_begin(cta, QKV_ROWS, y.G);
-    d.has_aux = 1;
+    d.n_items = r.q_rows;
     d.src = base;
+    d.aux = p.aux_layers + ((size_t)l * 2 + 0) * AUX_BYTES;
   } else if (ph == PH_O) {
-    d.n_items = 2 * (row_begin(cta + 1, H, y.G) - row_begin(cta, H, y.G));
-    d.has_aux = 0;
+    d.n_items = 2 * r.o_rows;
     d.src = base + (size_t)y.off_o * SEG_BYTES;
   } else if (ph == PH_GU) {
-    d.n_items = 2 * (row_begin(cta + 1, INTER, y.G) - row_begin(cta, INTER, y.G));
-    d.has_aux = 1;
+    d.n_items = 2 * r.gu_rows;
     d.src = base + (size_t)y.off_gu * SEG_BYTES;
-  } else if (ph == PH_DOWN) {
-    d.n_items = 3 * (row_begin(cta + 1, H, y.G) - row_begin(cta, H, y.G));
-    d.has_aux = 0;
+    d.aux = p.aux_layers + ((size_t)l * 2 + 1) * AUX_BYTES;
+  } else {  // PH_DOWN
+    d.n_items = 3 * r.o_rows;
     d.src = base + (size_t)y.off_down * SEG_BYTES;
-  } else {
-    d.n_items = 0;
-    d.has_aux = 0;
-    d.src = base;
   }
-  d.total_segs = d.n_items + d.has_aux;
   return d;
 }
-__device__ __forceinline__ PhaseDesc head_phase_desc(const Params& p, int cta) {
+__device__ __forceinline__ PhaseDesc head_phase_desc(const Params& p, const HeadDesc& h, int cta) {
   PhaseDesc d;
-  d.has_aux = 1;
-  if (p.head.rows > 0) {
-    d.n_items = row_begin(cta + 1, p.head.rows, p.lay.G) - row_begin(cta, p.head.rows, p.lay.G);
-    d.src = p.head.packed + ((size_t)cta * p.head.segs_max) * SEG_BYTES;
+  d.aux = h.aux;
+  if (h.rows > 0) {
+    d.n_items = row_begin(cta + 1, h.rows, p.lay.G) - row_begin(cta, h.rows, p.lay.G);
+    d.src = h.packed + ((size_t)cta * h.segs_max) * SEG_BYTES;
   } else {
     d.n_items = 0;
-    d.src = p.head.packed;  // single aux segment shared by all CTAs
+    d.src = h.aux;
   }
-  d.total_segs = d.n_items + 1;
   return d;
 }
-__device__ __forceinline__ int n_stages_of(const PhaseDesc& d) { return (d.total_segs + STAGE_SEGS - 1) / STAGE_SEGS; }
+// A phase with an aux block always has at least one stage.
+__device__ __forceinline__ int n_stages_of(const PhaseDesc& d) {
+  const int n = (d.n_items + NCW - 1) / NCW;
+  return (n == 0 && d.aux != nullptr) ? 1 : n;
+}
 
 // ------------------------------------------------------------------------------------------------
 // producer
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void produce_phase(Ctx& c, const PhaseDesc& d) {
+  const int nst = n_stages_of(d);
+  for (int s = 0; s < nst; ++s, ++c.k) {
+    const int slot = c.k % NSLOTS;
+    wait_empty(c, c.k);
+    int items = d.n_items - s * NCW;
+    if (items > NCW) items = NCW;
+    const bool aux = (s == 0 && d.aux != nullptr);
+    const uint32_t bytes = (uint32_t)items * SEG_BYTES + (aux ? AUX_BYTES : 0);
+    uint8_t* dst = c.ring + (size_t)slot * SLOT_BYTES;
+    mbar_arrive_expect_tx(&c.full[slot], bytes);
+    if (aux) tma_bulk_g2s(dst, d.aux, AUX_BYTES, &c.full[slot]);
+    if (items > 0)
+      tma_bulk_g2s(dst + AUX_BYTES, d.src + (size_t)s * NCW * SEG_BYTES, (uint32_t)items * SEG_BYTES, &c.full[slot]);
+  }
+}
+
 __device__ void producer_loop(Ctx& c) {
   const Params& p = c.p;
+  const CtaRows rows = cta_rows(p.lay, c.cta);
   const int nlayer_idx = p.lay.L * PH_PER_LAYER;
-  for (int idx = p.phase_begin; idx < p.phase_end; ++idx) {
-    c.cur_idx = idx;
-    PhaseDesc d;
-    if (idx < nlayer_idx) {
-      int ph = idx % PH_PER_LAYER;
-      if (ph == PH_ATTN) continue;
-      d = layer_phase_desc(p, idx / PH_PER_LAYER, ph, c.cta);
-    } else if (idx == nlayer_idx) {
-      d = head_phase_desc(p, c.cta);
-    } else {
-      continue;
-    }
-    const int nst = n_stages_of(d);
-    for (int s = 0; s < nst; ++s, ++c.k) {
-      const int slot = c.k % NSTAGES;
-      wait_empty(c, c.k);
-      int segs = d.total_segs - s * STAGE_SEGS;
-      if (segs > STAGE_SEGS) segs = STAGE_SEGS;
-      const uint32_t bytes = (uint32_t)segs * SEG_BYTES;
-      mbar_arrive_expect_tx(&c.full[slot], bytes);
-      tma_bulk_g2s(c.ring + (size_t)slot * STAGE_BYTES, d.src + (size_t)s * STAGE_BYTES, bytes, &c.full[slot]);
+  for (int step = 0; step < p.n_steps; ++step) {
+    const int begin = (step == 0) ? p.phase_begin : 0;
+    const int end = (p.n_steps == 1) ? p.phase_end : nlayer_idx + 2;
+    for (int idx = begin; idx < end; ++idx) {
+      c.cur_idx = idx;
+      if (idx < nlayer_idx) {
+        const int ph = idx % PH_PER_LAYER;
+        if (ph == PH_ATTN) continue;
+        produce_phase(c, layer_phase_desc(p, rows, idx / PH_PER_LAYER, ph, c.cta));
+      } else if (idx == nlayer_idx) {
+        produce_phase(c, head_phase_desc(p, p.steps[step].head, c.cta));
+      }
     }
   }
 }
@@ -390,30 +467,8 @@ __device__ __forceinline__ void load_xr(const float* vec1024, int lane, float (&
   }
 }
 
-// xr <- r( r(x) / sqrt(mean(r(x)^2) + eps) * w ), w = bf16[1024] laid out like a weight segment.
-__device__ __forceinline__ void rmsnorm_regs(const float* vec1024, const uint4* w_seg, int lane, float (&xr)[32]) {
-  load_xr(vec1024, lane, xr);
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    xr[i] = bf16_round(xr[i]);
-    ss = fmaf(xr[i], xr[i], ss);
-  }
-  ss = warp_sum(ss);
-  const float rms = sqrtf(ss * (1.0f / H) + EPS);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 wv = w_seg[j * 32 + lane];
-    uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      xr[j * 8 + 2 * q] = bf16_round((xr[j * 8 + 2 * q] / rms) * bf16_lo(ww[q]));
-      xr[j * 8 + 2 * q + 1] = bf16_round((xr[j * 8 + 2 * q + 1] / rms) * bf16_hi(ww[q]));
-    }
-  }
-}
-
-__device__ __forceinline__ float seg_dot(const uint4* w_seg, int lane, const float (&xr)[32]) {
+// per-lane partial dot product of one 2 KB weight segment with the register-resident activations
+__device__ __forceinline__ float seg_dot_partial(const uint4* w_seg, int lane, const float (&xr)[32]) {
   float acc[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -428,28 +483,121 @@ __device__ __forceinline__ float seg_dot(const uint4* w_seg, int lane, const flo
     a = fmaf(bf16_hi(wv.w), xr[j * 8 + 7], a);
     acc[j] = a;
   }
-  return warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
+  return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
-// Consume all stages of a phase: warp w owns segment 12*s + w of stage s; partial dot -> s_part[item].
-__device__ __forceinline__ void run_stages(Ctx& c, const PhaseDesc& d, const float (&xr)[32]) {
-  const int nst = n_stages_of(d);
-  for (int s = 0; s < nst; ++s, ++c.k) {
-    const int slot = c.k % NSTAGES;
-    wait_full(c, c.k);
-    const int seg = s * STAGE_SEGS + c.warp;
-    if (seg < d.total_segs && seg >= d.has_aux) {
-      const uint4* w = reinterpret_cast<const uint4*>(c.ring + (size_t)slot * STAGE_BYTES + c.warp * SEG_BYTES);
-      float v = seg_dot(w, c.lane, xr);
-      if (c.lane == 0) c.s_part[seg - d.has_aux] = v;
+// The wait window before a gather: spin until t_pub + delay, testing the next phase's ring barriers meanwhile.
+// Returns a bit mask of stages already observed full.
+__device__ __forceinline__ uint32_t wait_window(Ctx& c, int dslot, int nst, int delay_override = -1) {
+  const long long t_ready = c.t_pub + (delay_override >= 0 ? delay_override : c.s_delay[dslot]);
+  uint32_t ready = 0;
+  for (;;) {
+#pragma unroll
+    for (int s = 0; s < MAX_ST; ++s) {
+      if (s < nst && !((ready >> s) & 1u)) {
+        const uint32_t k = c.k + s;
+        if (mbar_test_wait(&c.full[k % NSLOTS], (k / NSLOTS) & 1u)) ready |= 1u << s;
+      }
     }
-    __syncwarp();
-    if (c.lane == 0) mbar_arrive(&c.empty[slot]);
+    if (clock64() >= t_ready) break;
   }
+  return ready;
+}
+// After a gather: consumer barrier that also counts the gathers in which some poll had to be repeated
+// (polling a line before it is written is what makes an exchange slow; the counts guide the delay tuning).
+__device__ __forceinline__ void adapt_delay(Ctx& c, int dslot, bool retried) {
+  const bool any = consumer_bar_or(retried);
+  if (any && c.tid == 0) c.s_delay[DL_N + dslot] += 1;
 }
 
-__device__ __forceinline__ const __nv_bfloat16* step_input(const Params& p) {
-  return p.token >= 0 ? p.embed + (size_t)p.token * H : p.in_vec;
+// Gather an H-wide bf16 vector (LL4) or the step input, RMS-normalise it with the aux weights of the first
+// stage and leave the normalised activations in s_vec[0..1023]:  n = r( r(x) / sqrt(mean(r(x)^2) + eps) * w ).
+// Ends with a consumer barrier.  `raw_out` (optional): thread t < 256 keeps its 4 raw values.
+template <bool FROM_INPUT>
+__device__ __forceinline__ void gather_norm(Ctx& c, const uint32_t* xw, uint32_t epoch, const __nv_bfloat16* x_in,
+                                            int dslot, int nst, uint32_t& ready, float (&raw)[4]) {
+  bool retried = false;
+  float ss = 0.f;
+  if (FROM_INPUT) {
+    ready = 0;
+    if (c.tid < 256) {
+      const uint2 v = *reinterpret_cast<const uint2*>(x_in + c.tid * 4);
+      raw[0] = bf16_lo(v.x); raw[1] = bf16_hi(v.x); raw[2] = bf16_lo(v.y); raw[3] = bf16_hi(v.y);
+    }
+  } else {
+    ready = wait_window(c, dslot, nst);
+    if (c.tid < 256) {
+      const uint4 w = ll4_wait(c, xw + c.tid * 4, epoch, retried);
+      raw[0] = ll4_val(w.x); raw[1] = ll4_val(w.y); raw[2] = ll4_val(w.z); raw[3] = ll4_val(w.w);
+    }
+  }
+  if (c.tid < 256) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ss = fmaf(raw[e], raw[e], ss);
+    ss = warp_sum(ss);
+    if (c.lane == 0) c.s_red[c.warp] = ss;
+  }
+  if (FROM_INPUT) consumer_bar(); else adapt_delay(c, dslot, retried);
+  // the norm weights arrive with the first stage of the phase
+  if (!(ready & 1u)) { wait_full(c, c.k); ready |= 1u; }
+  if (c.tid < 256) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += c.s_red[w];
+    const float rms = sqrtf(tot * (1.0f / H) + EPS);
+    const uint2 wv = *reinterpret_cast<const uint2*>(c.ring + (size_t)(c.k % NSLOTS) * SLOT_BYTES + c.tid * 8);
+    float4 n;
+    n.x = bf16_round((raw[0] / rms) * bf16_lo(wv.x));
+    n.y = bf16_round((raw[1] / rms) * bf16_hi(wv.x));
+    n.z = bf16_round((raw[2] / rms) * bf16_lo(wv.y));
+    n.w = bf16_round((raw[3] / rms) * bf16_hi(wv.y));
+    *reinterpret_cast<float4*>(c.s_vec + c.tid * 4) = n;
+  }
+  consumer_bar();
+}
+
+// Gather `n_words` LL4 words (a multiple of 4) into s_vec as floats.  Ends with a consumer barrier.
+__device__ __forceinline__ void gather_vec(Ctx& c, const uint32_t* xw, int n_words, uint32_t epoch, int dslot, int nst,
+                                           uint32_t& ready, int delay_override = -1) {
+  bool retried = false;
+  ready = wait_window(c, dslot, nst, delay_override);
+  for (int i = c.tid * 4; i < n_words; i += NCT * 4) {
+    const uint4 w = ll4_wait(c, xw + i, epoch, retried);
+    *reinterpret_cast<float4*>(c.s_vec + i) = make_float4(ll4_val(w.x), ll4_val(w.y), ll4_val(w.z), ll4_val(w.w));
+  }
+  adapt_delay(c, dslot, retried);
+}
+
+// Consume all stages of a phase: warp w owns item s*NCW + w of stage s.  The per-item dot products end up in
+// s_part[item]; ends with a consumer barrier.  XR_PER_STAGE: activations depend on the item (down: kb = item % 3).
+template <bool XR_PER_STAGE>
+__device__ __forceinline__ void run_stages(Ctx& c, const PhaseDesc& d, uint32_t ready, float (&xr)[32], int xr_mod) {
+  const int nst = n_stages_of(d);
+  float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int s = 0; s < MAX_ST; ++s) {
+    if (s < nst) {
+      const uint32_t k = c.k + s;
+      const int slot = k % NSLOTS;
+      if (!((ready >> s) & 1u)) wait_full(c, k);
+      const int item = s * NCW + c.warp;
+      if (item < d.n_items) {
+        if (XR_PER_STAGE) load_xr(c.s_vec + (item % xr_mod) * SEG_ELEMS, c.lane, xr);
+        const uint4* w = reinterpret_cast<const uint4*>(c.ring + (size_t)slot * SLOT_BYTES + AUX_BYTES + c.warp * SEG_BYTES);
+        part[s] = seg_dot_partial(w, c.lane, xr);
+      }
+      __syncwarp();
+      if (c.lane == 0) mbar_arrive(&c.empty[slot]);
+    }
+  }
+  c.k += nst;
+  const float tot = warp_sum4(part, c.lane);
+  const int q = c.lane >> 3;
+  if ((c.lane & 7) == 0 && q < nst) {
+    const int item = q * NCW + c.warp;
+    if (item < d.n_items) c.s_part[item] = tot;
+  }
+  consumer_bar();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -457,10 +605,10 @@ __device__ __forceinline__ const __nv_bfloat16* step_input(const Params& p) {
 // ------------------------------------------------------------------------------------------------
 struct AttnItem {
   int g, s, S, p0, p1;
-  bool owner;  // holds the new position (= p.position) -> takes k,v from the exchange and appends to the cache
+  bool owner;  // holds the new position (= position) -> takes k,v from the exchange and appends to the cache
 };
-__device__ __forceinline__ bool attn_item(const Params& p, int cta, AttnItem& it) {
-  const int n = p.position + 1;
+__device__ __forceinline__ bool attn_item(const Params& p, int position, int cta, AttnItem& it) {
+  const int n = position + 1;
   int smax = p.lay.G / NKVH;
   if (smax > S_MAX) smax = S_MAX;
   int S0 = (n + ATT_ROUND - 1) / ATT_ROUND;
@@ -481,13 +629,13 @@ struct KvRegs {
   uint2 k[ATT_PER_WARP];
   uint2 v[ATT_PER_WARP];
 };
-__device__ __forceinline__ void attn_prefetch(const Ctx& c, int l, const AttnItem& it, int round, KvRegs& r) {
+__device__ __forceinline__ void attn_prefetch(const Ctx& c, int l, int position, const AttnItem& it, int round, KvRegs& r) {
   const Params& p = c.p;
   const size_t base = ((size_t)(l * NKVH + it.g) * p.max_seq) * HD;
 #pragma unroll
   for (int i = 0; i < ATT_PER_WARP; ++i) {
     const int pos = it.p0 + round * ATT_ROUND + c.warp + NCW * i;
-    if (pos < it.p1 && pos != p.position) {
+    if (pos < it.p1 && pos != position) {
       const size_t off = base + (size_t)pos * HD + c.lane * 4;
       r.k[i] = ld_cg_u2(p.k_cache + off);
       r.v[i] = ld_cg_u2(p.v_cache + off);
@@ -495,99 +643,128 @@ __device__ __forceinline__ void attn_prefetch(const Ctx& c, int l, const AttnIte
   }
 }
 
-__device__ void phase_attn(Ctx& c, int l, uint32_t epoch, const AttnItem& it, KvRegs& kv, bool prefetched) {
-  const Params& p = c.p;
-  const u64* x_qkv = c.xrd + XW_RES;                  // this CTA's replica
-  u64* x_a = p.xbuf + XW_RES + XW_QKV;                // writers publish into every replica
-  u64* x_part = p.xbuf + (XW_TOTAL - XW_PART);        // split partials: replica 0 only (few readers)
-  float* s_small = c.s_small;
-  const int R = p.replicas;
-  if (!prefetched) attn_prefetch(c, l, it, 0, kv);
+// Transposed reduction of 2*ATT_PER_WARP (= 10) per-lane partial dot products; every lane ends up with all
+// ten totals (12 reduction shuffles + 10 broadcasts instead of 50 shuffles).
+__device__ __forceinline__ void warp_sum10_bcast(float (&v)[10], int lane) {
+  const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0, b1 = (lane & 2) != 0;
+  float u[6];
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+    u[k] = (b4 ? v[k + 5] : v[k]) + __shfl_xor_sync(0xffffffffu, b4 ? v[k] : v[k + 5], 16);
+  u[5] = 0.f;
+  float w[4];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    w[k] = (b3 ? u[k + 3] : u[k]) + __shfl_xor_sync(0xffffffffu, b3 ? u[k] : u[k + 3], 8);
+  w[3] = 0.f;
+  float x[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    x[k] = (b2 ? w[k + 2] : w[k]) + __shfl_xor_sync(0xffffffffu, b2 ? w[k] : w[k + 2], 4);
+  float y = (b1 ? x[1] : x[0]) + __shfl_xor_sync(0xffffffffu, b1 ? x[0] : x[1], 2);
+  y += __shfl_xor_sync(0xffffffffu, y, 1);
+  // value index held by a lane: b4*5 + b3*3 + b2*2 + b1  (valid combinations only)
+#pragma unroll
+  for (int idx = 0; idx < 10; ++idx) {
+    const int r = idx % 5, hi = idx / 5;
+    const int src = hi * 16 + (r >= 3 ? 8 : 0) + ((r % 3) >= 2 ? 4 : 0) + (((r % 3) % 2) ? 2 : 0);
+    v[idx] = __shfl_sync(0xffffffffu, y, src);
+  }
+}
 
-  // 1) raw q (2 heads), k, v of this kv group
-  {
-    const int t = c.tid;
-    if (t < 256) {
-      s_small[SS_QRAW + t] = __uint_as_float(ll_wait(c, x_qkv + (2 * it.g) * HD + t, epoch));
-    } else if (it.owner) {
-      const int d = t - 256;  // 0..127
-      s_small[SS_KRAW + d] = __uint_as_float(ll_wait(c, x_qkv + QSZ + it.g * HD + d, epoch));
-      s_small[SS_V + d] = __uint_as_float(ll_wait(c, x_qkv + QSZ + KVSZ + it.g * HD + d, epoch));
+struct AttnPre {  // per-layer constants a norm/rope warp needs, fetched while the QKV weights are resident
+  float nw[4];
+};
+
+__device__ void phase_attn(Ctx& c, int l, int position, uint32_t epoch, const AttnItem& it, KvRegs& kv,
+                           const AttnPre& pre) {
+  const Params& p = c.p;
+  const uint32_t* x_qkv = c.x32 + XW_QKV;
+  uint32_t* x_a = c.x32 + XW_A;
+  u64* x_part = reinterpret_cast<u64*>(p.xbuf + (size_t)XW_END32 * 4);
+  float* s_small = c.s_small;
+
+  // 1) gather q (2 heads), k, v of this kv group; per-head RMSNorm + rotate-half RoPE in bf16 steps.
+  //    warp 0,1: q heads; warp 2: k; warp 3: v (owner only).  Lane owns dims 4*lane .. 4*lane+3.
+  bool retried = false;
+  (void)wait_window(c, DL_ATTN, 0);
+  if (c.warp < 2 || (it.owner && c.warp < 4)) {
+    const int row0 = (c.warp < 2) ? (2 * it.g + c.warp) * HD : (c.warp == 2 ? QSZ + it.g * HD : QSZ + KVSZ + it.g * HD);
+    const uint4 w = ll4_wait(c, x_qkv + row0 + c.lane * 4, epoch, retried);
+    float t[4] = {ll4_val(w.x), ll4_val(w.y), ll4_val(w.z), ll4_val(w.w)};
+    if (c.warp == 3) {
+      *reinterpret_cast<float4*>(s_small + SS_V + c.lane * 4) = make_float4(t[0], t[1], t[2], t[3]);
+    } else {
+      float ss = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ss = fmaf(t[e], t[e], ss);
+      ss = warp_sum(ss);
+      const float rms = sqrtf(ss * (1.0f / HD) + EPS);
+      const int dbase = (c.lane * 4) & 63;
+      float o4[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float n = bf16_round((t[e] / rms) * pre.nw[e]);
+        const float o = __shfl_xor_sync(0xffffffffu, n, 16);
+        const float cs = s_small[SS_CS + dbase + e], sn = s_small[SS_CS + 64 + dbase + e];
+        const float a = bf16_round(n * cs), b = bf16_round(o * sn);
+        o4[e] = bf16_round(c.lane < 16 ? a - b : a + b);
+      }
+      float* dst = (c.warp < 2) ? s_small + SS_QN + c.warp * HD : s_small + SS_KN;
+      *reinterpret_cast<float4*>(dst + c.lane * 4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
     }
   }
-  consumer_bar();
+  adapt_delay(c, DL_ATTN, retried);   // barrier: q / k / v are in shared memory
   trace_sub(c, 1);
 
-  // 2) per-head RMSNorm + rotate-half RoPE in bf16 steps (warp 0,1: q heads; warp 2: k)
-  if (c.warp < 2 || (c.warp == 2 && it.owner)) {
-    const float* raw = (c.warp < 2) ? s_small + SS_QRAW + c.warp * HD : s_small + SS_KRAW;
-    float* dst = (c.warp < 2) ? s_small + SS_QN + c.warp * HD : s_small + SS_KN;
-    const __nv_bfloat16* wn = p.qk_norm + ((size_t)l * 2 + (c.warp < 2 ? 0 : 1)) * HD;
-    float t[4], ss = 0.f;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      t[e] = raw[c.lane * 4 + e];
-      ss = fmaf(t[e], t[e], ss);
-    }
-    ss = warp_sum(ss);
-    const float rms = sqrtf(ss * (1.0f / HD) + EPS);
-    const int dbase = (c.lane * 4) & 63;
-    const __nv_bfloat16* cr = p.cos_t + (size_t)p.position * HD + dbase;
-    const __nv_bfloat16* sr = p.sin_t + (size_t)p.position * HD + dbase;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float n = bf16_round((t[e] / rms) * __bfloat162float(wn[c.lane * 4 + e]));
-      const float o = __shfl_xor_sync(0xffffffffu, n, 16);
-      const float cs = __bfloat162float(cr[e]), sn = __bfloat162float(sr[e]);
-      const float a = bf16_round(n * cs), b = bf16_round(o * sn);
-      dst[c.lane * 4 + e] = bf16_round(c.lane < 16 ? a - b : a + b);
-    }
-  }
-  consumer_bar();
-  trace_sub(c, 2);
-
-  // 3) scores / online softmax / PV over this item's positions; lane owns dims 4*lane..4*lane+3
+  // 2) scores / online softmax / PV over this item's positions
   float q0[4], q1[4], acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    q0[e] = s_small[SS_QN + c.lane * 4 + e];
-    q1[e] = s_small[SS_QN + HD + c.lane * 4 + e];
+  {
+    const float4 a = *reinterpret_cast<const float4*>(s_small + SS_QN + c.lane * 4);
+    const float4 b = *reinterpret_cast<const float4*>(s_small + SS_QN + HD + c.lane * 4);
+    q0[0] = a.x; q0[1] = a.y; q0[2] = a.z; q0[3] = a.w;
+    q1[0] = b.x; q1[1] = b.y; q1[2] = b.z; q1[3] = b.w;
   }
   const int len = it.p1 - it.p0;
   const int nrounds = (len + ATT_ROUND - 1) / ATT_ROUND;
   for (int r = 0; r < nrounds; ++r) {
-    if (r > 0) attn_prefetch(c, l, it, r, kv);
-    float sc0[ATT_PER_WARP], sc1[ATT_PER_WARP];
-    float mx0 = m0, mx1 = m1;
+    if (r > 0) attn_prefetch(c, l, position, it, r, kv);
+    float sc[10];
+    const int pos_first = it.p0 + r * ATT_ROUND + c.warp;
+    if (pos_first < it.p1) {  // warp-uniform
 #pragma unroll
-    for (int i = 0; i < ATT_PER_WARP; ++i) {
-      const int pos = it.p0 + r * ATT_ROUND + c.warp + NCW * i;
-      const bool valid = pos < it.p1;
-      float kf[4];
-      if (valid && pos == p.position) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) kf[e] = s_small[SS_KN + c.lane * 4 + e];
-      } else {
-        kf[0] = bf16_lo(kv.k[i].x); kf[1] = bf16_hi(kv.k[i].x);
-        kf[2] = bf16_lo(kv.k[i].y); kf[3] = bf16_hi(kv.k[i].y);
-      }
-      float d0 = 0.f, d1 = 0.f;
-      if (valid) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          d0 = fmaf(q0[e], kf[e], d0);
-          d1 = fmaf(q1[e], kf[e], d1);
+      for (int i = 0; i < ATT_PER_WARP; ++i) {
+        const int pos = pos_first + NCW * i;
+        float kf[4];
+        if (pos == position) {
+          const float4 kk = *reinterpret_cast<const float4*>(s_small + SS_KN + c.lane * 4);
+          kf[0] = kk.x; kf[1] = kk.y; kf[2] = kk.z; kf[3] = kk.w;
+        } else {
+          kf[0] = bf16_lo(kv.k[i].x); kf[1] = bf16_hi(kv.k[i].x);
+          kf[2] = bf16_lo(kv.k[i].y); kf[3] = bf16_hi(kv.k[i].y);
         }
+        float d0 = 0.f, d1 = 0.f;
+        if (pos < it.p1) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            d0 = fmaf(q0[e], kf[e], d0);
+            d1 = fmaf(q1[e], kf[e], d1);
+          }
+        }
+        sc[i] = d0;
+        sc[5 + i] = d1;
       }
-      d0 = warp_sum(d0);
-      d1 = warp_sum(d1);
-      sc0[i] = valid ? d0 * p.attn_scale : -INFINITY;
-      sc1[i] = valid ? d1 * p.attn_scale : -INFINITY;
-      mx0 = fmaxf(mx0, sc0[i]);
-      mx1 = fmaxf(mx1, sc1[i]);
-    }
-    if (mx0 != -INFINITY) {  // warp-uniform (scores are warp-reduced)
+      warp_sum10_bcast(sc, c.lane);
+      float mx0 = m0, mx1 = m1;
+#pragma unroll
+      for (int i = 0; i < ATT_PER_WARP; ++i) {
+        const bool valid = pos_first + NCW * i < it.p1;
+        sc[i] = valid ? sc[i] * p.attn_scale : -INFINITY;
+        sc[5 + i] = valid ? sc[5 + i] * p.attn_scale : -INFINITY;
+        mx0 = fmaxf(mx0, sc[i]);
+        mx1 = fmaxf(mx1, sc[5 + i]);
+      }
       const float c0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - mx0);
       const float c1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - mx1);
       l0 *= c0; l1 *= c1;
@@ -595,17 +772,17 @@ __device__ void phase_attn(Ctx& c, int l, uint32_t epoch, const AttnItem& it, Kv
       for (int e = 0; e < 4; ++e) { acc0[e] *= c0; acc1[e] *= c1; }
 #pragma unroll
       for (int i = 0; i < ATT_PER_WARP; ++i) {
-        const int pos = it.p0 + r * ATT_ROUND + c.warp + NCW * i;
+        const int pos = pos_first + NCW * i;
         if (pos < it.p1) {
           float vf[4];
-          if (pos == p.position) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) vf[e] = s_small[SS_V + c.lane * 4 + e];
+          if (pos == position) {
+            const float4 vv = *reinterpret_cast<const float4*>(s_small + SS_V + c.lane * 4);
+            vf[0] = vv.x; vf[1] = vv.y; vf[2] = vv.z; vf[3] = vv.w;
           } else {
             vf[0] = bf16_lo(kv.v[i].x); vf[1] = bf16_hi(kv.v[i].x);
             vf[2] = bf16_lo(kv.v[i].y); vf[3] = bf16_hi(kv.v[i].y);
           }
-          const float e0 = __expf(sc0[i] - mx0), e1 = __expf(sc1[i] - mx1);
+          const float e0 = __expf(sc[i] - mx0), e1 = __expf(sc[5 + i] - mx1);
           l0 += e0; l1 += e1;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -617,75 +794,79 @@ __device__ void phase_attn(Ctx& c, int l, uint32_t epoch, const AttnItem& it, Kv
       m0 = mx0; m1 = mx1;
     }
   }
-  trace_sub(c, 3);
-  // 4) cross-warp merge through shared memory (s_vec region is free during attention)
-  float* s_acc = c.s_vec;  // [12][2][128]
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    s_acc[(c.warp * 2 + 0) * HD + c.lane * 4 + e] = acc0[e];
-    s_acc[(c.warp * 2 + 1) * HD + c.lane * 4 + e] = acc1[e];
-  }
+  trace_sub(c, 2);
+  // 3) cross-warp merge: common max first, then plain sums (s_vec is free during attention)
   if (c.lane == 0) {
-    s_small[SS_ML + (c.warp * 2 + 0) * 2 + 0] = m0; s_small[SS_ML + (c.warp * 2 + 0) * 2 + 1] = l0;
-    s_small[SS_ML + (c.warp * 2 + 1) * 2 + 0] = m1; s_small[SS_ML + (c.warp * 2 + 1) * 2 + 1] = l1;
+    s_small[SS_M + c.warp * 2 + 0] = m0;
+    s_small[SS_M + c.warp * 2 + 1] = m1;
   }
   consumer_bar();
-  trace_sub(c, 4);
-  if (c.tid < 128) {
-    const int h = c.tid >> 6, dp = c.tid & 63;
-    float M = -INFINITY;
+  float M0 = -INFINITY, M1 = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < NCW; ++w) M = fmaxf(M, s_small[SS_ML + (w * 2 + h) * 2]);
-    float Lsum = 0.f, A0 = 0.f, A1 = 0.f;
+  for (int w = 0; w < NCW; ++w) {
+    M0 = fmaxf(M0, s_small[SS_M + w * 2 + 0]);
+    M1 = fmaxf(M1, s_small[SS_M + w * 2 + 1]);
+  }
+  {
+    const float f0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - M0);
+    const float f1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - M1);
+    float* s_acc = c.s_vec;  // [NCW][2][128]
+    *reinterpret_cast<float4*>(s_acc + (c.warp * 2 + 0) * HD + c.lane * 4) =
+        make_float4(acc0[0] * f0, acc0[1] * f0, acc0[2] * f0, acc0[3] * f0);
+    *reinterpret_cast<float4*>(s_acc + (c.warp * 2 + 1) * HD + c.lane * 4) =
+        make_float4(acc1[0] * f1, acc1[1] * f1, acc1[2] * f1, acc1[3] * f1);
+    if (c.lane == 0) {
+      s_small[SS_L + c.warp * 2 + 0] = l0 * f0;
+      s_small[SS_L + c.warp * 2 + 1] = l1 * f1;
+    }
+  }
+  consumer_bar();
+  trace_sub(c, 3);
+  if (c.tid < 256) {
+    const int h = c.tid >> 7, d = c.tid & 127;
+    float A = 0.f, Lsum = 0.f;
 #pragma unroll
     for (int w = 0; w < NCW; ++w) {
-      const float mw = s_small[SS_ML + (w * 2 + h) * 2];
-      const float f = (mw == -INFINITY) ? 0.f : __expf(mw - M);
-      Lsum = fmaf(s_small[SS_ML + (w * 2 + h) * 2 + 1], f, Lsum);
-      A0 = fmaf(s_acc[(w * 2 + h) * HD + 2 * dp], f, A0);
-      A1 = fmaf(s_acc[(w * 2 + h) * HD + 2 * dp + 1], f, A1);
+      A += c.s_vec[(w * 2 + h) * HD + d];
+      Lsum += s_small[SS_L + w * 2 + h];
     }
+    const float Mh = h ? M1 : M0;
     const int hq = 2 * it.g + h;
     if (it.S == 1) {
-      const uint32_t pk = bf16_bits(A0 / Lsum) | (bf16_bits(A1 / Lsum) << 16);
-      ll_pub(x_a + hq * 64 + dp, pk, epoch, R, XW_TOTAL);
+      ll4_st(x_a + hq * HD + d, bf16_round(A / Lsum), epoch);
     } else {
       u64* part = x_part + ((size_t)hq * S_MAX + it.s) * PART_STRIDE;
-      ll_st(part + 2 + 2 * dp, __float_as_uint(A0), epoch);
-      ll_st(part + 3 + 2 * dp, __float_as_uint(A1), epoch);
-      if (dp == 0) {
-        ll_st(part + 0, __float_as_uint(M), epoch);
-        ll_st(part + 1, __float_as_uint(Lsum), epoch);
+      ll8_st(part + 2 + d, __float_as_uint(A), epoch);
+      if (d == 0) {
+        ll8_st(part + 0, __float_as_uint(Mh), epoch);
+        ll8_st(part + 1, __float_as_uint(Lsum), epoch);
       }
       if (it.s == 0) {  // this CTA merges the splits of its two q heads, fixed order s = 0..S-1
         float Mx = -INFINITY;
         for (int s = 0; s < it.S; ++s) {
           const u64* ps = x_part + ((size_t)hq * S_MAX + s) * PART_STRIDE;
-          Mx = fmaxf(Mx, __uint_as_float(ll_wait(c, ps, epoch)));
+          Mx = fmaxf(Mx, __uint_as_float(ll8_wait(c, ps, epoch)));
         }
-        float Lt = 0.f, B0 = 0.f, B1 = 0.f;
+        float Lt = 0.f, B = 0.f;
         for (int s = 0; s < it.S; ++s) {
           const u64* ps = x_part + ((size_t)hq * S_MAX + s) * PART_STRIDE;
-          const float f = __expf(__uint_as_float(ll_wait(c, ps, epoch)) - Mx);
-          Lt = fmaf(__uint_as_float(ll_wait(c, ps + 1, epoch)), f, Lt);
-          B0 = fmaf(__uint_as_float(ll_wait(c, ps + 2 + 2 * dp, epoch)), f, B0);
-          B1 = fmaf(__uint_as_float(ll_wait(c, ps + 3 + 2 * dp, epoch)), f, B1);
+          const float f = __expf(__uint_as_float(ll8_wait(c, ps, epoch)) - Mx);
+          Lt = fmaf(__uint_as_float(ll8_wait(c, ps + 1, epoch)), f, Lt);
+          B = fmaf(__uint_as_float(ll8_wait(c, ps + 2 + d, epoch)), f, B);
         }
-        const uint32_t pk = bf16_bits(B0 / Lt) | (bf16_bits(B1 / Lt) << 16);
-        ll_pub(x_a + hq * 64 + dp, pk, epoch, R, XW_TOTAL);
+        ll4_st(x_a + hq * HD + d, bf16_round(B / Lt), epoch);
       }
     }
   }
-  trace_sub(c, 5);
-  // 5) append the new K/V row (off the critical path: after `a` has been published)
+  c.t_pub = clock64();
+  trace_sub(c, 4);
+  // 4) append the new K/V row (off the critical path: after `a` has been published)
   if (it.owner && c.tid < 128) {
-    const size_t off = ((size_t)(l * NKVH + it.g) * p.max_seq + p.position) * HD + c.tid;
+    const size_t off = ((size_t)(l * NKVH + it.g) * p.max_seq + position) * HD + c.tid;
     p.k_cache[off] = __float2bfloat16_rn(s_small[SS_KN + c.tid]);
     p.v_cache[off] = __float2bfloat16_rn(s_small[SS_V + c.tid]);
-    __threadfence();
   }
-  consumer_bar();  // s_small / s_acc are reused by the next phase
-  trace_sub(c, 6);
+  consumer_bar();  // s_small / s_vec are reused by the next phase
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -695,175 +876,186 @@ __device__ void consumer_loop(Ctx& c) {
   const Params& p = c.p;
   const Layout& y = p.lay;
   const int nlayer_idx = y.L * PH_PER_LAYER;
-  // writer views (replica 0; ll_pub fans out) and reader views (replica cta % R)
-  u64* w_res = p.xbuf;
-  u64* w_qkv = w_res + XW_RES;
-  u64* w_res2 = w_qkv + XW_QKV + XW_A;
-  u64* w_m = w_res2 + XW_RES2;
-  u64* w_logits = w_m + XW_M;
-  const u64* x_res = c.xrd;
-  const u64* x_a = x_res + XW_RES + XW_QKV;
-  const u64* x_res2 = x_a + XW_A;
-  const u64* x_m = x_res2 + XW_RES2;
-  const u64* x_logits = x_m + XW_M;
-  const int R = p.replicas;
+  uint32_t* const x_res = c.x32 + XW_RES;
+  uint32_t* const x_qkv = c.x32 + XW_QKV;
+  uint32_t* const x_a = c.x32 + XW_A;
+  uint32_t* const x_res2 = c.x32 + XW_RES2;
+  uint32_t* const x_m = c.x32 + XW_M;
+  uint32_t* const x_logits = c.x32 + XW_LOGITS;
+  const CtaRows rows = cta_rows(y, c.cta);
   float xr[32];
+  float raw[4];
   KvRegs kv;
-  AttnItem item;
-  const bool has_item = attn_item(p, c.cta, item);
-  int prefetched_layer = -1;
-  const int o_row0 = row_begin(c.cta, H, y.G);
-  const int o_rows = row_begin(c.cta + 1, H, y.G) - o_row0;
+  AttnPre pre = {{0.f, 0.f, 0.f, 0.f}};
+  float res_mine = 0.f;  // fp32 residual of row o_row0 + tid (tid < o_rows)
 
-  for (int idx = p.phase_begin; idx < p.phase_end; ++idx) {
-    c.cur_idx = idx;
-    trace_sub(c, 0);
-    if (idx < nlayer_idx) {
-      const int l = idx / PH_PER_LAYER, ph = idx % PH_PER_LAYER;
-      const uint32_t epoch = p.epoch_base + 1u + (uint32_t)l;
-      if (ph == PH_QKV) {
-        const PhaseDesc d = layer_phase_desc(p, l, PH_QKV, c.cta);
-        if (has_item) {  // KV rows of older positions do not depend on this layer: fetch them now
-          attn_prefetch(c, l, item, 0, kv);
-          prefetched_layer = l;
+  for (int step = 0; step < p.n_steps; ++step) {
+    const StepDesc& sd = p.steps[step];
+    const uint32_t ebase = p.epoch_base + (uint32_t)step * (uint32_t)(y.L + 2);
+    const int position = sd.position;
+    const __nv_bfloat16* x_in = (sd.in_mode == 0) ? sd.in_table + (size_t)sd.token * H
+                                                  : reinterpret_cast<const __nv_bfloat16*>(sd.in_vec);
+    AttnItem item;
+    const bool has_item = attn_item(p, position, c.cta, item);
+    if (has_item && c.tid < 128) {  // RoPE row of this step: cos[0..63], sin[0..63]
+      const int d = c.tid & 63;
+      const __nv_bfloat16* t = (c.tid < 64) ? p.cos_t : p.sin_t;
+      c.s_small[SS_CS + c.tid] = __bfloat162float(t[(size_t)position * HD + d]);
+    }
+    consumer_bar();
+    int pre_layer = -1;  // layer whose KV rows / qk-norm weights were fetched during its QKV phase
+    const int begin = (step == 0) ? p.phase_begin : 0;
+    const int end = (p.n_steps == 1) ? p.phase_end : nlayer_idx + 2;
+    if (begin > 0 && c.tid < rows.o_rows) res_mine = p.res_spill[rows.o_row0 + c.tid];  // staged launches only
+
+    for (int idx = begin; idx < end; ++idx) {
+      c.cur_idx = idx;
+      trace_sub(c, 0);
+      if (idx < nlayer_idx) {
+        const int l = idx / PH_PER_LAYER, ph = idx % PH_PER_LAYER;
+        const uint32_t epoch = (ebase + 1u + (uint32_t)l) & 0xffffu;
+        const uint32_t epoch_prev = (ebase + (uint32_t)l) & 0xffffu;
+        if (ph == PH_QKV) {
+          const PhaseDesc d = layer_phase_desc(p, rows, l, PH_QKV, c.cta);
+          if (has_item) attn_prefetch(c, l, position, item, 0, kv);  // older KV rows do not depend on this layer
+          uint32_t ready;
+          if (l == 0) {
+            gather_norm<true>(c, nullptr, 0, x_in, DL_QKV, n_stages_of(d), ready, raw);
+            if (c.tid < rows.o_rows) {
+              res_mine = __bfloat162float(x_in[rows.o_row0 + c.tid]);
+              p.res_spill[rows.o_row0 + c.tid] = res_mine;
+            }
+          } else {
+            gather_norm<false>(c, x_res, epoch_prev, nullptr, DL_QKV, n_stages_of(d), ready, raw);
+          }
+          trace_sub(c, 1);
+          if (has_item && c.warp < 3) {  // q_norm / k_norm weights of this layer (aux of the resident first stage)
+            const uint2 wv = *reinterpret_cast<const uint2*>(c.ring + (size_t)(c.k % NSLOTS) * SLOT_BYTES + 2048 +
+                                                              (c.warp == 2 ? 256 : 0) + c.lane * 8);
+            pre.nw[0] = bf16_lo(wv.x); pre.nw[1] = bf16_hi(wv.x); pre.nw[2] = bf16_lo(wv.y); pre.nw[3] = bf16_hi(wv.y);
+          }
+          pre_layer = l;
+          load_xr(c.s_vec, c.lane, xr);
+          run_stages<false>(c, d, ready, xr, 1);
+          trace_sub(c, 2);
+          if (c.tid < d.n_items) ll4_st(x_qkv + rows.q_row0 + c.tid, bf16_round(c.s_part[c.tid]), epoch);
+          c.t_pub = clock64();
+        } else if (ph == PH_ATTN) {
+          if (has_item) {
+            if (pre_layer != l) {  // staged launch: the QKV phase ran in an earlier launch
+              attn_prefetch(c, l, position, item, 0, kv);
+              if (c.warp < 3) {
+                const uint2 wv = *reinterpret_cast<const uint2*>(p.aux_layers + ((size_t)l * 2) * AUX_BYTES + 2048 +
+                                                                  (c.warp == 2 ? 256 : 0) + c.lane * 8);
+                pre.nw[0] = bf16_lo(wv.x); pre.nw[1] = bf16_hi(wv.x); pre.nw[2] = bf16_lo(wv.y); pre.nw[3] = bf16_hi(wv.y);
+              }
+            }
+            phase_attn(c, l, position, epoch, item, kv, pre);
+          }
+        } else if (ph == PH_O) {
+          const PhaseDesc d = layer_phase_desc(p, rows, l, PH_O, c.cta);
+          uint32_t ready;
+          gather_vec(c, x_a, QSZ, epoch, DL_O, n_stages_of(d), ready, has_item ? -1 : p.delay_o_idle);
+          trace_sub(c, 1);
+          load_xr(c.s_vec + (c.warp % 2) * SEG_ELEMS, c.lane, xr);
+          run_stages<false>(c, d, ready, xr, 1);
+          trace_sub(c, 2);
+          if (c.tid < rows.o_rows) {
+            const float o = bf16_round(c.s_part[2 * c.tid] + c.s_part[2 * c.tid + 1]);
+            res_mine = p.residual_fp32 ? res_mine + o : bf16_round(res_mine + o);
+            ll4_st(x_res2 + rows.o_row0 + c.tid, bf16_round(res_mine), epoch);
+            p.res_spill[rows.o_row0 + c.tid] = res_mine;
+          }
+          c.t_pub = clock64();
+        } else if (ph == PH_GU) {
+          const PhaseDesc d = layer_phase_desc(p, rows, l, PH_GU, c.cta);
+          uint32_t ready;
+          gather_norm<false>(c, x_res2, epoch, nullptr, DL_GU, n_stages_of(d), ready, raw);
+          trace_sub(c, 1);
+          load_xr(c.s_vec, c.lane, xr);
+          run_stages<false>(c, d, ready, xr, 1);
+          trace_sub(c, 2);
+          if (c.tid < rows.gu_rows) {
+            const float g = bf16_round(c.s_part[2 * c.tid]);
+            const float u = bf16_round(c.s_part[2 * c.tid + 1]);
+            const float sg = bf16_round(g / (1.0f + expf(-g)));
+            ll4_st(x_m + rows.gu_row0 + c.tid, bf16_round(sg * u), epoch);
+          }
+          c.t_pub = clock64();
+        } else {  // PH_DOWN
+          const PhaseDesc d = layer_phase_desc(p, rows, l, PH_DOWN, c.cta);
+          uint32_t ready;
+          gather_vec(c, x_m, INTER, epoch, DL_DOWN, n_stages_of(d), ready);
+          trace_sub(c, 1);
+          run_stages<true>(c, d, ready, xr, 3);
+          trace_sub(c, 2);
+          if (c.tid < rows.o_rows) {
+            const float dn = bf16_round((c.s_part[3 * c.tid] + c.s_part[3 * c.tid + 1]) + c.s_part[3 * c.tid + 2]);
+            res_mine = p.residual_fp32 ? res_mine + dn : bf16_round(res_mine + dn);
+            ll4_st(x_res + rows.o_row0 + c.tid, bf16_round(res_mine), epoch);
+            p.res_spill[rows.o_row0 + c.tid] = res_mine;
+          }
+          c.t_pub = clock64();
         }
-        if (l == 0) {
-          const __nv_bfloat16* x = step_input(p);
-          for (int i = c.tid; i < H; i += NCT) c.s_vec[i] = __bfloat162float(x[i]);
-        } else {
-          gather_words<XW_RES>(c, x_res, epoch - 1u, [&](int i, uint32_t v) { c.s_vec[i] = __uint_as_float(v); });
+      } else if (idx == nlayer_idx) {
+        // final RMSNorm (+ LM head rows of this CTA)
+        const uint32_t epoch_last = (ebase + (uint32_t)y.L) & 0xffffu;
+        const uint32_t epoch_head = (ebase + (uint32_t)y.L + 1u) & 0xffffu;
+        const PhaseDesc d = head_phase_desc(p, sd.head, c.cta);
+        uint32_t ready;
+        gather_norm<false>(c, x_res, epoch_last, nullptr, DL_HEAD, n_stages_of(d), ready, raw);
+        if (c.cta == 0 && c.tid < 256) {
+          if (sd.hidden_out != nullptr) {
+            uint2 hv;
+            hv.x = (__float_as_uint(raw[0]) >> 16) | (__float_as_uint(raw[1]) & 0xffff0000u);
+            hv.y = (__float_as_uint(raw[2]) >> 16) | (__float_as_uint(raw[3]) & 0xffff0000u);
+            *reinterpret_cast<uint2*>(sd.hidden_out + c.tid * 4) = hv;
+          }
+          if (sd.out_norm != nullptr)
+            *reinterpret_cast<float4*>(sd.out_norm + c.tid * 4) = *reinterpret_cast<const float4*>(c.s_vec + c.tid * 4);
         }
-        consumer_bar();
-        trace_sub(c, 1);
-        wait_full(c, c.k);
-        trace_sub(c, 2);
-        rmsnorm_regs(c.s_vec, reinterpret_cast<const uint4*>(c.ring + (size_t)(c.k % NSTAGES) * STAGE_BYTES), c.lane, xr);
-        trace_sub(c, 3);
-        run_stages(c, d, xr);
-        trace_sub(c, 4);
-        consumer_bar();
-        trace_sub(c, 5);
-        if (c.tid < d.n_items) {
-          const int row = row_begin(c.cta, QKV_ROWS, y.G) + c.tid;
-          ll_pub(w_qkv + row, __float_as_uint(bf16_round(c.s_part[c.tid])), epoch, R, XW_TOTAL);
-        }
-      } else if (ph == PH_ATTN) {
-        if (has_item) phase_attn(c, l, epoch, item, kv, prefetched_layer == l);
-      } else if (ph == PH_O) {
-        const PhaseDesc d = layer_phase_desc(p, l, PH_O, c.cta);
-        float res_old = 0.f;
-        if (c.tid < o_rows) {
-          res_old = (l == 0) ? __bfloat162float(step_input(p)[o_row0 + c.tid])
-                             : __uint_as_float(ll_wait(c, x_res + o_row0 + c.tid, epoch - 1u));
-        }
-        gather_words<XW_A>(c, x_a, epoch, [&](int i, uint32_t v) {
-          c.s_vec[2 * i] = bf16_lo(v);
-          c.s_vec[2 * i + 1] = bf16_hi(v);
-        });
-        consumer_bar();
-        trace_sub(c, 1);
-        load_xr(c.s_vec + (c.warp % 2) * SEG_ELEMS, c.lane, xr);
-        run_stages(c, d, xr);
-        trace_sub(c, 4);
-        consumer_bar();
-        trace_sub(c, 5);
-        if (c.tid < o_rows) {
-          const float o = bf16_round(c.s_part[2 * c.tid] + c.s_part[2 * c.tid + 1]);
-          const float res = p.residual_fp32 ? res_old + o : bf16_round(res_old + o);
-          ll_pub(w_res2 + o_row0 + c.tid, __float_as_uint(res), epoch, R, XW_TOTAL);
-        }
-      } else if (ph == PH_GU) {
-        const PhaseDesc d = layer_phase_desc(p, l, PH_GU, c.cta);
-        gather_words<XW_RES2>(c, x_res2, epoch, [&](int i, uint32_t v) { c.s_vec[i] = __uint_as_float(v); });
-        consumer_bar();
-        trace_sub(c, 1);
-        wait_full(c, c.k);
-        trace_sub(c, 2);
-        rmsnorm_regs(c.s_vec, reinterpret_cast<const uint4*>(c.ring + (size_t)(c.k % NSTAGES) * STAGE_BYTES), c.lane, xr);
-        trace_sub(c, 3);
-        run_stages(c, d, xr);
-        trace_sub(c, 4);
-        consumer_bar();
-        trace_sub(c, 5);
-        if (c.tid < d.n_items / 2) {
-          const float g = bf16_round(c.s_part[2 * c.tid]);
-          const float u = bf16_round(c.s_part[2 * c.tid + 1]);
-          const float sg = bf16_round(g / (1.0f + expf(-g)));
-          const int pair = row_begin(c.cta, INTER, y.G) + c.tid;
-          ll_pub(w_m + pair, __float_as_uint(bf16_round(sg * u)), epoch, R, XW_TOTAL);
-        }
-      } else {  // PH_DOWN
-        const PhaseDesc d = layer_phase_desc(p, l, PH_DOWN, c.cta);
-        float res_old = 0.f;
-        if (c.tid < o_rows) res_old = __uint_as_float(ll_wait(c, x_res2 + o_row0 + c.tid, epoch));
-        gather_words<XW_M>(c, x_m, epoch, [&](int i, uint32_t v) { c.s_vec[i] = __uint_as_float(v); });
-        consumer_bar();
-        trace_sub(c, 1);
-        load_xr(c.s_vec + (c.warp % 3) * SEG_ELEMS, c.lane, xr);
-        run_stages(c, d, xr);
-        trace_sub(c, 4);
-        consumer_bar();
-        trace_sub(c, 5);
-        if (c.tid < o_rows) {
-          const float dn = bf16_round((c.s_part[3 * c.tid] + c.s_part[3 * c.tid + 1]) + c.s_part[3 * c.tid + 2]);
-          const float res = p.residual_fp32 ? res_old + dn : bf16_round(res_old + dn);
-          ll_pub(w_res + o_row0 + c.tid, __float_as_uint(res), epoch, R, XW_TOTAL);
-        }
-      }
-    } else if (idx == nlayer_idx) {
-      // final RMSNorm (+ LM head rows of this CTA)
-      const uint32_t epoch_last = p.epoch_base + (uint32_t)y.L;
-      const PhaseDesc d = head_phase_desc(p, c.cta);
-      gather_words<XW_RES>(c, x_res, epoch_last, [&](int i, uint32_t v) { c.s_vec[i] = __uint_as_float(v); });
-      consumer_bar();
-      wait_full(c, c.k);
-      if (c.cta == 0 && c.warp == 1 && p.hidden_out != nullptr) {
-        for (int i = c.lane; i < H; i += 32) p.hidden_out[i] = __float2bfloat16_rn(c.s_vec[i]);
-      }
-      rmsnorm_regs(c.s_vec, reinterpret_cast<const uint4*>(c.ring + (size_t)(c.k % NSTAGES) * STAGE_BYTES), c.lane, xr);
-      if (c.cta == 0 && c.warp == 0 && p.out_norm != nullptr) {
+        load_xr(c.s_vec, c.lane, xr);
+        run_stages<false>(c, d, ready, xr, 1);
+        if (c.tid < d.n_items)
+          ll4_st(x_logits + row_begin(c.cta, sd.head.rows, y.G) + c.tid, bf16_round(c.s_part[c.tid]), epoch_head);
+        c.t_pub = clock64();
+      } else {
+        // argmax over the bf16 logits, lowest index wins ties (CTA 0)
+        if (c.cta != 0 || sd.head.rows <= 0) continue;
+        const uint32_t epoch_head = (ebase + (uint32_t)y.L + 1u) & 0xffffu;
+        float best = -INFINITY;
+        int best_i = 0x7fffffff;
+        bool retried = false;
+        (void)wait_window(c, DL_ARGMAX, 0);
+        for (int i = c.tid * 4; i < sd.head.rows; i += NCT * 4) {   // indices ascend per thread
+          const uint4 w = ll4_wait(c, x_logits + i, epoch_head, retried);
+          const float v4[4] = {ll4_val(w.x), ll4_val(w.y), ll4_val(w.z), ll4_val(w.w)};
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+          for (int e = 0; e < 4; ++e)
+            if (v4[e] > best) { best = v4[e]; best_i = i + e; }
+        }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) p.out_norm[j * 256 + c.lane * 8 + e] = xr[j * 8 + e];
-      }
-      run_stages(c, d, xr);
-      consumer_bar();
-      if (c.tid < d.n_items) {
-        const int row = row_begin(c.cta, p.head.rows, y.G) + c.tid;
-        ll_pub(w_logits + row, __float_as_uint(bf16_round(c.s_part[c.tid])), epoch_last + 1u, R, XW_TOTAL);
-      }
-    } else {
-      // argmax over the bf16 logits, lowest index wins ties (CTA 0)
-      if (c.cta != 0 || p.head.rows <= 0) continue;
-      const uint32_t epoch_head = p.epoch_base + (uint32_t)y.L + 1u;
-      float best = -INFINITY;
-      int best_i = 0x7fffffff;
-      gather_words<XW_LOGITS>(c, x_logits, epoch_head, [&](int i, uint32_t u) {
-        const float v = __uint_as_float(u);   // indices arrive in ascending order per thread
-        if (v > best) { best = v; best_i = i; }
-      }, p.head.rows);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-        if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
-      }
-      consumer_bar();
-      if (c.lane == 0) {
-        c.s_red[c.warp * 2] = best;
-        c.s_red[c.warp * 2 + 1] = __int_as_float(best_i);
-      }
-      consumer_bar();
-      if (c.tid == 0) {
-        for (int w = 1; w < NCW; ++w) {
-          const float ov = c.s_red[w * 2];
-          const int oi = __float_as_int(c.s_red[w * 2 + 1]);
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
           if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
         }
-        // a failed launch must not look like a token: encode the watchdog code as a negative id
-        const int st = *((volatile int*)p.status);
-        *p.out_token = (st != 0 || *c.s_abort) ? -1000 - st : best_i;
+        if (c.lane == 0) {
+          c.s_red[c.warp * 2] = best;
+          c.s_red[c.warp * 2 + 1] = __int_as_float(best_i);
+        }
+        adapt_delay(c, DL_ARGMAX, retried);
+        if (c.tid == 0) {
+          for (int w = 1; w < NCW; ++w) {
+            const float ov = c.s_red[w * 2];
+            const int oi = __float_as_int(c.s_red[w * 2 + 1]);
+            if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+          }
+          // a failed launch must not look like a token: encode the watchdog code as a negative id
+          const int st = *((volatile int*)p.status);
+          *sd.out_token = (st != 0 || *c.s_abort) ? -1000 - st : best_i;
+        }
+        consumer_bar();
       }
     }
   }
@@ -879,27 +1071,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) qmk_decode_kernel(const __grid_co
   c.s_vec = reinterpret_cast<float*>(smem + SM_VEC);
   c.s_small = reinterpret_cast<float*>(smem + SM_SMALL);
   c.s_part = reinterpret_cast<float*>(smem + SM_PART);
+  c.s_red = reinterpret_cast<float*>(smem + SM_RED);
   c.full = reinterpret_cast<u64*>(smem + SM_BAR);
-  c.empty = c.full + NSTAGES;
+  c.empty = c.full + 8;
   c.s_abort = reinterpret_cast<volatile int*>(smem + SM_MISC);
-  c.s_red = reinterpret_cast<float*>(smem + SM_MISC + 16);
+  c.s_delay = reinterpret_cast<int*>(smem + SM_MISC + 16);
+  c.x32 = reinterpret_cast<uint32_t*>(p.xbuf);
   c.tid = threadIdx.x;
   c.warp = threadIdx.x >> 5;
   c.lane = threadIdx.x & 31;
   c.cta = blockIdx.x;
   c.k = 0;
   c.t0 = clock64();
+  c.t_pub = c.t0;
   c.cur_idx = p.phase_begin;
-  c.xrd = p.xbuf + (size_t)(blockIdx.x % p.replicas) * XW_TOTAL;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGES; ++i) {
+    for (int i = 0; i < NSLOTS; ++i) {
       mbar_init(&c.full[i], 1);
       mbar_init(&c.empty[i], NCW);
     }
     *c.s_abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (threadIdx.x < 2 * DL_N) c.s_delay[threadIdx.x] = p.delays[blockIdx.x * 2 * DL_N + threadIdx.x];
   __syncthreads();
 
   if (c.warp == NCW) {
@@ -910,6 +1105,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) qmk_decode_kernel(const __grid_co
   __syncthreads();
   c.cur_idx = p.phase_end;
   trace_sub(c, 0);
+  if (threadIdx.x >= DL_N && threadIdx.x < 2 * DL_N) p.delays[blockIdx.x * 2 * DL_N + threadIdx.x] = c.s_delay[threadIdx.x];
   if (*c.s_abort && threadIdx.x == 0) {
     // failure path only: give in-flight bulk copies time to land before the CTA's shared memory is released
     const long long t = clock64();
@@ -927,7 +1123,7 @@ struct LayerPtrs {  // = upstream LDGLayerWeights (kernel.cu:78-90)
 enum { W_IN = 0, W_Q, W_K, W_V, W_QN, W_KN, W_O, W_POST, W_GATE, W_UP, W_DOWN };
 
 // grid = (G, L), block = 128 threads: thread t copies uint4 t of each 2 KB segment.
-__global__ void qmk_pack_layers_kernel(const LayerPtrs* layers, Layout y, uint8_t* packed, __nv_bfloat16* qk_norm) {
+__global__ void qmk_pack_layers_kernel(const LayerPtrs* layers, Layout y, uint8_t* packed, uint8_t* aux_layers) {
   const int cta = blockIdx.x, l = blockIdx.y, t = threadIdx.x;
   const LayerPtrs lp = layers[l];
   uint4* dst = reinterpret_cast<uint4*>(packed + ((size_t)((size_t)cta * y.L + l) * y.layer_segs) * SEG_BYTES);
@@ -939,10 +1135,8 @@ __global__ void qmk_pack_layers_kernel(const LayerPtrs* layers, Layout y, uint8_
     uint4 v = zero;
     if (seg < y.off_o) {
       const int s = seg;
-      if (s == 0) {
-        v = lp.w[W_IN][t];
-      } else if (s - 1 < nq) {
-        const int row = q0 + s - 1;
+      if (s < nq) {
+        const int row = q0 + s;
         if (row < QSZ) v = lp.w[W_Q][(size_t)row * 128 + t];
         else if (row < QSZ + KVSZ) v = lp.w[W_K][(size_t)(row - QSZ) * 128 + t];
         else v = lp.w[W_V][(size_t)(row - QSZ - KVSZ) * 128 + t];
@@ -952,11 +1146,9 @@ __global__ void qmk_pack_layers_kernel(const LayerPtrs* layers, Layout y, uint8_
       if (s < 2 * no) v = lp.w[W_O][((size_t)(o0 + s / 2) * 2 + (s % 2)) * 128 + t];
     } else if (seg < y.off_down) {
       const int s = seg - y.off_gu;
-      if (s == 0) {
-        v = lp.w[W_POST][t];
-      } else if (s - 1 < 2 * ng) {
-        const int it = s - 1, row = g0 + it / 2;
-        v = (it % 2 == 0) ? lp.w[W_GATE][(size_t)row * 128 + t] : lp.w[W_UP][(size_t)row * 128 + t];
+      if (s < 2 * ng) {
+        const int row = g0 + s / 2;
+        v = (s % 2 == 0) ? lp.w[W_GATE][(size_t)row * 128 + t] : lp.w[W_UP][(size_t)row * 128 + t];
       }
     } else {
       const int s = seg - y.off_down;
@@ -964,24 +1156,28 @@ __global__ void qmk_pack_layers_kernel(const LayerPtrs* layers, Layout y, uint8_
     }
     dst[(size_t)seg * 128 + t] = v;
   }
-  if (cta == 0) {
-    const __nv_bfloat16* qn = reinterpret_cast<const __nv_bfloat16*>(lp.w[W_QN]);
-    const __nv_bfloat16* kn = reinterpret_cast<const __nv_bfloat16*>(lp.w[W_KN]);
-    qk_norm[((size_t)l * 2 + 0) * HD + t] = qn[t];
-    qk_norm[((size_t)l * 2 + 1) * HD + t] = kn[t];
+  if (cta == 0) {  // shared aux blocks: [input_ln | q_norm | k_norm] and [post_ln | 0]
+    uint4* a0 = reinterpret_cast<uint4*>(aux_layers + ((size_t)l * 2 + 0) * AUX_BYTES);
+    uint4* a1 = reinterpret_cast<uint4*>(aux_layers + ((size_t)l * 2 + 1) * AUX_BYTES);
+    a0[t] = lp.w[W_IN][t];
+    a1[t] = lp.w[W_POST][t];
+    if (t < 16) {
+      a0[128 + t] = lp.w[W_QN][t];
+      a0[144 + t] = lp.w[W_KN][t];
+      a1[128 + t] = zero;
+      a1[144 + t] = zero;
+    }
   }
 }
 
-// grid = G, block = 128: per CTA [aux: final norm][rows of this CTA]
-__global__ void qmk_pack_head_kernel(const uint4* head_w, const uint4* final_norm, int rows, int G, int segs_max,
-                                     uint8_t* packed) {
+// grid = G, block = 128: rows of this CTA
+__global__ void qmk_pack_head_kernel(const uint4* head_w, int rows, int G, int segs_max, uint8_t* packed) {
   const int cta = blockIdx.x, t = threadIdx.x;
   uint4* dst = reinterpret_cast<uint4*>(packed + ((size_t)cta * segs_max) * SEG_BYTES);
   const int r0 = row_begin(cta, rows, G), n = row_begin(cta + 1, rows, G) - r0;
   for (int seg = 0; seg < segs_max; ++seg) {
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (seg == 0) v = final_norm[t];
-    else if (seg - 1 < n) v = head_w[(size_t)(r0 + seg - 1) * 128 + t];
+    if (seg < n) v = head_w[(size_t)(r0 + seg) * 128 + t];
     dst[(size_t)seg * 128 + t] = v;
   }
 }

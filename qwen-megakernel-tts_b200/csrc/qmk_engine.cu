@@ -60,9 +60,10 @@ struct qmk_head {
 struct qmk_engine {
   int device = 0;
   int G = 0;
-  u64* xbuf = nullptr;
-  int replicas = 8;
-  int probe = 1;
+  uint8_t* xbuf = nullptr;
+  float* res_spill = nullptr;
+  int* delays = nullptr;
+  int delay_o_idle = 2500;
   long long* trace_dev = nullptr;
   int trace_stride = 0;
   int* status_dev = nullptr;
@@ -75,8 +76,8 @@ struct qmk_model {
   qmk_engine* e = nullptr;
   Layout lay{};
   uint8_t* packed_layers = nullptr;
-  __nv_bfloat16* qk_norm = nullptr;
-  uint8_t* norm_seg = nullptr;  // 2 KB: final RMSNorm weight (aux segment of a head-less final phase)
+    uint8_t* aux_layers = nullptr;  // [L][2][AUX_BYTES]: input_ln | q_norm | k_norm  and  post_ln
+  uint8_t* norm_seg = nullptr;    // AUX_BYTES: final RMSNorm weight (aux block of the head phase)
   int residual_fp32 = 1;
   int64_t packed_bytes = 0;
   std::vector<qmk_head> heads;
@@ -93,9 +94,9 @@ static Layout make_layout(int G, int L) {
   y.qkv_max = (QKV_ROWS + G - 1) / G;
   y.o_max = (H + G - 1) / G;
   y.gu_max = (INTER + G - 1) / G;
-  y.off_o = 1 + y.qkv_max;
+  y.off_o = y.qkv_max;
   y.off_gu = y.off_o + 2 * y.o_max;
-  y.off_down = y.off_gu + 1 + 2 * y.gu_max;
+  y.off_down = y.off_gu + 2 * y.gu_max;
   y.layer_segs = y.off_down + 3 * y.o_max;
   return y;
 }
@@ -120,8 +121,8 @@ extern "C" int qmk_engine_create(int device, int num_ctas, qmk_engine** out) {
   }
   int G = num_ctas > 0 ? num_ctas : prop.multiProcessorCount;
   if (G > prop.multiProcessorCount) G = prop.multiProcessorCount;
-  // every CTA must own >=1 row in every phase; per-phase item tables hold 128 entries
-  if (G < 64 || G > 1024) return set_error(QMK_ERR_UNSUPPORTED, "unsupported CTA count %d (need 64..1024)", G);
+  // every CTA must own >=1 row in every phase and a phase may span at most MAX_ST ring stages
+  if (G < 110 || G > 1024) return set_error(QMK_ERR_UNSUPPORTED, "unsupported CTA count %d (need 110..1024)", G);
   QMK_CUDA(cudaFuncSetAttribute(qmk_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   int occ = 0;
   QMK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qmk_decode_kernel, NTHREADS, SMEM_BYTES));
@@ -131,16 +132,24 @@ extern "C" int qmk_engine_create(int device, int num_ctas, qmk_engine** out) {
   e->device = device;
   e->G = G;
   if (const char* env = getenv("QMK_TIMEOUT_CYCLES")) e->timeout_cycles = atoll(env);
-  if (const char* env = getenv("QMK_REPLICAS")) e->replicas = atoi(env);
-  if (const char* env = getenv("QMK_PROBE")) e->probe = atoi(env);
-  if (e->replicas < 1) e->replicas = 1;
-  if (e->replicas > G) e->replicas = G;
-  cudaError_t err = cudaMalloc(&e->xbuf, sizeof(u64) * XW_TOTAL * e->replicas);
-  if (err == cudaSuccess) err = cudaMemset(e->xbuf, 0, sizeof(u64) * XW_TOTAL * e->replicas);
+  int delay0 = 450;
+  if (const char* env = getenv("QMK_POLL_DELAY")) delay0 = atoi(env);
+  if (const char* env = getenv("QMK_POLL_DELAY_O")) e->delay_o_idle = atoi(env);
+  std::vector<int> delays((size_t)G * 2 * DL_N, 0);
+  for (int c = 0; c < G; ++c)
+    for (int d = 0; d < DL_N; ++d) delays[(size_t)c * 2 * DL_N + d] = delay0;
+  cudaError_t err = cudaMalloc(&e->xbuf, XBUF_BYTES);
+  if (err == cudaSuccess) err = cudaMemset(e->xbuf, 0, XBUF_BYTES);
+  if (err == cudaSuccess) err = cudaMalloc(&e->res_spill, H * sizeof(float));
+  if (err == cudaSuccess) err = cudaMemset(e->res_spill, 0, H * sizeof(float));
+  if (err == cudaSuccess) err = cudaMalloc(&e->delays, delays.size() * sizeof(int));
+  if (err == cudaSuccess) err = cudaMemcpy(e->delays, delays.data(), delays.size() * sizeof(int), cudaMemcpyHostToDevice);
   if (err == cudaSuccess) err = cudaMalloc(&e->status_dev, 4 * sizeof(int));
   if (err == cudaSuccess) err = cudaMemset(e->status_dev, 0, 4 * sizeof(int));
   if (err != cudaSuccess) {
     if (e->xbuf) cudaFree(e->xbuf);
+    if (e->res_spill) cudaFree(e->res_spill);
+    if (e->delays) cudaFree(e->delays);
     if (e->status_dev) cudaFree(e->status_dev);
     delete e;
     return set_error(QMK_ERR_CUDA, "engine allocation failed: %s", cudaGetErrorString(err));
@@ -154,6 +163,8 @@ extern "C" void qmk_engine_destroy(qmk_engine* e) {
   DeviceGuard guard(e->device);
   cudaDeviceSynchronize();
   cudaFree(e->xbuf);
+  cudaFree(e->res_spill);
+  cudaFree(e->delays);
   cudaFree(e->status_dev);
   if (e->trace_dev) cudaFree(e->trace_dev);
   delete e;
@@ -186,6 +197,16 @@ extern "C" int qmk_engine_trace_read(qmk_engine* e, void* stream, long long* hos
 
 extern "C" int qmk_engine_num_ctas(const qmk_engine* e) { return e ? e->G : 0; }
 
+extern "C" int qmk_engine_poll_stats(qmk_engine* e, void* stream, int32_t* host_out, int64_t max_elems) {
+  if (!e || !host_out) return set_error(QMK_ERR_ARG, "qmk_engine_poll_stats: null argument");
+  DeviceGuard guard(e->device);
+  QMK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  int64_t n = (int64_t)e->G * 2 * DL_N;
+  if (n > max_elems) n = max_elems;
+  QMK_CUDA(cudaMemcpy(host_out, e->delays, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+  return 2 * DL_N;
+}
+
 extern "C" int qmk_engine_sync_status(qmk_engine* e, void* stream, int32_t* detail) {
   if (!e) return set_error(QMK_ERR_ARG, "qmk_engine_sync_status: engine is null");
   DeviceGuard guard(e->device);
@@ -215,11 +236,12 @@ extern "C" int qmk_model_create(qmk_engine* e, const LDGLayerWeights* layers, in
   m->residual_fp32 = residual_fp32 ? 1 : 0;
   const size_t bytes = (size_t)e->G * num_layers * m->lay.layer_segs * SEG_BYTES;
   cudaError_t err = cudaMalloc(&m->packed_layers, bytes);
-  if (err == cudaSuccess) err = cudaMalloc(&m->qk_norm, (size_t)num_layers * 2 * HD * sizeof(__nv_bfloat16));
-  if (err == cudaSuccess) err = cudaMalloc(&m->norm_seg, SEG_BYTES);
+  if (err == cudaSuccess) err = cudaMalloc(&m->aux_layers, (size_t)num_layers * 2 * AUX_BYTES);
+  if (err == cudaSuccess) err = cudaMalloc(&m->norm_seg, AUX_BYTES);
+  if (err == cudaSuccess) err = cudaMemsetAsync(m->norm_seg, 0, AUX_BYTES, st);
   if (err == cudaSuccess) {
     qmk_pack_layers_kernel<<<dim3(e->G, num_layers), 128, 0, st>>>(reinterpret_cast<const LayerPtrs*>(layers), m->lay,
-                                                                  m->packed_layers, m->qk_norm);
+                                                                  m->packed_layers, m->aux_layers);
     err = cudaGetLastError();
   }
   if (err == cudaSuccess) err = cudaMemcpyAsync(m->norm_seg, final_norm_weight, SEG_BYTES, cudaMemcpyDeviceToDevice, st);
@@ -240,12 +262,12 @@ extern "C" int qmk_model_add_head(qmk_model* m, const void* lm_head_weight, int 
   cudaStream_t st = (cudaStream_t)stream;
   qmk_head h;
   h.rows = rows;
-  h.segs_max = (rows + m->e->G - 1) / m->e->G + 1;
+  h.segs_max = (rows + m->e->G - 1) / m->e->G;
+  if (h.segs_max > MAX_ITEMS) return set_error(QMK_ERR_ARG, "qmk_model_add_head: %d rows per CTA exceed %d", h.segs_max, MAX_ITEMS);
   const size_t bytes = (size_t)m->e->G * h.segs_max * SEG_BYTES;
   QMK_CUDA(cudaMalloc(&h.packed, bytes));
-  qmk_pack_head_kernel<<<m->e->G, 128, 0, st>>>(reinterpret_cast<const uint4*>(lm_head_weight),
-                                                reinterpret_cast<const uint4*>(m->norm_seg), rows, m->e->G, h.segs_max,
-                                                h.packed);
+  qmk_pack_head_kernel<<<m->e->G, 128, 0, st>>>(reinterpret_cast<const uint4*>(lm_head_weight), rows, m->e->G,
+                                                h.segs_max, h.packed);
   cudaError_t err = cudaGetLastError();
   if (err == cudaSuccess) err = cudaStreamSynchronize(st);
   if (err != cudaSuccess) {
@@ -268,7 +290,7 @@ extern "C" void qmk_model_destroy(qmk_model* m) {
   DeviceGuard guard(m->e->device);
   cudaDeviceSynchronize();
   if (m->packed_layers) cudaFree(m->packed_layers);
-  if (m->qk_norm) cudaFree(m->qk_norm);
+  if (m->aux_layers) cudaFree(m->aux_layers);
   if (m->norm_seg) cudaFree(m->norm_seg);
   for (auto& h : m->heads) cudaFree(h.packed);
   delete m;
@@ -305,41 +327,46 @@ extern "C" int qmk_decode_step(qmk_model* m, int head_index, int input_token_id,
   memset(&p, 0, sizeof(p));
   p.lay = m->lay;
   p.packed_layers = m->packed_layers;
-  p.qk_norm = m->qk_norm;
-  if (head_index >= 0) {
-    p.head.packed = m->heads[head_index].packed;
-    p.head.rows = m->heads[head_index].rows;
-    p.head.segs_max = m->heads[head_index].segs_max;
-  } else {
-    p.head.packed = m->norm_seg;
-    p.head.rows = 0;
-    p.head.segs_max = 1;
-  }
-  p.embed = reinterpret_cast<const __nv_bfloat16*>(embed_weight);
-  p.in_vec = reinterpret_cast<const __nv_bfloat16*>(hidden_buffer);
+  p.aux_layers = m->aux_layers;
   p.cos_t = reinterpret_cast<const __nv_bfloat16*>(cos_table);
   p.sin_t = reinterpret_cast<const __nv_bfloat16*>(sin_table);
   p.k_cache = reinterpret_cast<__nv_bfloat16*>(k_cache);
   p.v_cache = reinterpret_cast<__nv_bfloat16*>(v_cache);
   p.max_seq = max_seq_len;
-  p.xbuf = e->xbuf;
-  p.token = input_token_id;
-  p.position = position;
-  p.out_token = out_token;
-  p.out_norm = normalized_out;
-  p.hidden_out = reinterpret_cast<__nv_bfloat16*>(hidden_buffer);
   p.attn_scale = attn_scale;
   p.residual_fp32 = m->residual_fp32;
+  p.xbuf = e->xbuf;
+  p.res_spill = e->res_spill;
+  p.delays = e->delays;
+  p.delay_o_idle = e->delay_o_idle;
   p.status = e->status_dev;
   p.timeout_cycles = e->timeout_cycles;
-  p.replicas = e->replicas;
-  p.probe = e->probe;
   p.trace = e->trace_dev;
   p.trace_stride = e->trace_stride;
+  p.n_steps = 1;
+  StepDesc& sd = p.steps[0];
+  sd.in_table = reinterpret_cast<const __nv_bfloat16*>(embed_weight);
+  sd.in_vec = hidden_buffer;
+  sd.in_mode = input_token_id >= 0 ? 0 : 1;
+  sd.token = input_token_id >= 0 ? input_token_id : 0;
+  sd.position = position;
+  sd.head.aux = m->norm_seg;
+  if (head_index >= 0) {
+    sd.head.packed = m->heads[head_index].packed;
+    sd.head.rows = m->heads[head_index].rows;
+    sd.head.segs_max = m->heads[head_index].segs_max;
+  } else {
+    sd.head.packed = nullptr;
+    sd.head.rows = 0;
+    sd.head.segs_max = 0;
+  }
+  sd.out_token = out_token;
+  sd.out_norm = normalized_out;
+  sd.hidden_out = reinterpret_cast<__nv_bfloat16*>(hidden_buffer);
 
   const uint32_t need = (uint32_t)m->lay.L + 2u;
-  if (e->epoch > 0xfff00000u) {  // wrap: clear the exchange words (stream-ordered) and restart the epochs
-    QMK_CUDA(cudaMemsetAsync(e->xbuf, 0, sizeof(u64) * XW_TOTAL * e->replicas, st));
+  if (e->epoch + need >= 0xfff0u) {  // 16-bit epochs: clear the exchange words (stream-ordered) and restart
+    QMK_CUDA(cudaMemsetAsync(e->xbuf, 0, XBUF_BYTES, st));
     e->epoch = 0;
   }
   p.epoch_base = e->epoch;

@@ -73,6 +73,7 @@ SIGNATURES = {
     "qmk_engine_sync_status": (_i32, [_vp, _vp, ctypes.POINTER(ctypes.c_int32)]),
     "qmk_engine_trace_enable": (_i32, [_vp, _i32]),
     "qmk_engine_trace_read": (_i32, [_vp, _vp, ctypes.POINTER(ctypes.c_longlong), _i64]),
+    "qmk_engine_poll_stats": (_i32, [_vp, _vp, ctypes.POINTER(ctypes.c_int32), _i64]),
     "qmk_model_create": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, ctypes.POINTER(_vp)]),
     "qmk_model_add_head": (_i32, [_vp, _vp, _i32, _vp]),
     "qmk_model_set_group_embedding": (_i32, [_vp, _i32, _vp]),

@@ -1,5 +1,4 @@
+# GPU round: parity tests, then the perf probe with the per-phase trace.
 set -x
-timeout 900 python -m pytest tests -m gpu -q -s --timeout 400 > gpurun_out/gpu_tests_r1b.log 2>&1; echo "pytest rc=$?"; grep -E "^\.?\[|passed|failed|Error" gpurun_out/gpu_tests_r1b.log | tail -40
-timeout 900 python bench.py --steps 200 --warmup 10 > gpurun_out/bench_r1b.json 2> gpurun_out/bench_r1b.err; echo "bench rc=$?"; cat gpurun_out/bench_r1b.json; tail -5 gpurun_out/bench_r1b.err
-timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/plain_small.log 2>&1 && timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r1b.csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/plain_small2.log 2>&1 && timeout 900 ncu --set full --clock-control none --import-source on -k regex:qmk_decode_kernel -s 40 -c 2 -o gpurun_out/prof_talker_r1b python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"; tail -5 gpurun_out/ncu_full.log
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 400 > gpurun_out/gpu_tests.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/gpu_tests.log
+timeout 300 python scripts/perf_probe.py --configs "450,2500;300,2500;600,3500;450,4500" --trace > gpurun_out/probe.log 2>&1; echo rc=$?; cat gpurun_out/probe.log | tail -20

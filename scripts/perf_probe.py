@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """GPU perf probe: talker / code-predictor step time under engine settings, plus a per-phase trace.
 
-    python scripts/perf_probe.py [--configs "R,probe;R,probe;..."] [--trace]
+    python scripts/perf_probe.py [--configs "500;800"] [--trace]
 """
 import argparse
 import ctypes
@@ -70,11 +70,11 @@ def trace(dec, x, lib, engine, L):
     start = t[:, :, 0]
     d = np.diff(start, axis=1)
     names = ["qkv", "attn", "o", "gu", "down"]
-    labels = {0: ["gather+bar", "wait_full", "norm", "stages", "bar", "publish->next"],
-              1: ["qkv wait+bar", "norm/rope+bar", "scores", "merge bar", "combine+publish", "kv store+fence+bar"],
-              2: ["gather+bar", None, None, "xr+stages", "bar", "publish->next"],
-              3: ["gather+bar", "wait_full", "norm", "stages", "bar", "publish->next"],
-              4: ["gather+bar", None, None, "xr+stages", "bar", "publish->next"]}
+    labels = {0: ["wait+gather+norm", "stages+reduce", None, None],
+              1: ["wait+gather+norm/rope", "scores", "merge", "combine+publish"],
+              2: ["wait+gather", "stages+reduce", None, None],
+              3: ["wait+gather+norm", "stages+reduce", None, None],
+              4: ["wait+gather", "stages+reduce", None, None]}
     layers = list(range(2, L))
     for grp_name, sl in (("attention CTAs 0-7", slice(0, 8)), ("other CTAs", slice(8, G))):
         print(f"--- {grp_name}: mean cycles per sub-step over layers 2..{L-1}")
@@ -83,7 +83,7 @@ def trace(dec, x, lib, engine, L):
             tot = d[sl][:, idxs].mean()
             parts = []
             prev = 0
-            for sub in range(1, 7):
+            for sub in range(1, 5):
                 lab = labels[ph][sub - 1]
                 if lab is None:
                     continue
@@ -102,7 +102,7 @@ def trace(dec, x, lib, engine, L):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="1,0")
+    ap.add_argument("--configs", default="500", help="';'-separated initial poll delays (QMK_POLL_DELAY)")
     ap.add_argument("--trace", action="store_true")
     ap.add_argument("--layers", type=int, default=28)
     args = ap.parse_args()
@@ -110,14 +110,22 @@ def main():
     w = weights_to(synthetic_tts_weights(max_seq_len=256, num_layers=args.layers), "cuda")
     x = synthetic_inputs(99, 16).cuda()
     for cfg in args.configs.split(";"):
-        R, probe = cfg.split(",")
-        os.environ["QMK_REPLICAS"], os.environ["QMK_PROBE"] = R, probe
+        dly = cfg.split(",")
+        os.environ["QMK_POLL_DELAY"] = dly[0]
+        if len(dly) > 1:
+            os.environ["QMK_POLL_DELAY_O"] = dly[1]
         model_tts._Native._engines.clear()
         dec = model_tts.TTSDecoder(weights=w, verbose=False, max_seq_len=256)
         cp = model_tts.CodePredictorKernel(w, device="cuda")
         us = time_steps(dec, x)
         us_cp = time_cp_steps(cp, x)
-        print(f"replicas={R:>3s} probe={probe}: talker {us:8.1f} us/step ({args.layers} layers)   cp step {us_cp:7.1f} us", flush=True)
+        print(f"poll_delay0={cfg:>5s}: talker {us:8.1f} us/step ({args.layers} layers)   cp step {us_cp:7.1f} us", flush=True)
+        G = dec._lib.qmk_engine_num_ctas(dec._engine)
+        st = (ctypes.c_int32 * (G * 16))()
+        dec._lib.qmk_engine_poll_stats(dec._engine, torch.cuda.current_stream().cuda_stream, st, G * 16)
+        a = np.frombuffer(st, dtype=np.int32).reshape(G, 2, 8)
+        print("   repeated-poll gathers [qkv attn o gu down head argmax token]: attn CTAs", a[:8, 1].sum(0).tolist(),
+              " others", a[8:, 1].sum(0).tolist(), flush=True)
         if args.trace:
             trace(dec, x, dec._lib, dec._engine, args.layers)
         del dec, cp
