@@ -80,9 +80,10 @@ int qmk_engine_sync_status(qmk_engine* e, void* stream, int32_t* detail);
 int qmk_engine_trace_enable(qmk_engine* e, int stride);
 int qmk_engine_trace_read(qmk_engine* e, void* stream, long long* host_out, int64_t max_elems);
 
-/* Exchange diagnostics: per CTA [2][8] int32 = {poll delay in cycles after the CTA's own publish, number of
- * gathers in which a poll had to be repeated} for the 8 exchange kinds (qkv-in, attention-in, o-in, gate/up-in,
- * down-in, head-in, argmax-in, token-in).  Synchronises `stream`; returns the row length (16). */
+/* Exchange diagnostics: per CTA [3][8] int32 = {poll delay in cycles after the CTA's own publish, number of
+ * gathers in which a poll had to be repeated, cycles/16 spent waiting for weights} for the 8 exchange kinds
+ * (qkv-in, attention-in, o-in, gate/up-in, down-in, head-in, argmax-in, token-in).  Synchronises `stream`;
+ * returns the row length (24). */
 int qmk_engine_poll_stats(qmk_engine* e, void* stream, int32_t* host_out, int64_t max_elems);
 
 /* ---- model (weight re-packing; replaces upstream _pack_layer_weights as the packing layer) ------ */

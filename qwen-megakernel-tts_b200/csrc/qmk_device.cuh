@@ -33,16 +33,19 @@ typedef unsigned long long u64;
 constexpr int H = 1024, INTER = 3072, QSZ = 2048, KVSZ = 1024, HD = 128, NQH = 16, NKVH = 8;
 constexpr int QKV_ROWS = QSZ + 2 * KVSZ;  // 4096
 constexpr int SEG_ELEMS = 1024, SEG_BYTES = 2048;
-constexpr int NCW = 14;              // consumer warps
-constexpr int NCT = NCW * 32;        // 448 consumer threads
+constexpr int NCW = 8;               // consumer warps: each owns 8 of the 64 k16-steps of a 1024-wide segment
+constexpr int KSTEPS = 64 / NCW;     // (8 + 1 warps keep the register budget at 224/thread: with ~10 KB of L1 left
+                                     //  beside 218 KB of shared memory, a single spilled register costs an L2 round trip)
+constexpr int NCT = NCW * 32;        // 256 consumer threads
 constexpr int NTHREADS = NCT + 32;   // + producer warp
+constexpr int STAGE_ITEMS = 14;      // 2 KB row segments per ring stage = rows of one m16 tensor-core tile
 constexpr int AUX_BYTES = 2560;      // norm weights (2048) + q_norm / k_norm (2 x 256)
-constexpr int SLOT_BYTES = AUX_BYTES + NCW * SEG_BYTES;  // 31232: [aux][one segment per consumer warp]
+constexpr int SLOT_BYTES = AUX_BYTES + STAGE_ITEMS * SEG_BYTES;  // 31232: [aux][14 row segments, 16-byte chunks swizzled]
 constexpr int NSLOTS = 6;
-constexpr int MAX_ST = 4;            // stages per phase (42 gate/up segments on 148 CTAs = 3 stages)
-constexpr int MAX_ITEMS = MAX_ST * NCW;
+constexpr int MAX_ST = 3;            // stages per phase (42 gate/up segments on 148 CTAs = 3 stages)
+constexpr int MAX_ITEMS = MAX_ST * STAGE_ITEMS;
 constexpr int ATT_PER_WARP = 5;
-constexpr int ATT_ROUND = NCW * ATT_PER_WARP;  // 70 cached positions per round per item
+constexpr int ATT_ROUND = NCW * ATT_PER_WARP;  // 40 cached positions per round per item
 constexpr int S_MAX = 18;                      // max KV splits per kv head (8 * 18 = 144 CTAs)
 constexpr int PART_STRIDE = 132;               // u64 words per (q head, split) partial: m, l, acc[128], pad
 constexpr int MAX_HEAD_ROWS = 3072;
@@ -105,7 +108,8 @@ struct Params {
   int residual_fp32;
   uint8_t* xbuf;                   // exchange words (XBUF_BYTES)
   float* res_spill;                // f32[1024]: fp32 residual of every row (read back only by staged launches)
-  int* delays;                     // [G][2][DL_N]: poll delays (cycles after own publish; in) and repeated-poll counts (in/out)
+  int* delays;                     // [G][3][DL_N]: poll delays (cycles after own publish; in), repeated-poll counts and
+                                   // cycles/16 spent waiting for weights per exchange kind (in/out)
   int delay_o_idle;                // O-phase delay of CTAs without an attention item (they wait for the attention CTAs)
   uint32_t epoch_base;             // epochs base+1 .. base+n_steps*(L+2) are used by this launch (16-bit, never 0)
   int* status;                     // int[4]: code, cta, phase index, aux
@@ -190,8 +194,8 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 }
 
 // LL4 words: {epoch (high 16), bf16 payload (low 16)} in one 32-bit relaxed gpu-scope access.
-__device__ __forceinline__ void ll4_st(uint32_t* p, float value_bf16, uint32_t epoch) {
-  const uint32_t v = (epoch << 16) | (__float_as_uint(value_bf16) >> 16);
+__device__ __forceinline__ void ll4_st(uint32_t* p, float value, uint32_t epoch) {   // rounds to bf16 (RNE)
+  const uint32_t v = (epoch << 16) | bf16_bits(value);
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint4 ll4_ld4(const uint32_t* p) {
@@ -240,17 +244,15 @@ __device__ __forceinline__ bool consumer_bar_or(bool pred) {
 // shared-memory carve-up
 // ------------------------------------------------------------------------------------------------
 constexpr int SM_RING = 0;
-constexpr int SM_VEC = SM_RING + NSLOTS * SLOT_BYTES;     // float[3584]: activation vector (<= 3072) / attention merge acc [14][2][128]
-constexpr int SM_VEC_FLOATS = NCW * 2 * HD;
-static_assert(SM_VEC_FLOATS >= INTER, "s_vec holds the widest activation vector");
-constexpr int SM_SMALL = SM_VEC + SM_VEC_FLOATS * 4;              // float[1024]  attention scratch
-constexpr int SM_PART = SM_SMALL + 1024 * 4;              // float[64]    per-item partial dot products
-constexpr int SM_RED = SM_PART + 64 * 4;                  // float[64]    cross-warp reductions
+constexpr int SM_VEC = SM_RING + NSLOTS * SLOT_BYTES;     // bf16[3072]: activation vector in weight-segment order
+constexpr int SM_ACC = SM_VEC + INTER * 2;                // float[NCW][2][128]: attention cross-warp merge
+constexpr int SM_SMALL = SM_ACC + NCW * 2 * HD * 4;              // float[1024]  attention scratch
+constexpr int SM_PART = SM_SMALL + 1024 * 4;              // float[56][NCW] per-item, per-warp (K slice) partial dot products
+constexpr int SM_RED = SM_PART + MAX_ITEMS * NCW * 4;     // float[64]    cross-warp reductions
 constexpr int SM_BAR = SM_RED + 64 * 4;                   // u64 full[NSLOTS], empty[NSLOTS]
 constexpr int SM_MISC = SM_BAR + 2 * 8 * 8;               // int abort; int delays[DL_N]; ...
 constexpr int SMEM_BYTES = SM_MISC + 256;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-static_assert(MAX_ITEMS <= 64, "s_part size");
 
 // s_small sub-offsets (floats)
 constexpr int SS_V = 0, SS_QN = 128, SS_KN = 384, SS_M = 512, SS_L = 544, SS_CS = 576;  // CS: cos[64], sin[64]
@@ -258,7 +260,8 @@ constexpr int SS_V = 0, SS_QN = 128, SS_KN = 384, SS_M = 512, SS_L = 544, SS_CS 
 struct Ctx {
   const Params& p;
   uint8_t* ring;
-  float* s_vec;
+  uint8_t* s_vec;   // bf16[3072]
+  float* s_acc;
   float* s_small;
   float* s_part;
   float* s_red;
@@ -345,8 +348,9 @@ __device__ __forceinline__ uint32_t ll8_wait(Ctx& c, const u64* p, uint32_t epoc
 }
 
 // Debug trace: trace[cta][(idx - phase_begin) * 8 + sub] = clock64() (thread 0 of the CTA only).
+template <bool TR>
 __device__ __forceinline__ void trace_sub(const Ctx& c, int sub) {
-  if (c.p.trace != nullptr && c.tid == 0) {
+  if (TR && c.p.trace != nullptr && c.tid == 0) {
     const int slot = (c.cur_idx - c.p.phase_begin) * 8 + sub;
     if (slot >= 0 && slot < c.p.trace_stride) c.p.trace[(size_t)c.cta * c.p.trace_stride + slot] = clock64();
   }
@@ -409,7 +413,7 @@ __device__ __forceinline__ PhaseDesc head_phase_desc(const Params& p, const Head
 }
 // A phase with an aux block always has at least one stage.
 __device__ __forceinline__ int n_stages_of(const PhaseDesc& d) {
-  const int n = (d.n_items + NCW - 1) / NCW;
+  const int n = (d.n_items + STAGE_ITEMS - 1) / STAGE_ITEMS;
   return (n == 0 && d.aux != nullptr) ? 1 : n;
 }
 
@@ -421,15 +425,15 @@ __device__ __forceinline__ void produce_phase(Ctx& c, const PhaseDesc& d) {
   for (int s = 0; s < nst; ++s, ++c.k) {
     const int slot = c.k % NSLOTS;
     wait_empty(c, c.k);
-    int items = d.n_items - s * NCW;
-    if (items > NCW) items = NCW;
+    int items = d.n_items - s * STAGE_ITEMS;
+    if (items > STAGE_ITEMS) items = STAGE_ITEMS;
     const bool aux = (s == 0 && d.aux != nullptr);
     const uint32_t bytes = (uint32_t)items * SEG_BYTES + (aux ? AUX_BYTES : 0);
     uint8_t* dst = c.ring + (size_t)slot * SLOT_BYTES;
     mbar_arrive_expect_tx(&c.full[slot], bytes);
     if (aux) tma_bulk_g2s(dst, d.aux, AUX_BYTES, &c.full[slot]);
     if (items > 0)
-      tma_bulk_g2s(dst + AUX_BYTES, d.src + (size_t)s * NCW * SEG_BYTES, (uint32_t)items * SEG_BYTES, &c.full[slot]);
+      tma_bulk_g2s(dst + AUX_BYTES, d.src + (size_t)s * STAGE_ITEMS * SEG_BYTES, (uint32_t)items * SEG_BYTES, &c.full[slot]);
   }
 }
 
@@ -456,148 +460,46 @@ __device__ void producer_loop(Ctx& c) {
 // ------------------------------------------------------------------------------------------------
 // consumer building blocks
 // ------------------------------------------------------------------------------------------------
-// 32 activations per lane: element (j, e) <-> k = j*256 + lane*8 + e of the warp's 1024-wide segment.
-__device__ __forceinline__ void load_xr(const float* vec1024, int lane, float (&xr)[32]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float4* v = reinterpret_cast<const float4*>(vec1024 + j * 256 + lane * 8);
-    float4 a = v[0], b = v[1];
-    xr[j * 8 + 0] = a.x; xr[j * 8 + 1] = a.y; xr[j * 8 + 2] = a.z; xr[j * 8 + 3] = a.w;
-    xr[j * 8 + 4] = b.x; xr[j * 8 + 5] = b.y; xr[j * 8 + 6] = b.z; xr[j * 8 + 7] = b.w;
-  }
+// GEMV on the legacy tensor path (mma.sync m16n8k16, bf16 x bf16 -> fp32).  Measured on B200
+// (scripts/ubench/mma_rate.cu): the CUDA-core version spends one conversion + one FMA issue slot per weight and
+// is issue-bound at ~4x the shared-memory time of a stage; HMMA sustains one 16x16 weight tile per ~2 cycles per
+// SM, so the stage becomes shared-memory-bandwidth bound.  A stage is a 14-row x 1024-k tile; the tile's rows
+// are the A operand (16-byte chunk c of row r is stored at chunk c ^ (r & 7): conflict-free ldmatrix), the
+// B operand's eight columns are the activation segments (column n = x[n*1024 ...]), so a row whose k-block is
+// kb reads its result from column kb.  Each consumer warp owns 4 of the 64 k16-steps.
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr)
+               : "memory");
 }
 
-// per-lane partial dot product of one 2 KB weight segment with the register-resident activations
-__device__ __forceinline__ float seg_dot_partial(const uint4* w_seg, int lane, const float (&xr)[32]) {
-  float acc[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 wv = w_seg[j * 32 + lane];
-    float a = bf16_lo(wv.x) * xr[j * 8 + 0];
-    a = fmaf(bf16_hi(wv.x), xr[j * 8 + 1], a);
-    a = fmaf(bf16_lo(wv.y), xr[j * 8 + 2], a);
-    a = fmaf(bf16_hi(wv.y), xr[j * 8 + 3], a);
-    a = fmaf(bf16_lo(wv.z), xr[j * 8 + 4], a);
-    a = fmaf(bf16_hi(wv.z), xr[j * 8 + 5], a);
-    a = fmaf(bf16_lo(wv.w), xr[j * 8 + 6], a);
-    a = fmaf(bf16_hi(wv.w), xr[j * 8 + 7], a);
-    acc[j] = a;
-  }
-  return (acc[0] + acc[1]) + (acc[2] + acc[3]);
-}
-
-// The wait window before a gather: spin until t_pub + delay, testing the next phase's ring barriers meanwhile.
-// Returns a bit mask of stages already observed full.
-__device__ __forceinline__ uint32_t wait_window(Ctx& c, int dslot, int nst, int delay_override = -1) {
-  const long long t_ready = c.t_pub + (delay_override >= 0 ? delay_override : c.s_delay[dslot]);
-  uint32_t ready = 0;
-  for (;;) {
-#pragma unroll
-    for (int s = 0; s < MAX_ST; ++s) {
-      if (s < nst && !((ready >> s) & 1u)) {
-        const uint32_t k = c.k + s;
-        if (mbar_test_wait(&c.full[k % NSLOTS], (k / NSLOTS) & 1u)) ready |= 1u << s;
-      }
+// The wait window before a gather: warp 0 (which issued the publish) spins until t_pub + delay while the other
+// consumer warps sleep at a hardware barrier -- spinning warps would steal issue slots from the warp that is
+// still finalising the previous phase.  Returns a bit mask of the next phase's ring stages already full.
+__device__ __forceinline__ void wait_window(Ctx& c, int delay) {
+  if (c.warp == 0) {
+    const long long t_ready = c.t_pub + delay;
+    while (clock64() < t_ready) {
     }
-    if (clock64() >= t_ready) break;
   }
-  return ready;
+  asm volatile("bar.sync 2, %0;" ::"n"(NCT) : "memory");
 }
 // After a gather: consumer barrier that also counts the gathers in which some poll had to be repeated
 // (polling a line before it is written is what makes an exchange slow; the counts guide the delay tuning).
-__device__ __forceinline__ void adapt_delay(Ctx& c, int dslot, bool retried) {
+__device__ __forceinline__ void gather_bar(Ctx& c, int dslot, bool retried) {
   const bool any = consumer_bar_or(retried);
   if (any && c.tid == 0) c.s_delay[DL_N + dslot] += 1;
 }
-
-// Gather an H-wide bf16 vector (LL4) or the step input, RMS-normalise it with the aux weights of the first
-// stage and leave the normalised activations in s_vec[0..1023]:  n = r( r(x) / sqrt(mean(r(x)^2) + eps) * w ).
-// Ends with a consumer barrier.  `raw_out` (optional): thread t < 256 keeps its 4 raw values.
-template <bool FROM_INPUT>
-__device__ __forceinline__ void gather_norm(Ctx& c, const uint32_t* xw, uint32_t epoch, const __nv_bfloat16* x_in,
-                                            int dslot, int nst, uint32_t& ready, float (&raw)[4]) {
-  bool retried = false;
-  float ss = 0.f;
-  if (FROM_INPUT) {
-    ready = 0;
-    if (c.tid < 256) {
-      const uint2 v = *reinterpret_cast<const uint2*>(x_in + c.tid * 4);
-      raw[0] = bf16_lo(v.x); raw[1] = bf16_hi(v.x); raw[2] = bf16_lo(v.y); raw[3] = bf16_hi(v.y);
-    }
-  } else {
-    ready = wait_window(c, dslot, nst);
-    if (c.tid < 256) {
-      const uint4 w = ll4_wait(c, xw + c.tid * 4, epoch, retried);
-      raw[0] = ll4_val(w.x); raw[1] = ll4_val(w.y); raw[2] = ll4_val(w.z); raw[3] = ll4_val(w.w);
-    }
-  }
-  if (c.tid < 256) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) ss = fmaf(raw[e], raw[e], ss);
-    ss = warp_sum(ss);
-    if (c.lane == 0) c.s_red[c.warp] = ss;
-  }
-  if (FROM_INPUT) consumer_bar(); else adapt_delay(c, dslot, retried);
-  // the norm weights arrive with the first stage of the phase
-  if (!(ready & 1u)) { wait_full(c, c.k); ready |= 1u; }
-  if (c.tid < 256) {
-    float tot = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) tot += c.s_red[w];
-    const float rms = sqrtf(tot * (1.0f / H) + EPS);
-    const uint2 wv = *reinterpret_cast<const uint2*>(c.ring + (size_t)(c.k % NSLOTS) * SLOT_BYTES + c.tid * 8);
-    float4 n;
-    n.x = bf16_round((raw[0] / rms) * bf16_lo(wv.x));
-    n.y = bf16_round((raw[1] / rms) * bf16_hi(wv.x));
-    n.z = bf16_round((raw[2] / rms) * bf16_lo(wv.y));
-    n.w = bf16_round((raw[3] / rms) * bf16_hi(wv.y));
-    *reinterpret_cast<float4*>(c.s_vec + c.tid * 4) = n;
-  }
-  consumer_bar();
-}
-
-// Gather `n_words` LL4 words (a multiple of 4) into s_vec as floats.  Ends with a consumer barrier.
-__device__ __forceinline__ void gather_vec(Ctx& c, const uint32_t* xw, int n_words, uint32_t epoch, int dslot, int nst,
-                                           uint32_t& ready, int delay_override = -1) {
-  bool retried = false;
-  ready = wait_window(c, dslot, nst, delay_override);
-  for (int i = c.tid * 4; i < n_words; i += NCT * 4) {
-    const uint4 w = ll4_wait(c, xw + i, epoch, retried);
-    *reinterpret_cast<float4*>(c.s_vec + i) = make_float4(ll4_val(w.x), ll4_val(w.y), ll4_val(w.z), ll4_val(w.w));
-  }
-  adapt_delay(c, dslot, retried);
-}
-
-// Consume all stages of a phase: warp w owns item s*NCW + w of stage s.  The per-item dot products end up in
-// s_part[item]; ends with a consumer barrier.  XR_PER_STAGE: activations depend on the item (down: kb = item % 3).
-template <bool XR_PER_STAGE>
-__device__ __forceinline__ void run_stages(Ctx& c, const PhaseDesc& d, uint32_t ready, float (&xr)[32], int xr_mod) {
-  const int nst = n_stages_of(d);
-  float part[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int s = 0; s < MAX_ST; ++s) {
-    if (s < nst) {
-      const uint32_t k = c.k + s;
-      const int slot = k % NSLOTS;
-      if (!((ready >> s) & 1u)) wait_full(c, k);
-      const int item = s * NCW + c.warp;
-      if (item < d.n_items) {
-        if (XR_PER_STAGE) load_xr(c.s_vec + (item % xr_mod) * SEG_ELEMS, c.lane, xr);
-        const uint4* w = reinterpret_cast<const uint4*>(c.ring + (size_t)slot * SLOT_BYTES + AUX_BYTES + c.warp * SEG_BYTES);
-        part[s] = seg_dot_partial(w, c.lane, xr);
-      }
-      __syncwarp();
-      if (c.lane == 0) mbar_arrive(&c.empty[slot]);
-    }
-  }
-  c.k += nst;
-  const float tot = warp_sum4(part, c.lane);
-  const int q = c.lane >> 3;
-  if ((c.lane & 7) == 0 && q < nst) {
-    const int item = q * NCW + c.warp;
-    if (item < d.n_items) c.s_part[item] = tot;
-  }
-  consumer_bar();
+// barrier-free variant for gathers whose consumers are the gathering warp itself
+__device__ __forceinline__ void gather_note(Ctx& c, int dslot, bool retried) {
+  if (__any_sync(0xffffffffu, retried) && c.lane == 0) atomicAdd(&c.s_delay[DL_N + dslot], 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -676,6 +578,7 @@ struct AttnPre {  // per-layer constants a norm/rope warp needs, fetched while t
   float nw[4];
 };
 
+template <bool TR>
 __device__ void phase_attn(Ctx& c, int l, int position, uint32_t epoch, const AttnItem& it, KvRegs& kv,
                            const AttnPre& pre) {
   const Params& p = c.p;
@@ -687,7 +590,7 @@ __device__ void phase_attn(Ctx& c, int l, int position, uint32_t epoch, const At
   // 1) gather q (2 heads), k, v of this kv group; per-head RMSNorm + rotate-half RoPE in bf16 steps.
   //    warp 0,1: q heads; warp 2: k; warp 3: v (owner only).  Lane owns dims 4*lane .. 4*lane+3.
   bool retried = false;
-  (void)wait_window(c, DL_ATTN, 0);
+  wait_window(c, c.s_delay[DL_ATTN]);
   if (c.warp < 2 || (it.owner && c.warp < 4)) {
     const int row0 = (c.warp < 2) ? (2 * it.g + c.warp) * HD : (c.warp == 2 ? QSZ + it.g * HD : QSZ + KVSZ + it.g * HD);
     const uint4 w = ll4_wait(c, x_qkv + row0 + c.lane * 4, epoch, retried);
@@ -714,8 +617,8 @@ __device__ void phase_attn(Ctx& c, int l, int position, uint32_t epoch, const At
       *reinterpret_cast<float4*>(dst + c.lane * 4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
     }
   }
-  adapt_delay(c, DL_ATTN, retried);   // barrier: q / k / v are in shared memory
-  trace_sub(c, 1);
+  gather_bar(c, DL_ATTN, retried);   // barrier: q / k / v are in shared memory
+  trace_sub<TR>(c, 1);
 
   // 2) scores / online softmax / PV over this item's positions
   float q0[4], q1[4], acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
@@ -794,7 +697,7 @@ __device__ void phase_attn(Ctx& c, int l, int position, uint32_t epoch, const At
       m0 = mx0; m1 = mx1;
     }
   }
-  trace_sub(c, 2);
+  trace_sub<TR>(c, 2);
   // 3) cross-warp merge: common max first, then plain sums (s_vec is free during attention)
   if (c.lane == 0) {
     s_small[SS_M + c.warp * 2 + 0] = m0;
@@ -810,7 +713,7 @@ __device__ void phase_attn(Ctx& c, int l, int position, uint32_t epoch, const At
   {
     const float f0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - M0);
     const float f1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - M1);
-    float* s_acc = c.s_vec;  // [NCW][2][128]
+    float* s_acc = c.s_acc;  // [NCW][2][128]
     *reinterpret_cast<float4*>(s_acc + (c.warp * 2 + 0) * HD + c.lane * 4) =
         make_float4(acc0[0] * f0, acc0[1] * f0, acc0[2] * f0, acc0[3] * f0);
     *reinterpret_cast<float4*>(s_acc + (c.warp * 2 + 1) * HD + c.lane * 4) =
@@ -821,13 +724,13 @@ __device__ void phase_attn(Ctx& c, int l, int position, uint32_t epoch, const At
     }
   }
   consumer_bar();
-  trace_sub(c, 3);
+  trace_sub<TR>(c, 3);
   if (c.tid < 256) {
     const int h = c.tid >> 7, d = c.tid & 127;
     float A = 0.f, Lsum = 0.f;
 #pragma unroll
     for (int w = 0; w < NCW; ++w) {
-      A += c.s_vec[(w * 2 + h) * HD + d];
+      A += c.s_acc[(w * 2 + h) * HD + d];
       Lsum += s_small[SS_L + w * 2 + h];
     }
     const float Mh = h ? M1 : M0;
@@ -859,7 +762,7 @@ __device__ void phase_attn(Ctx& c, int l, int position, uint32_t epoch, const At
     }
   }
   c.t_pub = clock64();
-  trace_sub(c, 4);
+  trace_sub<TR>(c, 4);
   // 4) append the new K/V row (off the critical path: after `a` has been published)
   if (it.owner && c.tid < 128) {
     const size_t off = ((size_t)(l * NKVH + it.g) * p.max_seq + position) * HD + c.tid;
@@ -870,8 +773,21 @@ __device__ void phase_attn(Ctx& c, int l, int position, uint32_t epoch, const At
 }
 
 // ------------------------------------------------------------------------------------------------
-// consumer main loop
+// consumer main loop.  All five GEMV-shaped phases (QKV, O, gate/up, down, LM head) run through ONE copy of
+// the gather / norm / stage / reduce code: the kernel's instruction footprint has to stay inside the SM's
+// instruction cache (a per-phase inlined version measured 2-3x slower on every sub-step).
 // ------------------------------------------------------------------------------------------------
+// sum of the NCW per-warp K-slice partials of one item, fixed order
+__device__ __forceinline__ float item_sum(const float* s_part, int it) {
+  static_assert(NCW == 8, "item_sum reads 8 partials");
+  const float4* v = reinterpret_cast<const float4*>(s_part + it * NCW);
+  const float4 a = v[0], b = v[1];
+  return ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+}
+
+enum Kind { K_QKV = PH_QKV, K_ATTN = PH_ATTN, K_O = PH_O, K_GU = PH_GU, K_DOWN = PH_DOWN, K_HEAD = 5, K_ARGMAX = 6 };
+
+template <bool TR>
 __device__ void consumer_loop(Ctx& c) {
   const Params& p = c.p;
   const Layout& y = p.lay;
@@ -883,11 +799,21 @@ __device__ void consumer_loop(Ctx& c) {
   uint32_t* const x_m = c.x32 + XW_M;
   uint32_t* const x_logits = c.x32 + XW_LOGITS;
   const CtaRows rows = cta_rows(y, c.cta);
-  float xr[32];
-  float raw[4];
   KvRegs kv;
   AttnPre pre = {{0.f, 0.f, 0.f, 0.f}};
   float res_mine = 0.f;  // fp32 residual of row o_row0 + tid (tid < o_rows)
+  // ldmatrix row address of this lane inside a stage tile; rows 14, 15 of the m16 tile alias rows 6, 7
+  // (their results are unused and the alias keeps the 8 rows of a matrix on distinct bank groups)
+  const int a_mi = c.lane >> 3;
+  int a_row = (c.lane & 7) + (a_mi & 1) * 8;
+  if (a_row >= STAGE_ITEMS) a_row -= 8;
+  const uint32_t a_off = (uint32_t)(AUX_BYTES + a_row * SEG_BYTES);
+  const int a_sw = a_row & 7, a_khalf = a_mi >> 1;
+  // down-projection: k-block of the item in tile row r of stage s is (14 s + r) % 3; 2 bits per (s, half)
+  uint32_t kb3_pack = 0;
+#pragma unroll
+  for (int sh = 0; sh < 2 * MAX_ST; ++sh)
+    kb3_pack |= (uint32_t)(((sh >> 1) * STAGE_ITEMS + (c.lane >> 2) + (sh & 1) * 8) % 3) << (2 * sh);
 
   for (int step = 0; step < p.n_steps; ++step) {
     const StepDesc& sd = p.steps[step];
@@ -897,6 +823,7 @@ __device__ void consumer_loop(Ctx& c) {
                                                   : reinterpret_cast<const __nv_bfloat16*>(sd.in_vec);
     AttnItem item;
     const bool has_item = attn_item(p, position, c.cta, item);
+    const int head_row0 = sd.head.rows > 0 ? row_begin(c.cta, sd.head.rows, y.G) : 0;
     if (has_item && c.tid < 128) {  // RoPE row of this step: cos[0..63], sin[0..63]
       const int d = c.tid & 63;
       const __nv_bfloat16* t = (c.tid < 64) ? p.cos_t : p.sin_t;
@@ -910,123 +837,33 @@ __device__ void consumer_loop(Ctx& c) {
 
     for (int idx = begin; idx < end; ++idx) {
       c.cur_idx = idx;
-      trace_sub(c, 0);
-      if (idx < nlayer_idx) {
-        const int l = idx / PH_PER_LAYER, ph = idx % PH_PER_LAYER;
-        const uint32_t epoch = (ebase + 1u + (uint32_t)l) & 0xffffu;
-        const uint32_t epoch_prev = (ebase + (uint32_t)l) & 0xffffu;
-        if (ph == PH_QKV) {
-          const PhaseDesc d = layer_phase_desc(p, rows, l, PH_QKV, c.cta);
-          if (has_item) attn_prefetch(c, l, position, item, 0, kv);  // older KV rows do not depend on this layer
-          uint32_t ready;
-          if (l == 0) {
-            gather_norm<true>(c, nullptr, 0, x_in, DL_QKV, n_stages_of(d), ready, raw);
-            if (c.tid < rows.o_rows) {
-              res_mine = __bfloat162float(x_in[rows.o_row0 + c.tid]);
-              p.res_spill[rows.o_row0 + c.tid] = res_mine;
+      trace_sub<TR>(c, 0);
+      const int l = idx / PH_PER_LAYER;
+      const int kind = idx < nlayer_idx ? idx % PH_PER_LAYER : (idx == nlayer_idx ? K_HEAD : K_ARGMAX);
+      const uint32_t epoch = (ebase + 1u + (uint32_t)l) & 0xffffu;  // layer l; for K_HEAD (l == L) the logits epoch
+
+      if (kind == K_ATTN) {
+        if (has_item) {
+          if (pre_layer != l) {  // staged launch: the QKV phase ran in an earlier launch
+            attn_prefetch(c, l, position, item, 0, kv);
+            if (c.warp < 3) {
+              const uint2 wv = *reinterpret_cast<const uint2*>(p.aux_layers + ((size_t)l * 2) * AUX_BYTES + 2048 +
+                                                                (c.warp == 2 ? 256 : 0) + c.lane * 8);
+              pre.nw[0] = bf16_lo(wv.x); pre.nw[1] = bf16_hi(wv.x); pre.nw[2] = bf16_lo(wv.y); pre.nw[3] = bf16_hi(wv.y);
             }
-          } else {
-            gather_norm<false>(c, x_res, epoch_prev, nullptr, DL_QKV, n_stages_of(d), ready, raw);
           }
-          trace_sub(c, 1);
-          if (has_item && c.warp < 3) {  // q_norm / k_norm weights of this layer (aux of the resident first stage)
-            const uint2 wv = *reinterpret_cast<const uint2*>(c.ring + (size_t)(c.k % NSLOTS) * SLOT_BYTES + 2048 +
-                                                              (c.warp == 2 ? 256 : 0) + c.lane * 8);
-            pre.nw[0] = bf16_lo(wv.x); pre.nw[1] = bf16_hi(wv.x); pre.nw[2] = bf16_lo(wv.y); pre.nw[3] = bf16_hi(wv.y);
-          }
-          pre_layer = l;
-          load_xr(c.s_vec, c.lane, xr);
-          run_stages<false>(c, d, ready, xr, 1);
-          trace_sub(c, 2);
-          if (c.tid < d.n_items) ll4_st(x_qkv + rows.q_row0 + c.tid, bf16_round(c.s_part[c.tid]), epoch);
-          c.t_pub = clock64();
-        } else if (ph == PH_ATTN) {
-          if (has_item) {
-            if (pre_layer != l) {  // staged launch: the QKV phase ran in an earlier launch
-              attn_prefetch(c, l, position, item, 0, kv);
-              if (c.warp < 3) {
-                const uint2 wv = *reinterpret_cast<const uint2*>(p.aux_layers + ((size_t)l * 2) * AUX_BYTES + 2048 +
-                                                                  (c.warp == 2 ? 256 : 0) + c.lane * 8);
-                pre.nw[0] = bf16_lo(wv.x); pre.nw[1] = bf16_hi(wv.x); pre.nw[2] = bf16_lo(wv.y); pre.nw[3] = bf16_hi(wv.y);
-              }
-            }
-            phase_attn(c, l, position, epoch, item, kv, pre);
-          }
-        } else if (ph == PH_O) {
-          const PhaseDesc d = layer_phase_desc(p, rows, l, PH_O, c.cta);
-          uint32_t ready;
-          gather_vec(c, x_a, QSZ, epoch, DL_O, n_stages_of(d), ready, has_item ? -1 : p.delay_o_idle);
-          trace_sub(c, 1);
-          load_xr(c.s_vec + (c.warp % 2) * SEG_ELEMS, c.lane, xr);
-          run_stages<false>(c, d, ready, xr, 1);
-          trace_sub(c, 2);
-          if (c.tid < rows.o_rows) {
-            const float o = bf16_round(c.s_part[2 * c.tid] + c.s_part[2 * c.tid + 1]);
-            res_mine = p.residual_fp32 ? res_mine + o : bf16_round(res_mine + o);
-            ll4_st(x_res2 + rows.o_row0 + c.tid, bf16_round(res_mine), epoch);
-            p.res_spill[rows.o_row0 + c.tid] = res_mine;
-          }
-          c.t_pub = clock64();
-        } else if (ph == PH_GU) {
-          const PhaseDesc d = layer_phase_desc(p, rows, l, PH_GU, c.cta);
-          uint32_t ready;
-          gather_norm<false>(c, x_res2, epoch, nullptr, DL_GU, n_stages_of(d), ready, raw);
-          trace_sub(c, 1);
-          load_xr(c.s_vec, c.lane, xr);
-          run_stages<false>(c, d, ready, xr, 1);
-          trace_sub(c, 2);
-          if (c.tid < rows.gu_rows) {
-            const float g = bf16_round(c.s_part[2 * c.tid]);
-            const float u = bf16_round(c.s_part[2 * c.tid + 1]);
-            const float sg = bf16_round(g / (1.0f + expf(-g)));
-            ll4_st(x_m + rows.gu_row0 + c.tid, bf16_round(sg * u), epoch);
-          }
-          c.t_pub = clock64();
-        } else {  // PH_DOWN
-          const PhaseDesc d = layer_phase_desc(p, rows, l, PH_DOWN, c.cta);
-          uint32_t ready;
-          gather_vec(c, x_m, INTER, epoch, DL_DOWN, n_stages_of(d), ready);
-          trace_sub(c, 1);
-          run_stages<true>(c, d, ready, xr, 3);
-          trace_sub(c, 2);
-          if (c.tid < rows.o_rows) {
-            const float dn = bf16_round((c.s_part[3 * c.tid] + c.s_part[3 * c.tid + 1]) + c.s_part[3 * c.tid + 2]);
-            res_mine = p.residual_fp32 ? res_mine + dn : bf16_round(res_mine + dn);
-            ll4_st(x_res + rows.o_row0 + c.tid, bf16_round(res_mine), epoch);
-            p.res_spill[rows.o_row0 + c.tid] = res_mine;
-          }
-          c.t_pub = clock64();
+          phase_attn<TR>(c, l, position, epoch, item, kv, pre);
         }
-      } else if (idx == nlayer_idx) {
-        // final RMSNorm (+ LM head rows of this CTA)
-        const uint32_t epoch_last = (ebase + (uint32_t)y.L) & 0xffffu;
-        const uint32_t epoch_head = (ebase + (uint32_t)y.L + 1u) & 0xffffu;
-        const PhaseDesc d = head_phase_desc(p, sd.head, c.cta);
-        uint32_t ready;
-        gather_norm<false>(c, x_res, epoch_last, nullptr, DL_HEAD, n_stages_of(d), ready, raw);
-        if (c.cta == 0 && c.tid < 256) {
-          if (sd.hidden_out != nullptr) {
-            uint2 hv;
-            hv.x = (__float_as_uint(raw[0]) >> 16) | (__float_as_uint(raw[1]) & 0xffff0000u);
-            hv.y = (__float_as_uint(raw[2]) >> 16) | (__float_as_uint(raw[3]) & 0xffff0000u);
-            *reinterpret_cast<uint2*>(sd.hidden_out + c.tid * 4) = hv;
-          }
-          if (sd.out_norm != nullptr)
-            *reinterpret_cast<float4*>(sd.out_norm + c.tid * 4) = *reinterpret_cast<const float4*>(c.s_vec + c.tid * 4);
-        }
-        load_xr(c.s_vec, c.lane, xr);
-        run_stages<false>(c, d, ready, xr, 1);
-        if (c.tid < d.n_items)
-          ll4_st(x_logits + row_begin(c.cta, sd.head.rows, y.G) + c.tid, bf16_round(c.s_part[c.tid]), epoch_head);
-        c.t_pub = clock64();
-      } else {
+        continue;
+      }
+      if (kind == K_ARGMAX) {
         // argmax over the bf16 logits, lowest index wins ties (CTA 0)
         if (c.cta != 0 || sd.head.rows <= 0) continue;
         const uint32_t epoch_head = (ebase + (uint32_t)y.L + 1u) & 0xffffu;
         float best = -INFINITY;
         int best_i = 0x7fffffff;
         bool retried = false;
-        (void)wait_window(c, DL_ARGMAX, 0);
+        wait_window(c, c.s_delay[DL_ARGMAX]);
         for (int i = c.tid * 4; i < sd.head.rows; i += NCT * 4) {   // indices ascend per thread
           const uint4 w = ll4_wait(c, x_logits + i, epoch_head, retried);
           const float v4[4] = {ll4_val(w.x), ll4_val(w.y), ll4_val(w.z), ll4_val(w.w)};
@@ -1044,7 +881,7 @@ __device__ void consumer_loop(Ctx& c) {
           c.s_red[c.warp * 2] = best;
           c.s_red[c.warp * 2 + 1] = __int_as_float(best_i);
         }
-        adapt_delay(c, DL_ARGMAX, retried);
+        gather_bar(c, DL_ARGMAX, retried);
         if (c.tid == 0) {
           for (int w = 1; w < NCW; ++w) {
             const float ov = c.s_red[w * 2];
@@ -1056,7 +893,196 @@ __device__ void consumer_loop(Ctx& c) {
           *sd.out_token = (st != 0 || *c.s_abort) ? -1000 - st : best_i;
         }
         consumer_bar();
+        continue;
       }
+
+      // ---- GEMV-shaped phases -------------------------------------------------------------------------
+      // Everything that does not depend on the gathered activations is computed BEFORE they are checked: a single
+      // warp executes dependent instructions at ~5 cycles each, so every instruction between "data arrived" and
+      // "row published" is on the critical path of the layer.
+      const uint32_t* xw = x_res;
+      uint32_t* xout = x_qkv + rows.q_row0;     // where thread tid publishes (finalize role depends on the kind)
+      int n_words = H, dslot = DL_QKV, xr_mod = 1;
+      uint32_t ep = epoch;
+      bool norm = true;
+      if (kind == K_QKV) { ep = (ebase + (uint32_t)l) & 0xffffu; }
+      else if (kind == K_O) { xw = x_a; n_words = QSZ; dslot = DL_O; xr_mod = 2; norm = false; xout = x_res2 + rows.o_row0; }
+      else if (kind == K_GU) { xw = x_res2; dslot = DL_GU; xout = x_m + rows.gu_row0; }
+      else if (kind == K_DOWN) { xw = x_m; n_words = INTER; dslot = DL_DOWN; xr_mod = 3; norm = false; xout = x_res + rows.o_row0; }
+      else { ep = (ebase + (uint32_t)y.L) & 0xffffu; dslot = DL_HEAD; xout = x_logits + head_row0; }
+      const bool from_input = (kind == K_QKV && l == 0);
+
+      // gather: thread tid owns elements [4 tid, 4 tid + 4) of each 1024-wide segment, i.e. warp w gathers exactly
+      // the K slice [128 w, 128 w + 128) that its own tensor-core steps consume -> no CTA barrier is needed
+      // between the gather and the B-fragment loads (only the RMS statistic crosses warps).
+      uint4 gw[3];
+      const int gi0 = c.tid * 4;
+      if (from_input) {
+        const uint2 v = *reinterpret_cast<const uint2*>(x_in + gi0);
+        gw[0] = make_uint4(v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16);
+        if (c.tid < rows.o_rows) {
+          res_mine = __bfloat162float(x_in[rows.o_row0 + c.tid]);
+          p.res_spill[rows.o_row0 + c.tid] = res_mine;
+        }
+      } else {
+        wait_window(c, (kind == K_O && !has_item) ? p.delay_o_idle : c.s_delay[dslot]);
+        trace_sub<TR>(c, 1);
+        gw[0] = ll4_ld4(xw + gi0);
+        if (n_words > H) gw[1] = ll4_ld4(xw + gi0 + H);
+        if (n_words > 2 * H) gw[2] = ll4_ld4(xw + gi0 + 2 * H);
+      }
+      // -- shadow of the load latency --
+      PhaseDesc d;
+      if (kind == K_HEAD) d = head_phase_desc(p, sd.head, c.cta);
+      else d = layer_phase_desc(p, rows, l, kind, c.cta);
+      const int nst = n_stages_of(d);
+      uint32_t ready = 0;
+      uint32_t sbase[MAX_ST];
+#pragma unroll
+      for (int s = 0; s < MAX_ST; ++s) {
+        const uint32_t k = c.k + s;
+        const int slot = k % NSLOTS;
+        sbase[s] = smem_u32(c.ring + (size_t)slot * SLOT_BYTES);
+        if (s < nst && mbar_test_wait(&c.full[slot], (k / NSLOTS) & 1u)) ready |= 1u << s;
+      }
+      const uint8_t* aux = c.ring + (size_t)(c.k % NSLOTS) * SLOT_BYTES;
+      uint2 wv = make_uint2(0, 0);
+      if (norm && (ready & 1u)) wv = *reinterpret_cast<const uint2*>(aux + c.tid * 8);
+      if (kind == K_QKV && has_item) attn_prefetch(c, l, position, item, 0, kv);  // older KV rows do not depend on this layer
+      const uint32_t* xs = reinterpret_cast<const uint32_t*>(c.s_vec + ((c.lane >> 2) < xr_mod ? (c.lane >> 2) : 0) * SEG_BYTES) +
+                           c.warp * KSTEPS * 8 + (c.lane & 3);
+      uint32_t* const my_x = reinterpret_cast<uint32_t*>(c.s_vec + gi0 * 2);
+      // -- data --
+      bool retried = false;
+      if (!from_input) {
+        if (!ll4_ok(gw[0], ep)) { retried = true; gw[0] = ll4_wait_slow(p.status, c.s_abort, c.t0, p.timeout_cycles, c.cta, idx, xw + gi0, ep, gi0); }
+        if (n_words > H && !ll4_ok(gw[1], ep)) { retried = true; gw[1] = ll4_wait_slow(p.status, c.s_abort, c.t0, p.timeout_cycles, c.cta, idx, xw + gi0 + H, ep, gi0); }
+        if (n_words > 2 * H && !ll4_ok(gw[2], ep)) { retried = true; gw[2] = ll4_wait_slow(p.status, c.s_abort, c.t0, p.timeout_cycles, c.cta, idx, xw + gi0 + 2 * H, ep, gi0); }
+      }
+      trace_sub<TR>(c, 2);
+      if (norm) {
+        // n = r( r(x) * rsqrt(mean(r(x)^2) + eps) * w ); the norm weights arrive with the first stage of the phase
+        const float r0 = ll4_val(gw[0].x), r1 = ll4_val(gw[0].y), r2 = ll4_val(gw[0].z), r3 = ll4_val(gw[0].w);
+        float ss = fmaf(r0, r0, r1 * r1) + fmaf(r2, r2, r3 * r3);
+        ss = warp_sum(ss);
+        if (c.lane == 0) c.s_red[c.warp] = ss;
+        if (from_input) consumer_bar(); else gather_bar(c, dslot, retried);
+        trace_sub<TR>(c, 3);
+        if (!(ready & 1u)) {
+          wait_full(c, c.k);
+          ready |= 1u;
+          wv = *reinterpret_cast<const uint2*>(aux + c.tid * 8);
+        }
+        const float4 q0 = *reinterpret_cast<const float4*>(c.s_red), q1 = *reinterpret_cast<const float4*>(c.s_red + 4);
+        const float inv = rsqrtf((((q0.x + q0.y) + (q0.z + q0.w)) + ((q1.x + q1.y) + (q1.z + q1.w))) * (1.0f / H) + EPS);
+        const __nv_bfloat162 n01 = __floats2bfloat162_rn((r0 * inv) * bf16_lo(wv.x), (r1 * inv) * bf16_hi(wv.x));
+        const __nv_bfloat162 n23 = __floats2bfloat162_rn((r2 * inv) * bf16_lo(wv.y), (r3 * inv) * bf16_hi(wv.y));
+        const uint2 packed = make_uint2(*reinterpret_cast<const uint32_t*>(&n01), *reinterpret_cast<const uint32_t*>(&n23));
+        *reinterpret_cast<uint2*>(my_x) = packed;
+        if (kind == K_HEAD && c.cta == 0) {
+          if (sd.hidden_out != nullptr)
+            *reinterpret_cast<uint2*>(sd.hidden_out + gi0) = make_uint2((gw[0].x & 0xffffu) | (gw[0].y << 16), (gw[0].z & 0xffffu) | (gw[0].w << 16));
+          if (sd.out_norm != nullptr)
+            *reinterpret_cast<float4*>(sd.out_norm + gi0) = make_float4(bf16_lo(packed.x), bf16_hi(packed.x), bf16_lo(packed.y), bf16_hi(packed.y));
+        }
+        if (kind == K_QKV && has_item) {
+          if (c.warp < 3) {  // q_norm / k_norm weights of this layer (aux of the resident first stage)
+            const uint2 nv = *reinterpret_cast<const uint2*>(aux + 2048 + (c.warp == 2 ? 256 : 0) + c.lane * 8);
+            pre.nw[0] = bf16_lo(nv.x); pre.nw[1] = bf16_hi(nv.x); pre.nw[2] = bf16_lo(nv.y); pre.nw[3] = bf16_hi(nv.y);
+          }
+          pre_layer = l;
+        }
+      } else {
+        gather_note(c, dslot, retried);
+        *reinterpret_cast<uint2*>(my_x) = make_uint2((gw[0].x & 0xffffu) | (gw[0].y << 16), (gw[0].z & 0xffffu) | (gw[0].w << 16));
+        *reinterpret_cast<uint2*>(my_x + H / 2) = make_uint2((gw[1].x & 0xffffu) | (gw[1].y << 16), (gw[1].z & 0xffffu) | (gw[1].w << 16));
+        if (n_words > 2 * H)
+          *reinterpret_cast<uint2*>(my_x + H) = make_uint2((gw[2].x & 0xffffu) | (gw[2].y << 16), (gw[2].z & 0xffffu) | (gw[2].w << 16));
+      }
+      __syncwarp();
+      trace_sub<TR>(c, 4);
+
+      // stages: each warp multiplies its KSTEPS k16-steps of every stage tile (rows = items) by the activation columns
+      uint32_t bfrag[KSTEPS][2];
+#pragma unroll
+      for (int j = 0; j < KSTEPS; ++j) {
+        bfrag[j][0] = xs[j * 8];
+        bfrag[j][1] = xs[j * 8 + 4];
+      }
+      float acc[MAX_ST][4];
+#pragma unroll
+      for (int s = 0; s < MAX_ST; ++s) {
+        acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.f;
+        if (s < nst) {
+          if (!((ready >> s) & 1u)) wait_full(c, c.k + s);
+          uint32_t afrag[KSTEPS][4];
+#pragma unroll
+          for (int j = 0; j < KSTEPS; ++j)
+            ldsm4(afrag[j], sbase[s] + a_off + ((uint32_t)((((c.warp * KSTEPS + j) * 2 + a_khalf) ^ a_sw)) << 4));
+          float acc2[4] = {0.f, 0.f, 0.f, 0.f};   // two accumulators halve the dependent HMMA chain
+#pragma unroll
+          for (int j = 0; j < KSTEPS; j += 2) {
+            mma16816(acc[s], afrag[j], bfrag[j]);
+            mma16816(acc2, afrag[j + 1], bfrag[j + 1]);
+          }
+          __syncwarp();
+          if (c.lane == 0) mbar_arrive(&c.empty[(c.k + s) % NSLOTS]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[s][e] += acc2[e];
+        }
+      }
+      c.k += nst;
+      trace_sub<TR>(c, 5);
+      // per-warp (K-slice) partial of item it -> s_part[it][warp]; the lane holding column kb(it) of row r writes it
+#pragma unroll
+      for (int s = 0; s < MAX_ST; ++s) {
+        if (s < nst) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int r = (c.lane >> 2) + half * 8;
+            const int it = s * STAGE_ITEMS + r;
+            const int kb = (xr_mod == 3) ? (int)((kb3_pack >> (2 * (s * 2 + half))) & 3u) : (xr_mod == 2 ? (r & 1) : 0);
+            if (r < STAGE_ITEMS && it < d.n_items && (kb >> 1) == (c.lane & 3))
+              c.s_part[it * NCW + c.warp] = (kb & 1) ? acc[s][half * 2 + 1] : acc[s][half * 2];
+          }
+        }
+      }
+      consumer_bar();
+      trace_sub<TR>(c, 6);
+
+      // finalize + publish: thread t sums the NCW K-slice partials of item t; the items of one output row sit in
+      // neighbouring lanes (an output row never straddles a warp: 2 | 32, and 3 * rows <= 30)
+      if (kind != K_O && kind != K_DOWN) {
+        if (c.warp < 2) {   // n_items <= 42: warps 0 and 1
+          const bool mine = c.tid < d.n_items;
+          const float v = mine ? item_sum(c.s_part, c.tid) : 0.f;
+          if (kind == K_GU) {  // gate in even lanes, up in the next lane
+            const float u = bf16_round(__shfl_down_sync(0xffffffffu, v, 1));
+            if (mine && (c.tid & 1) == 0) {
+              const float g = bf16_round(v);
+              const float sg = bf16_round(__fdividef(g, 1.0f + __expf(-g)));
+              ll4_st(xout + (c.tid >> 1), sg * u, epoch);
+            }
+          } else if (mine) {
+            ll4_st(xout + c.tid, v, epoch);
+          }
+        }
+      } else if (c.warp == 0) {   // 2 or 3 items per output row, all inside warp 0
+        const float v = c.lane < d.n_items ? item_sum(c.s_part, c.lane) : 0.f;
+        const int per = (kind == K_O) ? 2 : 3;
+        const int src = c.lane * per;
+        float tot = __shfl_sync(0xffffffffu, v, src & 31) + __shfl_sync(0xffffffffu, v, (src + 1) & 31);
+        const float v2 = __shfl_sync(0xffffffffu, v, (src + 2) & 31);
+        if (per == 3) tot += v2;
+        if (c.lane < rows.o_rows) {
+          const float o = bf16_round(tot);
+          res_mine = p.residual_fp32 ? res_mine + o : bf16_round(res_mine + o);
+          ll4_st(xout + c.lane, res_mine, epoch);
+          p.res_spill[rows.o_row0 + c.lane] = res_mine;
+        }
+      }
+      c.t_pub = clock64();
+      trace_sub<TR>(c, 7);
     }
   }
 }
@@ -1064,11 +1090,13 @@ __device__ void consumer_loop(Ctx& c) {
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 1) qmk_decode_kernel(const __grid_constant__ Params p) {
+template <bool TR>
+__device__ __forceinline__ void decode_kernel_body(const Params& p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctx c(p);
   c.ring = smem + SM_RING;
-  c.s_vec = reinterpret_cast<float*>(smem + SM_VEC);
+  c.s_vec = smem + SM_VEC;
+  c.s_acc = reinterpret_cast<float*>(smem + SM_ACC);
   c.s_small = reinterpret_cast<float*>(smem + SM_SMALL);
   c.s_part = reinterpret_cast<float*>(smem + SM_PART);
   c.s_red = reinterpret_cast<float*>(smem + SM_RED);
@@ -1094,24 +1122,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) qmk_decode_kernel(const __grid_co
     *c.s_abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < 2 * DL_N) c.s_delay[threadIdx.x] = p.delays[blockIdx.x * 2 * DL_N + threadIdx.x];
+  if (threadIdx.x < 3 * DL_N) c.s_delay[threadIdx.x] = p.delays[blockIdx.x * 3 * DL_N + threadIdx.x];
   __syncthreads();
 
   if (c.warp == NCW) {
     if (c.lane == 0) producer_loop(c);
   } else {
-    consumer_loop(c);
+    consumer_loop<TR>(c);
   }
   __syncthreads();
   c.cur_idx = p.phase_end;
-  trace_sub(c, 0);
-  if (threadIdx.x >= DL_N && threadIdx.x < 2 * DL_N) p.delays[blockIdx.x * 2 * DL_N + threadIdx.x] = c.s_delay[threadIdx.x];
+  trace_sub<TR>(c, 0);
+  if (threadIdx.x >= DL_N && threadIdx.x < 3 * DL_N) p.delays[blockIdx.x * 3 * DL_N + threadIdx.x] = c.s_delay[threadIdx.x];
   if (*c.s_abort && threadIdx.x == 0) {
     // failure path only: give in-flight bulk copies time to land before the CTA's shared memory is released
     const long long t = clock64();
     while (clock64() - t < 2000000) {
     }
   }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) qmk_decode_kernel(const __grid_constant__ Params p) {
+  decode_kernel_body<false>(p);
+}
+// same kernel with the per-phase clock trace compiled in (qmk_engine_trace_enable)
+__global__ void __launch_bounds__(NTHREADS, 1) qmk_decode_kernel_traced(const __grid_constant__ Params p) {
+  decode_kernel_body<true>(p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1133,8 +1169,10 @@ __global__ void qmk_pack_layers_kernel(const LayerPtrs* layers, Layout y, uint8_
   const int g0 = row_begin(cta, INTER, y.G), ng = row_begin(cta + 1, INTER, y.G) - g0;
   for (int seg = 0; seg < y.layer_segs; ++seg) {
     uint4 v = zero;
+    int s_in_phase;
     if (seg < y.off_o) {
       const int s = seg;
+      s_in_phase = s;
       if (s < nq) {
         const int row = q0 + s;
         if (row < QSZ) v = lp.w[W_Q][(size_t)row * 128 + t];
@@ -1143,18 +1181,22 @@ __global__ void qmk_pack_layers_kernel(const LayerPtrs* layers, Layout y, uint8_
       }
     } else if (seg < y.off_gu) {
       const int s = seg - y.off_o;
+      s_in_phase = s;
       if (s < 2 * no) v = lp.w[W_O][((size_t)(o0 + s / 2) * 2 + (s % 2)) * 128 + t];
     } else if (seg < y.off_down) {
       const int s = seg - y.off_gu;
+      s_in_phase = s;
       if (s < 2 * ng) {
         const int row = g0 + s / 2;
         v = (s % 2 == 0) ? lp.w[W_GATE][(size_t)row * 128 + t] : lp.w[W_UP][(size_t)row * 128 + t];
       }
     } else {
       const int s = seg - y.off_down;
+      s_in_phase = s;
       if (s < 3 * no) v = lp.w[W_DOWN][((size_t)(o0 + s / 3) * 3 + (s % 3)) * 128 + t];
     }
-    dst[(size_t)seg * 128 + t] = v;
+    // 16-byte chunk t of stage row r is stored at chunk t ^ (r & 7) (conflict-free ldmatrix of the 16 x 16 tiles)
+    dst[(size_t)seg * 128 + (t ^ ((s_in_phase % STAGE_ITEMS) & 7))] = v;
   }
   if (cta == 0) {  // shared aux blocks: [input_ln | q_norm | k_norm] and [post_ln | 0]
     uint4* a0 = reinterpret_cast<uint4*>(aux_layers + ((size_t)l * 2 + 0) * AUX_BYTES);
@@ -1178,7 +1220,7 @@ __global__ void qmk_pack_head_kernel(const uint4* head_w, int rows, int G, int s
   for (int seg = 0; seg < segs_max; ++seg) {
     uint4 v = make_uint4(0, 0, 0, 0);
     if (seg < n) v = head_w[(size_t)(r0 + seg) * 128 + t];
-    dst[(size_t)seg * 128 + t] = v;
+    dst[(size_t)seg * 128 + (t ^ ((seg % STAGE_ITEMS) & 7))] = v;
   }
 }
 

@@ -122,8 +122,9 @@ extern "C" int qmk_engine_create(int device, int num_ctas, qmk_engine** out) {
   int G = num_ctas > 0 ? num_ctas : prop.multiProcessorCount;
   if (G > prop.multiProcessorCount) G = prop.multiProcessorCount;
   // every CTA must own >=1 row in every phase and a phase may span at most MAX_ST ring stages
-  if (G < 110 || G > 1024) return set_error(QMK_ERR_UNSUPPORTED, "unsupported CTA count %d (need 110..1024)", G);
+  if (G < 147 || G > 1024) return set_error(QMK_ERR_UNSUPPORTED, "unsupported CTA count %d (need 147..1024: a phase spans at most 3 ring stages)", G);
   QMK_CUDA(cudaFuncSetAttribute(qmk_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  QMK_CUDA(cudaFuncSetAttribute(qmk_decode_kernel_traced, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   int occ = 0;
   QMK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qmk_decode_kernel, NTHREADS, SMEM_BYTES));
   if (occ < 1) return set_error(QMK_ERR_UNSUPPORTED, "decode kernel does not fit on an SM (smem %d B)", SMEM_BYTES);
@@ -135,9 +136,9 @@ extern "C" int qmk_engine_create(int device, int num_ctas, qmk_engine** out) {
   int delay0 = 450;
   if (const char* env = getenv("QMK_POLL_DELAY")) delay0 = atoi(env);
   if (const char* env = getenv("QMK_POLL_DELAY_O")) e->delay_o_idle = atoi(env);
-  std::vector<int> delays((size_t)G * 2 * DL_N, 0);
+  std::vector<int> delays((size_t)G * 3 * DL_N, 0);
   for (int c = 0; c < G; ++c)
-    for (int d = 0; d < DL_N; ++d) delays[(size_t)c * 2 * DL_N + d] = delay0;
+    for (int d = 0; d < DL_N; ++d) delays[(size_t)c * 3 * DL_N + d] = delay0;
   cudaError_t err = cudaMalloc(&e->xbuf, XBUF_BYTES);
   if (err == cudaSuccess) err = cudaMemset(e->xbuf, 0, XBUF_BYTES);
   if (err == cudaSuccess) err = cudaMalloc(&e->res_spill, H * sizeof(float));
@@ -201,10 +202,10 @@ extern "C" int qmk_engine_poll_stats(qmk_engine* e, void* stream, int32_t* host_
   if (!e || !host_out) return set_error(QMK_ERR_ARG, "qmk_engine_poll_stats: null argument");
   DeviceGuard guard(e->device);
   QMK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-  int64_t n = (int64_t)e->G * 2 * DL_N;
+  int64_t n = (int64_t)e->G * 3 * DL_N;
   if (n > max_elems) n = max_elems;
   QMK_CUDA(cudaMemcpy(host_out, e->delays, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
-  return 2 * DL_N;
+  return 3 * DL_N;
 }
 
 extern "C" int qmk_engine_sync_status(qmk_engine* e, void* stream, int32_t* detail) {
@@ -302,7 +303,8 @@ static int launch_slice(qmk_engine* e, Params& p, int begin, int end, cudaStream
   p.phase_begin = begin;
   p.phase_end = end;
   void* args[] = {&p};
-  QMK_CUDA(cudaLaunchCooperativeKernel((const void*)qmk_decode_kernel, dim3(e->G), dim3(NTHREADS), args, SMEM_BYTES, st));
+  const void* fn = e->trace_dev ? (const void*)qmk_decode_kernel_traced : (const void*)qmk_decode_kernel;
+  QMK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(e->G), dim3(NTHREADS), args, SMEM_BYTES, st));
   return QMK_OK;
 }
 

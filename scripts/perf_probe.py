@@ -70,11 +70,9 @@ def trace(dec, x, lib, engine, L):
     start = t[:, :, 0]
     d = np.diff(start, axis=1)
     names = ["qkv", "attn", "o", "gu", "down"]
-    labels = {0: ["wait+gather+norm", "stages+reduce", None, None],
-              1: ["wait+gather+norm/rope", "scores", "merge", "combine+publish"],
-              2: ["wait+gather", "stages+reduce", None, None],
-              3: ["wait+gather+norm", "stages+reduce", None, None],
-              4: ["wait+gather", "stages+reduce", None, None]}
+    gl = ["window", "gather", "bar+aux", "norm", "stages", "reduce+bar", "publish"]
+    ga = ["window", "gather", "bar+aux", None, "stages", "reduce+bar", "publish"]
+    labels = {0: gl, 1: ["wait+gather+norm/rope", "scores", "merge", "combine+publish", None, None, None], 2: ga, 3: gl, 4: ga}
     layers = list(range(2, L))
     for grp_name, sl in (("attention CTAs 0-7", slice(0, 8)), ("other CTAs", slice(8, G))):
         print(f"--- {grp_name}: mean cycles per sub-step over layers 2..{L-1}")
@@ -83,7 +81,7 @@ def trace(dec, x, lib, engine, L):
             tot = d[sl][:, idxs].mean()
             parts = []
             prev = 0
-            for sub in range(1, 5):
+            for sub in range(1, 8):
                 lab = labels[ph][sub - 1]
                 if lab is None:
                     continue
@@ -121,11 +119,13 @@ def main():
         us_cp = time_cp_steps(cp, x)
         print(f"poll_delay0={cfg:>5s}: talker {us:8.1f} us/step ({args.layers} layers)   cp step {us_cp:7.1f} us", flush=True)
         G = dec._lib.qmk_engine_num_ctas(dec._engine)
-        st = (ctypes.c_int32 * (G * 16))()
-        dec._lib.qmk_engine_poll_stats(dec._engine, torch.cuda.current_stream().cuda_stream, st, G * 16)
-        a = np.frombuffer(st, dtype=np.int32).reshape(G, 2, 8)
+        st = (ctypes.c_int32 * (G * 24))()
+        dec._lib.qmk_engine_poll_stats(dec._engine, torch.cuda.current_stream().cuda_stream, st, G * 24)
+        a = np.frombuffer(st, dtype=np.int32).reshape(G, 3, 8)
         print("   repeated-poll gathers [qkv attn o gu down head argmax token]: attn CTAs", a[:8, 1].sum(0).tolist(),
-              " others", a[8:, 1].sum(0).tolist(), flush=True)
+              " others", a[8:, 1].sum(0).tolist())
+        print("   mean weight-wait cycles per launch per CTA [qkv - o gu down head]:",
+              (a[:, 2].mean(0) * 16 / 186).round(0).tolist(), flush=True)
         if args.trace:
             trace(dec, x, dec._lib, dec._engine, args.layers)
         del dec, cp
