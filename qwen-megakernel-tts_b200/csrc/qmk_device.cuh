@@ -1,13 +1,13 @@
 // qmk_device.cuh — device side of the B200 decode engine (sm_100a).
 //
-// One persistent cooperative kernel, one CTA per SM, 15 warps per CTA:
-//   * warp 14 (one elected lane) is the PRODUCER: it streams this CTA's slice of the re-packed weights with
-//     1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) into a 6-slot x 30.5 KB shared-memory
-//     ring.  Weight addresses do not depend on activations, so the producer runs ahead through every data
-//     dependency of the layer and HBM stays busy while the consumers wait on each other.
-//   * warps 0-13 are CONSUMERS: one 1024-element row segment (2 KB) per warp per stage, activations in
-//     registers, 128-bit conflict-free shared loads, fp32 FMA, one transposed warp-shuffle reduction per
-//     phase (6 shuffles for up to 4 row segments).
+// One persistent cooperative kernel, one CTA per SM, 8 warps per CTA:
+//   * this CTA's slice of the re-packed weights streams through a 6-slot x 30.5 KB shared-memory ring with 1-D TMA
+//     bulk copies (cp.async.bulk ... mbarrier::complete_tx).  Weight addresses do not depend on activations, so
+//     the stream runs ~0.75 layer ahead through every data dependency and HBM stays busy while the CTAs wait
+//     on each other; a slot is refilled by one lane as soon as the phase that read it has passed its barrier.
+//   * a ring stage is a 14-row x 1024-k weight tile; each warp owns a 128-wide K slice of it and multiplies it
+//     with the activation vector on the tensor cores (mma.sync m16n8k16, fp32 accumulate); the K-slice partials
+//     are summed through shared memory in a fixed order.
 // CTAs exchange activations through "LL" words in global memory: every exchanged vector is bf16-valued
 // (the reference rounds to bf16 at exactly these points), so a 32-bit word carries {bf16 payload, 16-bit
 // epoch}.  Data and flag arrive in one single-copy-atomic access: there is no grid barrier, no fence and no
@@ -34,10 +34,10 @@ constexpr int H = 1024, INTER = 3072, QSZ = 2048, KVSZ = 1024, HD = 128, NQH = 1
 constexpr int QKV_ROWS = QSZ + 2 * KVSZ;  // 4096
 constexpr int SEG_ELEMS = 1024, SEG_BYTES = 2048;
 constexpr int NCW = 8;               // consumer warps: each owns 8 of the 64 k16-steps of a 1024-wide segment
-constexpr int KSTEPS = 64 / NCW;     // (8 + 1 warps keep the register budget at 224/thread: with ~10 KB of L1 left
-                                     //  beside 218 KB of shared memory, a single spilled register costs an L2 round trip)
+constexpr int KSTEPS = 64 / NCW;     // (exactly 2 warps per SM sub-partition = 255 registers/thread: with ~10 KB of L1 left
+                                     //  beside 200+ KB of shared memory, a single spilled register costs an L2 round trip)
 constexpr int NCT = NCW * 32;        // 256 consumer threads
-constexpr int NTHREADS = NCT + 32;   // + producer warp
+constexpr int NTHREADS = NCT;        // no dedicated producer warp: see Prod below
 constexpr int STAGE_ITEMS = 14;      // 2 KB row segments per ring stage = rows of one m16 tensor-core tile
 constexpr int AUX_BYTES = 2560;      // norm weights (2048) + q_norm / k_norm (2 x 256)
 constexpr int SLOT_BYTES = AUX_BYTES + STAGE_ITEMS * SEG_BYTES;  // 31232: [aux][14 row segments, 16-byte chunks swizzled]
@@ -249,7 +249,7 @@ constexpr int SM_ACC = SM_VEC + INTER * 2;                // float[NCW][2][128]:
 constexpr int SM_SMALL = SM_ACC + NCW * 2 * HD * 4;              // float[1024]  attention scratch
 constexpr int SM_PART = SM_SMALL + 1024 * 4;              // float[56][NCW] per-item, per-warp (K slice) partial dot products
 constexpr int SM_RED = SM_PART + MAX_ITEMS * NCW * 4;     // float[64]    cross-warp reductions
-constexpr int SM_BAR = SM_RED + 64 * 4;                   // u64 full[NSLOTS], empty[NSLOTS]
+constexpr int SM_BAR = SM_RED + 64 * 4;                   // u64 full[NSLOTS]
 constexpr int SM_MISC = SM_BAR + 2 * 8 * 8;               // int abort; int delays[DL_N]; ...
 constexpr int SMEM_BYTES = SM_MISC + 256;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -266,7 +266,6 @@ struct Ctx {
   float* s_part;
   float* s_red;
   u64* full;
-  u64* empty;
   volatile int* s_abort;
   int* s_delay;
   uint32_t* x32;
@@ -309,15 +308,6 @@ __device__ __forceinline__ void wait_full(Ctx& c, uint32_t k) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 63u) == 0 && check_abort(c, ST_TIMEOUT_FULL, (int)k)) return;
-  }
-}
-__device__ __forceinline__ void wait_empty(Ctx& c, uint32_t k) {
-  u64* bar = &c.empty[k % NSLOTS];
-  uint32_t parity = ((k / NSLOTS) & 1u) ^ 1u;
-  if (mbar_try_wait(bar, parity)) return;
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 63u) == 0 && check_abort(c, ST_TIMEOUT_EMPTY, (int)k)) return;
   }
 }
 __device__ __noinline__ uint4 ll4_wait_slow(int* status, volatile int* s_abort, long long t0, long long timeout, int cta,
@@ -420,40 +410,58 @@ __device__ __forceinline__ int n_stages_of(const PhaseDesc& d) {
 // ------------------------------------------------------------------------------------------------
 // producer
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void produce_phase(Ctx& c, const PhaseDesc& d) {
-  const int nst = n_stages_of(d);
-  for (int s = 0; s < nst; ++s, ++c.k) {
-    const int slot = c.k % NSLOTS;
-    wait_empty(c, c.k);
-    int items = d.n_items - s * STAGE_ITEMS;
-    if (items > STAGE_ITEMS) items = STAGE_ITEMS;
-    const bool aux = (s == 0 && d.aux != nullptr);
-    const uint32_t bytes = (uint32_t)items * SEG_BYTES + (aux ? AUX_BYTES : 0);
-    uint8_t* dst = c.ring + (size_t)slot * SLOT_BYTES;
-    mbar_arrive_expect_tx(&c.full[slot], bytes);
-    if (aux) tma_bulk_g2s(dst, d.aux, AUX_BYTES, &c.full[slot]);
-    if (items > 0)
-      tma_bulk_g2s(dst + AUX_BYTES, d.src + (size_t)s * STAGE_ITEMS * SEG_BYTES, (uint32_t)items * SEG_BYTES, &c.full[slot]);
-  }
+// Weight producer.  There is no producer warp: the ring is refilled by one lane of the last consumer warp right
+// after the barrier that ends a phase's tensor-core stages (every warp has finished reading those slots by then),
+// so the stage that is NSLOTS ahead is always issued as soon as its slot is free, without empty-barriers and
+// without a ninth warp (which would cap the kernel at 168 registers per thread).
+struct Prod {
+  int step, idx, s;   // next stage to issue: stage s of phase idx of step `step`
+  uint32_t k;         // its global stage number (slot = k % NSLOTS)
+  bool done;
+};
+__device__ __forceinline__ void prod_init(const Params& p, Prod& pr) {
+  pr.step = 0; pr.idx = p.phase_begin; pr.s = 0; pr.k = 0; pr.done = false;
 }
-
-__device__ void producer_loop(Ctx& c) {
+// Issue the next `n` stages of the weight stream (lane 0 of the calling warp; all lanes keep the cursor).
+__device__ void prod_issue(Ctx& c, const CtaRows& rows, Prod& pr, int n) {
   const Params& p = c.p;
-  const CtaRows rows = cta_rows(p.lay, c.cta);
   const int nlayer_idx = p.lay.L * PH_PER_LAYER;
-  for (int step = 0; step < p.n_steps; ++step) {
-    const int begin = (step == 0) ? p.phase_begin : 0;
-    const int end = (p.n_steps == 1) ? p.phase_end : nlayer_idx + 2;
-    for (int idx = begin; idx < end; ++idx) {
-      c.cur_idx = idx;
-      if (idx < nlayer_idx) {
-        const int ph = idx % PH_PER_LAYER;
-        if (ph == PH_ATTN) continue;
-        produce_phase(c, layer_phase_desc(p, rows, idx / PH_PER_LAYER, ph, c.cta));
-      } else if (idx == nlayer_idx) {
-        produce_phase(c, head_phase_desc(p, p.steps[step].head, c.cta));
-      }
+  const int end = (p.n_steps == 1) ? p.phase_end : nlayer_idx + 2;
+  while (n > 0 && !pr.done) {
+    PhaseDesc d;
+    d.n_items = 0; d.aux = nullptr; d.src = nullptr;
+    if (pr.idx < nlayer_idx) {
+      const int ph = pr.idx % PH_PER_LAYER;
+      if (ph != PH_ATTN) d = layer_phase_desc(p, rows, pr.idx / PH_PER_LAYER, ph, c.cta);
+    } else if (pr.idx == nlayer_idx) {
+      d = head_phase_desc(p, p.steps[pr.step].head, c.cta);
     }
+    const int nst = n_stages_of(d);
+    if (pr.s >= nst) {   // next phase
+      pr.s = 0;
+      if (++pr.idx >= end) {
+        pr.idx = 0;
+        if (++pr.step >= p.n_steps) pr.done = true;
+      }
+      continue;
+    }
+    if (c.lane == 0) {
+      const int slot = pr.k % NSLOTS;
+      int items = d.n_items - pr.s * STAGE_ITEMS;
+      if (items > STAGE_ITEMS) items = STAGE_ITEMS;
+      const bool aux = (pr.s == 0 && d.aux != nullptr);
+      const uint32_t bytes = (uint32_t)items * SEG_BYTES + (aux ? AUX_BYTES : 0);
+      uint8_t* dst = c.ring + (size_t)slot * SLOT_BYTES;
+      // the consumers read this slot through the generic proxy; order those reads before the async-proxy write
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive_expect_tx(&c.full[slot], bytes);
+      if (aux) tma_bulk_g2s(dst, d.aux, AUX_BYTES, &c.full[slot]);
+      if (items > 0)
+        tma_bulk_g2s(dst + AUX_BYTES, d.src + (size_t)pr.s * STAGE_ITEMS * SEG_BYTES, (uint32_t)items * SEG_BYTES, &c.full[slot]);
+    }
+    ++pr.s;
+    ++pr.k;
+    --n;
   }
 }
 
@@ -779,7 +787,7 @@ __device__ void phase_attn(Ctx& c, int l, int position, uint32_t epoch, const At
 // ------------------------------------------------------------------------------------------------
 // sum of the NCW per-warp K-slice partials of one item, fixed order
 __device__ __forceinline__ float item_sum(const float* s_part, int it) {
-  static_assert(NCW == 8, "item_sum reads 8 partials");
+  static_assert(NCW == 8 && KSTEPS == 8, "item_sum reads 8 partials; pack_chunk assumes 8 K-slices of 128");
   const float4* v = reinterpret_cast<const float4*>(s_part + it * NCW);
   const float4 a = v[0], b = v[1];
   return ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
@@ -799,6 +807,9 @@ __device__ void consumer_loop(Ctx& c) {
   uint32_t* const x_m = c.x32 + XW_M;
   uint32_t* const x_logits = c.x32 + XW_LOGITS;
   const CtaRows rows = cta_rows(y, c.cta);
+  Prod prod;
+  prod_init(p, prod);
+  if (c.warp == NCW - 1) prod_issue(c, rows, prod, NSLOTS);   // fill the ring
   KvRegs kv;
   AttnPre pre = {{0.f, 0.f, 0.f, 0.f}};
   float res_mine = 0.f;  // fp32 residual of row o_row0 + tid (tid < o_rows)
@@ -949,9 +960,21 @@ __device__ void consumer_loop(Ctx& c) {
       uint2 wv = make_uint2(0, 0);
       if (norm && (ready & 1u)) wv = *reinterpret_cast<const uint2*>(aux + c.tid * 8);
       if (kind == K_QKV && has_item) attn_prefetch(c, l, position, item, 0, kv);  // older KV rows do not depend on this layer
-      const uint32_t* xs = reinterpret_cast<const uint32_t*>(c.s_vec + ((c.lane >> 2) < xr_mod ? (c.lane >> 2) : 0) * SEG_BYTES) +
-                           c.warp * KSTEPS * 8 + (c.lane & 3);
+      const uint4* xs = reinterpret_cast<const uint4*>(c.s_vec + ((c.lane >> 2) < xr_mod ? (c.lane >> 2) : 0) * SEG_BYTES +
+                                                       c.warp * 256 + (c.lane & 3) * 64);
       uint32_t* const my_x = reinterpret_cast<uint32_t*>(c.s_vec + gi0 * 2);
+      // which of this lane's accumulator columns carry an item's K-slice partial: bit (2 s + half) of pw_mask set ->
+      // row r = lane/4 + 8 half of stage s is an item whose k-block column kb lives in this lane; pw_sel picks odd kb
+      uint32_t pw_mask = 0, pw_sel = 0;
+#pragma unroll
+      for (int sh = 0; sh < 2 * MAX_ST; ++sh) {
+        const int r = (c.lane >> 2) + (sh & 1) * 8;
+        const int it = (sh >> 1) * STAGE_ITEMS + r;
+        const int kb = (xr_mod == 3) ? (int)((kb3_pack >> (2 * sh)) & 3u) : (xr_mod == 2 ? (r & 1) : 0);
+        if (r < STAGE_ITEMS && it < d.n_items && (kb >> 1) == (c.lane & 3)) pw_mask |= 1u << sh;
+        if (kb & 1) pw_sel |= 1u << sh;
+      }
+      float* const pw_base = c.s_part + ((c.lane >> 2) * NCW + c.warp);
       // -- data --
       bool retried = false;
       if (!from_input) {
@@ -1005,9 +1028,9 @@ __device__ void consumer_loop(Ctx& c) {
       // stages: each warp multiplies its KSTEPS k16-steps of every stage tile (rows = items) by the activation columns
       uint32_t bfrag[KSTEPS][2];
 #pragma unroll
-      for (int j = 0; j < KSTEPS; ++j) {
-        bfrag[j][0] = xs[j * 8];
-        bfrag[j][1] = xs[j * 8 + 4];
+      for (int i = 0; i < KSTEPS / 2; ++i) {
+        const uint4 v = xs[i];
+        bfrag[2 * i][0] = v.x; bfrag[2 * i][1] = v.y; bfrag[2 * i + 1][0] = v.z; bfrag[2 * i + 1][1] = v.w;
       }
       float acc[MAX_ST][4];
 #pragma unroll
@@ -1015,40 +1038,34 @@ __device__ void consumer_loop(Ctx& c) {
         acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.f;
         if (s < nst) {
           if (!((ready >> s) & 1u)) wait_full(c, c.k + s);
-          uint32_t afrag[KSTEPS][4];
-#pragma unroll
-          for (int j = 0; j < KSTEPS; ++j)
-            ldsm4(afrag[j], sbase[s] + a_off + ((uint32_t)((((c.warp * KSTEPS + j) * 2 + a_khalf) ^ a_sw)) << 4));
           float acc2[4] = {0.f, 0.f, 0.f, 0.f};   // two accumulators halve the dependent HMMA chain
 #pragma unroll
-          for (int j = 0; j < KSTEPS; j += 2) {
-            mma16816(acc[s], afrag[j], bfrag[j]);
-            mma16816(acc2, afrag[j + 1], bfrag[j + 1]);
+          for (int jb = 0; jb < KSTEPS; jb += 4) {  // batches of 4 ldmatrix keep the live A fragments at 16 registers
+            uint32_t afrag[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              ldsm4(afrag[j], sbase[s] + a_off + ((uint32_t)((((c.warp * KSTEPS + jb + j) * 2 + a_khalf) ^ a_sw)) << 4));
+            mma16816(acc[s], afrag[0], bfrag[jb]);
+            mma16816(acc2, afrag[1], bfrag[jb + 1]);
+            mma16816(acc[s], afrag[2], bfrag[jb + 2]);
+            mma16816(acc2, afrag[3], bfrag[jb + 3]);
           }
-          __syncwarp();
-          if (c.lane == 0) mbar_arrive(&c.empty[(c.k + s) % NSLOTS]);
 #pragma unroll
           for (int e = 0; e < 4; ++e) acc[s][e] += acc2[e];
         }
       }
       c.k += nst;
       trace_sub<TR>(c, 5);
-      // per-warp (K-slice) partial of item it -> s_part[it][warp]; the lane holding column kb(it) of row r writes it
+      // per-warp (K-slice) partial of item it -> s_part[it][warp]
 #pragma unroll
-      for (int s = 0; s < MAX_ST; ++s) {
-        if (s < nst) {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int r = (c.lane >> 2) + half * 8;
-            const int it = s * STAGE_ITEMS + r;
-            const int kb = (xr_mod == 3) ? (int)((kb3_pack >> (2 * (s * 2 + half))) & 3u) : (xr_mod == 2 ? (r & 1) : 0);
-            if (r < STAGE_ITEMS && it < d.n_items && (kb >> 1) == (c.lane & 3))
-              c.s_part[it * NCW + c.warp] = (kb & 1) ? acc[s][half * 2 + 1] : acc[s][half * 2];
-          }
-        }
+      for (int sh = 0; sh < 2 * MAX_ST; ++sh) {
+        if ((pw_mask >> sh) & 1u)
+          pw_base[((sh >> 1) * STAGE_ITEMS + (sh & 1) * 8) * NCW] =
+              ((pw_sel >> sh) & 1u) ? acc[sh >> 1][(sh & 1) * 2 + 1] : acc[sh >> 1][(sh & 1) * 2];
       }
       consumer_bar();
       trace_sub<TR>(c, 6);
+      if (c.warp == NCW - 1) prod_issue(c, rows, prod, nst);   // refill the slots this phase has just released
 
       // finalize + publish: thread t sums the NCW K-slice partials of item t; the items of one output row sit in
       // neighbouring lanes (an output row never straddles a warp: 2 | 32, and 3 * rows <= 30)
@@ -1101,7 +1118,6 @@ __device__ __forceinline__ void decode_kernel_body(const Params& p) {
   c.s_part = reinterpret_cast<float*>(smem + SM_PART);
   c.s_red = reinterpret_cast<float*>(smem + SM_RED);
   c.full = reinterpret_cast<u64*>(smem + SM_BAR);
-  c.empty = c.full + 8;
   c.s_abort = reinterpret_cast<volatile int*>(smem + SM_MISC);
   c.s_delay = reinterpret_cast<int*>(smem + SM_MISC + 16);
   c.x32 = reinterpret_cast<uint32_t*>(p.xbuf);
@@ -1117,7 +1133,6 @@ __device__ __forceinline__ void decode_kernel_body(const Params& p) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOTS; ++i) {
       mbar_init(&c.full[i], 1);
-      mbar_init(&c.empty[i], NCW);
     }
     *c.s_abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1125,11 +1140,7 @@ __device__ __forceinline__ void decode_kernel_body(const Params& p) {
   if (threadIdx.x < 3 * DL_N) c.s_delay[threadIdx.x] = p.delays[blockIdx.x * 3 * DL_N + threadIdx.x];
   __syncthreads();
 
-  if (c.warp == NCW) {
-    if (c.lane == 0) producer_loop(c);
-  } else {
-    consumer_loop<TR>(c);
-  }
+  consumer_loop<TR>(c);
   __syncthreads();
   c.cur_idx = p.phase_end;
   trace_sub<TR>(c, 0);
@@ -1158,7 +1169,18 @@ struct LayerPtrs {  // = upstream LDGLayerWeights (kernel.cu:78-90)
 };
 enum { W_IN = 0, W_Q, W_K, W_V, W_QN, W_KN, W_O, W_POST, W_GATE, W_UP, W_DOWN };
 
-// grid = (G, L), block = 128 threads: thread t copies uint4 t of each 2 KB segment.
+// Packed order of one 2 KB row segment (1024 k): the segment is 8 K-slices of 128 (one per consumer warp); inside a
+// slice, 16-byte chunk m (= tensor-core step j = m / 2, k-half b = m % 2) holds, for q = 0..3, the two elements
+// k = 32 q + 2 m + {0, 1} of the slice.  With this order the B fragment of lane q is the CONTIGUOUS run
+// x[32 q .. 32 q + 32) of the activation slice (4 x LDS.128 instead of 16 x LDS.32).  Chunk t of stage row r is
+// stored at chunk t ^ (r & 7) (conflict-free ldmatrix of the 16 x 16 tiles).
+__device__ __forceinline__ uint4 pack_chunk(const uint32_t* row_words, int t) {
+  const int w = t >> 4, m = t & 15;
+  const uint32_t* s = row_words + w * 64 + m;
+  return make_uint4(s[0], s[16], s[32], s[48]);
+}
+
+// grid = (G, L), block = 128 threads: thread t builds 16-byte chunk t of each 2 KB segment.
 __global__ void qmk_pack_layers_kernel(const LayerPtrs* layers, Layout y, uint8_t* packed, uint8_t* aux_layers) {
   const int cta = blockIdx.x, l = blockIdx.y, t = threadIdx.x;
   const LayerPtrs lp = layers[l];
@@ -1168,35 +1190,34 @@ __global__ void qmk_pack_layers_kernel(const LayerPtrs* layers, Layout y, uint8_
   const int o0 = row_begin(cta, H, y.G), no = row_begin(cta + 1, H, y.G) - o0;
   const int g0 = row_begin(cta, INTER, y.G), ng = row_begin(cta + 1, INTER, y.G) - g0;
   for (int seg = 0; seg < y.layer_segs; ++seg) {
-    uint4 v = zero;
+    const uint32_t* src = nullptr;   // first 32-bit word of the 1024-element source segment
     int s_in_phase;
     if (seg < y.off_o) {
       const int s = seg;
       s_in_phase = s;
       if (s < nq) {
         const int row = q0 + s;
-        if (row < QSZ) v = lp.w[W_Q][(size_t)row * 128 + t];
-        else if (row < QSZ + KVSZ) v = lp.w[W_K][(size_t)(row - QSZ) * 128 + t];
-        else v = lp.w[W_V][(size_t)(row - QSZ - KVSZ) * 128 + t];
+        if (row < QSZ) src = reinterpret_cast<const uint32_t*>(lp.w[W_Q]) + (size_t)row * 512;
+        else if (row < QSZ + KVSZ) src = reinterpret_cast<const uint32_t*>(lp.w[W_K]) + (size_t)(row - QSZ) * 512;
+        else src = reinterpret_cast<const uint32_t*>(lp.w[W_V]) + (size_t)(row - QSZ - KVSZ) * 512;
       }
     } else if (seg < y.off_gu) {
       const int s = seg - y.off_o;
       s_in_phase = s;
-      if (s < 2 * no) v = lp.w[W_O][((size_t)(o0 + s / 2) * 2 + (s % 2)) * 128 + t];
+      if (s < 2 * no) src = reinterpret_cast<const uint32_t*>(lp.w[W_O]) + ((size_t)(o0 + s / 2) * 2 + (s % 2)) * 512;
     } else if (seg < y.off_down) {
       const int s = seg - y.off_gu;
       s_in_phase = s;
       if (s < 2 * ng) {
         const int row = g0 + s / 2;
-        v = (s % 2 == 0) ? lp.w[W_GATE][(size_t)row * 128 + t] : lp.w[W_UP][(size_t)row * 128 + t];
+        src = reinterpret_cast<const uint32_t*>((s % 2 == 0) ? lp.w[W_GATE] : lp.w[W_UP]) + (size_t)row * 512;
       }
     } else {
       const int s = seg - y.off_down;
       s_in_phase = s;
-      if (s < 3 * no) v = lp.w[W_DOWN][((size_t)(o0 + s / 3) * 3 + (s % 3)) * 128 + t];
+      if (s < 3 * no) src = reinterpret_cast<const uint32_t*>(lp.w[W_DOWN]) + ((size_t)(o0 + s / 3) * 3 + (s % 3)) * 512;
     }
-    // 16-byte chunk t of stage row r is stored at chunk t ^ (r & 7) (conflict-free ldmatrix of the 16 x 16 tiles)
-    dst[(size_t)seg * 128 + (t ^ ((s_in_phase % STAGE_ITEMS) & 7))] = v;
+    dst[(size_t)seg * 128 + (t ^ ((s_in_phase % STAGE_ITEMS) & 7))] = src ? pack_chunk(src, t) : zero;
   }
   if (cta == 0) {  // shared aux blocks: [input_ln | q_norm | k_norm] and [post_ln | 0]
     uint4* a0 = reinterpret_cast<uint4*>(aux_layers + ((size_t)l * 2 + 0) * AUX_BYTES);
@@ -1219,7 +1240,7 @@ __global__ void qmk_pack_head_kernel(const uint4* head_w, int rows, int G, int s
   const int r0 = row_begin(cta, rows, G), n = row_begin(cta + 1, rows, G) - r0;
   for (int seg = 0; seg < segs_max; ++seg) {
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (seg < n) v = head_w[(size_t)(r0 + seg) * 128 + t];
+    if (seg < n) v = pack_chunk(reinterpret_cast<const uint32_t*>(head_w) + (size_t)(r0 + seg) * 512, t);
     dst[(size_t)seg * 128 + (t ^ ((seg % STAGE_ITEMS) & 7))] = v;
   }
 }
