@@ -26,6 +26,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define QMK_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#define QMK_LIKELY(x) __builtin_expect(!!(x), 1)
+
 namespace qmk {
 
 typedef unsigned long long u64;
@@ -110,6 +113,7 @@ struct Params {
   float* res_spill;                // f32[1024]: fp32 residual of every row (read back only by staged launches)
   int* delays;                     // [G][3][DL_N]: poll delays (cycles after own publish; in), repeated-poll counts and
                                    // cycles/16 spent waiting for weights per exchange kind (in/out)
+  int warm_mma;                    // issue a dummy mma while waiting for activations (tensor-pipe wake-up experiment)
   int delay_o_idle;                // O-phase delay of CTAs without an attention item (they wait for the attention CTAs)
   uint32_t epoch_base;             // epochs base+1 .. base+n_steps*(L+2) are used by this launch (16-bit, never 0)
   int* status;                     // int[4]: code, cta, phase index, aux
@@ -250,7 +254,8 @@ constexpr int SM_SMALL = SM_ACC + NCW * 2 * HD * 4;              // float[1024] 
 constexpr int SM_PART = SM_SMALL + 1024 * 4;              // float[56][NCW] per-item, per-warp (K slice) partial dot products
 constexpr int SM_RED = SM_PART + MAX_ITEMS * NCW * 4;     // float[64]    cross-warp reductions
 constexpr int SM_BAR = SM_RED + 64 * 4;                   // u64 full[NSLOTS]
-constexpr int SM_MISC = SM_BAR + 2 * 8 * 8;               // int abort; int delays[DL_N]; ...
+constexpr int SM_TBL = SM_BAR + 2 * 8 * 8;                // uint4[16]: per-layer stage table of the weight stream
+constexpr int SM_MISC = SM_TBL + 16 * 16;                 // int abort; int delays[DL_N]; ...
 constexpr int SMEM_BYTES = SM_MISC + 256;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
@@ -268,6 +273,7 @@ struct Ctx {
   u64* full;
   volatile int* s_abort;
   int* s_delay;
+  uint4* s_tbl;   // [kind 0..4]: {first stage entry, #stages, #items, -}; [5 + j]: {src offset, item bytes, aux offset + 1, -}
   uint32_t* x32;
   int tid, warp, lane, cta;
   uint32_t k;     // stage counter (same sequence in producer and consumers)
@@ -301,14 +307,18 @@ __device__ __forceinline__ bool check_abort(Ctx& c, int code, int aux) {
   return check_abort_slow(c.p.status, c.s_abort, c.t0, c.p.timeout_cycles, c.cta, c.cur_idx, code, aux);
 }
 
-__device__ __forceinline__ void wait_full(Ctx& c, uint32_t k) {
-  u64* bar = &c.full[k % NSLOTS];
-  uint32_t parity = (k / NSLOTS) & 1u;
-  if (mbar_try_wait(bar, parity)) return;
+__device__ __noinline__ void wait_full_slow(int* status, volatile int* s_abort, long long t0, long long timeout, int cta,
+                                           int cur_idx, u64* bar, uint32_t parity, int k) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 63u) == 0 && check_abort(c, ST_TIMEOUT_FULL, (int)k)) return;
+    if ((++spins & 63u) == 0 && check_abort_slow(status, s_abort, t0, timeout, cta, cur_idx, ST_TIMEOUT_FULL, k)) return;
   }
+}
+__device__ __forceinline__ void wait_full(Ctx& c, uint32_t k) {
+  u64* bar = &c.full[k % NSLOTS];
+  const uint32_t parity = (k / NSLOTS) & 1u;
+  if (QMK_LIKELY(mbar_try_wait(bar, parity))) return;
+  wait_full_slow(c.p.status, c.s_abort, c.t0, c.p.timeout_cycles, c.cta, c.cur_idx, bar, parity, (int)k);
 }
 __device__ __noinline__ uint4 ll4_wait_slow(int* status, volatile int* s_abort, long long t0, long long timeout, int cta,
                                             int cur_idx, const uint32_t* p, uint32_t epoch, int aux) {
@@ -415,53 +425,101 @@ __device__ __forceinline__ int n_stages_of(const PhaseDesc& d) {
 // so the stage that is NSLOTS ahead is always issued as soon as its slot is free, without empty-barriers and
 // without a ninth warp (which would cap the kernel at 168 registers per thread).
 struct Prod {
-  int step, idx, s;   // next stage to issue: stage s of phase idx of step `step`
+  const uint8_t* layer_base;  // this CTA's packed block of layer `l`
+  const uint8_t* aux_base;    // aux blocks of layer `l`
+  int step, l, j;     // next stage to issue: entry j of the layer table (l == L: stage j of the head phase)
+  int j_end;          // entries per layer for this launch (staged launches cover a sub-range of one layer)
   uint32_t k;         // its global stage number (slot = k % NSLOTS)
-  bool done;
+  int pending;        // stages whose slots have been released but not refilled yet
+  int left;           // stages still to issue in this launch
 };
-__device__ __forceinline__ void prod_init(const Params& p, Prod& pr) {
-  pr.step = 0; pr.idx = p.phase_begin; pr.s = 0; pr.k = 0; pr.done = false;
+// Stage table of one layer (identical for every layer of this CTA), built once per launch by thread 0.
+//   s_tbl[kind 0..4] = {first entry, #stages, #items, -};  s_tbl[5 + j] = {src offset, item bytes, aux offset + 1, -}
+__device__ __forceinline__ void prod_build_table(Ctx& c, const CtaRows& rows) {
+  if (c.tid == 0) {
+    const Layout& y = c.p.lay;
+    const int n_items[5] = {rows.q_rows, 0, 2 * rows.o_rows, 2 * rows.gu_rows, 3 * rows.o_rows};
+    const int off_seg[5] = {0, 0, y.off_o, y.off_gu, y.off_down};
+    int e = 5;
+    for (int kind = 0; kind < 5; ++kind) {
+      const int nst = (n_items[kind] + STAGE_ITEMS - 1) / STAGE_ITEMS;
+      c.s_tbl[kind] = make_uint4((uint32_t)e, (uint32_t)nst, (uint32_t)n_items[kind], 0u);
+      for (int s = 0; s < nst; ++s, ++e) {
+        int items = n_items[kind] - s * STAGE_ITEMS;
+        if (items > STAGE_ITEMS) items = STAGE_ITEMS;
+        const uint32_t aux = (s == 0 && (kind == PH_QKV || kind == PH_GU)) ? (uint32_t)((kind == PH_GU) ? AUX_BYTES : 0) + 1u : 0u;
+        c.s_tbl[e] = make_uint4((uint32_t)((off_seg[kind] + s * STAGE_ITEMS) * SEG_BYTES), (uint32_t)(items * SEG_BYTES), aux, 0u);
+      }
+    }
+  }
+}
+__device__ __forceinline__ int head_stages(const Params& p, const HeadDesc& h, int cta) {
+  return h.rows > 0 ? (row_begin(cta + 1, h.rows, p.lay.G) - row_begin(cta, h.rows, p.lay.G) + STAGE_ITEMS - 1) / STAGE_ITEMS : 1;
+}
+// Call after prod_build_table + barrier.
+__device__ __forceinline__ void prod_init(Ctx& c, Prod& pr) {
+  const Params& p = c.p;
+  const int L = p.lay.L, nlayer_idx = L * PH_PER_LAYER;
+  const int per_layer = (int)(c.s_tbl[PH_DOWN].x + c.s_tbl[PH_DOWN].y) - 5;
+  pr.step = 0; pr.k = 0; pr.pending = 0;
+  if (p.n_steps > 1 || (p.phase_begin == 0 && p.phase_end == nlayer_idx + 2)) {   // whole steps
+    pr.l = 0; pr.j = 0; pr.j_end = per_layer;
+    pr.left = 0;
+    for (int st = 0; st < p.n_steps; ++st) pr.left += L * per_layer + head_stages(p, p.steps[st].head, c.cta);
+  } else {   // staged launch: exactly one phase
+    const int idx = p.phase_begin;
+    if (idx < nlayer_idx) {
+      const uint4 t = c.s_tbl[idx % PH_PER_LAYER];
+      pr.l = idx / PH_PER_LAYER; pr.j = (int)t.x - 5; pr.j_end = pr.j + (int)t.y; pr.left = (int)t.y;
+    } else {
+      pr.l = L; pr.j = 0; pr.j_end = 0;
+      pr.left = (idx == nlayer_idx) ? head_stages(p, p.steps[0].head, c.cta) : 0;
+    }
+  }
+  pr.layer_base = p.packed_layers + ((size_t)((size_t)c.cta * L + pr.l) * p.lay.layer_segs) * SEG_BYTES;
+  pr.aux_base = p.aux_layers + (size_t)pr.l * 2 * AUX_BYTES;
+}
+__device__ __forceinline__ void prod_tma(Ctx& c, uint32_t k, const uint8_t* src, uint32_t item_bytes, const uint8_t* aux) {
+  // No proxy fence: every generic-proxy read of the slot (ldmatrix / aux loads) has completed before the barrier
+  // that precedes the refill, exactly like the consumer-release of a TMA pipeline stage.
+  const int slot = k % NSLOTS;
+  uint8_t* dst = c.ring + (size_t)slot * SLOT_BYTES;
+  mbar_arrive_expect_tx(&c.full[slot], item_bytes + (aux ? AUX_BYTES : 0));
+  if (aux) tma_bulk_g2s(dst, aux, AUX_BYTES, &c.full[slot]);
+  if (item_bytes) tma_bulk_g2s(dst + AUX_BYTES, src, item_bytes, &c.full[slot]);
 }
 // Issue the next `n` stages of the weight stream (lane 0 of the calling warp; all lanes keep the cursor).
-__device__ void prod_issue(Ctx& c, const CtaRows& rows, Prod& pr, int n) {
+__device__ __forceinline__ void prod_issue(Ctx& c, Prod& pr, int n) {
   const Params& p = c.p;
-  const int nlayer_idx = p.lay.L * PH_PER_LAYER;
-  const int end = (p.n_steps == 1) ? p.phase_end : nlayer_idx + 2;
-  while (n > 0 && !pr.done) {
-    PhaseDesc d;
-    d.n_items = 0; d.aux = nullptr; d.src = nullptr;
-    if (pr.idx < nlayer_idx) {
-      const int ph = pr.idx % PH_PER_LAYER;
-      if (ph != PH_ATTN) d = layer_phase_desc(p, rows, pr.idx / PH_PER_LAYER, ph, c.cta);
-    } else if (pr.idx == nlayer_idx) {
-      d = head_phase_desc(p, p.steps[pr.step].head, c.cta);
-    }
-    const int nst = n_stages_of(d);
-    if (pr.s >= nst) {   // next phase
-      pr.s = 0;
-      if (++pr.idx >= end) {
-        pr.idx = 0;
-        if (++pr.step >= p.n_steps) pr.done = true;
+  if (n > pr.left) n = pr.left;
+  pr.left -= n;
+  for (; n > 0; --n, ++pr.k) {
+    if (QMK_LIKELY(pr.l < p.lay.L)) {
+      if (c.lane == 0) {
+        const uint4 e = c.s_tbl[5 + pr.j];
+        prod_tma(c, pr.k, pr.layer_base + e.x, e.y, e.z ? pr.aux_base + (e.z - 1u) : nullptr);
       }
-      continue;
-    }
-    if (c.lane == 0) {
-      const int slot = pr.k % NSLOTS;
-      int items = d.n_items - pr.s * STAGE_ITEMS;
+      if (++pr.j == pr.j_end) {
+        pr.j = 0;
+        ++pr.l;
+        pr.layer_base += (size_t)p.lay.layer_segs * SEG_BYTES;
+        pr.aux_base += 2 * AUX_BYTES;
+      }
+    } else {   // head phase of step pr.step
+      const PhaseDesc d = head_phase_desc(p, p.steps[pr.step].head, c.cta);
+      int items = d.n_items - pr.j * STAGE_ITEMS;
       if (items > STAGE_ITEMS) items = STAGE_ITEMS;
-      const bool aux = (pr.s == 0 && d.aux != nullptr);
-      const uint32_t bytes = (uint32_t)items * SEG_BYTES + (aux ? AUX_BYTES : 0);
-      uint8_t* dst = c.ring + (size_t)slot * SLOT_BYTES;
-      // the consumers read this slot through the generic proxy; order those reads before the async-proxy write
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive_expect_tx(&c.full[slot], bytes);
-      if (aux) tma_bulk_g2s(dst, d.aux, AUX_BYTES, &c.full[slot]);
-      if (items > 0)
-        tma_bulk_g2s(dst + AUX_BYTES, d.src + (size_t)pr.s * STAGE_ITEMS * SEG_BYTES, (uint32_t)items * SEG_BYTES, &c.full[slot]);
+      if (items < 0) items = 0;
+      if (c.lane == 0)
+        prod_tma(c, pr.k, d.src + (size_t)pr.j * STAGE_ITEMS * SEG_BYTES, (uint32_t)items * SEG_BYTES, pr.j == 0 ? d.aux : nullptr);
+      if (++pr.j >= n_stages_of(d)) {   // next step starts again at layer 0
+        pr.j = 0;
+        pr.l = 0;
+        ++pr.step;
+        pr.layer_base = p.packed_layers + ((size_t)((size_t)c.cta * p.lay.L) * p.lay.layer_segs) * SEG_BYTES;
+        pr.aux_base = p.aux_layers;
+      }
     }
-    ++pr.s;
-    ++pr.k;
-    --n;
   }
 }
 
@@ -507,7 +565,7 @@ __device__ __forceinline__ void gather_bar(Ctx& c, int dslot, bool retried) {
 }
 // barrier-free variant for gathers whose consumers are the gathering warp itself
 __device__ __forceinline__ void gather_note(Ctx& c, int dslot, bool retried) {
-  if (__any_sync(0xffffffffu, retried) && c.lane == 0) atomicAdd(&c.s_delay[DL_N + dslot], 1);
+  if (QMK_UNLIKELY(__any_sync(0xffffffffu, retried)) && c.lane == 0) atomicAdd(&c.s_delay[DL_N + dslot], 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -743,7 +801,7 @@ __device__ void phase_attn(Ctx& c, int l, int position, uint32_t epoch, const At
     }
     const float Mh = h ? M1 : M0;
     const int hq = 2 * it.g + h;
-    if (it.S == 1) {
+    if (QMK_LIKELY(it.S == 1)) {
       ll4_st(x_a + hq * HD + d, bf16_round(A / Lsum), epoch);
     } else {
       u64* part = x_part + ((size_t)hq * S_MAX + it.s) * PART_STRIDE;
@@ -808,8 +866,10 @@ __device__ void consumer_loop(Ctx& c) {
   uint32_t* const x_logits = c.x32 + XW_LOGITS;
   const CtaRows rows = cta_rows(y, c.cta);
   Prod prod;
-  prod_init(p, prod);
-  if (c.warp == NCW - 1) prod_issue(c, rows, prod, NSLOTS);   // fill the ring
+  prod_build_table(c, rows);
+  consumer_bar();
+  prod_init(c, prod);
+  if (c.warp == NCW - 1) prod_issue(c, prod, NSLOTS);   // fill the ring
   KvRegs kv;
   AttnPre pre = {{0.f, 0.f, 0.f, 0.f}};
   float res_mine = 0.f;  // fp32 residual of row o_row0 + tid (tid < o_rows)
@@ -855,7 +915,7 @@ __device__ void consumer_loop(Ctx& c) {
 
       if (kind == K_ATTN) {
         if (has_item) {
-          if (pre_layer != l) {  // staged launch: the QKV phase ran in an earlier launch
+          if (QMK_UNLIKELY(pre_layer != l)) {  // staged launch: the QKV phase ran in an earlier launch
             attn_prefetch(c, l, position, item, 0, kv);
             if (c.warp < 3) {
               const uint2 wv = *reinterpret_cast<const uint2*>(p.aux_layers + ((size_t)l * 2) * AUX_BYTES + 2048 +
@@ -867,7 +927,7 @@ __device__ void consumer_loop(Ctx& c) {
         }
         continue;
       }
-      if (kind == K_ARGMAX) {
+      if (QMK_UNLIKELY(kind == K_ARGMAX)) {
         // argmax over the bf16 logits, lowest index wins ties (CTA 0)
         if (c.cta != 0 || sd.head.rows <= 0) continue;
         const uint32_t epoch_head = (ebase + (uint32_t)y.L + 1u) & 0xffffu;
@@ -960,6 +1020,15 @@ __device__ void consumer_loop(Ctx& c) {
       uint2 wv = make_uint2(0, 0);
       if (norm && (ready & 1u)) wv = *reinterpret_cast<const uint2*>(aux + c.tid * 8);
       if (kind == K_QKV && has_item) attn_prefetch(c, l, position, item, 0, kv);  // older KV rows do not depend on this layer
+      if (c.warp == NCW - 1 && prod.pending > 0) {   // refill the ring slots released by the previous phase(s)
+        prod_issue(c, prod, prod.pending);
+        prod.pending = 0;
+      }
+      if (QMK_UNLIKELY(p.warm_mma)) {   // keep the tensor pipe awake while the activations are in flight
+        float wd[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t wa[4] = {0u, 0u, 0u, 0u}, wb[2] = {0u, 0u};
+        mma16816(wd, wa, wb);
+      }
       const uint4* xs = reinterpret_cast<const uint4*>(c.s_vec + ((c.lane >> 2) < xr_mod ? (c.lane >> 2) : 0) * SEG_BYTES +
                                                        c.warp * 256 + (c.lane & 3) * 64);
       uint32_t* const my_x = reinterpret_cast<uint32_t*>(c.s_vec + gi0 * 2);
@@ -978,9 +1047,9 @@ __device__ void consumer_loop(Ctx& c) {
       // -- data --
       bool retried = false;
       if (!from_input) {
-        if (!ll4_ok(gw[0], ep)) { retried = true; gw[0] = ll4_wait_slow(p.status, c.s_abort, c.t0, p.timeout_cycles, c.cta, idx, xw + gi0, ep, gi0); }
-        if (n_words > H && !ll4_ok(gw[1], ep)) { retried = true; gw[1] = ll4_wait_slow(p.status, c.s_abort, c.t0, p.timeout_cycles, c.cta, idx, xw + gi0 + H, ep, gi0); }
-        if (n_words > 2 * H && !ll4_ok(gw[2], ep)) { retried = true; gw[2] = ll4_wait_slow(p.status, c.s_abort, c.t0, p.timeout_cycles, c.cta, idx, xw + gi0 + 2 * H, ep, gi0); }
+        if (QMK_UNLIKELY(!ll4_ok(gw[0], ep))) { retried = true; gw[0] = ll4_wait_slow(p.status, c.s_abort, c.t0, p.timeout_cycles, c.cta, idx, xw + gi0, ep, gi0); }
+        if (QMK_UNLIKELY(n_words > H && !ll4_ok(gw[1], ep))) { retried = true; gw[1] = ll4_wait_slow(p.status, c.s_abort, c.t0, p.timeout_cycles, c.cta, idx, xw + gi0 + H, ep, gi0); }
+        if (QMK_UNLIKELY(n_words > 2 * H && !ll4_ok(gw[2], ep))) { retried = true; gw[2] = ll4_wait_slow(p.status, c.s_abort, c.t0, p.timeout_cycles, c.cta, idx, xw + gi0 + 2 * H, ep, gi0); }
       }
       trace_sub<TR>(c, 2);
       if (norm) {
@@ -991,7 +1060,7 @@ __device__ void consumer_loop(Ctx& c) {
         if (c.lane == 0) c.s_red[c.warp] = ss;
         if (from_input) consumer_bar(); else gather_bar(c, dslot, retried);
         trace_sub<TR>(c, 3);
-        if (!(ready & 1u)) {
+        if (QMK_UNLIKELY(!(ready & 1u))) {
           wait_full(c, c.k);
           ready |= 1u;
           wv = *reinterpret_cast<const uint2*>(aux + c.tid * 8);
@@ -1037,7 +1106,7 @@ __device__ void consumer_loop(Ctx& c) {
       for (int s = 0; s < MAX_ST; ++s) {
         acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.f;
         if (s < nst) {
-          if (!((ready >> s) & 1u)) wait_full(c, c.k + s);
+          if (QMK_UNLIKELY(!((ready >> s) & 1u))) wait_full(c, c.k + s);
           float acc2[4] = {0.f, 0.f, 0.f, 0.f};   // two accumulators halve the dependent HMMA chain
 #pragma unroll
           for (int jb = 0; jb < KSTEPS; jb += 4) {  // batches of 4 ldmatrix keep the live A fragments at 16 registers
@@ -1065,7 +1134,7 @@ __device__ void consumer_loop(Ctx& c) {
       }
       consumer_bar();
       trace_sub<TR>(c, 6);
-      if (c.warp == NCW - 1) prod_issue(c, rows, prod, nst);   // refill the slots this phase has just released
+      prod.pending += nst;   // slots released by this phase; refilled in the load shadow of the next phase
 
       // finalize + publish: thread t sums the NCW K-slice partials of item t; the items of one output row sit in
       // neighbouring lanes (an output row never straddles a warp: 2 | 32, and 3 * rows <= 30)
@@ -1120,6 +1189,7 @@ __device__ __forceinline__ void decode_kernel_body(const Params& p) {
   c.full = reinterpret_cast<u64*>(smem + SM_BAR);
   c.s_abort = reinterpret_cast<volatile int*>(smem + SM_MISC);
   c.s_delay = reinterpret_cast<int*>(smem + SM_MISC + 16);
+  c.s_tbl = reinterpret_cast<uint4*>(smem + SM_TBL);
   c.x32 = reinterpret_cast<uint32_t*>(p.xbuf);
   c.tid = threadIdx.x;
   c.warp = threadIdx.x >> 5;

@@ -64,6 +64,7 @@ struct qmk_engine {
   float* res_spill = nullptr;
   int* delays = nullptr;
   int delay_o_idle = 2500;
+  int warm_mma = 0;
   long long* trace_dev = nullptr;
   int trace_stride = 0;
   int* status_dev = nullptr;
@@ -136,6 +137,7 @@ extern "C" int qmk_engine_create(int device, int num_ctas, qmk_engine** out) {
   int delay0 = 450;
   if (const char* env = getenv("QMK_POLL_DELAY")) delay0 = atoi(env);
   if (const char* env = getenv("QMK_POLL_DELAY_O")) e->delay_o_idle = atoi(env);
+  if (const char* env = getenv("QMK_WARM_MMA")) e->warm_mma = atoi(env);
   std::vector<int> delays((size_t)G * 3 * DL_N, 0);
   for (int c = 0; c < G; ++c)
     for (int d = 0; d < DL_N; ++d) delays[(size_t)c * 3 * DL_N + d] = delay0;
@@ -341,6 +343,7 @@ extern "C" int qmk_decode_step(qmk_model* m, int head_index, int input_token_id,
   p.res_spill = e->res_spill;
   p.delays = e->delays;
   p.delay_o_idle = e->delay_o_idle;
+  p.warm_mma = e->warm_mma;
   p.status = e->status_dev;
   p.timeout_cycles = e->timeout_cycles;
   p.trace = e->trace_dev;
