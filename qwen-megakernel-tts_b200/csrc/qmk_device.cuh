@@ -86,14 +86,19 @@ struct HeadDesc {
   int segs_max;
 };
 
+enum InMode { IN_TABLE_TOKEN = 0, IN_VEC_BF16 = 1, IN_TABLE_PREV = 2, IN_VEC_F32 = 3 };
 struct StepDesc {
-  const __nv_bfloat16* in_table;  // in_mode 0: row `token` of this table
-  const void* in_vec;             // in_mode 1: bf16[1024]
+  const __nv_bfloat16* in_table;  // IN_TABLE_TOKEN: row `token`; IN_TABLE_PREV: row = token selected by the previous step
+  const void* in_vec;             // IN_VEC_BF16: bf16[1024]; IN_VEC_F32: f32[1024] (rounded to bf16 on load)
   int in_mode;
   int token;
   int position;
   HeadDesc head;
-  int* out_token;                 // int32[1] (head.rows > 0)
+  int select;                     // 0 = argmax, 1 = temperature / top-k / multinomial (Params::sample_*)
+  int group;                      // code-predictor group of this head (index into forced_tokens), or -1
+  int* out_token;                 // int32[1] (head.rows > 0) or null
+  long long* out_code;            // int64[1] or null
+  float* logits_out;              // f32[head.rows] or null
   float* out_norm;                // f32[1024] post-final-norm hidden (bf16-rounded values) or null
   __nv_bfloat16* hidden_out;      // bf16[1024] last-layer output or null
 };
@@ -121,9 +126,16 @@ struct Params {
   long long timeout_cycles;
   long long* trace;                // optional [G][trace_stride] clock64 stamps
   int trace_stride;
+  float sample_temperature;        // code-predictor sampling (upstream model_tts.py:756-762)
+  int sample_top_k;
+  unsigned long long sample_seed, sample_counter;
+  const int* forced_tokens;        // optional int32[15] (device): token fed to the next step instead of the selected one
+  long long* code0_out;            // optional: receives code0 (the talker's token, first entry of the frame's codes)
+  int code0;
   int n_steps;
   StepDesc steps[MAX_STEPS];
 };
+static_assert(sizeof(Params) <= 4000, "kernel parameter space");
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
@@ -886,12 +898,29 @@ __device__ void consumer_loop(Ctx& c) {
   for (int sh = 0; sh < 2 * MAX_ST; ++sh)
     kb3_pack |= (uint32_t)(((sh >> 1) * STAGE_ITEMS + (c.lane >> 2) + (sh & 1) * 8) % 3) << (2 * sh);
 
+  if (c.cta == 0 && c.tid == 0 && p.code0_out != nullptr) *p.code0_out = (long long)p.code0;
   for (int step = 0; step < p.n_steps; ++step) {
     const StepDesc& sd = p.steps[step];
     const uint32_t ebase = p.epoch_base + (uint32_t)step * (uint32_t)(y.L + 2);
     const int position = sd.position;
-    const __nv_bfloat16* x_in = (sd.in_mode == 0) ? sd.in_table + (size_t)sd.token * H
-                                                  : reinterpret_cast<const __nv_bfloat16*>(sd.in_vec);
+    int in_token = sd.token;
+    if (sd.in_mode == IN_TABLE_PREV) {
+      // the token chosen by CTA 0 at the end of the previous step (one LL8 word, epoch = that step's head epoch)
+      if (c.warp == 0) {
+        const long long t_ready = c.t_pub + c.s_delay[DL_TOKEN];
+        while (clock64() < t_ready) {
+        }
+        if (c.lane == 0) {
+          const u64* x_tok = reinterpret_cast<const u64*>(c.x32 + XW_TOKEN);
+          c.s_red[32] = __int_as_float((int)ll8_wait(c, x_tok + (step & 15), (ebase - 1u) & 0xffffu));
+        }
+      }
+      consumer_bar();
+      in_token = __float_as_int(c.s_red[32]);
+    }
+    const __nv_bfloat16* x_in = (sd.in_mode == IN_TABLE_TOKEN || sd.in_mode == IN_TABLE_PREV)
+                                    ? sd.in_table + (size_t)in_token * H
+                                    : reinterpret_cast<const __nv_bfloat16*>(sd.in_vec);
     AttnItem item;
     const bool has_item = attn_item(p, position, c.cta, item);
     const int head_row0 = sd.head.rows > 0 ? row_begin(c.cta, sd.head.rows, y.G) : 0;
@@ -928,16 +957,23 @@ __device__ void consumer_loop(Ctx& c) {
         continue;
       }
       if (QMK_UNLIKELY(kind == K_ARGMAX)) {
-        // argmax over the bf16 logits, lowest index wins ties (CTA 0)
+        // token selection on CTA 0: argmax over the bf16 logits (lowest index wins ties), or temperature / top-k /
+        // multinomial sampling (upstream model_tts.py:756-762: ties with the k-th value are kept)
         if (c.cta != 0 || sd.head.rows <= 0) continue;
+        const int hrows = sd.head.rows;
         const uint32_t epoch_head = (ebase + (uint32_t)y.L + 1u) & 0xffffu;
+        const bool sample = sd.select != 0 && hrows <= NCW * 2 * HD && (hrows % (NCT * 4)) == 0;
+        float* s_log = c.s_acc;   // up to 2048 logits
         float best = -INFINITY;
         int best_i = 0x7fffffff;
         bool retried = false;
         wait_window(c, c.s_delay[DL_ARGMAX]);
-        for (int i = c.tid * 4; i < sd.head.rows; i += NCT * 4) {   // indices ascend per thread
+        for (int i = c.tid * 4; i < hrows; i += NCT * 4) {   // indices ascend per thread
           const uint4 w = ll4_wait(c, x_logits + i, epoch_head, retried);
-          const float v4[4] = {ll4_val(w.x), ll4_val(w.y), ll4_val(w.z), ll4_val(w.w)};
+          const float4 v = make_float4(ll4_val(w.x), ll4_val(w.y), ll4_val(w.z), ll4_val(w.w));
+          if (sd.logits_out != nullptr) *reinterpret_cast<float4*>(sd.logits_out + i) = v;
+          if (sample) *reinterpret_cast<float4*>(s_log + i) = v;
+          const float v4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e)
             if (v4[e] > best) { best = v4[e]; best_i = i + e; }
@@ -953,15 +989,124 @@ __device__ void consumer_loop(Ctx& c) {
           c.s_red[c.warp * 2 + 1] = __int_as_float(best_i);
         }
         gather_bar(c, DL_ARGMAX, retried);
-        if (c.tid == 0) {
-          for (int w = 1; w < NCW; ++w) {
-            const float ov = c.s_red[w * 2];
-            const int oi = __float_as_int(c.s_red[w * 2 + 1]);
-            if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+#pragma unroll
+        for (int w = 0; w < NCW; ++w) {   // every thread: same result
+          const float ov = c.s_red[w * 2];
+          const int oi = __float_as_int(c.s_red[w * 2 + 1]);
+          if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+        }
+        int chosen = best_i;
+        if (sample) {
+          // (1) k-th largest logit by a two-pass radix select on the order-preserving 16-bit key of the bf16 value
+          unsigned* hist = reinterpret_cast<unsigned*>(c.s_part);   // 256 bins
+          unsigned* s_sel = reinterpret_cast<unsigned*>(c.s_red) + 40;  // [0] bin, [1] remaining rank, [2] chosen
+          const int per = hrows / NCT;                               // contiguous elements per thread (CDF in index order)
+          const int i0 = c.tid * per;
+          int k_rank = p.sample_top_k;
+          unsigned thr_key = 0;
+          if (k_rank > 0 && k_rank < hrows) {
+            unsigned prefix_hi = 0;
+            for (int pass = 0; pass < 2; ++pass) {
+              hist[c.tid] = 0;   // NCT == 256 bins
+              consumer_bar();
+              for (int e = 0; e < per; ++e) {
+                const unsigned bits = __float_as_uint(s_log[i0 + e]) >> 16;
+                const unsigned key = (bits & 0x8000u) ? (~bits & 0xffffu) : (bits | 0x8000u);
+                if (pass == 0) atomicAdd(&hist[key >> 8], 1u);
+                else if ((key >> 8) == prefix_hi) atomicAdd(&hist[key & 0xffu], 1u);
+              }
+              consumer_bar();
+              if (c.warp == 0) {   // lane l owns bins 255-8l .. 248-8l; suffix counts from the top
+                unsigned cnt[8], tot = 0;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { cnt[e] = hist[255 - 8 * c.lane - e]; tot += cnt[e]; }
+                unsigned incl = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                  const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                  if (c.lane >= o) incl += v;
+                }
+                const unsigned before = incl - tot;   // elements in higher bins
+                if (before < (unsigned)k_rank && incl >= (unsigned)k_rank) {
+                  unsigned run = before;
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    if (run < (unsigned)k_rank && run + cnt[e] >= (unsigned)k_rank) { s_sel[0] = 255 - 8 * c.lane - e; s_sel[1] = (unsigned)k_rank - run; }
+                    run += cnt[e];
+                  }
+                }
+              }
+              consumer_bar();
+              if (pass == 0) { prefix_hi = s_sel[0]; k_rank = (int)s_sel[1]; }
+              else thr_key = (prefix_hi << 8) | s_sel[0];
+              consumer_bar();
+            }
           }
+          // (2) softmax over the kept logits / temperature, inverse-CDF draw in index order
+          const float inv_t = 1.0f / p.sample_temperature;
+          const float zmax = best * inv_t;
+          float pe[8];
+          float local = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            pe[e] = 0.f;
+            if (e < per) {
+              const float v = s_log[i0 + e];
+              const unsigned bits = __float_as_uint(v) >> 16;
+              const unsigned key = (bits & 0x8000u) ? (~bits & 0xffffu) : (bits | 0x8000u);
+              if (key >= thr_key) pe[e] = __expf(v * inv_t - zmax);
+              local += pe[e];
+            }
+          }
+          float incl = local;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (c.lane >= o) incl += v;
+          }
+          if (c.lane == 31) c.s_red[16 + c.warp] = incl;
+          if (c.tid == 0) s_sel[2] = (unsigned)best_i;   // fallback if rounding leaves the target beyond the last element
+          consumer_bar();
+          float wbase = 0.f, total = 0.f;
+#pragma unroll
+          for (int w = 0; w < NCW; ++w) {
+            const float t = c.s_red[16 + w];
+            if (w < c.warp) wbase += t;
+            total += t;
+          }
+          // counter-based uniform in [0, 1): splitmix64 of (seed, frame counter, group)
+          unsigned long long zr = p.sample_seed + 0x9E3779B97F4A7C15ull * (p.sample_counter * 16ull + (unsigned long long)(sd.group + 1));
+          zr = (zr ^ (zr >> 30)) * 0xBF58476D1CE4E5B9ull;
+          zr = (zr ^ (zr >> 27)) * 0x94D049BB133111EBull;
+          zr ^= zr >> 31;
+          const float target = (float)(zr >> 40) * (1.0f / 16777216.0f) * total;
+          const float lo = wbase + incl - local;
+          if (target >= lo && target < lo + local) {
+            float run = lo;
+            int pick = -1;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              if (e < per && pe[e] > 0.f) {
+                if (pick < 0 && target < run + pe[e]) pick = i0 + e;
+                run += pe[e];
+              }
+            }
+            if (pick >= 0) s_sel[2] = (unsigned)pick;
+          }
+          consumer_bar();
+          chosen = (int)s_sel[2];
+        }
+        if (c.tid == 0) {
           // a failed launch must not look like a token: encode the watchdog code as a negative id
           const int st = *((volatile int*)p.status);
-          *sd.out_token = (st != 0 || *c.s_abort) ? -1000 - st : best_i;
+          const int out = (st != 0 || *c.s_abort) ? -1000 - st : chosen;
+          if (sd.out_token != nullptr) *sd.out_token = out;
+          if (sd.out_code != nullptr) *sd.out_code = (long long)out;
+          if (step + 1 < p.n_steps) {   // hand the (possibly teacher-forced) token to every CTA's next step
+            int fed = chosen;
+            if (p.forced_tokens != nullptr && sd.group >= 0) fed = p.forced_tokens[sd.group];
+            ll8_st(reinterpret_cast<u64*>(c.x32 + XW_TOKEN) + ((step + 1) & 15), (uint32_t)fed, epoch_head);
+          }
         }
         consumer_bar();
         continue;
@@ -989,12 +1134,17 @@ __device__ void consumer_loop(Ctx& c) {
       uint4 gw[3];
       const int gi0 = c.tid * 4;
       if (from_input) {
-        const uint2 v = *reinterpret_cast<const uint2*>(x_in + gi0);
-        gw[0] = make_uint4(v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16);
-        if (c.tid < rows.o_rows) {
-          res_mine = __bfloat162float(x_in[rows.o_row0 + c.tid]);
-          p.res_spill[rows.o_row0 + c.tid] = res_mine;
+        if (sd.in_mode == IN_VEC_F32) {
+          const float* xf = reinterpret_cast<const float*>(sd.in_vec);
+          const float4 v = *reinterpret_cast<const float4*>(xf + gi0);
+          gw[0] = make_uint4(bf16_bits(v.x), bf16_bits(v.y), bf16_bits(v.z), bf16_bits(v.w));
+          if (c.tid < rows.o_rows) res_mine = bf16_round(xf[rows.o_row0 + c.tid]);
+        } else {
+          const uint2 v = *reinterpret_cast<const uint2*>(x_in + gi0);
+          gw[0] = make_uint4(v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16);
+          if (c.tid < rows.o_rows) res_mine = __bfloat162float(x_in[rows.o_row0 + c.tid]);
         }
+        if (c.tid < rows.o_rows) p.res_spill[rows.o_row0 + c.tid] = res_mine;
       } else {
         wait_window(c, (kind == K_O && !has_item) ? p.delay_o_idle : c.s_delay[dslot]);
         trace_sub<TR>(c, 1);

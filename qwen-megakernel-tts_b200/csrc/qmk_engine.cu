@@ -135,12 +135,14 @@ extern "C" int qmk_engine_create(int device, int num_ctas, qmk_engine** out) {
   e->G = G;
   if (const char* env = getenv("QMK_TIMEOUT_CYCLES")) e->timeout_cycles = atoll(env);
   int delay0 = 450;
+  int delay_token = 2500;   // the next step's token arrives two exchanges after a CTA has published its logits
   if (const char* env = getenv("QMK_POLL_DELAY")) delay0 = atoi(env);
+  if (const char* env = getenv("QMK_POLL_DELAY_TOKEN")) delay_token = atoi(env);
   if (const char* env = getenv("QMK_POLL_DELAY_O")) e->delay_o_idle = atoi(env);
   if (const char* env = getenv("QMK_WARM_MMA")) e->warm_mma = atoi(env);
   std::vector<int> delays((size_t)G * 3 * DL_N, 0);
   for (int c = 0; c < G; ++c)
-    for (int d = 0; d < DL_N; ++d) delays[(size_t)c * 3 * DL_N + d] = delay0;
+    for (int d = 0; d < DL_N; ++d) delays[(size_t)c * 3 * DL_N + d] = (d == DL_TOKEN) ? delay_token : delay0;
   cudaError_t err = cudaMalloc(&e->xbuf, XBUF_BYTES);
   if (err == cudaSuccess) err = cudaMemset(e->xbuf, 0, XBUF_BYTES);
   if (err == cudaSuccess) err = cudaMalloc(&e->res_spill, H * sizeof(float));
@@ -310,24 +312,10 @@ static int launch_slice(qmk_engine* e, Params& p, int begin, int end, cudaStream
   return QMK_OK;
 }
 
-extern "C" int qmk_decode_step(qmk_model* m, int head_index, int input_token_id, const void* embed_weight,
-                               const void* cos_table, const void* sin_table, void* k_cache, void* v_cache,
-                               void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
-                               int max_seq_len, float attn_scale, int mode, void* stream) {
-  if (!m) return set_error(QMK_ERR_ARG, "qmk_decode_step: model is null");
-  if (!cos_table || !sin_table || !k_cache || !v_cache || !hidden_buffer)
-    return set_error(QMK_ERR_ARG, "qmk_decode_step: null table / cache / hidden_buffer pointer");
-  if (max_seq_len < 1 || position < 0 || position >= max_seq_len)
-    return set_error(QMK_ERR_ARG, "qmk_decode_step: position %d outside [0, max_seq_len=%d)", position, max_seq_len);
-  if (input_token_id >= 0 && !embed_weight) return set_error(QMK_ERR_ARG, "qmk_decode_step: token given but embed_weight is null");
-  if (head_index >= (int)m->heads.size()) return set_error(QMK_ERR_ARG, "qmk_decode_step: head index %d not registered", head_index);
-  if (head_index >= 0 && !out_token) return set_error(QMK_ERR_ARG, "qmk_decode_step: out_token is null");
+// Fields shared by every launch of `m` on its engine.
+static void fill_common(Params& p, qmk_model* m, const void* cos_table, const void* sin_table, void* k_cache,
+                        void* v_cache, int max_seq_len, float attn_scale) {
   qmk_engine* e = m->e;
-  DeviceGuard guard(e->device);
-  cudaStream_t st = (cudaStream_t)stream;
-  std::lock_guard<std::mutex> lock(e->mu);
-
-  Params p;
   memset(&p, 0, sizeof(p));
   p.lay = m->lay;
   p.packed_layers = m->packed_layers;
@@ -348,13 +336,9 @@ extern "C" int qmk_decode_step(qmk_model* m, int head_index, int input_token_id,
   p.timeout_cycles = e->timeout_cycles;
   p.trace = e->trace_dev;
   p.trace_stride = e->trace_stride;
-  p.n_steps = 1;
-  StepDesc& sd = p.steps[0];
-  sd.in_table = reinterpret_cast<const __nv_bfloat16*>(embed_weight);
-  sd.in_vec = hidden_buffer;
-  sd.in_mode = input_token_id >= 0 ? 0 : 1;
-  sd.token = input_token_id >= 0 ? input_token_id : 0;
-  sd.position = position;
+  p.sample_temperature = 1.0f;
+}
+static void set_head(StepDesc& sd, qmk_model* m, int head_index) {
   sd.head.aux = m->norm_seg;
   if (head_index >= 0) {
     sd.head.packed = m->heads[head_index].packed;
@@ -365,30 +349,117 @@ extern "C" int qmk_decode_step(qmk_model* m, int head_index, int input_token_id,
     sd.head.rows = 0;
     sd.head.segs_max = 0;
   }
+}
+// 16-bit epochs: when the counter would wrap, clear the exchange words (stream-ordered) and restart at 0.
+static int reserve_epochs(qmk_engine* e, uint32_t need, cudaStream_t st, uint32_t* base) {
+  if (e->epoch + need >= 0xfff0u) {
+    QMK_CUDA(cudaMemsetAsync(e->xbuf, 0, XBUF_BYTES, st));
+    e->epoch = 0;
+  }
+  *base = e->epoch;
+  e->epoch += need;
+  return QMK_OK;
+}
+
+extern "C" int qmk_decode_step(qmk_model* m, int head_index, int input_token_id, const void* embed_weight,
+                               const void* cos_table, const void* sin_table, void* k_cache, void* v_cache,
+                               void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
+                               int max_seq_len, float attn_scale, int mode, void* stream) {
+  if (!m) return set_error(QMK_ERR_ARG, "qmk_decode_step: model is null");
+  if (!cos_table || !sin_table || !k_cache || !v_cache || !hidden_buffer)
+    return set_error(QMK_ERR_ARG, "qmk_decode_step: null table / cache / hidden_buffer pointer");
+  if (max_seq_len < 1 || position < 0 || position >= max_seq_len)
+    return set_error(QMK_ERR_ARG, "qmk_decode_step: position %d outside [0, max_seq_len=%d)", position, max_seq_len);
+  if (input_token_id >= 0 && !embed_weight) return set_error(QMK_ERR_ARG, "qmk_decode_step: token given but embed_weight is null");
+  if (head_index >= (int)m->heads.size()) return set_error(QMK_ERR_ARG, "qmk_decode_step: head index %d not registered", head_index);
+  if (head_index >= 0 && !out_token) return set_error(QMK_ERR_ARG, "qmk_decode_step: out_token is null");
+  qmk_engine* e = m->e;
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> lock(e->mu);
+
+  Params p;
+  fill_common(p, m, cos_table, sin_table, k_cache, v_cache, max_seq_len, attn_scale);
+  p.n_steps = 1;
+  StepDesc& sd = p.steps[0];
+  sd.in_table = reinterpret_cast<const __nv_bfloat16*>(embed_weight);
+  sd.in_vec = hidden_buffer;
+  sd.in_mode = input_token_id >= 0 ? IN_TABLE_TOKEN : IN_VEC_BF16;
+  sd.token = input_token_id >= 0 ? input_token_id : 0;
+  sd.position = position;
+  set_head(sd, m, head_index);
+  sd.group = -1;
   sd.out_token = out_token;
   sd.out_norm = normalized_out;
   sd.hidden_out = reinterpret_cast<__nv_bfloat16*>(hidden_buffer);
 
-  const uint32_t need = (uint32_t)m->lay.L + 2u;
-  if (e->epoch + need >= 0xfff0u) {  // 16-bit epochs: clear the exchange words (stream-ordered) and restart
-    QMK_CUDA(cudaMemsetAsync(e->xbuf, 0, XBUF_BYTES, st));
-    e->epoch = 0;
-  }
-  p.epoch_base = e->epoch;
-  e->epoch += need;
+  int rc = reserve_epochs(e, (uint32_t)m->lay.L + 2u, st, &p.epoch_base);
+  if (rc != QMK_OK) return rc;
 
   const int n_idx = m->lay.L * PH_PER_LAYER + 2;
   if (mode == 0) return launch_slice(e, p, 0, n_idx, st);
   for (int idx = 0; idx < n_idx; ++idx) {
-    int rc = launch_slice(e, p, idx, idx + 1, st);
+    rc = launch_slice(e, p, idx, idx + 1, st);
     if (rc != QMK_OK) return rc;
   }
   return QMK_OK;
 }
 
-extern "C" int qmk_cp_predict(qmk_model*, const float*, int, const void*, const void*, const void*, void*, void*, int,
-                              int, float, int, uint64_t, uint64_t, const int32_t*, int64_t*, float*, float*, void*) {
-  return set_error(QMK_ERR_UNSUPPORTED, "qmk_cp_predict: fused frame kernel not built in this revision");
+extern "C" int qmk_cp_predict(qmk_model* m, const float* talker_hidden, int first_codebook_token,
+                              const void* talker_embed_weight, const void* cos_table, const void* sin_table,
+                              void* k_cache, void* v_cache, int max_seq_len, int do_sample, float temperature,
+                              int top_k, uint64_t seed, uint64_t frame_counter, const int32_t* forced_tokens,
+                              int64_t* out_codes, float* logits_out, float* hidden_out, void* stream) {
+  if (!m || !talker_hidden || !talker_embed_weight || !cos_table || !sin_table || !k_cache || !v_cache || !out_codes)
+    return set_error(QMK_ERR_ARG, "qmk_cp_predict: null argument");
+  if (max_seq_len < QMK_CP_GROUPS + 1) return set_error(QMK_ERR_ARG, "qmk_cp_predict: max_seq_len %d < 16", max_seq_len);
+  if (first_codebook_token < 0) return set_error(QMK_ERR_ARG, "qmk_cp_predict: negative first token");
+  if ((int)m->heads.size() < QMK_CP_GROUPS) return set_error(QMK_ERR_ARG, "qmk_cp_predict: %d group heads registered, need 15", (int)m->heads.size());
+  for (int g = 0; g < QMK_CP_GROUPS - 1; ++g)
+    if (!m->group_embed[g]) return set_error(QMK_ERR_ARG, "qmk_cp_predict: group embedding %d not set", g);
+  const bool sample = do_sample && temperature > 0.f;
+  qmk_engine* e = m->e;
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> lock(e->mu);
+
+  Params p;
+  fill_common(p, m, cos_table, sin_table, k_cache, v_cache, max_seq_len, 0.08838834764831845f /* 1/sqrt(128) */);
+  p.n_steps = QMK_CP_GROUPS + 1;
+  p.sample_temperature = sample ? temperature : 1.0f;
+  p.sample_top_k = top_k;
+  p.sample_seed = seed;
+  p.sample_counter = frame_counter;
+  p.forced_tokens = forced_tokens;
+  p.code0_out = reinterpret_cast<long long*>(out_codes);
+  p.code0 = first_codebook_token;
+  for (int s = 0; s < p.n_steps; ++s) {
+    StepDesc& sd = p.steps[s];
+    sd.position = s;
+    sd.group = s - 1;
+    if (s == 0) {           // the talker's hidden state (upstream model_tts.py:745)
+      sd.in_mode = IN_VEC_F32;
+      sd.in_vec = talker_hidden;
+      set_head(sd, m, -1);
+    } else {
+      if (s == 1) {         // embedding of the talker's token (model_tts.py:746-748)
+        sd.in_mode = IN_TABLE_TOKEN;
+        sd.in_table = reinterpret_cast<const __nv_bfloat16*>(talker_embed_weight);
+        sd.token = first_codebook_token;
+      } else {              // embedding of the previous group's code (model_tts.py:768-770)
+        sd.in_mode = IN_TABLE_PREV;
+        sd.in_table = reinterpret_cast<const __nv_bfloat16*>(m->group_embed[s - 2]);
+      }
+      set_head(sd, m, s - 1);
+      sd.select = sample ? 1 : 0;
+      sd.out_code = reinterpret_cast<long long*>(out_codes) + s;
+      sd.logits_out = logits_out ? logits_out + (size_t)(s - 1) * m->heads[s - 1].rows : nullptr;
+      sd.out_norm = hidden_out ? hidden_out + (size_t)(s - 1) * H : nullptr;
+    }
+  }
+  int rc = reserve_epochs(e, (uint32_t)p.n_steps * ((uint32_t)m->lay.L + 2u), st, &p.epoch_base);
+  if (rc != QMK_OK) return rc;
+  return launch_slice(e, p, 0, m->lay.L * PH_PER_LAYER + 2, st);
 }
 
 // ---------------------------------------------------------------------------------------------------

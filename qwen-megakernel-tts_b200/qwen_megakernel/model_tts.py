@@ -389,6 +389,7 @@ class CodePredictorKernel:
             self._norm_out = torch.zeros(HIDDEN_SIZE, dtype=torch.float32, device=dev)
             self._out_token = torch.zeros(1, dtype=torch.int32, device=dev)
             self._token_buf = torch.zeros(1, dtype=torch.long, device=dev)
+        self._frame_counter = 0
 
     def __del__(self):
         try:
@@ -417,12 +418,59 @@ class CodePredictorKernel:
 
     @torch.no_grad()
     def predict(self, talker_hidden: torch.Tensor, first_codebook_token: int, talker_embed_weight: torch.Tensor,
-                do_sample: bool = True, temperature: float = 0.9, top_k: int = 50) -> torch.Tensor:
-        """All 16 codebook groups of one frame: int64[16] on device = [first_token, g0..g14]."""
-        F = torch.nn.functional
+                do_sample: bool = True, temperature: float = 0.9, top_k: int = 50, *,
+                forced_tokens: Optional[torch.Tensor] = None, return_debug: bool = False):
+        """All 16 codebook groups of one frame: int64[16] on device = [first_token, g0..g14].
+
+        ONE kernel launch (``qmk_cp_predict``): 16 five-layer steps, the 15 group heads, greedy or temperature /
+        top-k / multinomial selection and the embedding gather of the next step all stay on the device
+        (upstream runs 16 launches plus ~10 torch ops per group, model_tts.py:742-773).  Sampling draws come from a
+        counter-based generator keyed by ``torch.initial_seed()`` and a per-instance frame counter.
+
+        ``forced_tokens`` (int32[15], device): teacher forcing -- the token fed to step g+1 (the returned codes are
+        still the model's own choices).  ``return_debug``: also return (logits f32[15, 2048], hidden f32[15, 1024]).
+        """
+        from .build_tts import check
         first_codebook_token = int(first_codebook_token)
         if not 0 <= first_codebook_token < talker_embed_weight.shape[0]:
             raise ValueError(f"first_codebook_token {first_codebook_token} out of range")
+        if talker_embed_weight.dtype != torch.bfloat16 or talker_embed_weight.device != self.device or \
+                talker_embed_weight.shape[1] != HIDDEN_SIZE or not talker_embed_weight.is_contiguous():
+            raise ValueError("talker_embed_weight: need a contiguous bf16 [*, 1024] tensor on the predictor's device")
+        sample = bool(do_sample) and temperature > 0
+        with torch.cuda.device(self.device):
+            hid = talker_hidden.to(self.device, torch.float32).reshape(-1).contiguous()
+            if hid.numel() != HIDDEN_SIZE:
+                raise ValueError("talker_hidden must have 1024 elements")
+            out = torch.empty(NUM_CODE_GROUPS, dtype=torch.int64, device=self.device)
+            logits = hidden = None
+            if return_debug:
+                logits = torch.empty(self.num_groups, CODE_PREDICTOR_VOCAB, dtype=torch.float32, device=self.device)
+                hidden = torch.empty(self.num_groups, HIDDEN_SIZE, dtype=torch.float32, device=self.device)
+            forced_ptr = None
+            if forced_tokens is not None:
+                forced_tokens = forced_tokens.to(self.device, torch.int32).contiguous()
+                if forced_tokens.numel() != self.num_groups:
+                    raise ValueError("forced_tokens must have 15 elements")
+                forced_ptr = forced_tokens.data_ptr()
+            self._frame_counter += 1
+            check(self._lib, self._lib.qmk_cp_predict(
+                self._model, hid.data_ptr(), first_codebook_token, talker_embed_weight.data_ptr(),
+                self._cos_table.data_ptr(), self._sin_table.data_ptr(), self._k_cache.data_ptr(),
+                self._v_cache.data_ptr(), self._max_seq, int(sample), float(temperature), int(top_k),
+                torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, self._frame_counter, forced_ptr, out.data_ptr(),
+                logits.data_ptr() if logits is not None else None,
+                hidden.data_ptr() if hidden is not None else None, _stream_ptr(self.device)), "qmk_cp_predict")
+            self._position = NUM_CODE_GROUPS
+        return (out, logits, hidden) if return_debug else out
+
+    @torch.no_grad()
+    def predict_stepwise(self, talker_hidden: torch.Tensor, first_codebook_token: int,
+                         talker_embed_weight: torch.Tensor, do_sample: bool = True, temperature: float = 0.9,
+                         top_k: int = 50) -> torch.Tensor:
+        """The upstream control flow (model_tts.py:742-773), one launch per step with torch glue in between."""
+        F = torch.nn.functional
+        first_codebook_token = int(first_codebook_token)
         sample = bool(do_sample) and temperature > 0
         with torch.cuda.device(self.device):
             self.reset()

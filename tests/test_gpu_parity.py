@@ -151,6 +151,52 @@ def test_code_predictor_predict_greedy_free_running(cp_kernel, gpu_weights, gold
                 break
 
 
+def test_code_predictor_fused_frame_teacher_forced(cp_kernel, gpu_weights, golden):
+    """ONE launch per frame (qmk_cp_predict) with the reference's tokens forced back: per-group choice and hidden
+    state vs the upstream CodePredictor fixtures, and the returned logits must carry the returned choice."""
+    g = golden["cp_config2"]
+    for f in range(g["tokens"].shape[0]):
+        th = bf16_from_bits(g["talker_hidden_bits"][f]).float().cuda()
+        forced = torch.tensor(np.asarray(g["tokens"][f][:15]), dtype=torch.int32).cuda()
+        out, logits, hidden = cp_kernel.predict(th, int(g["first_tokens"][f]), gpu_weights["embed_weight"],
+                                                do_sample=False, forced_tokens=forced, return_debug=True)
+        toks = out[1:].cpu().tolist()
+        assert int(out[0]) == int(g["first_tokens"][f])
+        assert toks == logits.argmax(dim=-1).cpu().tolist()
+        hids = [hidden[i].cpu() for i in range(15)]
+        ref_h = [bf16_from_bits(b).float() for b in g["hidden_bits"][f]]
+        assert_parity(compare(f"fused-frame-vs-upstream cp frame {f}", toks, hids, g["tokens"][f], g["margins"][f], ref_h))
+
+
+def test_code_predictor_fused_equals_stepwise(cp_kernel, gpu_weights):
+    """The fused frame kernel and the one-launch-per-step path run the same device code: identical greedy frames."""
+    from qwen_megakernel.synthetic import synthetic_inputs
+    for seed in (11, 12, 13):
+        th = synthetic_inputs(seed, 1)[0].float().cuda()
+        a = cp_kernel.predict(th, 100 + seed, gpu_weights["embed_weight"], do_sample=False).cpu().tolist()
+        b = cp_kernel.predict_stepwise(th, 100 + seed, gpu_weights["embed_weight"], do_sample=False).cpu().tolist()
+        assert a == b
+
+
+def test_code_predictor_sampler_distribution(cp_kernel, gpu_weights):
+    """Device sampler vs the upstream rule (model_tts.py:756-762) for group 0: support inside the top-k set (ties
+    kept) and empirical frequencies close to softmax(topk(logits / T))."""
+    from qwen_megakernel.synthetic import synthetic_inputs
+    th = synthetic_inputs(78, 1)[0].float().cuda()
+    _, logits, _ = cp_kernel.predict(th, 9, gpu_weights["embed_weight"], do_sample=False, return_debug=True)
+    z = logits[0].float() / 0.9
+    kth = torch.topk(z, 8).values[-1]
+    probs = torch.softmax(z.masked_fill(z < kth, float("-inf")), dim=-1).cpu()
+    n = 600
+    counts = torch.zeros(2048)
+    for _ in range(n):
+        out = cp_kernel.predict(th, 9, gpu_weights["embed_weight"], do_sample=True, temperature=0.9, top_k=8)
+        counts[int(out[1])] += 1
+    assert float(counts[probs == 0].sum()) == 0, "sampled a token outside the top-k set"
+    tv = 0.5 * float((counts / n - probs).abs().sum())
+    assert tv < 0.12, f"total variation {tv:.3f} between the sampler and the upstream distribution"
+
+
 def test_code_predictor_sampling_respects_top_k(cp_kernel, gpu_weights):
     from qwen_megakernel.synthetic import synthetic_inputs
     torch.manual_seed(3)
