@@ -118,6 +118,17 @@ int qmk_decode_step(qmk_model* m, int head_index, int input_token_id, const void
                     void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
                     int max_seq_len, float attn_scale, int mode, void* stream);
 
+/* Same step with the frame loop's embedding sum fused in front of it (upstream tts_engine.py:319-335):
+ *   input = talker_embed[codes[0]] + sum_{g<15} group_embedding_tables[g][codes[g+1]] + extra_embed   (bf16 adds,
+ *   upstream order), codes = the int64[16] device tensor predict() returned, extra_embed = the trailing-text or
+ *   tts_pad embedding (bf16[1024], device).  group_embedding_tables is a HOST array of 15 device pointers.
+ * Replaces 32 torch launches per frame; hidden_buffer is only written (last-layer output). */
+int qmk_decode_step_codes(qmk_model* m, int head_index, const int64_t* codes, const void* talker_embed_weight,
+                          const void* const* group_embedding_tables, const void* extra_embed_bf16,
+                          const void* cos_table, const void* sin_table, void* k_cache, void* v_cache,
+                          void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
+                          int max_seq_len, float attn_scale, void* stream);
+
 /* ---- one code-predictor frame in ONE launch (replaces the 16-step loop of
  *      CodePredictorKernel.predict, model_tts.py:729-773) ------------------------------------------ */
 /* talker_hidden: f32[1024]; talker_embed_weight: bf16[3072,1024]; out_codes: int64[16] =

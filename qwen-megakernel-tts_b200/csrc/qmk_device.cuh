@@ -86,10 +86,11 @@ struct HeadDesc {
   int segs_max;
 };
 
-enum InMode { IN_TABLE_TOKEN = 0, IN_VEC_BF16 = 1, IN_TABLE_PREV = 2, IN_VEC_F32 = 3 };
+enum InMode { IN_TABLE_TOKEN = 0, IN_VEC_BF16 = 1, IN_TABLE_PREV = 2, IN_VEC_F32 = 3, IN_CODES_SUM = 4 };
 struct StepDesc {
   const __nv_bfloat16* in_table;  // IN_TABLE_TOKEN: row `token`; IN_TABLE_PREV: row = token selected by the previous step
   const void* in_vec;             // IN_VEC_BF16: bf16[1024]; IN_VEC_F32: f32[1024] (rounded to bf16 on load)
+  const long long* codes;         // IN_CODES_SUM: int64[16] (device) -> in_table[codes[0]] + sum_g sum_tables[g][codes[g+1]] + in_vec
   int in_mode;
   int token;
   int position;
@@ -130,6 +131,7 @@ struct Params {
   int sample_top_k;
   unsigned long long sample_seed, sample_counter;
   const int* forced_tokens;        // optional int32[15] (device): token fed to the next step instead of the selected one
+  const __nv_bfloat16* sum_tables[15];   // IN_CODES_SUM: the 15 code-predictor embedding tables [2048, 1024]
   long long* code0_out;            // optional: receives code0 (the talker's token, first entry of the frame's codes)
   int code0;
   int n_steps;
@@ -1134,7 +1136,22 @@ __device__ void consumer_loop(Ctx& c) {
       uint4 gw[3];
       const int gi0 = c.tid * 4;
       if (from_input) {
-        if (sd.in_mode == IN_VEC_F32) {
+        if (sd.in_mode == IN_CODES_SUM) {
+          // the frame loop's 16-way embedding sum + trailing-text embedding (upstream tts_engine.py:319-333), bf16 adds
+          // in the upstream order, fused into the step that consumes it
+          const uint2 v0 = *reinterpret_cast<const uint2*>(sd.in_table + (size_t)sd.codes[0] * H + gi0);
+          float e4[4] = {bf16_lo(v0.x), bf16_hi(v0.x), bf16_lo(v0.y), bf16_hi(v0.y)};
+#pragma unroll 5
+          for (int g = 0; g < 15; ++g) {
+            const uint2 v = *reinterpret_cast<const uint2*>(p.sum_tables[g] + (size_t)sd.codes[g + 1] * H + gi0);
+            e4[0] = bf16_round(e4[0] + bf16_lo(v.x)); e4[1] = bf16_round(e4[1] + bf16_hi(v.x));
+            e4[2] = bf16_round(e4[2] + bf16_lo(v.y)); e4[3] = bf16_round(e4[3] + bf16_hi(v.y));
+          }
+          const uint2 vx = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(sd.in_vec) + gi0);
+          gw[0] = make_uint4(bf16_bits(e4[0] + bf16_lo(vx.x)), bf16_bits(e4[1] + bf16_hi(vx.x)),
+                             bf16_bits(e4[2] + bf16_lo(vx.y)), bf16_bits(e4[3] + bf16_hi(vx.y)));
+          *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(c.s_acc) + gi0 * 2) = make_uint2(gw[0].x | (gw[0].y << 16), gw[0].z | (gw[0].w << 16));
+        } else if (sd.in_mode == IN_VEC_F32) {
           const float* xf = reinterpret_cast<const float*>(sd.in_vec);
           const float4 v = *reinterpret_cast<const float4*>(xf + gi0);
           gw[0] = make_uint4(bf16_bits(v.x), bf16_bits(v.y), bf16_bits(v.z), bf16_bits(v.w));
@@ -1144,7 +1161,7 @@ __device__ void consumer_loop(Ctx& c) {
           gw[0] = make_uint4(v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16);
           if (c.tid < rows.o_rows) res_mine = __bfloat162float(x_in[rows.o_row0 + c.tid]);
         }
-        if (c.tid < rows.o_rows) p.res_spill[rows.o_row0 + c.tid] = res_mine;
+        if (sd.in_mode != IN_CODES_SUM && c.tid < rows.o_rows) p.res_spill[rows.o_row0 + c.tid] = res_mine;
       } else {
         wait_window(c, (kind == K_O && !has_item) ? p.delay_o_idle : c.s_delay[dslot]);
         trace_sub<TR>(c, 1);
@@ -1208,7 +1225,15 @@ __device__ void consumer_loop(Ctx& c) {
         float ss = fmaf(r0, r0, r1 * r1) + fmaf(r2, r2, r3 * r3);
         ss = warp_sum(ss);
         if (c.lane == 0) c.s_red[c.warp] = ss;
-        if (from_input) consumer_bar(); else gather_bar(c, dslot, retried);
+        if (from_input) {
+          consumer_bar();
+          if (sd.in_mode == IN_CODES_SUM && c.tid < rows.o_rows) {   // fp32 residual of this CTA's rows = the summed input
+            res_mine = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(c.s_acc)[rows.o_row0 + c.tid]);
+            p.res_spill[rows.o_row0 + c.tid] = res_mine;
+          }
+        } else {
+          gather_bar(c, dslot, retried);
+        }
         trace_sub<TR>(c, 3);
         if (QMK_UNLIKELY(!(ready & 1u))) {
           wait_full(c, c.k);

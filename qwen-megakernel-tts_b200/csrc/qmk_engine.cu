@@ -361,10 +361,11 @@ static int reserve_epochs(qmk_engine* e, uint32_t need, cudaStream_t st, uint32_
   return QMK_OK;
 }
 
-extern "C" int qmk_decode_step(qmk_model* m, int head_index, int input_token_id, const void* embed_weight,
-                               const void* cos_table, const void* sin_table, void* k_cache, void* v_cache,
-                               void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
-                               int max_seq_len, float attn_scale, int mode, void* stream) {
+static int decode_step_impl(qmk_model* m, int head_index, int input_token_id, const void* embed_weight,
+                            const int64_t* codes, const void* const* group_tables, const void* extra_bf16,
+                            const void* cos_table, const void* sin_table, void* k_cache, void* v_cache,
+                            void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
+                            int max_seq_len, float attn_scale, int mode, void* stream) {
   if (!m) return set_error(QMK_ERR_ARG, "qmk_decode_step: model is null");
   if (!cos_table || !sin_table || !k_cache || !v_cache || !hidden_buffer)
     return set_error(QMK_ERR_ARG, "qmk_decode_step: null table / cache / hidden_buffer pointer");
@@ -386,6 +387,12 @@ extern "C" int qmk_decode_step(qmk_model* m, int head_index, int input_token_id,
   sd.in_vec = hidden_buffer;
   sd.in_mode = input_token_id >= 0 ? IN_TABLE_TOKEN : IN_VEC_BF16;
   sd.token = input_token_id >= 0 ? input_token_id : 0;
+  if (codes) {
+    sd.in_mode = IN_CODES_SUM;
+    sd.codes = reinterpret_cast<const long long*>(codes);
+    sd.in_vec = extra_bf16;
+    for (int g = 0; g < 15; ++g) p.sum_tables[g] = reinterpret_cast<const __nv_bfloat16*>(group_tables[g]);
+  }
   sd.position = position;
   set_head(sd, m, head_index);
   sd.group = -1;
@@ -403,6 +410,29 @@ extern "C" int qmk_decode_step(qmk_model* m, int head_index, int input_token_id,
     if (rc != QMK_OK) return rc;
   }
   return QMK_OK;
+}
+
+extern "C" int qmk_decode_step(qmk_model* m, int head_index, int input_token_id, const void* embed_weight,
+                               const void* cos_table, const void* sin_table, void* k_cache, void* v_cache,
+                               void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
+                               int max_seq_len, float attn_scale, int mode, void* stream) {
+  return decode_step_impl(m, head_index, input_token_id, embed_weight, nullptr, nullptr, nullptr, cos_table, sin_table,
+                          k_cache, v_cache, hidden_buffer, normalized_out, out_token, position, max_seq_len, attn_scale,
+                          mode, stream);
+}
+
+extern "C" int qmk_decode_step_codes(qmk_model* m, int head_index, const int64_t* codes, const void* talker_embed_weight,
+                                     const void* const* group_embedding_tables, const void* extra_embed_bf16,
+                                     const void* cos_table, const void* sin_table, void* k_cache, void* v_cache,
+                                     void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
+                                     int max_seq_len, float attn_scale, void* stream) {
+  if (!codes || !talker_embed_weight || !group_embedding_tables || !extra_embed_bf16)
+    return set_error(QMK_ERR_ARG, "qmk_decode_step_codes: null argument");
+  for (int g = 0; g < 15; ++g)
+    if (!group_embedding_tables[g]) return set_error(QMK_ERR_ARG, "qmk_decode_step_codes: group table %d is null", g);
+  return decode_step_impl(m, head_index, -1, talker_embed_weight, codes, group_embedding_tables, extra_embed_bf16,
+                          cos_table, sin_table, k_cache, v_cache, hidden_buffer, normalized_out, out_token, position,
+                          max_seq_len, attn_scale, 0, stream);
 }
 
 extern "C" int qmk_cp_predict(qmk_model* m, const float* talker_hidden, int first_codebook_token,

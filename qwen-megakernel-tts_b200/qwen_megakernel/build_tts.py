@@ -80,6 +80,8 @@ SIGNATURES = {
     "qmk_model_destroy": (None, [_vp]),
     "qmk_model_packed_bytes": (_i64, [_vp]),
     "qmk_decode_step": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _vp]),
+    "qmk_decode_step_codes": (_i32, [_vp, _i32, _vp, _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
+                                     _i32, _f32, _vp]),
     "qmk_cp_predict": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _u64, _u64, _vp,
                               _vp, _vp, _vp, _vp]),
     "launch_ldg_decode_direct": (None, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

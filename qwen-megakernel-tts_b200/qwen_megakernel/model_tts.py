@@ -304,6 +304,34 @@ class TTSDecoder:
         self._launch(EMBED_FROM_BUFFER, self._hidden.data_ptr())
         return self._finish()
 
+    def step_with_codes(self, codes: torch.Tensor, code_embeddings, extra_embed_bf16: torch.Tensor) -> tuple[int, torch.Tensor]:
+        """Decode from a frame's 16 codes: the embedding sum of the upstream frame loop (tts_engine.py:319-335,
+        ``embed[codes[0]] + sum_g code_embeddings[g][codes[g+1]] + extra``, bf16 adds in that order) is evaluated
+        inside the step's launch instead of by 32 torch kernels.  ``codes``: int64[16] on this device (what
+        ``CodePredictorKernel.predict`` returns); ``code_embeddings``: the 15 ``codec_embedding.{g}.weight`` tables;
+        ``extra_embed_bf16``: trailing-text or tts_pad embedding, bf16[1024]."""
+        from .build_tts import check
+        if codes.dtype != torch.int64 or codes.numel() != NUM_CODE_GROUPS or codes.device != self.device:
+            raise ValueError("codes: need an int64[16] tensor on the decoder's device")
+        if len(code_embeddings) != NUM_CODE_GROUPS - 1:
+            raise ValueError("code_embeddings: need the 15 code-predictor embedding tables")
+        for t in code_embeddings:
+            if t.dtype != torch.bfloat16 or t.device != self.device or not t.is_contiguous() or t.shape[-1] != HIDDEN_SIZE:
+                raise ValueError("code_embeddings: need contiguous bf16 [*, 1024] tables on the decoder's device")
+        extra = extra_embed_bf16.to(self.device, torch.bfloat16).reshape(-1).contiguous()
+        _require_cuda_bf16(extra, HIDDEN_SIZE, "step_with_codes(extra_embed_bf16)")
+        if self._position >= self._max_seq:
+            raise IndexError(f"KV cache is full (position {self._position} == max_seq_len)")
+        tables = (ctypes.c_void_p * 15)(*[t.data_ptr() for t in code_embeddings])
+        codes = codes.contiguous()
+        check(self._lib, self._lib.qmk_decode_step_codes(
+            self._model, self._head, codes.data_ptr(), self._embed_weight.data_ptr(), tables, extra.data_ptr(),
+            self._cos_table.data_ptr(), self._sin_table.data_ptr(), self._k_cache.data_ptr(), self._v_cache.data_ptr(),
+            self._hidden.data_ptr(), self._norm_out.data_ptr(), self._out_token.data_ptr(), self._position,
+            self._max_seq, self._attn_scale, _stream_ptr(self.device)), "qmk_decode_step_codes")
+        self._position += 1
+        return self._finish()
+
     def reset(self):
         """New utterance.  O(1): rows beyond ``position`` are never read."""
         self._position = 0

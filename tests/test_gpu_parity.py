@@ -197,6 +197,27 @@ def test_code_predictor_sampler_distribution(cp_kernel, gpu_weights):
     assert tv < 0.12, f"total variation {tv:.3f} between the sampler and the upstream distribution"
 
 
+def test_step_with_codes_equals_torch_embed_sum(talker, cp_kernel, gpu_weights):
+    """TTSDecoder.step_with_codes == step_with_embed on the torch-evaluated upstream sum (tts_engine.py:319-335)."""
+    from qwen_megakernel.synthetic import synthetic_inputs
+    F = torch.nn.functional
+    extra = synthetic_inputs(4242, 3).cuda()
+    gen = torch.Generator().manual_seed(5)
+    for i in range(3):
+        codes = torch.cat([torch.randint(0, 3072, (1,), generator=gen), torch.randint(0, 2048, (15,), generator=gen)]).cuda()
+        e = F.embedding(codes[0:1], gpu_weights["embed_weight"]).squeeze(0)
+        for g in range(15):
+            e = e + F.embedding(codes[g + 1:g + 2], cp_kernel.codec_embeddings[g]).squeeze(0)
+        e = e + extra[i]
+        talker.reset()
+        talker.step(CODEC_BOS)
+        t0, h0 = talker.step_with_embed(e)
+        talker.reset()
+        talker.step(CODEC_BOS)
+        t1, h1 = talker.step_with_codes(codes, cp_kernel.codec_embeddings, extra[i])
+        assert t0 == t1 and torch.equal(h0, h1)
+
+
 def test_code_predictor_sampling_respects_top_k(cp_kernel, gpu_weights):
     from qwen_megakernel.synthetic import synthetic_inputs
     torch.manual_seed(3)
