@@ -65,6 +65,7 @@ struct qmk_engine {
   int* delays = nullptr;
   int delay_o_idle = 2500;
   int warm_mma = 0;
+  int coop = 1;   // cooperative launch = co-residency of all CTAs is checked by the driver
   long long* trace_dev = nullptr;
   int trace_stride = 0;
   int* status_dev = nullptr;
@@ -140,6 +141,7 @@ extern "C" int qmk_engine_create(int device, int num_ctas, qmk_engine** out) {
   if (const char* env = getenv("QMK_POLL_DELAY_TOKEN")) delay_token = atoi(env);
   if (const char* env = getenv("QMK_POLL_DELAY_O")) e->delay_o_idle = atoi(env);
   if (const char* env = getenv("QMK_WARM_MMA")) e->warm_mma = atoi(env);
+  if (const char* env = getenv("QMK_COOP")) e->coop = atoi(env);
   std::vector<int> delays((size_t)G * 3 * DL_N, 0);
   for (int c = 0; c < G; ++c)
     for (int d = 0; d < DL_N; ++d) delays[(size_t)c * 3 * DL_N + d] = (d == DL_TOKEN) ? delay_token : delay0;
@@ -308,7 +310,8 @@ static int launch_slice(qmk_engine* e, Params& p, int begin, int end, cudaStream
   p.phase_end = end;
   void* args[] = {&p};
   const void* fn = e->trace_dev ? (const void*)qmk_decode_kernel_traced : (const void*)qmk_decode_kernel;
-  QMK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(e->G), dim3(NTHREADS), args, SMEM_BYTES, st));
+  if (e->coop) QMK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(e->G), dim3(NTHREADS), args, SMEM_BYTES, st));
+  else QMK_CUDA(cudaLaunchKernel(fn, dim3(e->G), dim3(NTHREADS), args, SMEM_BYTES, st));
   return QMK_OK;
 }
 
