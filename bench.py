@@ -324,18 +324,17 @@ def main():
     ms_e2e, _ = time_frames(loop, K, W, trail_dev, trail_host, barrier)
     clocks = sampler.stop() if rank == 0 else {}
 
-    if world > 1:
-        t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e = float(t[0]), float(t[1])
+    from qwen_megakernel.replicas import combine
+    frames_dev, ms_dev = combine(K, ms_dev, device=dev)      # sum of frames over ranks, max of device time
+    frames_e2e, ms_e2e = combine(K, ms_e2e, device=dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     peak, peak_src = measured_peaks()
-    value = world * K / (ms_dev / 1000.0)
-    e2e = world * K / (ms_e2e / 1000.0)
+    value = frames_dev / (ms_dev / 1000.0)
+    e2e = frames_e2e / (ms_e2e / 1000.0)
     achieved = talker_b / (talker_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
