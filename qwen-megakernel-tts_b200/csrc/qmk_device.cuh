@@ -203,6 +203,24 @@ __device__ __forceinline__ bool mbar_test_wait(u64* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Three phase tests issued back to back (their ~150-cycle latencies overlap); bit s of the result = barrier s complete.
+__device__ __forceinline__ uint32_t mbar_test_wait3(u64* b0, uint32_t p0, u64* b1, uint32_t p1, u64* b2, uint32_t p2) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred q0, q1, q2;\n\t.reg .u32 r0, r1, r2;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q0, [%1], %2;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q1, [%3], %4;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 q2, [%5], %6;\n\t"
+      "selp.u32 r0, 1, 0, q0;\n\t"
+      "selp.u32 r1, 2, 0, q1;\n\t"
+      "selp.u32 r2, 4, 0, q2;\n\t"
+      "or.b32 r0, r0, r1;\n\t"
+      "or.b32 %0, r0, r2;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(b0)), "r"(p0), "r"(smem_u32(b1)), "r"(p1), "r"(smem_u32(b2)), "r"(p2)
+      : "memory");
+  return ok;
+}
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, u64* bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -1174,23 +1192,39 @@ __device__ void consumer_loop(Ctx& c) {
       if (kind == K_HEAD) d = head_phase_desc(p, sd.head, c.cta);
       else d = layer_phase_desc(p, rows, l, kind, c.cta);
       const int nst = n_stages_of(d);
-      uint32_t ready = 0;
+      uint32_t ready;
       uint32_t sbase[MAX_ST];
+      {
+        static_assert(MAX_ST == 3, "mbar_test_wait3");
+        u64* fb[MAX_ST];
+        uint32_t fp[MAX_ST];
 #pragma unroll
-      for (int s = 0; s < MAX_ST; ++s) {
-        const uint32_t k = c.k + s;
-        const int slot = k % NSLOTS;
-        sbase[s] = smem_u32(c.ring + (size_t)slot * SLOT_BYTES);
-        if (s < nst && mbar_test_wait(&c.full[slot], (k / NSLOTS) & 1u)) ready |= 1u << s;
+        for (int s = 0; s < MAX_ST; ++s) {
+          const uint32_t k = c.k + (s < nst ? s : 0);
+          const int slot = k % NSLOTS;
+          sbase[s] = smem_u32(c.ring + (size_t)slot * SLOT_BYTES);
+          fb[s] = &c.full[slot];
+          fp[s] = (k / NSLOTS) & 1u;
+        }
+        ready = mbar_test_wait3(fb[0], fp[0], fb[1], fp[1], fb[2], fp[2]) & ((1u << nst) - 1u);
+      }
+      // A fragments of the first two stages move from the ring into registers while the activations are in flight:
+      // the shared-memory reads (~280 cycles per 28 KB stage, the floor of the stage loop) leave the critical path
+      constexpr int PRE_ST = 2;
+      uint32_t apre[PRE_ST][KSTEPS][4];
+      const uint32_t preloaded = ready;   // stages whose tile was resident at this point
+#pragma unroll
+      for (int s = 0; s < PRE_ST; ++s) {
+        if (s < nst && ((preloaded >> s) & 1u)) {
+#pragma unroll
+          for (int j = 0; j < KSTEPS; ++j)
+            ldsm4(apre[s][j], sbase[s] + a_off + ((uint32_t)((((c.warp * KSTEPS + j) * 2 + a_khalf) ^ a_sw)) << 4));
+        }
       }
       const uint8_t* aux = c.ring + (size_t)(c.k % NSLOTS) * SLOT_BYTES;
       uint2 wv = make_uint2(0, 0);
       if (norm && (ready & 1u)) wv = *reinterpret_cast<const uint2*>(aux + c.tid * 8);
       if (kind == K_QKV && has_item) attn_prefetch(c, l, position, item, 0, kv);  // older KV rows do not depend on this layer
-      if (c.warp == NCW - 1 && prod.pending > 0) {   // refill the ring slots released by the previous phase(s)
-        prod_issue(c, prod, prod.pending);
-        prod.pending = 0;
-      }
       if (QMK_UNLIKELY(p.warm_mma)) {   // keep the tensor pipe awake while the activations are in flight
         float wd[4] = {0.f, 0.f, 0.f, 0.f};
         const uint32_t wa[4] = {0u, 0u, 0u, 0u}, wb[2] = {0u, 0u};
@@ -1281,18 +1315,26 @@ __device__ void consumer_loop(Ctx& c) {
       for (int s = 0; s < MAX_ST; ++s) {
         acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.f;
         if (s < nst) {
-          if (QMK_UNLIKELY(!((ready >> s) & 1u))) wait_full(c, c.k + s);
           float acc2[4] = {0.f, 0.f, 0.f, 0.f};   // two accumulators halve the dependent HMMA chain
+          if (s < PRE_ST && QMK_LIKELY((preloaded >> s) & 1u)) {
 #pragma unroll
-          for (int jb = 0; jb < KSTEPS; jb += 4) {  // batches of 4 ldmatrix keep the live A fragments at 16 registers
-            uint32_t afrag[4][4];
+            for (int j = 0; j < KSTEPS; j += 2) {
+              mma16816(acc[s], apre[s][j], bfrag[j]);
+              mma16816(acc2, apre[s][j + 1], bfrag[j + 1]);
+            }
+          } else {
+            if (QMK_UNLIKELY(!((ready >> s) & 1u))) wait_full(c, c.k + s);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              ldsm4(afrag[j], sbase[s] + a_off + ((uint32_t)((((c.warp * KSTEPS + jb + j) * 2 + a_khalf) ^ a_sw)) << 4));
-            mma16816(acc[s], afrag[0], bfrag[jb]);
-            mma16816(acc2, afrag[1], bfrag[jb + 1]);
-            mma16816(acc[s], afrag[2], bfrag[jb + 2]);
-            mma16816(acc2, afrag[3], bfrag[jb + 3]);
+            for (int jb = 0; jb < KSTEPS; jb += 4) {  // batches of 4 ldmatrix keep the live A fragments at 16 registers
+              uint32_t afrag[4][4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                ldsm4(afrag[j], sbase[s] + a_off + ((uint32_t)((((c.warp * KSTEPS + jb + j) * 2 + a_khalf) ^ a_sw)) << 4));
+              mma16816(acc[s], afrag[0], bfrag[jb]);
+              mma16816(acc2, afrag[1], bfrag[jb + 1]);
+              mma16816(acc[s], afrag[2], bfrag[jb + 2]);
+              mma16816(acc2, afrag[3], bfrag[jb + 3]);
+            }
           }
 #pragma unroll
           for (int e = 0; e < 4; ++e) acc[s][e] += acc2[e];
@@ -1309,7 +1351,7 @@ __device__ void consumer_loop(Ctx& c) {
       }
       consumer_bar();
       trace_sub<TR>(c, 6);
-      prod.pending += nst;   // slots released by this phase; refilled in the load shadow of the next phase
+      if (c.warp == NCW - 1) prod_issue(c, prod, nst);   // refill the slots this phase released (warps 0-1 finalize meanwhile)
 
       // finalize + publish: thread t sums the NCW K-slice partials of item t; the items of one output row sit in
       // neighbouring lanes (an output row never straddles a warp: 2 | 32, and 3 * rows <= 30)

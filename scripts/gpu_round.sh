@@ -1,4 +1,4 @@
-# GPU round: parity tests, bench, perf probe.
+# GPU round: parity tests + perf probe with trace.
 set -x
-timeout 900 python -m pytest tests -m gpu -q -x --timeout 400 > gpurun_out/gpu_tests.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/gpu_tests.log
-timeout 900 python bench.py --steps 200 --warmup 10 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 400 > gpurun_out/gpu_tests.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/gpu_tests.log
+timeout 300 python scripts/perf_probe.py --configs "450,4500" --trace > gpurun_out/probe.log 2>&1; echo rc=$?; tail -20 gpurun_out/probe.log
