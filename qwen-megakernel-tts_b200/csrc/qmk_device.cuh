@@ -384,7 +384,10 @@ template <bool TR>
 __device__ __forceinline__ void trace_sub(const Ctx& c, int sub) {
   if (TR && c.p.trace != nullptr && c.tid == 0) {
     const int slot = (c.cur_idx - c.p.phase_begin) * 8 + sub;
-    if (slot >= 0 && slot < c.p.trace_stride) c.p.trace[(size_t)c.cta * c.p.trace_stride + slot] = clock64();
+    // sub-slot 7 (row published) records the GLOBAL timer in ns so that publish times compare across SMs
+    long long t;
+    if (sub == 7) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); else t = clock64();
+    if (slot >= 0 && slot < c.p.trace_stride) c.p.trace[(size_t)c.cta * c.p.trace_stride + slot] = t;
   }
 }
 
@@ -484,6 +487,9 @@ __device__ __forceinline__ void prod_build_table(Ctx& c, const CtaRows& rows) {
       }
     }
   }
+}
+__device__ __forceinline__ bool step_has_final(const StepDesc& sd) {
+  return sd.head.rows > 0 || sd.out_norm != nullptr || sd.hidden_out != nullptr;
 }
 __device__ __forceinline__ int head_stages(const Params& p, const HeadDesc& h, int cta) {
   return h.rows > 0 ? (row_begin(cta + 1, h.rows, p.lay.G) - row_begin(cta, h.rows, p.lay.G) + STAGE_ITEMS - 1) / STAGE_ITEMS : 1;
@@ -756,7 +762,16 @@ __device__ void phase_attn(Ctx& c, int l, int position, uint32_t epoch, const At
         sc[i] = d0;
         sc[5 + i] = d1;
       }
-      warp_sum10_bcast(sc, c.lane);
+      if (pos_first + 2 * NCW >= it.p1) {   // warp-uniform: at most 2 positions for this warp in this round
+        const float v4[4] = {sc[0], sc[1], sc[5], sc[6]};
+        const float tot = warp_sum4(v4, c.lane);      // 8-lane group q holds the total of v4[q]
+        sc[0] = __shfl_sync(0xffffffffu, tot, 0);
+        sc[1] = __shfl_sync(0xffffffffu, tot, 8);
+        sc[5] = __shfl_sync(0xffffffffu, tot, 16);
+        sc[6] = __shfl_sync(0xffffffffu, tot, 24);
+      } else {
+        warp_sum10_bcast(sc, c.lane);
+      }
       float mx0 = m0, mx1 = m1;
 #pragma unroll
       for (int i = 0; i < ATT_PER_WARP; ++i) {

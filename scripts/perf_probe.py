@@ -70,8 +70,8 @@ def trace(dec, x, lib, engine, L):
     start = t[:, :, 0]
     d = np.diff(start, axis=1)
     names = ["qkv", "attn", "o", "gu", "down"]
-    gl = ["window", "gather", "bar+aux", "norm", "stages", "reduce+bar", "publish"]
-    ga = ["window", "gather", "bar+aux", None, "stages", "reduce+bar", "publish"]
+    gl = ["window", "gather", "bar+aux", "norm", "stages", "reduce+bar", None]
+    ga = ["window", "gather", "bar+aux", None, "stages", "reduce+bar", None]
     labels = {0: gl, 1: ["wait+gather+norm/rope", "scores", "merge", "combine+publish", None, None, None], 2: ga, 3: gl, 4: ga}
     layers = list(range(2, L))
     for grp_name, sl in (("attention CTAs 0-7", slice(0, 8)), ("other CTAs", slice(8, G))):
@@ -95,6 +95,17 @@ def trace(dec, x, lib, engine, L):
             nxt = start[sl][:, [i + 1 for i in idxs]]
             parts.append(f"tail={np.mean(nxt - last):.0f}")
             print(f"  {names[ph]:5s} total {tot:7.0f} : " + "  ".join(parts))
+    # publish skew across CTAs (global timer, ns): per phase, spread of the publish time and who is last
+    for ph in (0, 2, 3, 4):
+        pub = t[:, [l * 5 + ph for l in layers], 7]                      # [G, layers] ns
+        rel = pub - np.median(pub, axis=0, keepdims=True)
+        last = np.argmax(pub, axis=0)
+        cnt = np.bincount(last, minlength=G)
+        worst = np.argsort(-cnt)[:5]
+        print(f"  {names[ph]:5s} publish skew ns: p10={np.percentile(rel,10):6.0f} p50={np.percentile(rel,50):6.0f} "
+              f"p90={np.percentile(rel,90):6.0f} max={rel.max():6.0f}; mean per-CTA offset min/max "
+              f"{rel.mean(1).min():6.0f}/{rel.mean(1).max():6.0f} (cta {int(np.argmax(rel.mean(1)))}); most often last: "
+              + ", ".join(f"cta{int(w)}x{int(cnt[w])}" for w in worst))
     print(f"  per-layer total (cta 0): {d[0, :L*5].sum() / L:9.0f} cycles;  kernel total cta0 {start[0, n_idx] - start[0, 0]:.0f} cycles")
 
 
