@@ -143,7 +143,7 @@ static_assert(sizeof(Params) <= 4000, "kernel parameter space");
 // small helpers
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ int row_begin(int cta, int n_rows, int G) {
-  return (int)(((long long)cta * n_rows) / G);
+  return (int)(((unsigned)cta * (unsigned)n_rows) / (unsigned)G);   // cta <= 1024, n_rows <= 4096: fits 32 bits
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ uint32_t bf16_bits(float x) {
@@ -470,23 +470,27 @@ struct Prod {
 };
 // Stage table of one layer (identical for every layer of this CTA), built once per launch by thread 0.
 //   s_tbl[kind 0..4] = {first entry, #stages, #items, -};  s_tbl[5 + j] = {src offset, item bytes, aux offset + 1, -}
-__device__ __forceinline__ void prod_build_table(Ctx& c, const CtaRows& rows) {
-  if (c.tid == 0) {
-    const Layout& y = c.p.lay;
-    const int n_items[5] = {rows.q_rows, 0, 2 * rows.o_rows, 2 * rows.gu_rows, 3 * rows.o_rows};
-    const int off_seg[5] = {0, 0, y.off_o, y.off_gu, y.off_down};
-    int e = 5;
-    for (int kind = 0; kind < 5; ++kind) {
-      const int nst = (n_items[kind] + STAGE_ITEMS - 1) / STAGE_ITEMS;
-      c.s_tbl[kind] = make_uint4((uint32_t)e, (uint32_t)nst, (uint32_t)n_items[kind], 0u);
-      for (int s = 0; s < nst; ++s, ++e) {
-        int items = n_items[kind] - s * STAGE_ITEMS;
-        if (items > STAGE_ITEMS) items = STAGE_ITEMS;
-        const uint32_t aux = (s == 0 && (kind == PH_QKV || kind == PH_GU)) ? (uint32_t)((kind == PH_GU) ? AUX_BYTES : 0) + 1u : 0u;
-        c.s_tbl[e] = make_uint4((uint32_t)((off_seg[kind] + s * STAGE_ITEMS) * SEG_BYTES), (uint32_t)(items * SEG_BYTES), aux, 0u);
-      }
+__device__ __noinline__ void prod_build_table_slow(uint4* s_tbl, int q_rows, int o_rows, int gu_rows, int off_o, int off_gu,
+                                                   int off_down) {
+  const int n_items[5] = {q_rows, 0, 2 * o_rows, 2 * gu_rows, 3 * o_rows};
+  const int off_seg[5] = {0, 0, off_o, off_gu, off_down};
+  int e = 5;
+#pragma unroll 1
+  for (int kind = 0; kind < 5; ++kind) {
+    const int nst = (n_items[kind] + STAGE_ITEMS - 1) / STAGE_ITEMS;
+    s_tbl[kind] = make_uint4((uint32_t)e, (uint32_t)nst, (uint32_t)n_items[kind], 0u);
+#pragma unroll 1
+    for (int s = 0; s < nst; ++s, ++e) {
+      int items = n_items[kind] - s * STAGE_ITEMS;
+      if (items > STAGE_ITEMS) items = STAGE_ITEMS;
+      const uint32_t aux = (s == 0 && (kind == PH_QKV || kind == PH_GU)) ? (uint32_t)((kind == PH_GU) ? AUX_BYTES : 0) + 1u : 0u;
+      s_tbl[e] = make_uint4((uint32_t)((off_seg[kind] + s * STAGE_ITEMS) * SEG_BYTES), (uint32_t)(items * SEG_BYTES), aux, 0u);
     }
   }
+}
+__device__ __forceinline__ void prod_build_table(Ctx& c, const CtaRows& rows) {
+  if (c.tid == 0)
+    prod_build_table_slow(c.s_tbl, rows.q_rows, rows.o_rows, rows.gu_rows, c.p.lay.off_o, c.p.lay.off_gu, c.p.lay.off_down);
 }
 __device__ __forceinline__ bool step_has_final(const StepDesc& sd) {
   return sd.head.rows > 0 || sd.out_norm != nullptr || sd.hidden_out != nullptr;
@@ -890,6 +894,113 @@ __device__ void phase_attn(Ctx& c, int l, int position, uint32_t epoch, const At
 // the gather / norm / stage / reduce code: the kernel's instruction footprint has to stay inside the SM's
 // instruction cache (a per-phase inlined version measured 2-3x slower on every sub-step).
 // ------------------------------------------------------------------------------------------------
+// Temperature / top-k (ties kept) / multinomial selection over `hrows` bf16 logits held as floats in s_log; every
+// consumer thread of the CTA calls it (it contains consumer barriers) and every thread returns the same token.
+// Out of line: it runs on one CTA once per step and would otherwise sit in the middle of the hot loop's code.
+__device__ __noinline__ int sample_token(const float* s_log, unsigned* hist, float* s_red, int tid, int warp, int lane,
+                                         int hrows, int top_k, float temperature, unsigned long long seed,
+                                         unsigned long long counter, int group, float best, int best_i) {
+  // (1) k-th largest logit by a two-pass radix select on the order-preserving 16-bit key of the bf16 value
+  unsigned* s_sel = reinterpret_cast<unsigned*>(s_red) + 40;  // [0] bin, [1] remaining rank, [2] chosen
+  const int per = hrows / NCT;                               // contiguous elements per thread (CDF in index order)
+  const int i0 = tid * per;
+  int k_rank = top_k;
+  unsigned thr_key = 0;
+  if (k_rank > 0 && k_rank < hrows) {
+    unsigned prefix_hi = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      hist[tid] = 0;   // NCT == 256 bins
+      consumer_bar();
+#pragma unroll 1
+      for (int e = 0; e < per; ++e) {
+        const unsigned bits = __float_as_uint(s_log[i0 + e]) >> 16;
+        const unsigned key = (bits & 0x8000u) ? (~bits & 0xffffu) : (bits | 0x8000u);
+        if (pass == 0) atomicAdd(&hist[key >> 8], 1u);
+        else if ((key >> 8) == prefix_hi) atomicAdd(&hist[key & 0xffu], 1u);
+      }
+      consumer_bar();
+      if (warp == 0) {   // lane l owns bins 255-8l .. 248-8l; suffix counts from the top
+        unsigned cnt[8], tot = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { cnt[e] = hist[255 - 8 * lane - e]; tot += cnt[e]; }
+        unsigned incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const unsigned before = incl - tot;   // elements in higher bins
+        if (before < (unsigned)k_rank && incl >= (unsigned)k_rank) {
+          unsigned run = before;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (run < (unsigned)k_rank && run + cnt[e] >= (unsigned)k_rank) { s_sel[0] = 255 - 8 * lane - e; s_sel[1] = (unsigned)k_rank - run; }
+            run += cnt[e];
+          }
+        }
+      }
+      consumer_bar();
+      if (pass == 0) { prefix_hi = s_sel[0]; k_rank = (int)s_sel[1]; }
+      else thr_key = (prefix_hi << 8) | s_sel[0];
+      consumer_bar();
+    }
+  }
+  // (2) softmax over the kept logits / temperature, inverse-CDF draw in index order
+  const float inv_t = 1.0f / temperature;
+  const float zmax = best * inv_t;
+  float pe[8];
+  float local = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    pe[e] = 0.f;
+    if (e < per) {
+      const float v = s_log[i0 + e];
+      const unsigned bits = __float_as_uint(v) >> 16;
+      const unsigned key = (bits & 0x8000u) ? (~bits & 0xffffu) : (bits | 0x8000u);
+      if (key >= thr_key) pe[e] = __expf(v * inv_t - zmax);
+      local += pe[e];
+    }
+  }
+  float incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_red[16 + warp] = incl;
+  if (tid == 0) s_sel[2] = (unsigned)best_i;   // fallback if rounding leaves the target beyond the last element
+  consumer_bar();
+  float wbase = 0.f, total = 0.f;
+#pragma unroll
+  for (int w = 0; w < NCW; ++w) {
+    const float t = s_red[16 + w];
+    if (w < warp) wbase += t;
+    total += t;
+  }
+  // counter-based uniform in [0, 1): splitmix64 of (seed, frame counter, group)
+  unsigned long long zr = seed + 0x9E3779B97F4A7C15ull * (counter * 16ull + (unsigned long long)(group + 1));
+  zr = (zr ^ (zr >> 30)) * 0xBF58476D1CE4E5B9ull;
+  zr = (zr ^ (zr >> 27)) * 0x94D049BB133111EBull;
+  zr ^= zr >> 31;
+  const float target = (float)(zr >> 40) * (1.0f / 16777216.0f) * total;
+  const float lo = wbase + incl - local;
+  if (target >= lo && target < lo + local) {
+    float run = lo;
+    int pick = -1;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (e < per && pe[e] > 0.f) {
+        if (pick < 0 && target < run + pe[e]) pick = i0 + e;
+        run += pe[e];
+      }
+    }
+    if (pick >= 0) s_sel[2] = (unsigned)pick;
+  }
+  consumer_bar();
+  return (int)s_sel[2];
+}
+
 // sum of the NCW per-warp K-slice partials of one item, fixed order
 __device__ __forceinline__ float item_sum(const float* s_part, int it) {
   static_assert(NCW == 8 && KSTEPS == 8, "item_sum reads 8 partials; pack_chunk assumes 8 K-slices of 128");
@@ -1031,106 +1142,9 @@ __device__ void consumer_loop(Ctx& c) {
           if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
         }
         int chosen = best_i;
-        if (sample) {
-          // (1) k-th largest logit by a two-pass radix select on the order-preserving 16-bit key of the bf16 value
-          unsigned* hist = reinterpret_cast<unsigned*>(c.s_part);   // 256 bins
-          unsigned* s_sel = reinterpret_cast<unsigned*>(c.s_red) + 40;  // [0] bin, [1] remaining rank, [2] chosen
-          const int per = hrows / NCT;                               // contiguous elements per thread (CDF in index order)
-          const int i0 = c.tid * per;
-          int k_rank = p.sample_top_k;
-          unsigned thr_key = 0;
-          if (k_rank > 0 && k_rank < hrows) {
-            unsigned prefix_hi = 0;
-            for (int pass = 0; pass < 2; ++pass) {
-              hist[c.tid] = 0;   // NCT == 256 bins
-              consumer_bar();
-              for (int e = 0; e < per; ++e) {
-                const unsigned bits = __float_as_uint(s_log[i0 + e]) >> 16;
-                const unsigned key = (bits & 0x8000u) ? (~bits & 0xffffu) : (bits | 0x8000u);
-                if (pass == 0) atomicAdd(&hist[key >> 8], 1u);
-                else if ((key >> 8) == prefix_hi) atomicAdd(&hist[key & 0xffu], 1u);
-              }
-              consumer_bar();
-              if (c.warp == 0) {   // lane l owns bins 255-8l .. 248-8l; suffix counts from the top
-                unsigned cnt[8], tot = 0;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { cnt[e] = hist[255 - 8 * c.lane - e]; tot += cnt[e]; }
-                unsigned incl = tot;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                  const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-                  if (c.lane >= o) incl += v;
-                }
-                const unsigned before = incl - tot;   // elements in higher bins
-                if (before < (unsigned)k_rank && incl >= (unsigned)k_rank) {
-                  unsigned run = before;
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    if (run < (unsigned)k_rank && run + cnt[e] >= (unsigned)k_rank) { s_sel[0] = 255 - 8 * c.lane - e; s_sel[1] = (unsigned)k_rank - run; }
-                    run += cnt[e];
-                  }
-                }
-              }
-              consumer_bar();
-              if (pass == 0) { prefix_hi = s_sel[0]; k_rank = (int)s_sel[1]; }
-              else thr_key = (prefix_hi << 8) | s_sel[0];
-              consumer_bar();
-            }
-          }
-          // (2) softmax over the kept logits / temperature, inverse-CDF draw in index order
-          const float inv_t = 1.0f / p.sample_temperature;
-          const float zmax = best * inv_t;
-          float pe[8];
-          float local = 0.f;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            pe[e] = 0.f;
-            if (e < per) {
-              const float v = s_log[i0 + e];
-              const unsigned bits = __float_as_uint(v) >> 16;
-              const unsigned key = (bits & 0x8000u) ? (~bits & 0xffffu) : (bits | 0x8000u);
-              if (key >= thr_key) pe[e] = __expf(v * inv_t - zmax);
-              local += pe[e];
-            }
-          }
-          float incl = local;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const float v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (c.lane >= o) incl += v;
-          }
-          if (c.lane == 31) c.s_red[16 + c.warp] = incl;
-          if (c.tid == 0) s_sel[2] = (unsigned)best_i;   // fallback if rounding leaves the target beyond the last element
-          consumer_bar();
-          float wbase = 0.f, total = 0.f;
-#pragma unroll
-          for (int w = 0; w < NCW; ++w) {
-            const float t = c.s_red[16 + w];
-            if (w < c.warp) wbase += t;
-            total += t;
-          }
-          // counter-based uniform in [0, 1): splitmix64 of (seed, frame counter, group)
-          unsigned long long zr = p.sample_seed + 0x9E3779B97F4A7C15ull * (p.sample_counter * 16ull + (unsigned long long)(sd.group + 1));
-          zr = (zr ^ (zr >> 30)) * 0xBF58476D1CE4E5B9ull;
-          zr = (zr ^ (zr >> 27)) * 0x94D049BB133111EBull;
-          zr ^= zr >> 31;
-          const float target = (float)(zr >> 40) * (1.0f / 16777216.0f) * total;
-          const float lo = wbase + incl - local;
-          if (target >= lo && target < lo + local) {
-            float run = lo;
-            int pick = -1;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              if (e < per && pe[e] > 0.f) {
-                if (pick < 0 && target < run + pe[e]) pick = i0 + e;
-                run += pe[e];
-              }
-            }
-            if (pick >= 0) s_sel[2] = (unsigned)pick;
-          }
-          consumer_bar();
-          chosen = (int)s_sel[2];
-        }
+        if (sample)
+          chosen = sample_token(s_log, reinterpret_cast<unsigned*>(c.s_part), c.s_red, c.tid, c.warp, c.lane, hrows,
+                                p.sample_top_k, p.sample_temperature, p.sample_seed, p.sample_counter, sd.group, best, best_i);
         if (c.tid == 0) {
           // a failed launch must not look like a token: encode the watchdog code as a negative id
           const int st = *((volatile int*)p.status);
@@ -1174,7 +1188,7 @@ __device__ void consumer_loop(Ctx& c) {
           // in the upstream order, fused into the step that consumes it
           const uint2 v0 = *reinterpret_cast<const uint2*>(sd.in_table + (size_t)sd.codes[0] * H + gi0);
           float e4[4] = {bf16_lo(v0.x), bf16_hi(v0.x), bf16_lo(v0.y), bf16_hi(v0.y)};
-#pragma unroll 5
+#pragma unroll 1
           for (int g = 0; g < 15; ++g) {
             const uint2 v = *reinterpret_cast<const uint2*>(p.sum_tables[g] + (size_t)sd.codes[g + 1] * H + gi0);
             e4[0] = bf16_round(e4[0] + bf16_lo(v.x)); e4[1] = bf16_round(e4[1] + bf16_hi(v.x));
