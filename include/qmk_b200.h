@@ -144,6 +144,24 @@ int qmk_cp_predict(qmk_model* m, const float* talker_hidden, int first_codebook_
                    int top_k, uint64_t seed, uint64_t frame_counter, const int32_t* forced_tokens,
                    int64_t* out_codes, float* logits_out, float* hidden_out, void* stream);
 
+/* ---- batched multi-stream decode (no upstream counterpart: upstream is strictly B = 1) ----
+ * B = 16 .. 64 concurrent utterances, each numerically the B = 1 step (own position, own KV cache).  The projections
+ * run on tcgen05 / TMEM tensor-core tiles (csrc/qmk_bgemm.cuh), weights are read in place in the upstream [out, in]
+ * layout.  `layers_host` is a HOST array of num_layers LDGLayerWeights structs holding device pointers. */
+typedef struct qmk_batched qmk_batched;
+int qmk_batched_create(int device, const LDGLayerWeights* layers_host, int num_layers, const void* final_norm_weight,
+                       const void* lm_head_weight, int lm_head_rows, const void* embed_weight, const void* cos_table,
+                       const void* sin_table, int residual_fp32, int batch, int max_seq_len, qmk_batched** out);
+void qmk_batched_destroy(qmk_batched* h);
+/* One decode step for all B streams (asynchronous on `stream`, no host sync):
+ *   token_ids  int32[B] device or NULL; an entry < 0 (or NULL) takes row b of `embeds` (bf16[B][1024]) as the input
+ *   positions  int32[B] device, per-stream KV row to write; advanced by one by the call
+ *   k_cache / v_cache  bf16 [B][L][8][max_seq_len][128]
+ *   hidden_out f32[B][1024] post-final-norm hidden (optional), tokens_out int32[B] argmax (lowest index on ties) */
+int qmk_batched_step(qmk_batched* h, const int32_t* token_ids, const void* embeds, int32_t* positions, void* k_cache,
+                     void* v_cache, float* hidden_out, int32_t* tokens_out, void* stream);
+const char* qmk_batched_last_error(void);
+
 /* ---- upstream-compatible entry point (same symbol, same argument list) ---------------------------- */
 /* The scratch arguments (g_activations .. g_mlp_intermediate, block_max_*) are accepted and ignored:
  * the engine keeps its own exchange buffers.  The first call for a given `layer_weights` blob re-packs

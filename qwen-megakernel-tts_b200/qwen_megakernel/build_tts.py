@@ -44,8 +44,9 @@ def _nvcc() -> str | None:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/qmk_engine.cu -> libqmk_b200.so (cross-compiles without a GPU)."""
-    srcs = [os.path.join(_CSRC, "qmk_engine.cu")]
-    deps = srcs + [os.path.join(_CSRC, "qmk_device.cuh"), os.path.join(_INCLUDE, "qmk_b200.h")]
+    srcs = [os.path.join(_CSRC, "qmk_engine.cu"), os.path.join(_CSRC, "qmk_batched.cu")]
+    deps = srcs + [os.path.join(_CSRC, "qmk_device.cuh"), os.path.join(_CSRC, "qmk_bgemm.cuh"),
+                   os.path.join(_INCLUDE, "qmk_b200.h")]
     if not force and os.path.exists(LIB_PATH):
         if all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps if os.path.exists(d)):
             return LIB_PATH
@@ -84,6 +85,10 @@ SIGNATURES = {
                                      _i32, _f32, _vp]),
     "qmk_cp_predict": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _u64, _u64, _vp,
                               _vp, _vp, _vp, _vp]),
+    "qmk_batched_create": (_i32, [_i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, ctypes.POINTER(_vp)]),
+    "qmk_batched_destroy": (None, [_vp]),
+    "qmk_batched_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qmk_batched_last_error": (ctypes.c_char_p, []),
     "launch_ldg_decode_direct": (None, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
     "qmk_legacy_configure": (_i32, [_vp, _i32, _i32]),

@@ -346,6 +346,92 @@ class TTSDecoder:
         return self._embed_weight
 
 
+class BatchedTTSDecoder:
+    """B concurrent utterance streams (B = 16, 32, 48 or 64) decoded together; no upstream counterpart.
+
+    Every stream is numerically the B = 1 ``TTSDecoder`` step (same rounding points, own position, own KV cache);
+    the projections run as tcgen05 / TMEM tensor-core GEMMs so each weight byte is read once per step for all
+    streams.  ``step`` / ``step_with_embed`` are asynchronous: they return device tensors and never sync the host.
+    """
+
+    def __init__(self, weights: dict, batch: int, *, device=None, max_seq_len: int = 2048,
+                 num_layers: Optional[int] = None, residual_fp32: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedTTSDecoder needs a CUDA device (sm_100a); there is no CPU fallback")
+        dev = torch.device(device if device is not None else "cuda")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device, self.batch, self._max_seq = dev, int(batch), int(max_seq_len)
+        self._num_layers = int(num_layers) if num_layers is not None else len(weights["layer_weights"]) // 11
+        self._weights = weights
+        lw = weights["layer_weights"][:11 * self._num_layers]
+        _check_layer_tensors(lw, self._num_layers, dev)
+        if weights["cos_table"].shape[0] < self._max_seq:
+            raise ValueError("RoPE tables are shorter than max_seq_len")
+        from .build_tts import NativeError
+        self._lib = _Native.lib()
+        host_blob = (ctypes.c_void_p * (11 * self._num_layers))(*[t.data_ptr() for t in lw])
+        h = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            rc = self._lib.qmk_batched_create(
+                dev.index, host_blob, self._num_layers, weights["final_norm_weight"].data_ptr(),
+                weights["lm_head_weight"].data_ptr(), weights["lm_head_weight"].shape[0], weights["embed_weight"].data_ptr(),
+                weights["cos_table"].data_ptr(), weights["sin_table"].data_ptr(), int(residual_fp32), self.batch,
+                self._max_seq, ctypes.byref(h))
+            if rc < 0:
+                raise NativeError(f"qmk_batched_create: {self._lib.qmk_batched_last_error().decode()} (code {rc})")
+            self._handle = h
+            B, L = self.batch, self._num_layers
+            self._k_cache = torch.zeros(B, L, NUM_KV_HEADS, self._max_seq, HEAD_DIM, dtype=torch.bfloat16, device=dev)
+            self._v_cache = torch.zeros_like(self._k_cache)
+            self.positions = torch.zeros(B, dtype=torch.int32, device=dev)
+            self._tokens = torch.zeros(B, dtype=torch.int32, device=dev)
+            self._hidden = torch.zeros(B, HIDDEN_SIZE, dtype=torch.float32, device=dev)
+        self._steps = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                self._lib.qmk_batched_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    def _run(self, token_ptr, embed_ptr):
+        from .build_tts import NativeError
+        if self._steps >= self._max_seq:
+            raise IndexError("KV cache is full for at least one stream")
+        rc = self._lib.qmk_batched_step(self._handle, token_ptr, embed_ptr, self.positions.data_ptr(),
+                                        self._k_cache.data_ptr(), self._v_cache.data_ptr(), self._hidden.data_ptr(),
+                                        self._tokens.data_ptr(), _stream_ptr(self.device))
+        if rc < 0:
+            raise NativeError(f"qmk_batched_step: {self._lib.qmk_batched_last_error().decode()} (code {rc})")
+        self._steps += 1
+        return self._tokens, self._hidden
+
+    def step(self, token_ids: torch.Tensor):
+        """token_ids: int[B] on this device.  Returns (next_tokens int32[B], hidden f32[B, 1024]) — views of internal
+        buffers that the next step overwrites."""
+        t = token_ids.to(self.device, torch.int32).contiguous()
+        if t.numel() != self.batch:
+            raise ValueError(f"token_ids must have {self.batch} elements")
+        self._keep = t
+        return self._run(t.data_ptr(), None)
+
+    def step_with_embed(self, embeds_bf16: torch.Tensor):
+        """embeds_bf16: bf16[B, 1024] (the upstream sentinel path, one precomputed embedding per stream)."""
+        e = embeds_bf16.to(self.device, torch.bfloat16).contiguous()
+        if tuple(e.shape) != (self.batch, HIDDEN_SIZE):
+            raise ValueError(f"embeds must be [{self.batch}, {HIDDEN_SIZE}]")
+        self._keep = e
+        return self._run(None, e.data_ptr())
+
+    def reset(self):
+        """New utterances on every stream (O(1): rows beyond a stream's position are never read)."""
+        self.positions.zero_()
+        self._steps = 0
+
+
 class TextProjection:
     """text ids -> talker hidden size: embedding(151936 -> 2048) -> fc1 + SiLU -> fc2 (-> 1024).
 
