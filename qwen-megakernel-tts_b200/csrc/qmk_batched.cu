@@ -60,6 +60,8 @@ __device__ __forceinline__ uint2 rmsnorm4(const float (&x)[4], const __nv_bfloat
 __global__ void kb_input(const int* token_ids, const __nv_bfloat16* embed_table, const __nv_bfloat16* embeds, float* res,
                          const __nv_bfloat16* w_in, __nv_bfloat16* xn) {
   __shared__ float s_red[8];
+  qmkb::pdl_wait();
+  qmkb::pdl_launch_dependents();
   const int b = blockIdx.x, t = threadIdx.x;
   const int tok = token_ids ? token_ids[b] : -1;
   const __nv_bfloat16* src = tok >= 0 ? embed_table + (size_t)tok * H : embeds + (size_t)b * H;
@@ -74,6 +76,8 @@ __global__ void kb_input(const int* token_ids, const __nv_bfloat16* embed_table,
 __global__ void kb_resid_norm(const float* partial, int splits, int B, float* res, int residual_fp32,
                               const __nv_bfloat16* w_norm, __nv_bfloat16* xn, float* hidden_out) {
   __shared__ float s_red[8];
+  qmkb::pdl_wait();
+  qmkb::pdl_launch_dependents();
   const int b = blockIdx.x, t = threadIdx.x;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int s = 0; s < splits; ++s) {
@@ -94,69 +98,69 @@ __global__ void kb_resid_norm(const float* partial, int splits, int B, float* re
     *reinterpret_cast<float4*>(hidden_out + (size_t)b * H + t * 4) = make_float4(bf16_lo(n.x), bf16_hi(n.x), bf16_lo(n.y), bf16_hi(n.y));
 }
 
-// ---- QKV epilogue: split-K sum -> bf16 -> per-head RMSNorm + rotate-half RoPE (bf16 steps) -> q buffer / KV append ----
-// grid = (B, 4), block = 256: warp = one of the 32 "heads" (16 q, 8 k, 8 v) of stream b; lane owns 4 dims.
-__global__ void kb_qkv_epilogue(const float* partial, int splits, int B, const int* positions, const __nv_bfloat16* q_norm,
-                                const __nv_bfloat16* k_norm, const __nv_bfloat16* cos_t, const __nv_bfloat16* sin_t,
-                                __nv_bfloat16* qbuf, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int layer, int L,
-                                int max_seq) {
-  const int b = blockIdx.x, lane = threadIdx.x & 31;
-  const int head = blockIdx.y * 8 + (threadIdx.x >> 5);   // 0..15 q, 16..23 k, 24..31 v
-  const int pos = positions[b];
-  float t[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int s = 0; s < splits; ++s) {
-    const float4 p = *reinterpret_cast<const float4*>(partial + ((size_t)s * B + b) * QKV_ROWS + head * HD + lane * 4);
-    t[0] += p.x; t[1] += p.y; t[2] += p.z; t[3] += p.w;
-  }
-#pragma unroll
-  for (int e = 0; e < 4; ++e) t[e] = bf16_round(t[e]);
-  const size_t cache_row = (((size_t)b * L + layer) * NKVH + (head & 7)) * max_seq + pos;
-  if (head >= 24) {
-    *reinterpret_cast<uint2*>(v_cache + cache_row * HD + lane * 4) =
-        make_uint2(bf16_bits(t[0]) | (bf16_bits(t[1]) << 16), bf16_bits(t[2]) | (bf16_bits(t[3]) << 16));
-    return;
-  }
-  const __nv_bfloat16* wn = head < 16 ? q_norm : k_norm;
-  float ss = 0.f;
-#pragma unroll
-  for (int e = 0; e < 4; ++e) ss = fmaf(t[e], t[e], ss);
-  ss = warp_sum(ss);
-  const float rms = sqrtf(ss * (1.0f / HD) + EPS);
-  const int dbase = (lane * 4) & 63;
-  uint32_t o[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float n = bf16_round((t[e] / rms) * __bfloat162float(wn[lane * 4 + e]));
-    const float other = __shfl_xor_sync(0xffffffffu, n, 16);
-    const float cs = __bfloat162float(cos_t[(size_t)pos * HD + dbase + e]), sn = __bfloat162float(sin_t[(size_t)pos * HD + dbase + e]);
-    const float a = bf16_round(n * cs), bb = bf16_round(other * sn);
-    o[e] = bf16_bits(lane < 16 ? a - bb : a + bb);
-  }
-  const uint2 packed = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
-  if (head < 16) *reinterpret_cast<uint2*>(qbuf + ((size_t)b * 16 + head) * HD + lane * 4) = packed;
-  else *reinterpret_cast<uint2*>(k_cache + cache_row * HD + lane * 4) = packed;
-}
-
-// ---- decode attention: one CTA per (stream, kv head), 2 q heads, online softmax, fp32 ----------------------------------
-// grid = (B, 8), block = 256 (8 warps stride over positions 0 .. pos[b]; lane owns 4 dims)
-__global__ void kb_attention(const __nv_bfloat16* qbuf, const __nv_bfloat16* k_cache, const __nv_bfloat16* v_cache,
-                             const int* positions, __nv_bfloat16* a_out, int layer, int L, int max_seq, float scale) {
+// ---- QKV epilogue + decode attention, one CTA per (stream, kv head) --------------------------------------------------
+// Warps 0-3 first finish the projection for this group: split-K sum -> bf16 -> per-head RMSNorm + rotate-half RoPE in
+// bf16 steps (q heads 2g, 2g+1 and k) -> q into shared memory, k / v appended to the cache row positions[b].  Then all
+// 8 warps stride over positions 0 .. pos (lane owns 4 dims), fp32 online softmax, fixed-order cross-warp merge.
+// grid = (B, 8), block = 256.  partial: [splits][B][4096] (q rows 0..2047, k 2048..3071, v 3072..4095).
+__global__ void kb_qkv_attention(const float* partial, int splits, int B, const int* positions, const __nv_bfloat16* q_norm,
+                                 const __nv_bfloat16* k_norm, const __nv_bfloat16* cos_t, const __nv_bfloat16* sin_t,
+                                 __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, __nv_bfloat16* a_out, int layer, int L,
+                                 int max_seq, float scale) {
+  __shared__ float s_q[2][HD];
   __shared__ float s_acc[8][2][HD];
   __shared__ float s_m[8][2], s_l[8][2];
+  qmkb::pdl_wait();
+  qmkb::pdl_launch_dependents();
   const int b = blockIdx.x, g = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = positions[b] + 1;
-  float q0[4], q1[4];
-  {
-    const uint2 a = *reinterpret_cast<const uint2*>(qbuf + ((size_t)b * 16 + 2 * g) * HD + lane * 4);
-    const uint2 c = *reinterpret_cast<const uint2*>(qbuf + ((size_t)b * 16 + 2 * g + 1) * HD + lane * 4);
-    q0[0] = bf16_lo(a.x); q0[1] = bf16_hi(a.x); q0[2] = bf16_lo(a.y); q0[3] = bf16_hi(a.y);
-    q1[0] = bf16_lo(c.x); q1[1] = bf16_hi(c.x); q1[2] = bf16_lo(c.y); q1[3] = bf16_hi(c.y);
-  }
+  const int pos = positions[b];
   const size_t base = (((size_t)b * L + layer) * NKVH + g) * max_seq * HD;
+  if (warp < 4) {
+    // warp 0, 1: q heads 2g, 2g+1; warp 2: k head g; warp 3: v head g
+    const int row0 = warp < 2 ? (2 * g + warp) * HD : (warp == 2 ? QSZ + g * HD : QSZ + KVSZ + g * HD);
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < splits; ++s) {
+      const float4 p = *reinterpret_cast<const float4*>(partial + ((size_t)s * B + b) * QKV_ROWS + row0 + lane * 4);
+      t[0] += p.x; t[1] += p.y; t[2] += p.z; t[3] += p.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) t[e] = bf16_round(t[e]);
+    if (warp == 3) {
+      *reinterpret_cast<uint2*>(v_cache + base + (size_t)pos * HD + lane * 4) =
+          make_uint2(bf16_bits(t[0]) | (bf16_bits(t[1]) << 16), bf16_bits(t[2]) | (bf16_bits(t[3]) << 16));
+    } else {
+      const __nv_bfloat16* wn = warp < 2 ? q_norm : k_norm;
+      float ss = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ss = fmaf(t[e], t[e], ss);
+      ss = warp_sum(ss);
+      const float rms = sqrtf(ss * (1.0f / HD) + EPS);
+      const int dbase = (lane * 4) & 63;
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float n = bf16_round((t[e] / rms) * __bfloat162float(wn[lane * 4 + e]));
+        const float other = __shfl_xor_sync(0xffffffffu, n, 16);
+        const float cs = __bfloat162float(cos_t[(size_t)pos * HD + dbase + e]), sn = __bfloat162float(sin_t[(size_t)pos * HD + dbase + e]);
+        const float x = bf16_round(n * cs), y = bf16_round(other * sn);
+        o[e] = bf16_round(lane < 16 ? x - y : x + y);
+      }
+      if (warp < 2) {
+        *reinterpret_cast<float4*>(&s_q[warp][lane * 4]) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+        *reinterpret_cast<uint2*>(k_cache + base + (size_t)pos * HD + lane * 4) =
+            make_uint2(bf16_bits(o[0]) | (bf16_bits(o[1]) << 16), bf16_bits(o[2]) | (bf16_bits(o[3]) << 16));
+      }
+    }
+  }
+  __syncthreads();   // q in shared memory; the new K / V row (global, written by this CTA) is visible to the whole CTA
+  const int n = pos + 1;
+  const float4 qa = *reinterpret_cast<const float4*>(&s_q[0][lane * 4]), qb = *reinterpret_cast<const float4*>(&s_q[1][lane * 4]);
+  const float q0[4] = {qa.x, qa.y, qa.z, qa.w}, q1[4] = {qb.x, qb.y, qb.z, qb.w};
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f, acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
-  for (int pos = warp; pos < n; pos += 8) {
-    const uint2 kk = *reinterpret_cast<const uint2*>(k_cache + base + (size_t)pos * HD + lane * 4);
-    const uint2 vv = *reinterpret_cast<const uint2*>(v_cache + base + (size_t)pos * HD + lane * 4);
+  for (int p = warp; p < n; p += 8) {
+    const uint2 kk = *reinterpret_cast<const uint2*>(k_cache + base + (size_t)p * HD + lane * 4);
+    const uint2 vv = *reinterpret_cast<const uint2*>(v_cache + base + (size_t)p * HD + lane * 4);
     const float kf[4] = {bf16_lo(kk.x), bf16_hi(kk.x), bf16_lo(kk.y), bf16_hi(kk.y)};
     const float vf[4] = {bf16_lo(vv.x), bf16_hi(vv.x), bf16_lo(vv.y), bf16_hi(vv.y)};
     float d0 = 0.f, d1 = 0.f;
@@ -193,6 +197,8 @@ __global__ void kb_attention(const __nv_bfloat16* qbuf, const __nv_bfloat16* k_c
 // ---- gate/up epilogue: m = r( r(silu(r(g))) * r(u) ) -------------------------------------------------------------------
 // grid = (B, 3), block = 256; partial: [splits][B][6144] (gate rows 0..3071, up rows 3072..6143)
 __global__ void kb_gu_epilogue(const float* partial, int splits, int B, __nv_bfloat16* m_out) {
+  qmkb::pdl_wait();
+  qmkb::pdl_launch_dependents();
   const int b = blockIdx.x, j = blockIdx.y * 1024 + threadIdx.x * 4;
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f), u = g;
   for (int s = 0; s < splits; ++s) {
@@ -217,6 +223,8 @@ __global__ void kb_gu_epilogue(const float* partial, int splits, int B, __nv_bfl
 __global__ void kb_head_epilogue(const float* partial, int splits, int B, int rows, int* tokens_out, int* positions) {
   __shared__ float s_v[8];
   __shared__ int s_i[8];
+  qmkb::pdl_wait();
+  qmkb::pdl_launch_dependents();
   const int b = blockIdx.x;
   float best = -INFINITY;
   int best_i = 0x7fffffff;
@@ -335,9 +343,24 @@ extern "C" void qmk_batched_destroy(qmk_batched* h) {
   delete h;
 }
 
+// Every kernel of the step chain is launched with programmatic stream serialization (PDL).
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 static void gemm(qmk_batched* h, const CUtensorMap& mw, const CUtensorMap& mx, int M, int K, int splits, cudaStream_t st) {
   qmkb::BgemmArgs a{h->partial, M, h->B, K, splits};
-  qmkb::qmk_bgemm_kernel<<<dim3(M / qmkb::BM, splits), 128, qmkb::SMEM_BYTES, st>>>(mw, mx, a);
+  launch_pdl(qmkb::qmk_bgemm_kernel, dim3(M / qmkb::BM, splits), dim3(128), (size_t)qmkb::SMEM_BYTES, st, mw, mx, a);
 }
 
 // One decode step for all B streams.  token_ids (int32[B], device; entry < 0 or null pointer -> the stream's row of
@@ -354,28 +377,26 @@ extern "C" int qmk_batched_step(qmk_batched* h, const int32_t* token_ids, const 
   __nv_bfloat16* vc = reinterpret_cast<__nv_bfloat16*>(v_cache);
   const __nv_bfloat16* cos_t = reinterpret_cast<const __nv_bfloat16*>(h->cos_t);
   const __nv_bfloat16* sin_t = reinterpret_cast<const __nv_bfloat16*>(h->sin_t);
-  kb_input<<<B, 256, 0, st>>>(token_ids, reinterpret_cast<const __nv_bfloat16*>(h->embed),
-                              reinterpret_cast<const __nv_bfloat16*>(embeds), h->res,
-                              reinterpret_cast<const __nv_bfloat16*>(h->ln_in[0]), h->xn);
+  launch_pdl(kb_input, dim3(B), dim3(256), 0, st, (const int*)token_ids, reinterpret_cast<const __nv_bfloat16*>(h->embed),
+             reinterpret_cast<const __nv_bfloat16*>(embeds), h->res, reinterpret_cast<const __nv_bfloat16*>(h->ln_in[0]), h->xn);
   for (int l = 0; l < L; ++l) {
     gemm(h, h->map_qkv[l], h->map_x1024, QKV_ROWS, H, 4, st);                       // 32 tiles x 4 K-slices
-    kb_qkv_epilogue<<<dim3(B, 4), 256, 0, st>>>(h->partial, 4, B, positions, reinterpret_cast<const __nv_bfloat16*>(h->qn[l]),
-                                                reinterpret_cast<const __nv_bfloat16*>(h->kn[l]), cos_t, sin_t, h->qbuf, kc, vc, l, L,
-                                                h->max_seq);
-    kb_attention<<<dim3(B, NKVH), 256, 0, st>>>(h->qbuf, kc, vc, positions, h->abuf, l, L, h->max_seq, scale);
+    launch_pdl(kb_qkv_attention, dim3(B, NKVH), dim3(256), 0, st, (const float*)h->partial, 4, B, (const int*)positions,
+               reinterpret_cast<const __nv_bfloat16*>(h->qn[l]), reinterpret_cast<const __nv_bfloat16*>(h->kn[l]), cos_t, sin_t,
+               kc, vc, h->abuf, l, L, h->max_seq, scale);
     gemm(h, h->map_o[l], h->map_x2048, H, QSZ, 16, st);                              // 8 tiles x 16 K-slices
-    kb_resid_norm<<<B, 256, 0, st>>>(h->partial, 16, B, h->res, h->residual_fp32,
-                                     reinterpret_cast<const __nv_bfloat16*>(h->ln_post[l]), h->xn, nullptr);
+    launch_pdl(kb_resid_norm, dim3(B), dim3(256), 0, st, (const float*)h->partial, 16, B, h->res, h->residual_fp32,
+               reinterpret_cast<const __nv_bfloat16*>(h->ln_post[l]), h->xn, (float*)nullptr);
     gemm(h, h->map_gu[l], h->map_x1024, GU_ROWS, H, 4, st);                          // 48 tiles x 4 K-slices
-    kb_gu_epilogue<<<dim3(B, 3), 256, 0, st>>>(h->partial, 4, B, h->mbuf);
+    launch_pdl(kb_gu_epilogue, dim3(B, 3), dim3(256), 0, st, (const float*)h->partial, 4, B, h->mbuf);
     gemm(h, h->map_down[l], h->map_x3072, H, INTER, 16, st);                         // 8 tiles x 16 K-slices
     const bool last = (l == L - 1);
-    kb_resid_norm<<<B, 256, 0, st>>>(h->partial, 16, B, h->res, h->residual_fp32,
-                                     reinterpret_cast<const __nv_bfloat16*>(last ? h->final_norm : h->ln_in[l + 1]), h->xn,
-                                     last ? hidden_out : nullptr);
+    launch_pdl(kb_resid_norm, dim3(B), dim3(256), 0, st, (const float*)h->partial, 16, B, h->res, h->residual_fp32,
+               reinterpret_cast<const __nv_bfloat16*>(last ? h->final_norm : h->ln_in[l + 1]), h->xn,
+               last ? hidden_out : (float*)nullptr);
   }
   gemm(h, h->map_head, h->map_x1024, h->head_rows, H, 4, st);
-  kb_head_epilogue<<<B, 256, 0, st>>>(h->partial, 4, B, h->head_rows, tokens_out, positions);
+  launch_pdl(kb_head_epilogue, dim3(B), dim3(256), 0, st, (const float*)h->partial, 4, B, h->head_rows, (int*)tokens_out, (int*)positions);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(QMK_ERR_CUDA, cudaGetErrorString(e));
   return QMK_OK;

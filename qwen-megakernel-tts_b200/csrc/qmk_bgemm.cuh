@@ -31,6 +31,12 @@ constexpr int SMEM_BYTES = MAX_KB * (A_TILE_BYTES + B_TILE_BYTES) + 1024 /*align
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Programmatic dependent launch (PDL): a kernel of the step chain lets its successor start early and waits for its
+// predecessor's results only where it needs them, so launch latency, barrier / TMEM set-up and -- for the GEMM -- the
+// weight TMA loads overlap with the tail of the previous kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -130,14 +136,17 @@ __global__ void __launch_bounds__(128, 1) qmk_bgemm_kernel(const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
-    // ===== TMA producer: every k-block of the slice, up front =====
+    // ===== TMA producer: every k-block of the slice, up front.  The weight tiles do not depend on the previous
+    //       kernel: they are in flight before the grid dependency is resolved; the activations follow it. =====
     for (int kb = 0; kb < nkb; ++kb) {
       mbar_expect_tx(&full[kb], (uint32_t)(A_TILE_BYTES + a.N * BK * 2));
       tma_load_2d(sA + kb * A_TILE_BYTES, &map_w, k0 + kb * BK, m0, &full[kb]);
-      tma_load_2d(sB + kb * B_TILE_BYTES, &map_x, k0 + kb * BK, 0, &full[kb]);
     }
+    pdl_wait();
+    for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sB + kb * B_TILE_BYTES, &map_x, k0 + kb * BK, 0, &full[kb]);
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer =====
     const uint32_t idesc = make_instr_desc(a.N);
@@ -155,6 +164,7 @@ __global__ void __launch_bounds__(128, 1) qmk_bgemm_kernel(const __grid_constant
   __syncwarp();
 
   // ===== epilogue: TMEM lane = row of the tile, column = stream; warp w owns lanes 32 w .. 32 w + 31 =====
+  pdl_wait();   // the previous epilogue kernel has finished reading the partial buffer this kernel overwrites
   mbar_wait(done, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int row = m0 + warp * 32 + lane;
