@@ -254,6 +254,32 @@ def time_cp_frame(loop: FrameLoop, n: int = 30, warmup: int = 5):
     return start.elapsed_time(end) / n
 
 
+def time_batched(weights_gpu, dev, batch: int, steps: int = 100, warmup: int = 10, max_seq: int = 512):
+    """BASELINE.json configs[3]: B concurrent utterance streams, tcgen05 projections (BatchedTTSDecoder).  One step =
+    one token for every stream; tokens are fed back on the device, no host sync inside the timed region."""
+    from qwen_megakernel.model_tts import BatchedTTSDecoder
+    bd = BatchedTTSDecoder(weights_gpu, batch, device=dev, max_seq_len=max_seq)
+    tok = torch.full((batch,), CODEC_BOS, dtype=torch.int32, device=dev)
+    for _ in range(warmup):
+        t, _ = bd.step(tok)
+        tok.copy_(t)
+    bd.reset()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(steps):
+        t, _ = bd.step(tok)
+        tok.copy_(t)
+    end.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(end) / steps
+    bytes_step = TALKER_STEP_BYTES + batch * sum(TALKER_KV_BYTES_PER_POS * (p + 2) for p in range(steps)) / steps
+    del bd
+    return {"streams": batch, "ms_per_step": ms, "stream_steps_per_s": batch * 1000.0 / ms,
+            "algorithmic_gbs": bytes_step / (ms * 1e-3) / 1e9, "launches_per_step": 6 * 28 + 3,
+            "note": "talker step for B streams: tcgen05/TMEM split-K GEMMs + fused epilogues, PDL chain; positions 0..%d" % steps}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -351,6 +377,8 @@ def main():
                      "achieved_gbs": cp_frame_bytes() / (cp_ms * 1e-3) / 1e9, "note": "greedy predict(): one fused launch (16 steps + 15 heads + selection)"},
         "clocks": clocks,
     }
+    if world == 1:
+        line["batched"] = {f"B{b}": time_batched(w_gpu, dev, b) for b in (16, 64)}
     if world == 1 and not args.no_cpu_baseline:
         fps, done, dt = cpu_frame_loop(w_cpu, 10_000, 1, args.cpu_budget)
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
