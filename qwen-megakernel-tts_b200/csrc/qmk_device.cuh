@@ -119,6 +119,7 @@ struct Params {
   float* res_spill;                // f32[1024]: fp32 residual of every row (read back only by staged launches)
   int* delays;                     // [G][3][DL_N]: poll delays (cycles after own publish; in), repeated-poll counts and
                                    // cycles/16 spent waiting for weights per exchange kind (in/out)
+  int o_sentinel;                  // O phase of idle CTAs: one warp polls sample words before the CTA-wide gather
   int warm_mma;                    // issue a dummy mma while waiting for activations (tensor-pipe wake-up experiment)
   int delay_o_idle;                // O-phase delay of CTAs without an attention item (they wait for the attention CTAs)
   uint32_t epoch_base;             // epochs base+1 .. base+n_steps*(L+2) are used by this launch (16-bit, never 0)
@@ -591,10 +592,22 @@ __device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
 // The wait window before a gather: warp 0 (which issued the publish) spins until t_pub + delay while the other
 // consumer warps sleep at a hardware barrier -- spinning warps would steal issue slots from the warp that is
 // still finalising the previous phase.  Returns a bit mask of the next phase's ring stages already full.
-__device__ __forceinline__ void wait_window(Ctx& c, int delay) {
+// `sentinel` (optional): after the delay warp 0 alone polls 32 sample words of the vector (one per 64) until they
+// carry `epoch`, so that a long wait (the O phase waiting for the attention CTAs) does not have every thread of 140
+// CTAs re-reading the lines the producers are about to write.
+__device__ __forceinline__ void wait_window(Ctx& c, int delay, const uint32_t* sentinel = nullptr, uint32_t epoch = 0) {
   if (c.warp == 0) {
     const long long t_ready = c.t_pub + delay;
     while (clock64() < t_ready) {
+    }
+    if (sentinel != nullptr) {
+      uint32_t spins = 0;
+      for (;;) {
+        uint32_t w;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(w) : "l"(sentinel + c.lane * 64) : "memory");
+        if (__all_sync(0xffffffffu, (w >> 16) == epoch)) break;
+        if ((++spins & 63u) == 0 && check_abort(c, ST_TIMEOUT_LL, -2)) break;
+      }
     }
   }
   asm volatile("bar.sync 2, %0;" ::"n"(NCT) : "memory");
@@ -1210,7 +1223,8 @@ __device__ void consumer_loop(Ctx& c) {
         }
         if (sd.in_mode != IN_CODES_SUM && c.tid < rows.o_rows) p.res_spill[rows.o_row0 + c.tid] = res_mine;
       } else {
-        wait_window(c, (kind == K_O && !has_item) ? p.delay_o_idle : c.s_delay[dslot]);
+        if (kind == K_O && !has_item) wait_window(c, p.delay_o_idle, p.o_sentinel ? xw : nullptr, ep);
+        else wait_window(c, c.s_delay[dslot]);
         trace_sub<TR>(c, 1);
         gw[0] = ll4_ld4(xw + gi0);
         if (n_words > H) gw[1] = ll4_ld4(xw + gi0 + H);
