@@ -310,6 +310,7 @@ def main():
             return
         w = synthetic_tts_weights(seed=SEED, max_seq_len=MAX_SEQ)
         budget = 150.0
+        config["frame_glue"] = "torch ops on the CPU (oracle port of tts_engine.py:319-333)"
         fps, done, dt = cpu_frame_loop(w, K, W, budget)
         line = {"metric": METRIC, "value": fps, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": K,
                 "steps_timed": done, "warmup": W, "ms_per_step": 1000.0 / fps, "higher_is_better": True,

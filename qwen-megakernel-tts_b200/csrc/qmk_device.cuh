@@ -757,8 +757,14 @@ __device__ void phase_attn(Ctx& c, int l, int position, uint32_t epoch, const At
     float sc[10];
     const int pos_first = it.p0 + r * ATT_ROUND + c.warp;
     if (pos_first < it.p1) {  // warp-uniform
+      // positions of this warp in this round (warp-uniform): a short context (every code-predictor step, the first
+      // talker steps) has 1-2, so the loops below stop early instead of predicating five iterations off
+      const int nv = min(ATT_PER_WARP, (it.p1 - pos_first + NCW - 1) / NCW);
+#pragma unroll
+      for (int i = 0; i < 10; ++i) sc[i] = 0.f;
 #pragma unroll
       for (int i = 0; i < ATT_PER_WARP; ++i) {
+        if (i >= nv) break;
         const int pos = pos_first + NCW * i;
         float kf[4];
         if (pos == position) {
@@ -769,17 +775,15 @@ __device__ void phase_attn(Ctx& c, int l, int position, uint32_t epoch, const At
           kf[2] = bf16_lo(kv.k[i].y); kf[3] = bf16_hi(kv.k[i].y);
         }
         float d0 = 0.f, d1 = 0.f;
-        if (pos < it.p1) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            d0 = fmaf(q0[e], kf[e], d0);
-            d1 = fmaf(q1[e], kf[e], d1);
-          }
+        for (int e = 0; e < 4; ++e) {
+          d0 = fmaf(q0[e], kf[e], d0);
+          d1 = fmaf(q1[e], kf[e], d1);
         }
         sc[i] = d0;
         sc[5 + i] = d1;
       }
-      if (pos_first + 2 * NCW >= it.p1) {   // warp-uniform: at most 2 positions for this warp in this round
+      if (nv <= 2) {
         const float v4[4] = {sc[0], sc[1], sc[5], sc[6]};
         const float tot = warp_sum4(v4, c.lane);      // 8-lane group q holds the total of v4[q]
         sc[0] = __shfl_sync(0xffffffffu, tot, 0);
@@ -792,9 +796,9 @@ __device__ void phase_attn(Ctx& c, int l, int position, uint32_t epoch, const At
       float mx0 = m0, mx1 = m1;
 #pragma unroll
       for (int i = 0; i < ATT_PER_WARP; ++i) {
-        const bool valid = pos_first + NCW * i < it.p1;
-        sc[i] = valid ? sc[i] * p.attn_scale : -INFINITY;
-        sc[5 + i] = valid ? sc[5 + i] * p.attn_scale : -INFINITY;
+        if (i >= nv) break;
+        sc[i] *= p.attn_scale;
+        sc[5 + i] *= p.attn_scale;
         mx0 = fmaxf(mx0, sc[i]);
         mx1 = fmaxf(mx1, sc[5 + i]);
       }
@@ -805,23 +809,22 @@ __device__ void phase_attn(Ctx& c, int l, int position, uint32_t epoch, const At
       for (int e = 0; e < 4; ++e) { acc0[e] *= c0; acc1[e] *= c1; }
 #pragma unroll
       for (int i = 0; i < ATT_PER_WARP; ++i) {
+        if (i >= nv) break;
         const int pos = pos_first + NCW * i;
-        if (pos < it.p1) {
-          float vf[4];
-          if (pos == position) {
-            const float4 vv = *reinterpret_cast<const float4*>(s_small + SS_V + c.lane * 4);
-            vf[0] = vv.x; vf[1] = vv.y; vf[2] = vv.z; vf[3] = vv.w;
-          } else {
-            vf[0] = bf16_lo(kv.v[i].x); vf[1] = bf16_hi(kv.v[i].x);
-            vf[2] = bf16_lo(kv.v[i].y); vf[3] = bf16_hi(kv.v[i].y);
-          }
-          const float e0 = __expf(sc[i] - mx0), e1 = __expf(sc[5 + i] - mx1);
-          l0 += e0; l1 += e1;
+        float vf[4];
+        if (pos == position) {
+          const float4 vv = *reinterpret_cast<const float4*>(s_small + SS_V + c.lane * 4);
+          vf[0] = vv.x; vf[1] = vv.y; vf[2] = vv.z; vf[3] = vv.w;
+        } else {
+          vf[0] = bf16_lo(kv.v[i].x); vf[1] = bf16_hi(kv.v[i].x);
+          vf[2] = bf16_lo(kv.v[i].y); vf[3] = bf16_hi(kv.v[i].y);
+        }
+        const float e0 = __expf(sc[i] - mx0), e1 = __expf(sc[5 + i] - mx1);
+        l0 += e0; l1 += e1;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            acc0[e] = fmaf(e0, vf[e], acc0[e]);
-            acc1[e] = fmaf(e1, vf[e], acc1[e]);
-          }
+        for (int e = 0; e < 4; ++e) {
+          acc0[e] = fmaf(e0, vf[e], acc0[e]);
+          acc1[e] = fmaf(e1, vf[e], acc1[e]);
         }
       }
       m0 = mx0; m1 = mx1;
