@@ -171,6 +171,18 @@ class FrameLoop:
         for i in range(N_PREFILL):
             self.talker.step_with_embed(self.prefill[i])
         self.tok, self.hid = self.talker.step(CODEC_BOS)
+        # device-resident (token, hidden) of the last talker step for the sync-free pipeline
+        self.tok_dev, self.hid_dev = self.talker._out_token, self.talker._norm_out
+
+    def frame_async(self, extra_bf16, sample=True):
+        """Same frame without a host round trip: predict() takes the talker's token from device memory and the talker
+        step returns device tensors; the host reads tokens / codes asynchronously (EOS would be seen one frame late)."""
+        if self.talker.position >= MAX_SEQ - 1:
+            self.start_utterance()
+        codes = self.cp.predict(self.hid_dev, self.tok_dev, self.embed, do_sample=sample, temperature=0.9, top_k=50)
+        self.tok_dev, self.hid_dev = self.talker.step_with_codes(codes, self.cp_embeds, extra_bf16, sync=False)
+        self.launches += 2
+        return codes
 
     def frame(self, extra_bf16, sample=True):
         """tts_engine.py:306-335: predict -> embed sum -> step_with_embed."""
@@ -190,27 +202,42 @@ class FrameLoop:
         return codes
 
 
-def time_frames(loop: FrameLoop, n: int, warmup: int, trail_dev, trail_host=None, barrier=None):
-    """Returns elapsed ms for n frames (CUDA events on the current stream)."""
+def time_frames(loop: FrameLoop, n: int, warmup: int, trail_dev, trail_host=None, barrier=None, dropin=False):
+    """Returns elapsed ms for n frames (CUDA events on the current stream).
+
+    dropin=False: the sync-free pipeline (frame_async).  With trail_host, every frame's input comes from pinned host
+    memory (H2D inside the timed region) and every frame's 16 codes + talker token are copied to pinned host memory
+    (D2H inside the timed region, read by the host after the final synchronise).
+    dropin=True: the upstream caller's control flow (tts_engine.py:301-335): step() returns a Python int, i.e. one
+    blocking device->host read per frame."""
     loop.start_utterance()
+    step = loop.frame if dropin else loop.frame_async
     for f in range(warmup):
-        loop.frame(trail_dev[f])
+        step(trail_dev[f])
     torch.cuda.synchronize()
     if barrier:
         barrier()
+    host_codes = torch.empty(n, 16, dtype=torch.int64).pin_memory() if trail_host is not None else None
+    host_tok = torch.empty(n, 1, dtype=torch.int32).pin_memory() if trail_host is not None else None
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = loop.launches
     start.record()
     sink = 0
     for f in range(n):
         if trail_host is None:
-            codes = loop.frame(trail_dev[warmup + f])
+            codes = step(trail_dev[warmup + f])
         else:
             extra = trail_host[warmup + f].to(loop.dev, non_blocking=True)       # H2D of this frame's input
-            codes = loop.frame(extra)
-            sink += int(codes.cpu()[15])                                          # D2H of this frame's result
+            codes = step(extra)
+            if dropin:
+                sink += int(codes.cpu()[15])                                      # blocking D2H of this frame's result
+            else:
+                host_codes[f].copy_(codes, non_blocking=True)                     # D2H of this frame's result
+                host_tok[f].copy_(loop.tok_dev, non_blocking=True)
     end.record()
     torch.cuda.synchronize()
+    if host_codes is not None and not dropin:
+        sink += int(host_codes[:, 15].sum()) + int(host_tok.sum())
     if barrier:
         barrier()
     return start.elapsed_time(end), loop.launches - l0
@@ -349,11 +376,13 @@ def main():
         sampler.start()
     ms_dev, launches = time_frames(loop, K, W, trail_dev, None, barrier)
     ms_e2e, _ = time_frames(loop, K, W, trail_dev, trail_host, barrier)
+    ms_dropin, _ = time_frames(loop, K, W, trail_dev, trail_host, barrier, dropin=True)
     clocks = sampler.stop() if rank == 0 else {}
 
     from qwen_megakernel.replicas import combine
     frames_dev, ms_dev = combine(K, ms_dev, device=dev)      # sum of frames over ranks, max of device time
     frames_e2e, ms_e2e = combine(K, ms_e2e, device=dev)
+    frames_dropin, ms_dropin = combine(K, ms_dropin, device=dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -367,7 +396,11 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic", "config": config,
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2048, "d2h_bytes_per_step": 16 * 8 + 4},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2048, "d2h_bytes_per_step": 16 * 8 + 4,
+                "note": "public API, sync-free pipeline: input embedding from pinned host memory, codes + token copied to pinned "
+                        "host memory every frame"},
+        "e2e_dropin_loop": {"value": frames_dropin / (ms_dropin / 1000.0), "unit": UNIT,
+                            "note": "upstream caller's control flow: step() returns a Python int (blocking D2H per frame)"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "qmk_decode_kernel (talker: 28 layers + LM head, one launch per step)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",

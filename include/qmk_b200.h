@@ -144,6 +144,14 @@ int qmk_cp_predict(qmk_model* m, const float* talker_hidden, int first_codebook_
                    int top_k, uint64_t seed, uint64_t frame_counter, const int32_t* forced_tokens,
                    int64_t* out_codes, float* logits_out, float* hidden_out, void* stream);
 
+/* Same frame with the talker's token taken from DEVICE memory (the int32 out_token of the preceding talker step on the
+ * same stream), so a frame loop can queue predict(f+1) behind step(f) without a host round trip; the token is clamped
+ * to [0, talker_vocab).  The host reads tokens / codes asynchronously (EOS is then detected one frame late). */
+int qmk_cp_predict_dev(qmk_model* m, const float* talker_hidden, const int32_t* first_token_dev, int talker_vocab,
+                       const void* talker_embed_weight, const void* cos_table, const void* sin_table, void* k_cache,
+                       void* v_cache, int max_seq_len, int do_sample, float temperature, int top_k, uint64_t seed,
+                       uint64_t frame_counter, int64_t* out_codes, void* stream);
+
 /* ---- batched multi-stream decode (no upstream counterpart: upstream is strictly B = 1) ----
  * B = 16 .. 64 concurrent utterances, each numerically the B = 1 step (own position, own KV cache).  The projections
  * run on tcgen05 / TMEM tensor-core tiles (csrc/qmk_bgemm.cuh), weights are read in place in the upstream [out, in]

@@ -93,6 +93,7 @@ struct StepDesc {
   const long long* codes;         // IN_CODES_SUM: int64[16] (device) -> in_table[codes[0]] + sum_g sum_tables[g][codes[g+1]] + in_vec
   int in_mode;
   int token;
+  const int* token_ptr;           // IN_TABLE_TOKEN: if non-null the row index is read from device memory (clamped)
   int position;
   HeadDesc head;
   int select;                     // 0 = argmax, 1 = temperature / top-k / multinomial (Params::sample_*)
@@ -133,6 +134,7 @@ struct Params {
   unsigned long long sample_seed, sample_counter;
   const int* forced_tokens;        // optional int32[15] (device): token fed to the next step instead of the selected one
   const __nv_bfloat16* sum_tables[15];   // IN_CODES_SUM: the 15 code-predictor embedding tables [2048, 1024]
+  const int* code0_ptr;            // optional: code0 comes from device memory (the talker's out_token)
   long long* code0_out;            // optional: receives code0 (the talker's token, first entry of the frame's codes)
   int code0;
   int n_steps;
@@ -1060,12 +1062,16 @@ __device__ void consumer_loop(Ctx& c) {
   for (int sh = 0; sh < 2 * MAX_ST; ++sh)
     kb3_pack |= (uint32_t)(((sh >> 1) * STAGE_ITEMS + (c.lane >> 2) + (sh & 1) * 8) % 3) << (2 * sh);
 
-  if (c.cta == 0 && c.tid == 0 && p.code0_out != nullptr) *p.code0_out = (long long)p.code0;
+  if (c.cta == 0 && c.tid == 0 && p.code0_out != nullptr) *p.code0_out = (long long)(p.code0_ptr ? *p.code0_ptr : p.code0);
   for (int step = 0; step < p.n_steps; ++step) {
     const StepDesc& sd = p.steps[step];
     const uint32_t ebase = p.epoch_base + (uint32_t)step * (uint32_t)(y.L + 2);
     const int position = sd.position;
     int in_token = sd.token;
+    if (sd.in_mode == IN_TABLE_TOKEN && sd.token_ptr != nullptr) {   // written by an earlier launch on the same stream
+      in_token = *sd.token_ptr;
+      in_token = in_token < 0 ? 0 : (in_token > sd.token ? sd.token : in_token);   // sd.token = last valid row
+    }
     if (sd.in_mode == IN_TABLE_PREV) {
       // the token chosen by CTA 0 at the end of the previous step (one LL8 word, epoch = that step's head epoch)
       if (c.warp == 0) {

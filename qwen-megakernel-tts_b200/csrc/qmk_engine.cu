@@ -441,15 +441,17 @@ extern "C" int qmk_decode_step_codes(qmk_model* m, int head_index, const int64_t
                           max_seq_len, attn_scale, 0, stream);
 }
 
-extern "C" int qmk_cp_predict(qmk_model* m, const float* talker_hidden, int first_codebook_token,
-                              const void* talker_embed_weight, const void* cos_table, const void* sin_table,
-                              void* k_cache, void* v_cache, int max_seq_len, int do_sample, float temperature,
-                              int top_k, uint64_t seed, uint64_t frame_counter, const int32_t* forced_tokens,
-                              int64_t* out_codes, float* logits_out, float* hidden_out, void* stream) {
+static int cp_predict_impl(qmk_model* m, const float* talker_hidden, int first_codebook_token,
+                           const int32_t* first_token_dev, int talker_vocab, const void* talker_embed_weight,
+                           const void* cos_table, const void* sin_table, void* k_cache, void* v_cache, int max_seq_len,
+                           int do_sample, float temperature, int top_k, uint64_t seed, uint64_t frame_counter,
+                           const int32_t* forced_tokens, int64_t* out_codes, float* logits_out, float* hidden_out,
+                           void* stream) {
   if (!m || !talker_hidden || !talker_embed_weight || !cos_table || !sin_table || !k_cache || !v_cache || !out_codes)
     return set_error(QMK_ERR_ARG, "qmk_cp_predict: null argument");
   if (max_seq_len < QMK_CP_GROUPS + 1) return set_error(QMK_ERR_ARG, "qmk_cp_predict: max_seq_len %d < 16", max_seq_len);
-  if (first_codebook_token < 0) return set_error(QMK_ERR_ARG, "qmk_cp_predict: negative first token");
+  if (!first_token_dev && first_codebook_token < 0) return set_error(QMK_ERR_ARG, "qmk_cp_predict: negative first token");
+  if (first_token_dev && talker_vocab < 1) return set_error(QMK_ERR_ARG, "qmk_cp_predict_dev: talker_vocab must be positive");
   if ((int)m->heads.size() < QMK_CP_GROUPS) return set_error(QMK_ERR_ARG, "qmk_cp_predict: %d group heads registered, need 15", (int)m->heads.size());
   for (int g = 0; g < QMK_CP_GROUPS - 1; ++g)
     if (!m->group_embed[g]) return set_error(QMK_ERR_ARG, "qmk_cp_predict: group embedding %d not set", g);
@@ -469,6 +471,7 @@ extern "C" int qmk_cp_predict(qmk_model* m, const float* talker_hidden, int firs
   p.forced_tokens = forced_tokens;
   p.code0_out = reinterpret_cast<long long*>(out_codes);
   p.code0 = first_codebook_token;
+  p.code0_ptr = first_token_dev;
   for (int s = 0; s < p.n_steps; ++s) {
     StepDesc& sd = p.steps[s];
     sd.position = s;
@@ -481,7 +484,8 @@ extern "C" int qmk_cp_predict(qmk_model* m, const float* talker_hidden, int firs
       if (s == 1) {         // embedding of the talker's token (model_tts.py:746-748)
         sd.in_mode = IN_TABLE_TOKEN;
         sd.in_table = reinterpret_cast<const __nv_bfloat16*>(talker_embed_weight);
-        sd.token = first_codebook_token;
+        sd.token = first_token_dev ? talker_vocab - 1 : first_codebook_token;   // device token: clamp bound
+        sd.token_ptr = first_token_dev;
       } else {              // embedding of the previous group's code (model_tts.py:768-770)
         sd.in_mode = IN_TABLE_PREV;
         sd.in_table = reinterpret_cast<const __nv_bfloat16*>(m->group_embed[s - 2]);
@@ -496,6 +500,26 @@ extern "C" int qmk_cp_predict(qmk_model* m, const float* talker_hidden, int firs
   int rc = reserve_epochs(e, (uint32_t)p.n_steps * ((uint32_t)m->lay.L + 2u), st, &p.epoch_base);
   if (rc != QMK_OK) return rc;
   return launch_slice(e, p, 0, m->lay.L * PH_PER_LAYER + 2, st);
+}
+
+extern "C" int qmk_cp_predict(qmk_model* m, const float* talker_hidden, int first_codebook_token,
+                              const void* talker_embed_weight, const void* cos_table, const void* sin_table,
+                              void* k_cache, void* v_cache, int max_seq_len, int do_sample, float temperature,
+                              int top_k, uint64_t seed, uint64_t frame_counter, const int32_t* forced_tokens,
+                              int64_t* out_codes, float* logits_out, float* hidden_out, void* stream) {
+  return cp_predict_impl(m, talker_hidden, first_codebook_token, nullptr, 0, talker_embed_weight, cos_table, sin_table,
+                         k_cache, v_cache, max_seq_len, do_sample, temperature, top_k, seed, frame_counter, forced_tokens,
+                         out_codes, logits_out, hidden_out, stream);
+}
+
+extern "C" int qmk_cp_predict_dev(qmk_model* m, const float* talker_hidden, const int32_t* first_token_dev, int talker_vocab,
+                                  const void* talker_embed_weight, const void* cos_table, const void* sin_table,
+                                  void* k_cache, void* v_cache, int max_seq_len, int do_sample, float temperature,
+                                  int top_k, uint64_t seed, uint64_t frame_counter, int64_t* out_codes, void* stream) {
+  if (!first_token_dev) return set_error(QMK_ERR_ARG, "qmk_cp_predict_dev: first_token_dev is null");
+  return cp_predict_impl(m, talker_hidden, 0, first_token_dev, talker_vocab, talker_embed_weight, cos_table, sin_table,
+                         k_cache, v_cache, max_seq_len, do_sample, temperature, top_k, seed, frame_counter, nullptr,
+                         out_codes, nullptr, nullptr, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -85,6 +85,7 @@ SIGNATURES = {
                                      _i32, _f32, _vp]),
     "qmk_cp_predict": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _u64, _u64, _vp,
                               _vp, _vp, _vp, _vp]),
+    "qmk_cp_predict_dev": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _u64, _u64, _vp, _vp]),
     "qmk_batched_create": (_i32, [_i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, ctypes.POINTER(_vp)]),
     "qmk_batched_destroy": (None, [_vp]),
     "qmk_batched_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

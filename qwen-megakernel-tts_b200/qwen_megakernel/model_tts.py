@@ -304,12 +304,16 @@ class TTSDecoder:
         self._launch(EMBED_FROM_BUFFER, self._hidden.data_ptr())
         return self._finish()
 
-    def step_with_codes(self, codes: torch.Tensor, code_embeddings, extra_embed_bf16: torch.Tensor) -> tuple[int, torch.Tensor]:
+    def step_with_codes(self, codes: torch.Tensor, code_embeddings, extra_embed_bf16: torch.Tensor, *, sync: bool = True):
         """Decode from a frame's 16 codes: the embedding sum of the upstream frame loop (tts_engine.py:319-335,
         ``embed[codes[0]] + sum_g code_embeddings[g][codes[g+1]] + extra``, bf16 adds in that order) is evaluated
         inside the step's launch instead of by 32 torch kernels.  ``codes``: int64[16] on this device (what
         ``CodePredictorKernel.predict`` returns); ``code_embeddings``: the 15 ``codec_embedding.{g}.weight`` tables;
-        ``extra_embed_bf16``: trailing-text or tts_pad embedding, bf16[1024]."""
+        ``extra_embed_bf16``: trailing-text or tts_pad embedding, bf16[1024].
+
+        ``sync=False`` returns the device tensors ``(token int32[1], hidden f32[1024])`` that the next step overwrites,
+        without the host round trip of ``.item()``: feed them straight to ``CodePredictorKernel.predict`` and read
+        tokens / codes back asynchronously."""
         from .build_tts import check
         if codes.dtype != torch.int64 or codes.numel() != NUM_CODE_GROUPS or codes.device != self.device:
             raise ValueError("codes: need an int64[16] tensor on the decoder's device")
@@ -330,7 +334,7 @@ class TTSDecoder:
             self._hidden.data_ptr(), self._norm_out.data_ptr(), self._out_token.data_ptr(), self._position,
             self._max_seq, self._attn_scale, _stream_ptr(self.device)), "qmk_decode_step_codes")
         self._position += 1
-        return self._finish()
+        return self._finish() if sync else (self._out_token, self._norm_out)
 
     def reset(self):
         """New utterance.  O(1): rows beyond ``position`` are never read."""
@@ -545,9 +549,17 @@ class CodePredictorKernel:
         still the model's own choices).  ``return_debug``: also return (logits f32[15, 2048], hidden f32[15, 1024]).
         """
         from .build_tts import check
-        first_codebook_token = int(first_codebook_token)
-        if not 0 <= first_codebook_token < talker_embed_weight.shape[0]:
-            raise ValueError(f"first_codebook_token {first_codebook_token} out of range")
+        token_dev = None
+        if isinstance(first_codebook_token, torch.Tensor):      # device token of the preceding talker step: no host sync
+            token_dev = first_codebook_token
+            if token_dev.dtype != torch.int32 or token_dev.numel() != 1 or token_dev.device != self.device:
+                raise ValueError("first_codebook_token tensor: need int32[1] on the predictor's device")
+            if forced_tokens is not None or return_debug:
+                raise ValueError("forced_tokens / return_debug need a host token")
+        else:
+            first_codebook_token = int(first_codebook_token)
+            if not 0 <= first_codebook_token < talker_embed_weight.shape[0]:
+                raise ValueError(f"first_codebook_token {first_codebook_token} out of range")
         if talker_embed_weight.dtype != torch.bfloat16 or talker_embed_weight.device != self.device or \
                 talker_embed_weight.shape[1] != HIDDEN_SIZE or not talker_embed_weight.is_contiguous():
             raise ValueError("talker_embed_weight: need a contiguous bf16 [*, 1024] tensor on the predictor's device")
@@ -568,6 +580,15 @@ class CodePredictorKernel:
                     raise ValueError("forced_tokens must have 15 elements")
                 forced_ptr = forced_tokens.data_ptr()
             self._frame_counter += 1
+            if token_dev is not None:
+                check(self._lib, self._lib.qmk_cp_predict_dev(
+                    self._model, hid.data_ptr(), token_dev.data_ptr(), int(talker_embed_weight.shape[0]),
+                    talker_embed_weight.data_ptr(), self._cos_table.data_ptr(), self._sin_table.data_ptr(),
+                    self._k_cache.data_ptr(), self._v_cache.data_ptr(), self._max_seq, int(sample), float(temperature),
+                    int(top_k), torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, self._frame_counter, out.data_ptr(),
+                    _stream_ptr(self.device)), "qmk_cp_predict_dev")
+                self._position = NUM_CODE_GROUPS
+                return out
             check(self._lib, self._lib.qmk_cp_predict(
                 self._model, hid.data_ptr(), first_codebook_token, talker_embed_weight.data_ptr(),
                 self._cos_table.data_ptr(), self._sin_table.data_ptr(), self._k_cache.data_ptr(),

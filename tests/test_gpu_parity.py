@@ -218,6 +218,35 @@ def test_step_with_codes_equals_torch_embed_sum(talker, cp_kernel, gpu_weights):
         assert t0 == t1 and torch.equal(h0, h1)
 
 
+def test_sync_free_frame_pipeline_equals_synchronous_loop(talker, cp_kernel, gpu_weights):
+    """predict() fed with the talker's DEVICE token + step_with_codes(sync=False) produce the same greedy frames as the
+    synchronous loop (host int token, .item() per frame)."""
+    from qwen_megakernel.synthetic import synthetic_inputs
+    extra = synthetic_inputs(909, 4).cuda()
+    emb = gpu_weights["embed_weight"]
+
+    def run(sync):
+        talker.reset()
+        tok, hid = talker.step(CODEC_BOS)
+        tok_d, hid_d = talker._out_token, talker._norm_out
+        frames = []
+        for f in range(4):
+            if sync:
+                codes = cp_kernel.predict(hid, tok, emb, do_sample=False)
+                tok, hid = talker.step_with_codes(codes, cp_kernel.codec_embeddings, extra[f])
+                frames.append((codes.cpu().tolist(), tok))
+            else:
+                codes = cp_kernel.predict(hid_d, tok_d, emb, do_sample=False)
+                tok_d, hid_d = talker.step_with_codes(codes, cp_kernel.codec_embeddings, extra[f], sync=False)
+                frames.append((codes.clone(), tok_d.clone()))
+        if not sync:
+            torch.cuda.synchronize()
+            frames = [(c.cpu().tolist(), int(t.item())) for c, t in frames]
+        return frames
+
+    assert run(True) == run(False)
+
+
 def test_code_predictor_sampling_respects_top_k(cp_kernel, gpu_weights):
     from qwen_megakernel.synthetic import synthetic_inputs
     torch.manual_seed(3)
