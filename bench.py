@@ -70,6 +70,22 @@ def measured_peaks() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one talker launch, from the committed `ncu --set full` capture
+    (profiles/r01_ncu_final_raw.csv, transposed raw page); None if the file is missing."""
+    path = os.path.join(REPO, "profiles", "r01_ncu_final_raw.csv")
+    try:
+        import csv
+        vals = {}
+        for row in csv.reader(open(path)):
+            if row and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[row[1]]
+                vals[row[0]] = float(row[2]) * scale
+        return vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -404,7 +420,8 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "qmk_decode_kernel (talker: 28 layers + LM head, one launch per step)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None,
+                     "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
+                     "traffic_source": "profiles/r01_ncu_final_raw.csv (ncu --set full, one talker launch, bytes)",
                      "algorithmic_bytes_per_launch": talker_b, "launch_us": talker_ms * 1e3},
         "talker_steps_per_s": 1000.0 / talker_ms,
         "cp_frame": {"ms": cp_ms, "frames_per_s": 1000.0 / cp_ms, "algorithmic_bytes": cp_frame_bytes(),

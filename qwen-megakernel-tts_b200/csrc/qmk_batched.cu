@@ -271,7 +271,7 @@ struct qmk_batched {
   std::vector<CUtensorMap> map_qkv, map_o, map_gu, map_down;
   CUtensorMap map_head, map_x1024, map_x2048, map_x3072;
   float *res = nullptr, *partial = nullptr;
-  __nv_bfloat16 *xn = nullptr, *qbuf = nullptr, *abuf = nullptr, *mbuf = nullptr;
+  __nv_bfloat16 *xn = nullptr, *abuf = nullptr, *mbuf = nullptr;
 };
 
 extern "C" const char* qmk_batched_last_error(void) { return g_err.c_str(); }
@@ -297,7 +297,7 @@ extern "C" int qmk_batched_create(int device, const LDGLayerWeights* layers_host
   const size_t L = num_layers;
   bool ok = cudaMalloc(&h->w_qkv, L * QKV_ROWS * H * 2) == cudaSuccess && cudaMalloc(&h->w_gu, L * GU_ROWS * H * 2) == cudaSuccess &&
             cudaMalloc(&h->res, (size_t)batch * H * 4) == cudaSuccess && cudaMalloc(&h->partial, (size_t)2 * 1024 * 1024 * sizeof(float)) == cudaSuccess  /* max splits x B x rows = 4 x 64 x 6144 */ &&
-            cudaMalloc(&h->xn, (size_t)batch * H * 2) == cudaSuccess && cudaMalloc(&h->qbuf, (size_t)batch * QSZ * 2) == cudaSuccess &&
+            cudaMalloc(&h->xn, (size_t)batch * H * 2) == cudaSuccess &&
             cudaMalloc(&h->abuf, (size_t)batch * QSZ * 2) == cudaSuccess && cudaMalloc(&h->mbuf, (size_t)batch * INTER * 2) == cudaSuccess;
   if (!ok) { delete h; return fail(QMK_ERR_CUDA, "qmk_batched_create: allocation failed"); }
   for (int l = 0; l < num_layers; ++l) {
@@ -339,7 +339,7 @@ extern "C" void qmk_batched_destroy(qmk_batched* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   cudaFree(h->w_qkv); cudaFree(h->w_gu); cudaFree(h->res); cudaFree(h->partial);
-  cudaFree(h->xn); cudaFree(h->qbuf); cudaFree(h->abuf); cudaFree(h->mbuf);
+  cudaFree(h->xn); cudaFree(h->abuf); cudaFree(h->mbuf);
   delete h;
 }
 

@@ -121,7 +121,6 @@ struct Params {
   int* delays;                     // [G][3][DL_N]: poll delays (cycles after own publish; in), repeated-poll counts and
                                    // cycles/16 spent waiting for weights per exchange kind (in/out)
   int o_sentinel;                  // O phase of idle CTAs: one warp polls sample words before the CTA-wide gather
-  int warm_mma;                    // issue a dummy mma while waiting for activations (tensor-pipe wake-up experiment)
   int delay_o_idle;                // O-phase delay of CTAs without an attention item (they wait for the attention CTAs)
   uint32_t epoch_base;             // epochs base+1 .. base+n_steps*(L+2) are used by this launch (16-bit, never 0)
   int* status;                     // int[4]: code, cta, phase index, aux
@@ -1277,11 +1276,6 @@ __device__ void consumer_loop(Ctx& c) {
       uint2 wv = make_uint2(0, 0);
       if (norm && (ready & 1u)) wv = *reinterpret_cast<const uint2*>(aux + c.tid * 8);
       if (kind == K_QKV && has_item) attn_prefetch(c, l, position, item, 0, kv);  // older KV rows do not depend on this layer
-      if (QMK_UNLIKELY(p.warm_mma)) {   // keep the tensor pipe awake while the activations are in flight
-        float wd[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint32_t wa[4] = {0u, 0u, 0u, 0u}, wb[2] = {0u, 0u};
-        mma16816(wd, wa, wb);
-      }
       const uint4* xs = reinterpret_cast<const uint4*>(c.s_vec + ((c.lane >> 2) < xr_mod ? (c.lane >> 2) : 0) * SEG_BYTES +
                                                        c.warp * 256 + (c.lane & 3) * 64);
       uint32_t* const my_x = reinterpret_cast<uint32_t*>(c.s_vec + gi0 * 2);

@@ -64,7 +64,6 @@ struct qmk_engine {
   float* res_spill = nullptr;
   int* delays = nullptr;
   int delay_o_idle = 4500;
-  int warm_mma = 0;
   int o_sentinel = 0;   // measured: the extra hop costs more than the avoided early polls
   int coop = 1;   // cooperative launch = co-residency of all CTAs is checked by the driver
   long long* trace_dev = nullptr;
@@ -141,7 +140,6 @@ extern "C" int qmk_engine_create(int device, int num_ctas, qmk_engine** out) {
   if (const char* env = getenv("QMK_POLL_DELAY")) delay0 = atoi(env);
   if (const char* env = getenv("QMK_POLL_DELAY_TOKEN")) delay_token = atoi(env);
   if (const char* env = getenv("QMK_POLL_DELAY_O")) e->delay_o_idle = atoi(env);
-  if (const char* env = getenv("QMK_WARM_MMA")) e->warm_mma = atoi(env);
   if (const char* env = getenv("QMK_O_SENTINEL")) e->o_sentinel = atoi(env);
   if (const char* env = getenv("QMK_COOP")) e->coop = atoi(env);
   std::vector<int> delays((size_t)G * 3 * DL_N, 0);
@@ -336,7 +334,6 @@ static void fill_common(Params& p, qmk_model* m, const void* cos_table, const vo
   p.res_spill = e->res_spill;
   p.delays = e->delays;
   p.delay_o_idle = e->delay_o_idle;
-  p.warm_mma = e->warm_mma;
   p.o_sentinel = e->o_sentinel;
   p.status = e->status_dev;
   p.timeout_cycles = e->timeout_cycles;

@@ -123,7 +123,6 @@ def main():
         os.environ["QMK_POLL_DELAY"] = dly[0]
         if len(dly) > 1:
             os.environ["QMK_POLL_DELAY_O"] = dly[1]
-        os.environ["QMK_WARM_MMA"] = dly[2] if len(dly) > 2 else "0"
         os.environ["QMK_COOP"] = dly[3] if len(dly) > 3 else "1"
         os.environ["QMK_O_SENTINEL"] = dly[4] if len(dly) > 4 else "1"
         model_tts._Native._engines.clear()
