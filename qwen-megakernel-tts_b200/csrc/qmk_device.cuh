@@ -382,10 +382,11 @@ __device__ __forceinline__ uint32_t ll8_wait(Ctx& c, const u64* p, uint32_t epoc
 }
 
 // Debug trace: trace[cta][(idx - phase_begin) * 8 + sub] = clock64() (thread 0 of the CTA only).
+constexpr int TRACE_SUBS = 24;   // per phase: 8 coarse 64-bit stamps + 16 fine 32-bit stamps of the GEMV path
 template <bool TR>
 __device__ __forceinline__ void trace_sub(const Ctx& c, int sub) {
   if (TR && c.p.trace != nullptr && c.tid == 0) {
-    const int slot = (c.cur_idx - c.p.phase_begin) * 8 + sub;
+    const int slot = (c.cur_idx - c.p.phase_begin) * TRACE_SUBS + sub;
     // sub-slot 7 (row published) records the GLOBAL timer in ns so that publish times compare across SMs
     long long t;
     if (sub == 7) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); else t = clock64();
@@ -1183,6 +1184,14 @@ __device__ void consumer_loop(Ctx& c) {
       }
 
       // ---- GEMV-shaped phases -------------------------------------------------------------------------
+      // (traced build only) fine-grained 32-bit clock stamps of thread 0, flushed to trace slots 8..23 of the phase
+      uint32_t fs[16];
+#define QMK_FS(i) do { if (TR) fs[i] = (uint32_t)clock(); } while (0)
+      if (TR) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) fs[i] = 0;
+      }
+      QMK_FS(0);
       // Everything that does not depend on the gathered activations is computed BEFORE they are checked: a single
       // warp executes dependent instructions at ~5 cycles each, so every instruction between "data arrived" and
       // "row published" is on the critical path of the layer.
@@ -1234,10 +1243,12 @@ __device__ void consumer_loop(Ctx& c) {
         if (kind == K_O && !has_item) wait_window(c, p.delay_o_idle, p.o_sentinel ? xw : nullptr, ep);
         else wait_window(c, c.s_delay[dslot]);
         trace_sub<TR>(c, 1);
+        QMK_FS(1);
         gw[0] = ll4_ld4(xw + gi0);
         if (n_words > H) gw[1] = ll4_ld4(xw + gi0 + H);
         if (n_words > 2 * H) gw[2] = ll4_ld4(xw + gi0 + 2 * H);
       }
+      QMK_FS(2);
       // -- shadow of the load latency --
       PhaseDesc d;
       if (kind == K_HEAD) d = head_phase_desc(p, sd.head, c.cta);
@@ -1291,6 +1302,7 @@ __device__ void consumer_loop(Ctx& c) {
         if (kb & 1) pw_sel |= 1u << sh;
       }
       float* const pw_base = c.s_part + ((c.lane >> 2) * NCW + c.warp);
+      QMK_FS(3);
       // -- data --
       bool retried = false;
       if (!from_input) {
@@ -1299,12 +1311,14 @@ __device__ void consumer_loop(Ctx& c) {
         if (QMK_UNLIKELY(n_words > 2 * H && !ll4_ok(gw[2], ep))) { retried = true; gw[2] = ll4_wait_slow(p.status, c.s_abort, c.t0, p.timeout_cycles, c.cta, idx, xw + gi0 + 2 * H, ep, gi0); }
       }
       trace_sub<TR>(c, 2);
+      QMK_FS(4);
       if (norm) {
         // n = r( r(x) * rsqrt(mean(r(x)^2) + eps) * w ); the norm weights arrive with the first stage of the phase
         const float r0 = ll4_val(gw[0].x), r1 = ll4_val(gw[0].y), r2 = ll4_val(gw[0].z), r3 = ll4_val(gw[0].w);
         float ss = fmaf(r0, r0, r1 * r1) + fmaf(r2, r2, r3 * r3);
         ss = warp_sum(ss);
         if (c.lane == 0) c.s_red[c.warp] = ss;
+        QMK_FS(5);
         if (from_input) {
           consumer_bar();
           if (sd.in_mode == IN_CODES_SUM && c.tid < rows.o_rows) {   // fp32 residual of this CTA's rows = the summed input
@@ -1315,6 +1329,7 @@ __device__ void consumer_loop(Ctx& c) {
           gather_bar(c, dslot, retried);
         }
         trace_sub<TR>(c, 3);
+        QMK_FS(6);
         if (QMK_UNLIKELY(!(ready & 1u))) {
           wait_full(c, c.k);
           ready |= 1u;
@@ -1348,6 +1363,7 @@ __device__ void consumer_loop(Ctx& c) {
       }
       __syncwarp();
       trace_sub<TR>(c, 4);
+      QMK_FS(7);
 
       // stages: each warp multiplies its KSTEPS k16-steps of every stage tile (rows = items) by the activation columns
       uint32_t bfrag[KSTEPS][2];
@@ -1356,6 +1372,7 @@ __device__ void consumer_loop(Ctx& c) {
         const uint4 v = xs[i];
         bfrag[2 * i][0] = v.x; bfrag[2 * i][1] = v.y; bfrag[2 * i + 1][0] = v.z; bfrag[2 * i + 1][1] = v.w;
       }
+      QMK_FS(8);
       float acc[MAX_ST][4];
 #pragma unroll
       for (int s = 0; s < MAX_ST; ++s) {
@@ -1385,6 +1402,7 @@ __device__ void consumer_loop(Ctx& c) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) acc[s][e] += acc2[e];
         }
+        if (TR) { if (s == 0) fs[9] = __float_as_uint(acc[0][0]) * 0u + (uint32_t)clock(); else if (s == 1) fs[10] = __float_as_uint(acc[1][0]) * 0u + (uint32_t)clock(); else fs[11] = __float_as_uint(acc[2][0]) * 0u + (uint32_t)clock(); }
       }
       c.k += nst;
       trace_sub<TR>(c, 5);
@@ -1395,7 +1413,9 @@ __device__ void consumer_loop(Ctx& c) {
           pw_base[((sh >> 1) * STAGE_ITEMS + (sh & 1) * 8) * NCW] =
               ((pw_sel >> sh) & 1u) ? acc[sh >> 1][(sh & 1) * 2 + 1] : acc[sh >> 1][(sh & 1) * 2];
       }
+      QMK_FS(12);
       consumer_bar();
+      QMK_FS(13);
       trace_sub<TR>(c, 6);
       if (c.warp == NCW - 1) prod_issue(c, prod, nst);   // refill the slots this phase released (warps 0-1 finalize meanwhile)
 
@@ -1431,6 +1451,14 @@ __device__ void consumer_loop(Ctx& c) {
         }
       }
       c.t_pub = clock64();
+      QMK_FS(14);
+      if (TR && c.p.trace != nullptr && c.tid == 0) {
+        const int slot0 = (c.cur_idx - c.p.phase_begin) * TRACE_SUBS + 8;
+        if (slot0 + 16 <= c.p.trace_stride) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) c.p.trace[(size_t)c.cta * c.p.trace_stride + slot0 + i] = (long long)fs[i];
+        }
+      }
       trace_sub<TR>(c, 7);
     }
   }

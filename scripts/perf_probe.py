@@ -57,7 +57,7 @@ def time_cp_steps(cp, x, n=64, warm=16):
 
 def trace(dec, x, lib, engine, L):
     n_idx = L * 5 + 2
-    stride = (n_idx + 1) * 8
+    stride = (n_idx + 1) * 24
     assert lib.qmk_engine_trace_enable(engine, stride) == 0
     dec.reset()
     for i in range(12):
@@ -66,7 +66,9 @@ def trace(dec, x, lib, engine, L):
     buf = (ctypes.c_longlong * (G * stride))()
     lib.qmk_engine_trace_read(engine, torch.cuda.current_stream().cuda_stream, buf, G * stride)
     lib.qmk_engine_trace_enable(engine, 0)
-    t = np.frombuffer(buf, dtype=np.int64).reshape(G, n_idx + 1, 8).astype(np.float64)
+    raw = np.frombuffer(buf, dtype=np.int64).reshape(G, n_idx + 1, 24)
+    t = raw[:, :, :8].astype(np.float64)
+    fine = raw[:, :, 8:24].astype(np.int64)
     start = t[:, :, 0]
     d = np.diff(start, axis=1)
     names = ["qkv", "attn", "o", "gu", "down"]
@@ -95,6 +97,24 @@ def trace(dec, x, lib, engine, L):
             nxt = start[sl][:, [i + 1 for i in idxs]]
             parts.append(f"tail={np.mean(nxt - last):.0f}")
             print(f"  {names[ph]:5s} total {tot:7.0f} : " + "  ".join(parts))
+    # fine-grained stamps of thread 0 inside the GEMV phases (32-bit clock, wrap-safe deltas)
+    fl = ["start->window", "issue loads", "shadow work", "data arrived", "sumsq+sts", "gather bar", "normalize+sts",
+          "bfrag lds", "stage0 mma", "stage1 mma", "stage2 mma", "partial sts", "partial bar", "finalize+publish"]
+    for grp_name, sl in (("attention CTAs 0-7", slice(0, 8)), ("other CTAs", slice(8, G))):
+        print(f"--- {grp_name}: fine stamps (cycles between consecutive stamps; 0 = stamp not taken)")
+        for ph in (0, 2, 3, 4):
+            f = fine[sl][:, [l * 5 + ph for l in layers], :]
+            parts = []
+            prev = f[:, :, 0]
+            for i in range(1, 15):
+                cur = f[:, :, i]
+                taken = cur != 0
+                if not taken.any():
+                    continue
+                dlt = ((cur - prev) & 0xFFFFFFFF)[taken]
+                parts.append(f"{fl[i-1]}={dlt.mean():.0f}")
+                prev = np.where(taken, cur, prev)
+            print(f"  {names[ph]:5s}: " + "  ".join(parts))
     # publish skew across CTAs (global timer, ns): per phase, spread of the publish time and who is last
     for ph in (0, 2, 3, 4):
         pub = t[:, [l * 5 + ph for l in layers], 7]                      # [G, layers] ns
