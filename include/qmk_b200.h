@@ -59,6 +59,8 @@ typedef struct LDGLayerWeights {
   const void* down_proj_weight;           /* [1024, 3072]  */
 } LDGLayerWeights;
 
+/* An engine owns one set of inter-SM exchange buffers: all launches on it (every model created on it) must be
+ * ordered on ONE stream; use one engine per concurrent stream / per GPU. */
 typedef struct qmk_engine qmk_engine; /* per-device context: exchange buffers, watchdog word, epoch */
 typedef struct qmk_model qmk_model;   /* a layer stack re-packed into per-SM weight streams */
 

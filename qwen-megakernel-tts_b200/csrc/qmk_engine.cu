@@ -139,12 +139,17 @@ extern "C" int qmk_engine_create(int device, int num_ctas, qmk_engine** out) {
   int delay_token = 2500;   // the next step's token arrives two exchanges after a CTA has published its logits
   if (const char* env = getenv("QMK_POLL_DELAY")) delay0 = atoi(env);
   if (const char* env = getenv("QMK_POLL_DELAY_TOKEN")) delay_token = atoi(env);
+  // attention CTAs: wait for q/k/v (DL_ATTN) and, in the O phase, for the other attention CTAs' output (DL_O)
+  int delay_attn = 400, delay_oa = 300;
+  if (const char* env = getenv("QMK_POLL_DELAY_ATTN")) delay_attn = atoi(env);
+  if (const char* env = getenv("QMK_POLL_DELAY_OA")) delay_oa = atoi(env);
   if (const char* env = getenv("QMK_POLL_DELAY_O")) e->delay_o_idle = atoi(env);
   if (const char* env = getenv("QMK_O_SENTINEL")) e->o_sentinel = atoi(env);
   if (const char* env = getenv("QMK_COOP")) e->coop = atoi(env);
   std::vector<int> delays((size_t)G * 3 * DL_N, 0);
   for (int c = 0; c < G; ++c)
-    for (int d = 0; d < DL_N; ++d) delays[(size_t)c * 3 * DL_N + d] = (d == DL_TOKEN) ? delay_token : delay0;
+    for (int d = 0; d < DL_N; ++d)
+      delays[(size_t)c * 3 * DL_N + d] = (d == DL_TOKEN) ? delay_token : (d == DL_ATTN) ? delay_attn : (d == DL_O) ? delay_oa : delay0;
   cudaError_t err = cudaMalloc(&e->xbuf, XBUF_BYTES);
   if (err == cudaSuccess) err = cudaMemset(e->xbuf, 0, XBUF_BYTES);
   if (err == cudaSuccess) err = cudaMalloc(&e->res_spill, H * sizeof(float));

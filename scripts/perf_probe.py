@@ -144,7 +144,9 @@ def main():
         if len(dly) > 1:
             os.environ["QMK_POLL_DELAY_O"] = dly[1]
         os.environ["QMK_COOP"] = dly[3] if len(dly) > 3 else "1"
-        os.environ["QMK_O_SENTINEL"] = dly[4] if len(dly) > 4 else "1"
+        os.environ["QMK_O_SENTINEL"] = dly[4] if len(dly) > 4 else "0"
+        os.environ["QMK_POLL_DELAY_ATTN"] = dly[5] if len(dly) > 5 else dly[0]
+        os.environ["QMK_POLL_DELAY_OA"] = dly[6] if len(dly) > 6 else dly[0]
         model_tts._Native._engines.clear()
         dec = model_tts.TTSDecoder(weights=w, verbose=False, max_seq_len=256)
         cp = model_tts.CodePredictorKernel(w, device="cuda")

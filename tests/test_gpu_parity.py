@@ -247,6 +247,17 @@ def test_sync_free_frame_pipeline_equals_synchronous_loop(talker, cp_kernel, gpu
     assert run(True) == run(False)
 
 
+def test_epoch_wrap_is_transparent(cp_kernel, gpu_weights):
+    """The exchange words carry 16-bit epochs (112 per frame): 700 frames cross the wrap (buffer clear + restart);
+    greedy frames before and after must be identical."""
+    from qwen_megakernel.synthetic import synthetic_inputs
+    th = synthetic_inputs(4711, 1)[0].float().cuda()
+    first = cp_kernel.predict(th, 17, gpu_weights["embed_weight"], do_sample=False).cpu().tolist()
+    for _ in range(700):
+        out = cp_kernel.predict(th, 17, gpu_weights["embed_weight"], do_sample=False)
+    assert out.cpu().tolist() == first
+
+
 def test_code_predictor_sampling_respects_top_k(cp_kernel, gpu_weights):
     from qwen_megakernel.synthetic import synthetic_inputs
     torch.manual_seed(3)
