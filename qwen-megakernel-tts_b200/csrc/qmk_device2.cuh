@@ -1,0 +1,913 @@
+// qmk_device2.cuh — second-generation device side of the B200 decode engine (sm_100a): "group" kernel.
+//
+// Same contract, numerics and host ABI as qmk_device.cuh; what changes is how a layer is cut across SMs.
+// The first kernel splits every projection by output rows over all CTAs, which makes five grid-wide exchanges per
+// layer (x -> QKV -> attention on 8 CTAs -> O -> gate/up -> down) and leaves 140 SMs waiting while 8 of them do the
+// attention.  Here the grid is 8 groups x 16 CTAs, one group per KV head:
+//   * QKV rows of kv head g (2 q heads + k + v = 512 rows) live on group g; q/k/v are exchanged inside the group only.
+//   * every CTA of the group evaluates the attention of its head pair itself (short context) or one position chunk
+//     of it (long context, partials merged through a group-local exchange) -> `a` never crosses groups.
+//   * O and down are K-SPLIT: group g multiplies its own 256 (O) / 384 (down) input columns, rows split over the
+//     group's 16 CTAs, and the eight group partials of a row meet in L2: one red.add.u64 per row and group on a
+//     word {arrival count : 8, fixed-point sum : 56}.  Integer adds commute, so the sum is order-independent
+//     (deterministic), it is exact to 2^-24 absolute, and the arrival count rides in the same word: a consumer that
+//     reads count == previous + 8 has the complete sum -- reduction and all-gather are ONE exchange, there is no
+//     zeroing and no epoch (totals are cumulative; every consumer subtracts the total it read last time).
+//   * gate/up rows are the ones whose SwiGLU output feeds the group's own down columns, so `m` is group-local too.
+// Per layer: 2 grid-wide exchanges (h, h') + 2 group-local ones instead of 5 grid-wide ones, and no idle SMs.
+// Measured (scripts/ubench/xchg7.cu, 128 CTAs): red-gather 2310 cycles, group exchange 1650, layer-shaped sequence
+// of the four 6400 cycles.  Thread-block clusters with DSMEM pushes (215 cycles) were the first choice for the
+// group exchanges, but this B200 hosts only seven co-resident 16-CTA clusters (one GPC is smaller), so the groups
+// talk through L2 like everything else.
+//
+// Weight stream: per (CTA, layer) eight ring slots [QKV tile 0,1 | O | gate/up tile 0,1,2 | down half 0,1] of 32 KB
+// (24 KB for the down halves); a tile is 16 rows x 1024 k, chunk-swizzled for ldmatrix and K-permuted so that a lane's
+// B fragments are a contiguous run of the activation vector (same scheme as the first kernel, generalised to
+// 2 / 3 / 8 tensor-core steps per warp).
+#pragma once
+
+#include "qmk_device.cuh"
+
+namespace qmk2 {
+using namespace qmk;
+
+constexpr int G2 = 128, NGRP = 8, GSZ = 16;
+constexpr int SLOT2 = 32768, NSL = NSLOTS;       // 6 slots x 32 KB
+static_assert(NSL == 6, "wait_full() of the first kernel is reused: same slot count");
+constexpr int QKV_LOC = 32, O_LOC = 64, GU_LOC = 48, M_LOC = 24, KB_O = 256, KB_D = 384;
+constexpr int DOWN_SLOT = 32 * KB_D * 2;         // 24576: 32 rows x 384 k
+constexpr int LAYER_BYTES2 = 6 * SLOT2 + 2 * DOWN_SLOT;   // 245760
+constexpr int ENT_PER_LAYER = 8;
+constexpr int HEAD_TILES_MAX = 2;                // 3072 / 128 = 24 rows -> 2 tiles
+constexpr int S2_MAX = GSZ;                      // attention position chunks per kv head
+constexpr int FIX_SHIFT = 24;
+constexpr u64 CNT_ONE = 1ull << 56;
+
+// exchange buffer (bytes)
+constexpr size_t XB_ACC = 0;                               // u64[2][1024]  accumulators A (h: down), B (h': O)
+constexpr size_t XB_SNAP = XB_ACC + 2 * 1024 * 8;          // u64[2][1024]  totals at the end of the previous launch
+constexpr size_t XB_LL = XB_SNAP + 2 * 1024 * 8;           // start of the epoch-tagged region (cleared on epoch wrap)
+constexpr size_t XB_Q = XB_LL;                             // u32[8][512]   q0 | q1 | k | v of the group
+constexpr size_t XB_M = XB_Q + NGRP * 512 * 4;             // u32[8][384]
+constexpr size_t XB_LOGITS = XB_M + NGRP * 384 * 4;        // u32[3072]
+constexpr size_t XB_TOKEN = XB_LOGITS + MAX_HEAD_ROWS * 4; // u64[16]
+constexpr size_t XB_PART = XB_TOKEN + 16 * 8;              // u64[8][2][16][PART_STRIDE]
+constexpr size_t XBUF2_BYTES = XB_PART + (size_t)NGRP * 2 * S2_MAX * PART_STRIDE * 8;
+
+// shared memory
+constexpr int S2_RING = 0;
+constexpr int S2_VEC = S2_RING + NSL * SLOT2;      // bf16[1024] normalised input of QKV / gate-up / head
+constexpr int S2_A = S2_VEC + 2048;                // bf16[384]  attention output (256) or m (384): input of O / down
+constexpr int S2_ACC = S2_A + 768;                 // float[8][2][128] attention cross-warp merge / sampling logits
+constexpr int S2_SMALL = S2_ACC + NCW * 2 * HD * 4;  // float[1024] attention scratch
+constexpr int S2_PART = S2_SMALL + 4096;           // float[64][8]
+constexpr int S2_RED = S2_PART + 64 * NCW * 4;     // float[64]
+constexpr int S2_BAR = S2_RED + 256;               // u64[8]
+constexpr int S2_MISC = S2_BAR + 64;               // abort, delays
+constexpr int SMEM2_BYTES = S2_MISC + 256;
+static_assert(SMEM2_BYTES <= 232448, "shared memory budget");
+
+enum Kind2 { K2_QKV = 0, K2_ATTN = 1, K2_O = 2, K2_GU = 3, K2_DOWN = 4, K2_HEAD = 5, K2_ARGMAX = 6 };
+
+__device__ __forceinline__ void red_add64(u64* p, u64 v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void ld_acc2(const u64* p, u64& a, u64& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ bool acc_done(u64 now, u64 prev) { return (uint32_t)(((now - prev) + (1ull << 55)) >> 56) == (uint32_t)NGRP; }
+__device__ __forceinline__ float acc_value(u64 now, u64 prev) {
+  return (float)(long long)((now - prev) - (u64)NGRP * CNT_ONE) * (1.0f / (float)(1 << FIX_SHIFT));
+}
+__device__ __forceinline__ u64 acc_word(float v) { return CNT_ONE + (u64)__float2ll_rn(v * (float)(1 << FIX_SHIFT)); }
+
+struct Ctx2 : Ctx {
+  uint8_t* s_a;      // bf16[384]
+  u64* acc;          // [2][1024]
+  uint8_t* xb;       // exchange buffer base
+  int g, j;          // group (kv head), rank in group
+  __device__ Ctx2(const Params& pp) : Ctx(pp) {}
+};
+
+// Out of line, by-value arguments only (the totals stay in registers): returns once all four words are complete; the
+// caller then re-reads them.
+__device__ __noinline__ void acc_wait_slow(int* status, volatile int* s_abort, long long t0, long long timeout, int cta, int cur_idx,
+                                           const u64* p, u64 p0, u64 p1, u64 p2, u64 p3) {
+  uint32_t spins = 0;
+  for (;;) {
+    u64 n0, n1, n2, n3;
+    ld_acc2(p, n0, n1);
+    ld_acc2(p + 2, n2, n3);
+    if (acc_done(n0, p0) & acc_done(n1, p1) & acc_done(n2, p2) & acc_done(n3, p3)) return;
+    if ((++spins & 127u) == 0 && check_abort_slow(status, s_abort, t0, timeout, cta, cur_idx, ST_TIMEOUT_LL, -3)) return;
+  }
+}
+
+// ---- weight producer: one lane refills the slots a phase has released ------------------------------------------
+struct Prod2 {
+  const uint8_t* layer_base;
+  int step, l, e;
+  uint32_t k;
+  int left;
+};
+__device__ __forceinline__ int head_tiles(const HeadDesc& h) { return h.rows > 0 ? (h.rows / G2 + 15) / 16 : 0; }
+__device__ __forceinline__ void prod2_init(Ctx2& c, Prod2& pr) {
+  const Params& p = c.p;
+  pr.step = 0; pr.l = 0; pr.e = 0; pr.k = 0; pr.left = 0;
+  for (int st = 0; st < p.n_steps; ++st) pr.left += p.lay.L * ENT_PER_LAYER + head_tiles(p.steps[st].head);
+  pr.layer_base = p.packed_layers + (size_t)c.cta * p.lay.L * LAYER_BYTES2;
+}
+__device__ __forceinline__ void prod2_tma(Ctx2& c, uint32_t k, const uint8_t* src, uint32_t bytes) {
+  const int slot = k % NSL;
+  mbar_arrive_expect_tx(&c.full[slot], bytes);
+  tma_bulk_g2s(c.ring + (size_t)slot * SLOT2, src, bytes, &c.full[slot]);
+}
+__device__ __forceinline__ void prod2_issue(Ctx2& c, Prod2& pr, int n) {
+  const Params& p = c.p;
+  if (n > pr.left) n = pr.left;
+  pr.left -= n;
+  for (; n > 0; --n, ++pr.k) {
+    // skip steps without a head (their head phase has no stage)
+    while (pr.l == p.lay.L && pr.e >= head_tiles(p.steps[pr.step].head)) {
+      pr.l = 0; pr.e = 0; ++pr.step;
+      pr.layer_base = p.packed_layers + (size_t)c.cta * p.lay.L * LAYER_BYTES2;
+    }
+    if (pr.l < p.lay.L) {
+      const uint32_t off = pr.e < 6 ? (uint32_t)pr.e * SLOT2 : 6u * SLOT2 + (uint32_t)(pr.e - 6) * DOWN_SLOT;
+      if (c.lane == 0) prod2_tma(c, pr.k, pr.layer_base + off, pr.e < 6 ? SLOT2 : DOWN_SLOT);
+      if (++pr.e == ENT_PER_LAYER) { pr.e = 0; ++pr.l; pr.layer_base += LAYER_BYTES2; }
+    } else {
+      const HeadDesc& h = p.steps[pr.step].head;
+      if (c.lane == 0) prod2_tma(c, pr.k, h.packed + ((size_t)c.cta * head_tiles(h) + pr.e) * SLOT2, SLOT2);
+      ++pr.e;
+    }
+  }
+}
+
+// ---- attention ---------------------------------------------------------------------------------------------------
+struct AttnItem2 {
+  int S, p0, p1;
+  bool has;
+};
+__device__ __forceinline__ AttnItem2 attn_item2(int position, int j) {
+  AttnItem2 it;
+  const int n = position + 1;
+  int S0 = (n + ATT_ROUND - 1) / ATT_ROUND;
+  if (S0 > S2_MAX) S0 = S2_MAX;
+  const int C = (n + S0 - 1) / S0;
+  it.S = (n + C - 1) / C;
+  if (it.S == 1) { it.p0 = 0; it.p1 = n; it.has = true; return it; }   // short context: every CTA of the group, redundantly
+  it.has = j < it.S;
+  it.p0 = j * C;
+  it.p1 = it.p0 + C < n ? it.p0 + C : n;
+  return it;
+}
+__device__ __forceinline__ void attn_prefetch2(const Ctx2& c, int l, int position, const AttnItem2& it, int round, KvRegs& r) {
+  const Params& p = c.p;
+  const size_t base = ((size_t)(l * NKVH + c.g) * p.max_seq) * HD;
+#pragma unroll
+  for (int i = 0; i < ATT_PER_WARP; ++i) {
+    const int pos = it.p0 + round * ATT_ROUND + c.warp + NCW * i;
+    if (pos < it.p1 && pos != position) {
+      const size_t off = base + (size_t)pos * HD + c.lane * 4;
+      r.k[i] = ld_cg_u2(p.k_cache + off);
+      r.v[i] = ld_cg_u2(p.v_cache + off);
+    }
+  }
+}
+
+// q (2 heads), k, v of the group arrive as LL4 words; per-head RMSNorm + rotate-half RoPE; scores / online softmax / PV
+// over this CTA's positions; cross-warp merge; (long context) cross-chunk merge through group-local LL8 words.
+// Result: bf16 a[256] of the group's two q heads in c.s_a (every CTA of the group holds the same values).
+template <bool TR>
+__device__ void phase_attn2(Ctx2& c, int l, int position, uint32_t epoch, const AttnItem2& it, KvRegs& kv, const AttnPre& pre) {
+  const Params& p = c.p;
+  const uint32_t* x_q = reinterpret_cast<const uint32_t*>(c.xb + XB_Q) + c.g * 512;
+  u64* x_part = reinterpret_cast<u64*>(c.xb + XB_PART) + (size_t)c.g * 2 * S2_MAX * PART_STRIDE;
+  float* s_small = c.s_small;
+  __nv_bfloat16* s_a = reinterpret_cast<__nv_bfloat16*>(c.s_a);
+
+  bool retried = false;
+  wait_window(c, c.s_delay[DL_ATTN]);
+  if (c.warp < 4) {
+    const uint4 w = ll4_wait(c, x_q + c.warp * HD + c.lane * 4, epoch, retried);
+    float t[4] = {ll4_val(w.x), ll4_val(w.y), ll4_val(w.z), ll4_val(w.w)};
+    if (c.warp == 3) {
+      *reinterpret_cast<float4*>(s_small + SS_V + c.lane * 4) = make_float4(t[0], t[1], t[2], t[3]);
+    } else {
+      float ss = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ss = fmaf(t[e], t[e], ss);
+      ss = warp_sum(ss);
+      const float rms = sqrtf(ss * (1.0f / HD) + EPS);
+      const int dbase = (c.lane * 4) & 63;
+      float o4[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float n = bf16_round((t[e] / rms) * pre.nw[e]);
+        const float o = __shfl_xor_sync(0xffffffffu, n, 16);
+        const float cs = s_small[SS_CS + dbase + e], sn = s_small[SS_CS + 64 + dbase + e];
+        const float a = bf16_round(n * cs), b = bf16_round(o * sn);
+        o4[e] = bf16_round(c.lane < 16 ? a - b : a + b);
+      }
+      float* dst = (c.warp < 2) ? s_small + SS_QN + c.warp * HD : s_small + SS_KN;
+      *reinterpret_cast<float4*>(dst + c.lane * 4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+    }
+  }
+  gather_bar(c, DL_ATTN, retried);
+  trace_sub<TR>(c, 1);
+
+  float q0[4], q1[4], acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  {
+    const float4 a = *reinterpret_cast<const float4*>(s_small + SS_QN + c.lane * 4);
+    const float4 b = *reinterpret_cast<const float4*>(s_small + SS_QN + HD + c.lane * 4);
+    q0[0] = a.x; q0[1] = a.y; q0[2] = a.z; q0[3] = a.w;
+    q1[0] = b.x; q1[1] = b.y; q1[2] = b.z; q1[3] = b.w;
+  }
+  const int len = it.has ? it.p1 - it.p0 : 0;
+  const int nrounds = (len + ATT_ROUND - 1) / ATT_ROUND;
+  for (int r = 0; r < nrounds; ++r) {
+    if (r > 0) attn_prefetch2(c, l, position, it, r, kv);
+    float sc[10];
+    const int pos_first = it.p0 + r * ATT_ROUND + c.warp;
+    if (pos_first < it.p1) {  // warp-uniform
+      const int nv = min(ATT_PER_WARP, (it.p1 - pos_first + NCW - 1) / NCW);
+#pragma unroll
+      for (int i = 0; i < 10; ++i) sc[i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < ATT_PER_WARP; ++i) {
+        if (i >= nv) break;
+        const int pos = pos_first + NCW * i;
+        float kf[4];
+        if (pos == position) {
+          const float4 kk = *reinterpret_cast<const float4*>(s_small + SS_KN + c.lane * 4);
+          kf[0] = kk.x; kf[1] = kk.y; kf[2] = kk.z; kf[3] = kk.w;
+        } else {
+          kf[0] = bf16_lo(kv.k[i].x); kf[1] = bf16_hi(kv.k[i].x);
+          kf[2] = bf16_lo(kv.k[i].y); kf[3] = bf16_hi(kv.k[i].y);
+        }
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          d0 = fmaf(q0[e], kf[e], d0);
+          d1 = fmaf(q1[e], kf[e], d1);
+        }
+        sc[i] = d0;
+        sc[5 + i] = d1;
+      }
+      if (nv <= 2) {
+        const float v4[4] = {sc[0], sc[1], sc[5], sc[6]};
+        const float tot = warp_sum4(v4, c.lane);
+        sc[0] = __shfl_sync(0xffffffffu, tot, 0);
+        sc[1] = __shfl_sync(0xffffffffu, tot, 8);
+        sc[5] = __shfl_sync(0xffffffffu, tot, 16);
+        sc[6] = __shfl_sync(0xffffffffu, tot, 24);
+      } else {
+        warp_sum10_bcast(sc, c.lane);
+      }
+      float mx0 = m0, mx1 = m1;
+#pragma unroll
+      for (int i = 0; i < ATT_PER_WARP; ++i) {
+        if (i >= nv) break;
+        sc[i] *= p.attn_scale;
+        sc[5 + i] *= p.attn_scale;
+        mx0 = fmaxf(mx0, sc[i]);
+        mx1 = fmaxf(mx1, sc[5 + i]);
+      }
+      const float c0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - mx0);
+      const float c1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - mx1);
+      l0 *= c0; l1 *= c1;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { acc0[e] *= c0; acc1[e] *= c1; }
+#pragma unroll
+      for (int i = 0; i < ATT_PER_WARP; ++i) {
+        if (i >= nv) break;
+        const int pos = pos_first + NCW * i;
+        float vf[4];
+        if (pos == position) {
+          const float4 vv = *reinterpret_cast<const float4*>(s_small + SS_V + c.lane * 4);
+          vf[0] = vv.x; vf[1] = vv.y; vf[2] = vv.z; vf[3] = vv.w;
+        } else {
+          vf[0] = bf16_lo(kv.v[i].x); vf[1] = bf16_hi(kv.v[i].x);
+          vf[2] = bf16_lo(kv.v[i].y); vf[3] = bf16_hi(kv.v[i].y);
+        }
+        const float e0 = __expf(sc[i] - mx0), e1 = __expf(sc[5 + i] - mx1);
+        l0 += e0; l1 += e1;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc0[e] = fmaf(e0, vf[e], acc0[e]);
+          acc1[e] = fmaf(e1, vf[e], acc1[e]);
+        }
+      }
+      m0 = mx0; m1 = mx1;
+    }
+  }
+  trace_sub<TR>(c, 2);
+  // cross-warp merge: common max first, then plain sums in a fixed order
+  if (c.lane == 0) {
+    s_small[SS_M + c.warp * 2 + 0] = m0;
+    s_small[SS_M + c.warp * 2 + 1] = m1;
+  }
+  consumer_bar();
+  float M0 = -INFINITY, M1 = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < NCW; ++w) {
+    M0 = fmaxf(M0, s_small[SS_M + w * 2 + 0]);
+    M1 = fmaxf(M1, s_small[SS_M + w * 2 + 1]);
+  }
+  {
+    const float f0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - M0);
+    const float f1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - M1);
+    float* s_acc = c.s_acc;  // [NCW][2][128]
+    *reinterpret_cast<float4*>(s_acc + (c.warp * 2 + 0) * HD + c.lane * 4) =
+        make_float4(acc0[0] * f0, acc0[1] * f0, acc0[2] * f0, acc0[3] * f0);
+    *reinterpret_cast<float4*>(s_acc + (c.warp * 2 + 1) * HD + c.lane * 4) =
+        make_float4(acc1[0] * f1, acc1[1] * f1, acc1[2] * f1, acc1[3] * f1);
+    if (c.lane == 0) {
+      s_small[SS_L + c.warp * 2 + 0] = l0 * f0;
+      s_small[SS_L + c.warp * 2 + 1] = l1 * f1;
+    }
+  }
+  consumer_bar();
+  {
+    const int h = c.tid >> 7, d = c.tid & 127;
+    float A = 0.f, Lsum = 0.f;
+#pragma unroll
+    for (int w = 0; w < NCW; ++w) {
+      A += c.s_acc[(w * 2 + h) * HD + d];
+      Lsum += s_small[SS_L + w * 2 + h];
+    }
+    const float Mh = h ? M1 : M0;
+    if (QMK_LIKELY(it.S == 1)) {
+      s_a[c.tid] = __float2bfloat16_rn(A / Lsum);
+    } else {
+      if (it.has) {
+        u64* part = x_part + ((size_t)h * S2_MAX + c.j) * PART_STRIDE;
+        ll8_st(part + 2 + d, __float_as_uint(A), epoch);
+        if (d == 0) {
+          ll8_st(part + 0, __float_as_uint(Mh), epoch);
+          ll8_st(part + 1, __float_as_uint(Lsum), epoch);
+        }
+      }
+      // every CTA of the group merges the chunks of both heads in the fixed order s = 0..S-1
+      float* s_ml = c.s_part;   // [2][16] m then [2][16] l (s_part is free during the attention)
+      consumer_bar();
+      if (c.tid < 2 * S2_MAX) {
+        const int hh = c.tid >> 4, s = c.tid & 15;
+        float mm = -INFINITY, ll = 0.f;
+        if (s < it.S) {
+          const u64* ps = x_part + ((size_t)hh * S2_MAX + s) * PART_STRIDE;
+          mm = __uint_as_float(ll8_wait(c, ps, epoch));
+          ll = __uint_as_float(ll8_wait(c, ps + 1, epoch));
+        }
+        s_ml[hh * 16 + s] = mm;
+        s_ml[32 + hh * 16 + s] = ll;
+      }
+      consumer_bar();
+      float Mx = -INFINITY;
+      for (int s = 0; s < it.S; ++s) Mx = fmaxf(Mx, s_ml[h * 16 + s]);
+      float Lt = 0.f, B = 0.f;
+      for (int s0 = 0; s0 < it.S; s0 += 8) {
+        u64 w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (s0 + i < it.S) w[i] = ll8_ld(x_part + ((size_t)h * S2_MAX + s0 + i) * PART_STRIDE + 2 + d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (s0 + i < it.S) {
+            uint32_t v = (uint32_t)w[i];
+            if (QMK_UNLIKELY((uint32_t)(w[i] >> 32) != epoch))
+              v = ll8_wait(c, x_part + ((size_t)h * S2_MAX + s0 + i) * PART_STRIDE + 2 + d, epoch);
+            const float f = __expf(s_ml[h * 16 + s0 + i] - Mx);
+            Lt = fmaf(s_ml[32 + h * 16 + s0 + i], f, Lt);
+            B = fmaf(__uint_as_float(v), f, B);
+          }
+        }
+      }
+      s_a[c.tid] = __float2bfloat16_rn(B / Lt);
+    }
+  }
+  trace_sub<TR>(c, 3);
+  // append the new K/V row (one CTA per group)
+  if (c.j == 0 && c.tid < 128) {
+    const size_t off = ((size_t)(l * NKVH + c.g) * p.max_seq + position) * HD + c.tid;
+    p.k_cache[off] = __float2bfloat16_rn(s_small[SS_KN + c.tid]);
+    p.v_cache[off] = __float2bfloat16_rn(s_small[SS_V + c.tid]);
+  }
+  consumer_bar();   // s_a complete; s_small / s_acc free again
+}
+
+// ---- tensor-core stages, specialised by phase shape (NT tiles, NK steps per warp, first PRE tiles preloaded) --------
+template <int NT, int NK, int PRE>
+__device__ __forceinline__ void preload_a(uint32_t (&apre)[16][4], const uint32_t (&tb)[4], int warp, int a_khalf, int a_sw) {
+  static_assert(PRE * NK <= 16, "preload registers");
+#pragma unroll
+  for (int t = 0; t < PRE; ++t)
+#pragma unroll
+    for (int jx = 0; jx < NK; ++jx)
+      ldsm4(apre[t * NK + jx], tb[t] + ((uint32_t)((((warp * NK + jx) * 2 + a_khalf) ^ a_sw)) << 4));
+}
+// acc[t] = tile t x activation slice of this warp.  `bvec`: bf16 vector in natural order; lane q4 owns the contiguous run
+// of 4 NK elements at  warp * 16 NK + q4 * 4 NK  (the weights are K-permuted to match, see pack_chunk2).
+template <int NT, int NK, int PRE>
+__device__ __forceinline__ void mma_tiles(float (&acc)[4][4], const uint32_t (&apre)[16][4], const uint32_t (&tb)[4], const uint8_t* bvec,
+                                          int ntiles, int warp, int q4, int a_khalf, int a_sw) {
+  uint32_t bfrag[NK][2];
+  const uint8_t* bp = bvec + warp * (32 * NK) + q4 * (8 * NK);
+  if (NK % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < NK / 2; ++i) {
+      const uint4 v = *reinterpret_cast<const uint4*>(bp + i * 16);
+      bfrag[2 * i][0] = v.x; bfrag[2 * i][1] = v.y; bfrag[2 * i + 1][0] = v.z; bfrag[2 * i + 1][1] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int jx = 0; jx < NK; ++jx) {
+      const uint2 v = *reinterpret_cast<const uint2*>(bp + jx * 8);
+      bfrag[jx][0] = v.x; bfrag[jx][1] = v.y;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    if (t < PRE) {   // tiles below PRE always exist
+      if (NK >= 4) {
+        float acc2[4] = {0.f, 0.f, 0.f, 0.f};   // two accumulators halve the dependent HMMA chain
+#pragma unroll
+        for (int jx = 0; jx < NK; jx += 2) {
+          mma16816(acc[t], apre[t * NK + jx], bfrag[jx]);
+          if (jx + 1 < NK) mma16816(acc2, apre[t * NK + jx + 1], bfrag[jx + 1]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[t][e] += acc2[e];
+      } else {
+#pragma unroll
+        for (int jx = 0; jx < NK; ++jx) mma16816(acc[t], apre[t * NK + jx], bfrag[jx]);
+      }
+    } else if (t < ntiles) {
+      float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int jb = 0; jb < NK; jb += 4) {
+        uint32_t afrag[4][4];
+#pragma unroll
+        for (int jx = 0; jx < 4; ++jx)
+          if (jb + jx < NK) ldsm4(afrag[jx], tb[t] + ((uint32_t)((((warp * NK + jb + jx) * 2 + a_khalf) ^ a_sw)) << 4));
+        if (jb + 0 < NK) mma16816(acc[t], afrag[0], bfrag[jb]);
+        if (jb + 1 < NK) mma16816(acc2, afrag[1], bfrag[jb + 1]);
+        if (jb + 2 < NK) mma16816(acc[t], afrag[2], bfrag[jb + 2]);
+        if (jb + 3 < NK) mma16816(acc2, afrag[3], bfrag[jb + 3]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[t][e] += acc2[e];
+    }
+  }
+}
+
+// ---- main loop -----------------------------------------------------------------------------------------------------
+template <bool TR>
+__device__ void consumer_loop2(Ctx2& c) {
+  const Params& p = c.p;
+  const int L = p.lay.L;
+  uint32_t* const x_q = reinterpret_cast<uint32_t*>(c.xb + XB_Q) + c.g * 512;
+  uint32_t* const x_m = reinterpret_cast<uint32_t*>(c.xb + XB_M) + c.g * 384;
+  uint32_t* const x_logits = reinterpret_cast<uint32_t*>(c.xb + XB_LOGITS);
+  u64* const x_tok = reinterpret_cast<u64*>(c.xb + XB_TOKEN);
+  u64* const accA = c.acc, * const accB = c.acc + 1024;
+  Prod2 prod;
+  prod2_init(c, prod);
+  if (c.warp == NCW - 1) prod2_issue(c, prod, NSL);
+  KvRegs kv;
+  AttnPre pre = {{0.f, 0.f, 0.f, 0.f}};
+  const int gi0 = c.tid * 4;
+  // totals of this thread's accumulator words at the end of the previous launch
+  u64 prevA[4], prevB[4];
+  {
+    const u64* snap = reinterpret_cast<const u64*>(c.xb + XB_SNAP);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { prevA[e] = snap[gi0 + e]; prevB[e] = snap[1024 + gi0 + e]; }
+  }
+  float res[4] = {0.f, 0.f, 0.f, 0.f};   // residual stream, elements 4 tid .. 4 tid + 3 (every CTA holds all of it)
+  // ldmatrix roles of this lane
+  const int a_mi = c.lane >> 3;
+  const int a_row = (c.lane & 7) + (a_mi & 1) * 8;
+  const int a_sw = a_row & 7, a_khalf = a_mi >> 1;
+  const int g8 = c.lane >> 2, q4 = c.lane & 3;
+
+  if (c.cta == 0 && c.tid == 0 && p.code0_out != nullptr) *p.code0_out = (long long)(p.code0_ptr ? *p.code0_ptr : p.code0);
+  for (int step = 0; step < p.n_steps; ++step) {
+    const StepDesc& sd = p.steps[step];
+    const uint32_t ebase = p.epoch_base + (uint32_t)step * (uint32_t)(L + 2);
+    const int position = sd.position;
+    int in_token = sd.token;
+    if (sd.in_mode == IN_TABLE_TOKEN && sd.token_ptr != nullptr) {
+      in_token = *sd.token_ptr;
+      in_token = in_token < 0 ? 0 : (in_token > sd.token ? sd.token : in_token);
+    }
+    if (sd.in_mode == IN_TABLE_PREV) {
+      if (c.warp == 0) {
+        const long long t_ready = c.t_pub + c.s_delay[DL_TOKEN];
+        while (clock64() < t_ready) {
+        }
+        if (c.lane == 0) c.s_red[32] = __int_as_float((int)ll8_wait(c, x_tok + (step & 15), (ebase - 1u) & 0xffffu));
+      }
+      consumer_bar();
+      in_token = __float_as_int(c.s_red[32]);
+    }
+    const __nv_bfloat16* x_in = (sd.in_mode == IN_TABLE_TOKEN || sd.in_mode == IN_TABLE_PREV)
+                                    ? sd.in_table + (size_t)in_token * H
+                                    : reinterpret_cast<const __nv_bfloat16*>(sd.in_vec);
+    const AttnItem2 item = attn_item2(position, c.j);
+    const int hrows_loc = sd.head.rows > 0 ? sd.head.rows / G2 : 0;
+    if (c.tid < 128) {  // RoPE row of this step
+      const int d = c.tid & 63;
+      const __nv_bfloat16* t = (c.tid < 64) ? p.cos_t : p.sin_t;
+      c.s_small[SS_CS + c.tid] = __bfloat162float(t[(size_t)position * HD + d]);
+    }
+    consumer_bar();
+
+    const int n_idx = L * PH_PER_LAYER + 2;
+    for (int idx = 0; idx < n_idx; ++idx) {
+      c.cur_idx = idx;
+      trace_sub<TR>(c, 0);
+      const int l = idx / PH_PER_LAYER;
+      const int kind = idx < L * PH_PER_LAYER ? idx % PH_PER_LAYER : (idx == L * PH_PER_LAYER ? K2_HEAD : K2_ARGMAX);
+      const uint32_t epoch = (ebase + 1u + (uint32_t)l) & 0xffffu;
+
+      if (kind == K2_ATTN) {
+        phase_attn2<TR>(c, l, position, epoch, item, kv, pre);
+        continue;
+      }
+      if (QMK_UNLIKELY(kind == K2_ARGMAX)) {
+        if (c.cta != 0 || sd.head.rows <= 0) continue;
+        const int hrows = sd.head.rows;
+        const uint32_t epoch_head = (ebase + (uint32_t)L + 1u) & 0xffffu;
+        const bool sample = sd.select != 0 && hrows <= NCW * 2 * HD && (hrows % (NCT * 4)) == 0;
+        float* s_log = c.s_acc;
+        float best = -INFINITY;
+        int best_i = 0x7fffffff;
+        bool retried = false;
+        wait_window(c, c.s_delay[DL_ARGMAX]);
+        for (int i = c.tid * 4; i < hrows; i += NCT * 4) {
+          const uint4 w = ll4_wait(c, x_logits + i, epoch_head, retried);
+          const float4 v = make_float4(ll4_val(w.x), ll4_val(w.y), ll4_val(w.z), ll4_val(w.w));
+          if (sd.logits_out != nullptr) *reinterpret_cast<float4*>(sd.logits_out + i) = v;
+          if (sample) *reinterpret_cast<float4*>(s_log + i) = v;
+          const float v4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (v4[e] > best) { best = v4[e]; best_i = i + e; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+          if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+        }
+        if (c.lane == 0) {
+          c.s_red[c.warp * 2] = best;
+          c.s_red[c.warp * 2 + 1] = __int_as_float(best_i);
+        }
+        gather_bar(c, DL_ARGMAX, retried);
+#pragma unroll
+        for (int w = 0; w < NCW; ++w) {
+          const float ov = c.s_red[w * 2];
+          const int oi = __float_as_int(c.s_red[w * 2 + 1]);
+          if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+        }
+        int chosen = best_i;
+        if (sample)
+          chosen = sample_token(s_log, reinterpret_cast<unsigned*>(c.s_part), c.s_red, c.tid, c.warp, c.lane, hrows,
+                                p.sample_top_k, p.sample_temperature, p.sample_seed, p.sample_counter, sd.group, best, best_i);
+        if (c.tid == 0) {
+          const int st = *((volatile int*)p.status);
+          const int out = (st != 0 || *c.s_abort) ? -1000 - st : chosen;
+          if (sd.out_token != nullptr) *sd.out_token = out;
+          if (sd.out_code != nullptr) *sd.out_code = (long long)out;
+          if (step + 1 < p.n_steps) {
+            int fed = chosen;
+            if (p.forced_tokens != nullptr && sd.group >= 0) fed = p.forced_tokens[sd.group];
+            ll8_st(x_tok + ((step + 1) & 15), (uint32_t)fed, epoch_head);
+          }
+        }
+        consumer_bar();
+        continue;
+      }
+
+      // ---- GEMV-shaped phases ----------------------------------------------------------------------------------
+      // Shape of a phase: `ntiles` tiles of 16 rows; each warp owns a K slice of 16 nk (nk tensor-core steps per tile).
+      // Everything that does not depend on the gathered activations runs BEFORE they are checked (the A fragments move
+      // from the ring into registers while the exchange is in flight): a single warp executes dependent instructions
+      // at ~5+ cycles each, so every instruction between "data arrived" and "published" is on the layer's critical path.
+      int ntiles, nst;
+      uint32_t stride;
+      if (kind == K2_QKV) { ntiles = 2; nst = 2; stride = 2048; }
+      else if (kind == K2_O) { ntiles = 4; nst = 1; stride = 512; }
+      else if (kind == K2_GU) { ntiles = 3; nst = 3; stride = 2048; }
+      else if (kind == K2_DOWN) { ntiles = 4; nst = 2; stride = 768; }
+      else { ntiles = (hrows_loc + 15) / 16; nst = ntiles; stride = 2048; }
+      const bool norm = (kind == K2_QKV || kind == K2_GU || kind == K2_HEAD);
+      const bool from_input = (kind == K2_QKV && l == 0);
+      const bool useB = (kind == K2_GU);
+      u64* const acc = useB ? accB : accA;
+      const int dslot = kind == K2_GU ? DL_GU : (kind == K2_QKV ? DL_QKV : (kind == K2_DOWN ? DL_DOWN : DL_HEAD));
+      const uint8_t* nw_ptr = (kind == K2_HEAD) ? sd.head.aux : p.aux_layers + ((size_t)l * 2 + (kind == K2_GU ? 1 : 0)) * AUX_BYTES;
+
+      // ---- 1. wait window, then issue the gather loads ----
+      u64 now[4];
+      uint4 mw = make_uint4(0, 0, 0, 0);
+      if (kind != K2_O && !from_input) {
+        wait_window(c, c.s_delay[dslot]);
+        trace_sub<TR>(c, 1);
+        if (norm) {
+          ld_acc2(acc + gi0, now[0], now[1]);
+          ld_acc2(acc + gi0 + 2, now[2], now[3]);
+        } else if (c.lane < 12) {   // down: warp w gathers its own K slice m[48 w .. 48 w + 48) of the group's 384 values
+          mw = ll4_ld4(x_m + c.warp * 48 + c.lane * 4);
+        }
+      }
+      // ---- 2. shadow of the load latency: weights of this phase -> registers, norm weights, older KV rows ----
+      uint2 wv = make_uint2(0, 0);
+      if (norm) wv = *reinterpret_cast<const uint2*>(nw_ptr + c.tid * 8);
+      if (kind == K2_QKV) {
+        if (item.has) attn_prefetch2(c, l, position, item, 0, kv);
+        if (c.warp < 3) {
+          const uint2 nv = *reinterpret_cast<const uint2*>(p.aux_layers + ((size_t)l * 2) * AUX_BYTES + 2048 + (c.warp == 2 ? 256 : 0) + c.lane * 8);
+          pre.nw[0] = bf16_lo(nv.x); pre.nw[1] = bf16_hi(nv.x); pre.nw[2] = bf16_lo(nv.y); pre.nw[3] = bf16_hi(nv.y);
+        }
+      }
+      uint32_t tb[4];   // shared-memory address of this lane's ldmatrix row in tile t
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int slot_i = (kind == K2_DOWN) ? (t >> 1) : (kind == K2_O ? 0 : (t < nst ? t : 0));
+        const uint32_t toff = (kind == K2_O) ? (uint32_t)t * 8192u : (kind == K2_DOWN ? (uint32_t)(t & 1) * 12288u : 0u);
+        tb[t] = smem_u32(c.ring + (size_t)((c.k + slot_i) % NSL) * SLOT2) + toff + (uint32_t)a_row * stride;
+      }
+#pragma unroll
+      for (int sidx = 0; sidx < 3; ++sidx)
+        if (sidx < nst) wait_full(c, c.k + sidx);
+      uint32_t apre[16][4];
+      if (kind == K2_O) preload_a<4, 2, 4>(apre, tb, c.warp, a_khalf, a_sw);
+      else if (kind == K2_DOWN) preload_a<4, 3, 4>(apre, tb, c.warp, a_khalf, a_sw);
+      else preload_a<3, 8, 2>(apre, tb, c.warp, a_khalf, a_sw);   // QKV / head: both tiles; gate/up: tiles 0, 1
+      trace_sub<TR>(c, 2);
+
+      // ---- 3. data ----
+      if (norm) {
+        bool retried = false;
+        if (from_input) {
+          if (sd.in_mode == IN_CODES_SUM) {
+            const uint2 v0 = *reinterpret_cast<const uint2*>(sd.in_table + (size_t)sd.codes[0] * H + gi0);
+            float e4[4] = {bf16_lo(v0.x), bf16_hi(v0.x), bf16_lo(v0.y), bf16_hi(v0.y)};
+#pragma unroll 1
+            for (int g = 0; g < 15; ++g) {
+              const uint2 v = *reinterpret_cast<const uint2*>(p.sum_tables[g] + (size_t)sd.codes[g + 1] * H + gi0);
+              e4[0] = bf16_round(e4[0] + bf16_lo(v.x)); e4[1] = bf16_round(e4[1] + bf16_hi(v.x));
+              e4[2] = bf16_round(e4[2] + bf16_lo(v.y)); e4[3] = bf16_round(e4[3] + bf16_hi(v.y));
+            }
+            const uint2 vx = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(sd.in_vec) + gi0);
+            res[0] = bf16_round(e4[0] + bf16_lo(vx.x)); res[1] = bf16_round(e4[1] + bf16_hi(vx.x));
+            res[2] = bf16_round(e4[2] + bf16_lo(vx.y)); res[3] = bf16_round(e4[3] + bf16_hi(vx.y));
+          } else if (sd.in_mode == IN_VEC_F32) {
+            const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sd.in_vec) + gi0);
+            res[0] = bf16_round(v.x); res[1] = bf16_round(v.y); res[2] = bf16_round(v.z); res[3] = bf16_round(v.w);
+          } else {
+            const uint2 v = *reinterpret_cast<const uint2*>(x_in + gi0);
+            res[0] = bf16_lo(v.x); res[1] = bf16_hi(v.x); res[2] = bf16_lo(v.y); res[3] = bf16_hi(v.y);
+          }
+        } else {
+          u64 prev[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) prev[e] = useB ? prevB[e] : prevA[e];
+          if (QMK_UNLIKELY(!(acc_done(now[0], prev[0]) & acc_done(now[1], prev[1]) & acc_done(now[2], prev[2]) & acc_done(now[3], prev[3])))) {
+            retried = true;
+            acc_wait_slow(p.status, c.s_abort, c.t0, p.timeout_cycles, c.cta, idx, acc + gi0, prev[0], prev[1], prev[2], prev[3]);
+            ld_acc2(acc + gi0, now[0], now[1]);
+            ld_acc2(acc + gi0 + 2, now[2], now[3]);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float o = bf16_round(acc_value(now[e], prev[e]));
+            res[e] = p.residual_fp32 ? res[e] + o : bf16_round(res[e] + o);
+            if (useB) prevB[e] = now[e]; else prevA[e] = now[e];
+          }
+        }
+        const float r0 = bf16_round(res[0]), r1 = bf16_round(res[1]), r2 = bf16_round(res[2]), r3 = bf16_round(res[3]);
+        float ss = fmaf(r0, r0, r1 * r1) + fmaf(r2, r2, r3 * r3);
+        ss = warp_sum(ss);
+        if (c.lane == 0) c.s_red[c.warp] = ss;
+        if (from_input) consumer_bar(); else gather_bar(c, dslot, retried);
+        trace_sub<TR>(c, 3);
+        const float4 s0 = *reinterpret_cast<const float4*>(c.s_red), s1 = *reinterpret_cast<const float4*>(c.s_red + 4);
+        const float inv = rsqrtf((((s0.x + s0.y) + (s0.z + s0.w)) + ((s1.x + s1.y) + (s1.z + s1.w))) * (1.0f / H) + EPS);
+        const __nv_bfloat162 n01 = __floats2bfloat162_rn((r0 * inv) * bf16_lo(wv.x), (r1 * inv) * bf16_hi(wv.x));
+        const __nv_bfloat162 n23 = __floats2bfloat162_rn((r2 * inv) * bf16_lo(wv.y), (r3 * inv) * bf16_hi(wv.y));
+        const uint2 packed = make_uint2(*reinterpret_cast<const uint32_t*>(&n01), *reinterpret_cast<const uint32_t*>(&n23));
+        *reinterpret_cast<uint2*>(c.s_vec + gi0 * 2) = packed;
+        if (kind == K2_HEAD && c.cta == 0) {
+          if (sd.hidden_out != nullptr) {
+            const __nv_bfloat162 h01 = __floats2bfloat162_rn(r0, r1), h23 = __floats2bfloat162_rn(r2, r3);
+            *reinterpret_cast<uint2*>(sd.hidden_out + gi0) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+          }
+          if (sd.out_norm != nullptr)
+            *reinterpret_cast<float4*>(sd.out_norm + gi0) = make_float4(bf16_lo(packed.x), bf16_hi(packed.x), bf16_lo(packed.y), bf16_hi(packed.y));
+        }
+      } else if (kind == K2_DOWN) {
+        bool retried = false;
+        if (c.lane < 12) {
+          if (QMK_UNLIKELY(!ll4_ok(mw, epoch))) {
+            retried = true;
+            mw = ll4_wait_slow(p.status, c.s_abort, c.t0, p.timeout_cycles, c.cta, idx, x_m + c.warp * 48 + c.lane * 4, epoch, c.lane);
+          }
+          *reinterpret_cast<uint2*>(c.s_a + (c.warp * 48 + c.lane * 4) * 2) = make_uint2((mw.x & 0xffffu) | (mw.y << 16), (mw.z & 0xffffu) | (mw.w << 16));
+        }
+        gather_note(c, DL_DOWN, retried);
+      }
+      __syncwarp();   // warp w consumes exactly the K slice its own lanes wrote (O: phase_attn2 ended with a CTA barrier)
+      trace_sub<TR>(c, 4);
+      if (kind == K2_HEAD && ntiles == 0) continue;   // step without an LM head: only the final norm / outputs
+
+      // ---- 4. tensor-core stages ----
+      float acc4[4][4];
+      if (kind == K2_O) mma_tiles<4, 2, 4>(acc4, apre, tb, c.s_a, 4, c.warp, q4, a_khalf, a_sw);
+      else if (kind == K2_DOWN) mma_tiles<4, 3, 4>(acc4, apre, tb, c.s_a, 4, c.warp, q4, a_khalf, a_sw);
+      else mma_tiles<3, 8, 2>(acc4, apre, tb, c.s_vec, ntiles, c.warp, q4, a_khalf, a_sw);
+      c.k += nst;
+      if (TR) { if (__float_as_uint(acc4[0][0]) == 0x7fc12345u) c.s_red[40] = 1.f; }   // stamp 5 after the tensor-core results exist
+      trace_sub<TR>(c, 5);
+      // per-warp (K-slice) partials of rows 16 t + g8 and 16 t + g8 + 8 (every B column is the same vector: take column 0)
+      if (q4 == 0) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (t < ntiles) {
+            c.s_part[((t * 16 + g8) * NCW) + c.warp] = acc4[t][0];
+            c.s_part[((t * 16 + g8 + 8) * NCW) + c.warp] = acc4[t][2];
+          }
+        }
+      }
+      consumer_bar();
+      trace_sub<TR>(c, 6);
+      if (c.warp == NCW - 1) prod2_issue(c, prod, nst);
+
+      // ---- 5. finalize + publish ----
+      if (kind == K2_QKV) {
+        if (c.tid < QKV_LOC) {   // local rows: 0..15 q (16 j + r of the head pair), 16..23 k, 24..31 v
+          const float v = item_sum(c.s_part, c.tid);
+          const int r = c.tid;
+          const int w = r < 16 ? GSZ * c.j + r : (r < 24 ? 256 + 8 * c.j + (r - 16) : 384 + 8 * c.j + (r - 24));
+          ll4_st(x_q + w, v, epoch);
+        }
+      } else if (kind == K2_GU) {
+        if (c.warp < 2) {   // gate in even lanes, up in the next lane
+          const bool mine = c.tid < GU_LOC;
+          const float v = mine ? item_sum(c.s_part, c.tid) : 0.f;
+          const float u = bf16_round(__shfl_down_sync(0xffffffffu, v, 1));
+          if (mine && (c.tid & 1) == 0) {
+            const float gt = bf16_round(v);
+            const float sg = bf16_round(__fdividef(gt, 1.0f + __expf(-gt)));
+            ll4_st(x_m + M_LOC * c.j + (c.tid >> 1), sg * u, epoch);
+          }
+        }
+      } else if (kind == K2_O || kind == K2_DOWN) {
+        if (c.tid < O_LOC) {   // one fixed-point add per row: the eight groups' K-split partials meet in L2
+          const float v = item_sum(c.s_part, c.tid);
+          red_add64((kind == K2_O ? accB : accA) + O_LOC * c.j + c.tid, acc_word(v));
+        }
+      } else {   // head: logits as LL4 words for CTA 0
+        if (c.tid < hrows_loc) ll4_st(x_logits + hrows_loc * c.cta + c.tid, item_sum(c.s_part, c.tid), (ebase + (uint32_t)L + 1u) & 0xffffu);
+      }
+      c.t_pub = clock64();
+      trace_sub<TR>(c, 8);
+    }
+  }
+  // totals for the next launch
+  if (c.cta == 0) {
+    u64* snap = reinterpret_cast<u64*>(c.xb + XB_SNAP);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { snap[gi0 + e] = prevA[e]; snap[1024 + gi0 + e] = prevB[e]; }
+  }
+}
+
+template <bool TR>
+__device__ __forceinline__ void decode2_body(const Params& p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Ctx2 c(p);
+  c.ring = smem + S2_RING;
+  c.s_vec = smem + S2_VEC;
+  c.s_a = smem + S2_A;
+  c.s_acc = reinterpret_cast<float*>(smem + S2_ACC);
+  c.s_small = reinterpret_cast<float*>(smem + S2_SMALL);
+  c.s_part = reinterpret_cast<float*>(smem + S2_PART);
+  c.s_red = reinterpret_cast<float*>(smem + S2_RED);
+  c.full = reinterpret_cast<u64*>(smem + S2_BAR);
+  c.s_abort = reinterpret_cast<volatile int*>(smem + S2_MISC);
+  c.s_delay = reinterpret_cast<int*>(smem + S2_MISC + 16);
+  c.s_tbl = nullptr;
+  c.xb = p.xbuf;
+  c.x32 = reinterpret_cast<uint32_t*>(p.xbuf + XB_LL);
+  c.acc = reinterpret_cast<u64*>(p.xbuf + XB_ACC);
+  c.tid = threadIdx.x;
+  c.warp = threadIdx.x >> 5;
+  c.lane = threadIdx.x & 31;
+  c.cta = blockIdx.x;
+  c.g = blockIdx.x / GSZ;
+  c.j = blockIdx.x % GSZ;
+  c.k = 0;
+  c.t0 = clock64();
+  c.t_pub = c.t0;
+  c.cur_idx = 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSL; ++i) mbar_init(&c.full[i], 1);
+    *c.s_abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 3 * DL_N) c.s_delay[threadIdx.x] = p.delays[blockIdx.x * 3 * DL_N + threadIdx.x];
+  __syncthreads();
+  consumer_loop2<TR>(c);
+  __syncthreads();
+  if (threadIdx.x >= DL_N && threadIdx.x < 3 * DL_N) p.delays[blockIdx.x * 3 * DL_N + threadIdx.x] = c.s_delay[threadIdx.x];
+  if (*c.s_abort && threadIdx.x == 0) {
+    const long long t = clock64();
+    while (clock64() - t < 2000000) {
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) qmk2_decode_kernel(const __grid_constant__ Params p) { decode2_body<false>(p); }
+__global__ void __launch_bounds__(NTHREADS, 1) qmk2_decode_kernel_traced(const __grid_constant__ Params p) { decode2_body<true>(p); }
+
+// ---- weight re-packing for the group layout -----------------------------------------------------------------------
+// 16-byte chunk `ch` of a packed row whose K block starts at 32-bit word `kw0` of the source row: slice w = ch / (2 nk),
+// m = ch % (2 nk); the chunk holds, for q = 0..3, source words  w * 8 nk + 2 nk q + m.
+__device__ __forceinline__ uint4 pack_chunk2(const uint32_t* row_words, int kw0, int nk, int ch) {
+  const int w = ch / (2 * nk), m = ch % (2 * nk);
+  const uint32_t* s = row_words + kw0 + w * 8 * nk + m;
+  return make_uint4(s[0], s[2 * nk], s[4 * nk], s[6 * nk]);
+}
+// grid = (128, L), block = 128
+__global__ void qmk2_pack_layers_kernel(const LayerPtrs* layers, int L, uint8_t* packed, uint8_t* aux_layers) {
+  const int cta = blockIdx.x, l = blockIdx.y, t = threadIdx.x;
+  const int g = cta / GSZ, j = cta % GSZ;
+  const LayerPtrs lp = layers[l];
+  uint8_t* dst = packed + ((size_t)cta * L + l) * LAYER_BYTES2;
+  const uint32_t* wq = reinterpret_cast<const uint32_t*>(lp.w[W_Q]);
+  const uint32_t* wk = reinterpret_cast<const uint32_t*>(lp.w[W_K]);
+  const uint32_t* wv = reinterpret_cast<const uint32_t*>(lp.w[W_V]);
+  const uint32_t* wo = reinterpret_cast<const uint32_t*>(lp.w[W_O]);
+  const uint32_t* wg = reinterpret_cast<const uint32_t*>(lp.w[W_GATE]);
+  const uint32_t* wu = reinterpret_cast<const uint32_t*>(lp.w[W_UP]);
+  const uint32_t* wd = reinterpret_cast<const uint32_t*>(lp.w[W_DOWN]);
+  // QKV: 32 rows x 2 KB (128 chunks per row)
+  for (int r = 0; r < QKV_LOC; ++r) {
+    const uint32_t* src = r < 16 ? wq + (size_t)(2 * g * HD + GSZ * j + r) * 512
+                                 : (r < 24 ? wk + (size_t)(g * HD + 8 * j + (r - 16)) * 512 : wv + (size_t)(g * HD + 8 * j + (r - 24)) * 512);
+    uint4* d = reinterpret_cast<uint4*>(dst + (size_t)(r >> 4) * SLOT2 + (size_t)(r & 15) * 2048);
+    d[t ^ (r & 7)] = pack_chunk2(src, 0, 8, t);
+  }
+  // O: 64 rows x 512 B (32 chunks per row), K block = columns 256 g ..
+  for (int r = 0; r < O_LOC; ++r) {
+    const uint32_t* src = wo + (size_t)(O_LOC * j + r) * 1024;
+    uint4* d = reinterpret_cast<uint4*>(dst + 2 * (size_t)SLOT2 + (size_t)r * 512);
+    if (t < 32) d[t ^ (r & 7)] = pack_chunk2(src, KB_O * g / 2, 2, t);
+  }
+  // gate/up: 48 rows, gate_i and up_i interleaved
+  for (int r = 0; r < GU_LOC; ++r) {
+    const int row = KB_D * g + M_LOC * j + (r >> 1);
+    const uint32_t* src = ((r & 1) ? wu : wg) + (size_t)row * 512;
+    uint4* d = reinterpret_cast<uint4*>(dst + (size_t)(3 + (r >> 4)) * SLOT2 + (size_t)(r & 15) * 2048);
+    d[t ^ (r & 7)] = pack_chunk2(src, 0, 8, t);
+  }
+  // down: 64 rows x 768 B (48 chunks per row), K block = columns 384 g ..; two 24 KB slots of 32 rows
+  for (int r = 0; r < O_LOC; ++r) {
+    const uint32_t* src = wd + (size_t)(O_LOC * j + r) * 1536;
+    uint4* d = reinterpret_cast<uint4*>(dst + 6 * (size_t)SLOT2 + (size_t)(r >> 5) * DOWN_SLOT + (size_t)(r & 31) * 768);
+    if (t < 48) d[t ^ (r & 7)] = pack_chunk2(src, KB_D * g / 2, 3, t);
+  }
+  if (cta == 0) {  // shared norm-weight blocks, same format as the first kernel
+    uint4* a0 = reinterpret_cast<uint4*>(aux_layers + ((size_t)l * 2 + 0) * AUX_BYTES);
+    uint4* a1 = reinterpret_cast<uint4*>(aux_layers + ((size_t)l * 2 + 1) * AUX_BYTES);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    a0[t] = lp.w[W_IN][t];
+    a1[t] = lp.w[W_POST][t];
+    if (t < 16) {
+      a0[128 + t] = lp.w[W_QN][t];
+      a0[144 + t] = lp.w[W_KN][t];
+      a1[128 + t] = zero;
+      a1[144 + t] = zero;
+    }
+  }
+}
+// grid = 128, block = 128: rows_loc = rows / 128 rows of this CTA, padded to whole 16-row tiles
+__global__ void qmk2_pack_head_kernel(const uint4* head_w, int rows, uint8_t* packed) {
+  const int cta = blockIdx.x, t = threadIdx.x;
+  const int rows_loc = rows / G2, tiles = (rows_loc + 15) / 16;
+  uint8_t* dst = packed + (size_t)cta * tiles * SLOT2;
+  for (int r = 0; r < tiles * 16; ++r) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < rows_loc) v = pack_chunk2(reinterpret_cast<const uint32_t*>(head_w) + (size_t)(rows_loc * cta + r) * 512, 0, 8, t);
+    reinterpret_cast<uint4*>(dst + (size_t)(r >> 4) * SLOT2 + (size_t)(r & 15) * 2048)[t ^ (r & 7)] = v;
+  }
+}
+
+}  // namespace qmk2

@@ -17,6 +17,7 @@
 
 #include "qmk_b200.h"
 #include "qmk_device.cuh"
+#include "qmk_device2.cuh"
 
 using namespace qmk;
 
@@ -60,6 +61,9 @@ struct qmk_head {
 struct qmk_engine {
   int device = 0;
   int G = 0;
+  int version = 1;      // 1 = row-split kernel (qmk_device.cuh), 2 = group kernel (qmk_device2.cuh)
+  size_t xbuf_bytes = 0;
+  size_t xbuf_ll_off = 0;   // start of the epoch-tagged words (the part that is cleared when the epoch wraps)
   uint8_t* xbuf = nullptr;
   float* res_spill = nullptr;
   int* delays = nullptr;
@@ -121,26 +125,43 @@ extern "C" int qmk_engine_create(int device, int num_ctas, qmk_engine** out) {
   if (const char* env = getenv("QMK_NUM_CTAS")) {
     if (num_ctas <= 0) num_ctas = atoi(env);
   }
+  int version = 1;
+  if (const char* env = getenv("QMK_ENGINE")) version = atoi(env);
+  if (version != 1 && version != 2) return set_error(QMK_ERR_ARG, "QMK_ENGINE=%d: expected 1 or 2", version);
+  if (version == 2 && num_ctas > 0 && num_ctas != qmk2::G2) version = 1;   // an explicit CTA count selects the row-split kernel
   int G = num_ctas > 0 ? num_ctas : prop.multiProcessorCount;
   if (G > prop.multiProcessorCount) G = prop.multiProcessorCount;
+  if (version == 2) {
+    if (prop.multiProcessorCount < qmk2::G2)
+      return set_error(QMK_ERR_UNSUPPORTED, "the group kernel needs %d SMs, device %d has %d", qmk2::G2, device, prop.multiProcessorCount);
+    G = qmk2::G2;
+  }
   // every CTA must own >=1 row in every phase and a phase may span at most MAX_ST ring stages
-  if (G < 147 || G > 1024) return set_error(QMK_ERR_UNSUPPORTED, "unsupported CTA count %d (need 147..1024: a phase spans at most 3 ring stages)", G);
+  if (version == 1 && (G < 147 || G > 1024)) return set_error(QMK_ERR_UNSUPPORTED, "unsupported CTA count %d (need 147..1024: a phase spans at most 3 ring stages)", G);
   QMK_CUDA(cudaFuncSetAttribute(qmk_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   QMK_CUDA(cudaFuncSetAttribute(qmk_decode_kernel_traced, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  QMK_CUDA(cudaFuncSetAttribute(qmk2::qmk2_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, qmk2::SMEM2_BYTES));
+  QMK_CUDA(cudaFuncSetAttribute(qmk2::qmk2_decode_kernel_traced, cudaFuncAttributeMaxDynamicSharedMemorySize, qmk2::SMEM2_BYTES));
   int occ = 0;
-  QMK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qmk_decode_kernel, NTHREADS, SMEM_BYTES));
-  if (occ < 1) return set_error(QMK_ERR_UNSUPPORTED, "decode kernel does not fit on an SM (smem %d B)", SMEM_BYTES);
+  if (version == 1) QMK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qmk_decode_kernel, NTHREADS, SMEM_BYTES));
+  else QMK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qmk2::qmk2_decode_kernel, NTHREADS, qmk2::SMEM2_BYTES));
+  if (occ < 1) return set_error(QMK_ERR_UNSUPPORTED, "decode kernel does not fit on an SM");
 
   qmk_engine* e = new qmk_engine();
   e->device = device;
   e->G = G;
+  e->version = version;
+  e->xbuf_bytes = version == 2 ? qmk2::XBUF2_BYTES : XBUF_BYTES;
+  e->xbuf_ll_off = version == 2 ? qmk2::XB_LL : 0;
   if (const char* env = getenv("QMK_TIMEOUT_CYCLES")) e->timeout_cycles = atoll(env);
-  int delay0 = 800;
+  int delay0 = version == 2 ? 500 : 800;
   int delay_token = 2500;   // the next step's token arrives two exchanges after a CTA has published its logits
   if (const char* env = getenv("QMK_POLL_DELAY")) delay0 = atoi(env);
   if (const char* env = getenv("QMK_POLL_DELAY_TOKEN")) delay_token = atoi(env);
   // attention CTAs: wait for q/k/v (DL_ATTN) and, in the O phase, for the other attention CTAs' output (DL_O)
-  int delay_attn = 400, delay_oa = 300;
+  int delay_attn = version == 2 ? 200 : 400, delay_oa = 300;
+  int delay_down = version == 2 ? 200 : delay0;
+  if (const char* env = getenv("QMK_POLL_DELAY_DOWN")) delay_down = atoi(env);
   if (const char* env = getenv("QMK_POLL_DELAY_ATTN")) delay_attn = atoi(env);
   if (const char* env = getenv("QMK_POLL_DELAY_OA")) delay_oa = atoi(env);
   if (const char* env = getenv("QMK_POLL_DELAY_O")) e->delay_o_idle = atoi(env);
@@ -149,9 +170,9 @@ extern "C" int qmk_engine_create(int device, int num_ctas, qmk_engine** out) {
   std::vector<int> delays((size_t)G * 3 * DL_N, 0);
   for (int c = 0; c < G; ++c)
     for (int d = 0; d < DL_N; ++d)
-      delays[(size_t)c * 3 * DL_N + d] = (d == DL_TOKEN) ? delay_token : (d == DL_ATTN) ? delay_attn : (d == DL_O) ? delay_oa : delay0;
-  cudaError_t err = cudaMalloc(&e->xbuf, XBUF_BYTES);
-  if (err == cudaSuccess) err = cudaMemset(e->xbuf, 0, XBUF_BYTES);
+      delays[(size_t)c * 3 * DL_N + d] = (d == DL_TOKEN) ? delay_token : (d == DL_ATTN) ? delay_attn : (d == DL_O) ? delay_oa : (d == DL_DOWN) ? delay_down : delay0;
+  cudaError_t err = cudaMalloc(&e->xbuf, e->xbuf_bytes);
+  if (err == cudaSuccess) err = cudaMemset(e->xbuf, 0, e->xbuf_bytes);
   if (err == cudaSuccess) err = cudaMalloc(&e->res_spill, H * sizeof(float));
   if (err == cudaSuccess) err = cudaMemset(e->res_spill, 0, H * sizeof(float));
   if (err == cudaSuccess) err = cudaMalloc(&e->delays, delays.size() * sizeof(int));
@@ -228,6 +249,8 @@ extern "C" int qmk_engine_sync_status(qmk_engine* e, void* stream, int32_t* deta
   if (detail) memcpy(detail, st, sizeof(st));
   if (st[0] != 0) {
     cudaMemset(e->status_dev, 0, sizeof(st));
+    cudaMemset(e->xbuf, 0, e->xbuf_bytes);   // an aborted launch leaves the cumulative totals of the group kernel undefined
+    e->epoch = 0;
     return set_error(QMK_ERR_KERNEL, "device watchdog fired: code %d (1=exchange wait 2=ring full wait 3=ring empty wait) cta %d phase %d aux %d",
                      st[0], st[1], st[2], st[3]);
   }
@@ -246,14 +269,19 @@ extern "C" int qmk_model_create(qmk_engine* e, const LDGLayerWeights* layers, in
   m->e = e;
   m->lay = make_layout(e->G, num_layers);
   m->residual_fp32 = residual_fp32 ? 1 : 0;
-  const size_t bytes = (size_t)e->G * num_layers * m->lay.layer_segs * SEG_BYTES;
+  const size_t bytes = e->version == 2 ? (size_t)qmk2::G2 * num_layers * qmk2::LAYER_BYTES2
+                                       : (size_t)e->G * num_layers * m->lay.layer_segs * SEG_BYTES;
   cudaError_t err = cudaMalloc(&m->packed_layers, bytes);
   if (err == cudaSuccess) err = cudaMalloc(&m->aux_layers, (size_t)num_layers * 2 * AUX_BYTES);
   if (err == cudaSuccess) err = cudaMalloc(&m->norm_seg, AUX_BYTES);
   if (err == cudaSuccess) err = cudaMemsetAsync(m->norm_seg, 0, AUX_BYTES, st);
   if (err == cudaSuccess) {
-    qmk_pack_layers_kernel<<<dim3(e->G, num_layers), 128, 0, st>>>(reinterpret_cast<const LayerPtrs*>(layers), m->lay,
-                                                                  m->packed_layers, m->aux_layers);
+    if (e->version == 2)
+      qmk2::qmk2_pack_layers_kernel<<<dim3(qmk2::G2, num_layers), 128, 0, st>>>(reinterpret_cast<const LayerPtrs*>(layers), num_layers,
+                                                                               m->packed_layers, m->aux_layers);
+    else
+      qmk_pack_layers_kernel<<<dim3(e->G, num_layers), 128, 0, st>>>(reinterpret_cast<const LayerPtrs*>(layers), m->lay,
+                                                                    m->packed_layers, m->aux_layers);
     err = cudaGetLastError();
   }
   if (err == cudaSuccess) err = cudaMemcpyAsync(m->norm_seg, final_norm_weight, SEG_BYTES, cudaMemcpyDeviceToDevice, st);
@@ -274,12 +302,22 @@ extern "C" int qmk_model_add_head(qmk_model* m, const void* lm_head_weight, int 
   cudaStream_t st = (cudaStream_t)stream;
   qmk_head h;
   h.rows = rows;
+  size_t bytes;
+  if (m->e->version == 2) {
+    if (rows % qmk2::G2 != 0 || rows / qmk2::G2 > 16 * qmk2::HEAD_TILES_MAX)
+      return set_error(QMK_ERR_ARG, "qmk_model_add_head: the group kernel needs rows %% 128 == 0 and rows <= 4096 (got %d)", rows);
+    h.segs_max = (rows / qmk2::G2 + 15) / 16;   // 16-row tiles per CTA
+    bytes = (size_t)qmk2::G2 * h.segs_max * qmk2::SLOT2;
+    QMK_CUDA(cudaMalloc(&h.packed, bytes));
+    qmk2::qmk2_pack_head_kernel<<<qmk2::G2, 128, 0, st>>>(reinterpret_cast<const uint4*>(lm_head_weight), rows, h.packed);
+  } else {
   h.segs_max = (rows + m->e->G - 1) / m->e->G;
   if (h.segs_max > MAX_ITEMS) return set_error(QMK_ERR_ARG, "qmk_model_add_head: %d rows per CTA exceed %d", h.segs_max, MAX_ITEMS);
-  const size_t bytes = (size_t)m->e->G * h.segs_max * SEG_BYTES;
+  bytes = (size_t)m->e->G * h.segs_max * SEG_BYTES;
   QMK_CUDA(cudaMalloc(&h.packed, bytes));
   qmk_pack_head_kernel<<<m->e->G, 128, 0, st>>>(reinterpret_cast<const uint4*>(lm_head_weight), rows, m->e->G,
                                                 h.segs_max, h.packed);
+  }
   cudaError_t err = cudaGetLastError();
   if (err == cudaSuccess) err = cudaStreamSynchronize(st);
   if (err != cudaSuccess) {
@@ -315,8 +353,13 @@ static int launch_slice(qmk_engine* e, Params& p, int begin, int end, cudaStream
   p.phase_end = end;
   void* args[] = {&p};
   const void* fn = e->trace_dev ? (const void*)qmk_decode_kernel_traced : (const void*)qmk_decode_kernel;
-  if (e->coop) QMK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(e->G), dim3(NTHREADS), args, SMEM_BYTES, st));
-  else QMK_CUDA(cudaLaunchKernel(fn, dim3(e->G), dim3(NTHREADS), args, SMEM_BYTES, st));
+  size_t smem = SMEM_BYTES;
+  if (e->version == 2) {
+    fn = e->trace_dev ? (const void*)qmk2::qmk2_decode_kernel_traced : (const void*)qmk2::qmk2_decode_kernel;
+    smem = qmk2::SMEM2_BYTES;
+  }
+  if (e->coop) QMK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(e->G), dim3(NTHREADS), args, smem, st));
+  else QMK_CUDA(cudaLaunchKernel(fn, dim3(e->G), dim3(NTHREADS), args, smem, st));
   return QMK_OK;
 }
 
@@ -361,7 +404,7 @@ static void set_head(StepDesc& sd, qmk_model* m, int head_index) {
 // 16-bit epochs: when the counter would wrap, clear the exchange words (stream-ordered) and restart at 0.
 static int reserve_epochs(qmk_engine* e, uint32_t need, cudaStream_t st, uint32_t* base) {
   if (e->epoch + need >= 0xfff0u) {
-    QMK_CUDA(cudaMemsetAsync(e->xbuf, 0, XBUF_BYTES, st));
+    QMK_CUDA(cudaMemsetAsync(e->xbuf + e->xbuf_ll_off, 0, e->xbuf_bytes - e->xbuf_ll_off, st));
     e->epoch = 0;
   }
   *base = e->epoch;
@@ -412,7 +455,7 @@ static int decode_step_impl(qmk_model* m, int head_index, int input_token_id, co
   if (rc != QMK_OK) return rc;
 
   const int n_idx = m->lay.L * PH_PER_LAYER + 2;
-  if (mode == 0) return launch_slice(e, p, 0, n_idx, st);
+  if (mode == 0 || e->version == 2) return launch_slice(e, p, 0, n_idx, st);   // the group kernel has no staged mode
   for (int idx = 0; idx < n_idx; ++idx) {
     rc = launch_slice(e, p, idx, idx + 1, st);
     if (rc != QMK_OK) return rc;
