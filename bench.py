@@ -70,10 +70,13 @@ def measured_peaks() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+NCU_RAW = "r01_ncu_group_raw.csv"   # ncu --set full of one talker launch of the default (group) kernel
+
+
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of one talker launch, from the committed `ncu --set full` capture
-    (profiles/r01_ncu_final_raw.csv, transposed raw page); None if the file is missing."""
-    path = os.path.join(REPO, "profiles", "r01_ncu_final_raw.csv")
+    (profiles/<NCU_RAW>, transposed raw page); None if the file is missing."""
+    path = os.path.join(REPO, "profiles", NCU_RAW)
     try:
         import csv
         vals = {}
@@ -405,6 +408,10 @@ def main():
         return
 
     peak, peak_src = measured_peaks()
+    n_ctas = loop.talker._lib.qmk_engine_num_ctas(loop.talker._engine)
+    kernel_name = "qmk2_decode_kernel" if n_ctas == 128 else "qmk_decode_kernel"
+    config["engine"] = ("group kernel: 8 kv-head groups x 16 CTAs, K-split O/down reduced in L2" if n_ctas == 128
+                        else "row-split kernel: one CTA per SM")
     value = frames_dev / (ms_dev / 1000.0)
     e2e = frames_e2e / (ms_e2e / 1000.0)
     achieved = talker_b / (talker_ms * 1e-3) / 1e9
@@ -418,10 +425,10 @@ def main():
         "e2e_dropin_loop": {"value": frames_dropin / (ms_dropin / 1000.0), "unit": UNIT,
                             "note": "upstream caller's control flow: step() returns a Python int (blocking D2H per frame)"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "qmk_decode_kernel (talker: 28 layers + LM head, one launch per step)",
+        "roofline": {"bound": "hbm", "kernel": f"{kernel_name} (talker: 28 layers + LM head, one launch per step, {n_ctas} CTAs)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
-                     "traffic_source": "profiles/r01_ncu_final_raw.csv (ncu --set full, one talker launch, bytes)",
+                     "traffic_source": f"profiles/{NCU_RAW} (ncu --set full, one talker launch, bytes)",
                      "algorithmic_bytes_per_launch": talker_b, "launch_us": talker_ms * 1e3},
         "talker_steps_per_s": 1000.0 / talker_ms,
         "cp_frame": {"ms": cp_ms, "frames_per_s": 1000.0 / cp_ms, "algorithmic_bytes": cp_frame_bytes(),

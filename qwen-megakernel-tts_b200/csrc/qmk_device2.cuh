@@ -119,6 +119,7 @@ __device__ __forceinline__ void prod2_init(Ctx2& c, Prod2& pr) {
 }
 __device__ __forceinline__ void prod2_tma(Ctx2& c, uint32_t k, const uint8_t* src, uint32_t bytes) {
   const int slot = k % NSL;
+  if (c.p.delay_o_idle == -1) bytes = 16;   // experiment (QMK_POLL_DELAY_O=-1): no weight traffic, exchanges on an idle memory system
   mbar_arrive_expect_tx(&c.full[slot], bytes);
   tma_bulk_g2s(c.ring + (size_t)slot * SLOT2, src, bytes, &c.full[slot]);
 }
@@ -144,6 +145,73 @@ __device__ __forceinline__ void prod2_issue(Ctx2& c, Prod2& pr, int n) {
   }
 }
 
+// ---- tensor-core stages, specialised by phase shape (NT tiles, NK steps per warp, first PRE tiles preloaded) --------
+template <int NT, int NK, int PRE>
+__device__ __forceinline__ void preload_a(uint32_t (&apre)[16][4], const uint32_t (&tb)[4], int warp, int a_khalf, int a_sw) {
+  static_assert(PRE * NK <= 16, "preload registers");
+#pragma unroll
+  for (int t = 0; t < PRE; ++t)
+#pragma unroll
+    for (int jx = 0; jx < NK; ++jx)
+      ldsm4(apre[t * NK + jx], tb[t] + ((uint32_t)((((warp * NK + jx) * 2 + a_khalf) ^ a_sw)) << 4));
+}
+// acc[t] = tile t x activation slice of this warp.  `bvec`: bf16 vector in natural order; lane q4 owns the contiguous run
+// of 4 NK elements at  warp * 16 NK + q4 * 4 NK  (the weights are K-permuted to match, see pack_chunk2).
+template <int NT, int NK, int PRE>
+__device__ __forceinline__ void mma_tiles(float (&acc)[4][4], const uint32_t (&apre)[16][4], const uint32_t (&tb)[4], const uint8_t* bvec,
+                                          int ntiles, int warp, int q4, int a_khalf, int a_sw) {
+  uint32_t bfrag[NK][2];
+  const uint8_t* bp = bvec + warp * (32 * NK) + q4 * (8 * NK);
+  if (NK % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < NK / 2; ++i) {
+      const uint4 v = *reinterpret_cast<const uint4*>(bp + i * 16);
+      bfrag[2 * i][0] = v.x; bfrag[2 * i][1] = v.y; bfrag[2 * i + 1][0] = v.z; bfrag[2 * i + 1][1] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int jx = 0; jx < NK; ++jx) {
+      const uint2 v = *reinterpret_cast<const uint2*>(bp + jx * 8);
+      bfrag[jx][0] = v.x; bfrag[jx][1] = v.y;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    if (t < PRE) {   // tiles below PRE always exist
+      if (NK >= 4) {
+        float acc2[4] = {0.f, 0.f, 0.f, 0.f};   // two accumulators halve the dependent HMMA chain
+#pragma unroll
+        for (int jx = 0; jx < NK; jx += 2) {
+          mma16816(acc[t], apre[t * NK + jx], bfrag[jx]);
+          if (jx + 1 < NK) mma16816(acc2, apre[t * NK + jx + 1], bfrag[jx + 1]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[t][e] += acc2[e];
+      } else {
+#pragma unroll
+        for (int jx = 0; jx < NK; ++jx) mma16816(acc[t], apre[t * NK + jx], bfrag[jx]);
+      }
+    } else if (t < ntiles) {
+      float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int jb = 0; jb < NK; jb += 4) {
+        uint32_t afrag[4][4];
+#pragma unroll
+        for (int jx = 0; jx < 4; ++jx)
+          if (jb + jx < NK) ldsm4(afrag[jx], tb[t] + ((uint32_t)((((warp * NK + jb + jx) * 2 + a_khalf) ^ a_sw)) << 4));
+        if (jb + 0 < NK) mma16816(acc[t], afrag[0], bfrag[jb]);
+        if (jb + 1 < NK) mma16816(acc2, afrag[1], bfrag[jb + 1]);
+        if (jb + 2 < NK) mma16816(acc[t], afrag[2], bfrag[jb + 2]);
+        if (jb + 3 < NK) mma16816(acc2, afrag[3], bfrag[jb + 3]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[t][e] += acc2[e];
+    }
+  }
+}
+
 // ---- attention ---------------------------------------------------------------------------------------------------
 struct AttnItem2 {
   int S, p0, p1;
@@ -161,6 +229,17 @@ __device__ __forceinline__ AttnItem2 attn_item2(int position, int j) {
   it.p0 = j * C;
   it.p1 = it.p0 + C < n ? it.p0 + C : n;
   return it;
+}
+__device__ __forceinline__ void attn_l2_prefetch(const Ctx2& c, int l, int position, const AttnItem2& it) {
+  const Params& p = c.p;
+  const size_t base = ((size_t)(l * NKVH + c.g) * p.max_seq) * HD;
+  for (int i = c.tid; i < (it.p1 - it.p0) * 4; i += NCT) {   // (row, K|V, half row): 128-byte lines
+    const int pos = it.p0 + (i >> 2);
+    if (pos != position) {
+      const __nv_bfloat16* ptr = ((i & 2) ? p.v_cache : p.k_cache) + base + (size_t)pos * HD + (i & 1) * 64;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+    }
+  }
 }
 __device__ __forceinline__ void attn_prefetch2(const Ctx2& c, int l, int position, const AttnItem2& it, int round, KvRegs& r) {
   const Params& p = c.p;
@@ -180,7 +259,8 @@ __device__ __forceinline__ void attn_prefetch2(const Ctx2& c, int l, int positio
 // over this CTA's positions; cross-warp merge; (long context) cross-chunk merge through group-local LL8 words.
 // Result: bf16 a[256] of the group's two q heads in c.s_a (every CTA of the group holds the same values).
 template <bool TR>
-__device__ void phase_attn2(Ctx2& c, int l, int position, uint32_t epoch, const AttnItem2& it, KvRegs& kv, const AttnPre& pre) {
+__device__ void phase_attn2(Ctx2& c, int l, int position, uint32_t epoch, const AttnItem2& it, KvRegs& kv, uint32_t (&apre)[16][4],
+                            int a_row, int a_khalf, int a_sw) {
   const Params& p = c.p;
   const uint32_t* x_q = reinterpret_cast<const uint32_t*>(c.xb + XB_Q) + c.g * 512;
   u64* x_part = reinterpret_cast<u64*>(c.xb + XB_PART) + (size_t)c.g * 2 * S2_MAX * PART_STRIDE;
@@ -188,6 +268,9 @@ __device__ void phase_attn2(Ctx2& c, int l, int position, uint32_t epoch, const 
   __nv_bfloat16* s_a = reinterpret_cast<__nv_bfloat16*>(c.s_a);
 
   bool retried = false;
+  if (it.has) attn_prefetch2(c, l, position, it, 0, kv);   // L2 hits (prefetched during the QKV phase)
+  uint2 nw_raw = make_uint2(0, 0);
+  if (c.warp < 3) nw_raw = *reinterpret_cast<const uint2*>(p.aux_layers + ((size_t)l * 2) * AUX_BYTES + 2048 + (c.warp == 2 ? 256 : 0) + c.lane * 8);
   wait_window(c, c.s_delay[DL_ATTN]);
   if (c.warp < 4) {
     const uint4 w = ll4_wait(c, x_q + c.warp * HD + c.lane * 4, epoch, retried);
@@ -201,10 +284,11 @@ __device__ void phase_attn2(Ctx2& c, int l, int position, uint32_t epoch, const 
       ss = warp_sum(ss);
       const float rms = sqrtf(ss * (1.0f / HD) + EPS);
       const int dbase = (c.lane * 4) & 63;
+      const float nw[4] = {bf16_lo(nw_raw.x), bf16_hi(nw_raw.x), bf16_lo(nw_raw.y), bf16_hi(nw_raw.y)};
       float o4[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float n = bf16_round((t[e] / rms) * pre.nw[e]);
+        const float n = bf16_round((t[e] / rms) * nw[e]);
         const float o = __shfl_xor_sync(0xffffffffu, n, 16);
         const float cs = s_small[SS_CS + dbase + e], sn = s_small[SS_CS + 64 + dbase + e];
         const float a = bf16_round(n * cs), b = bf16_round(o * sn);
@@ -304,6 +388,17 @@ __device__ void phase_attn2(Ctx2& c, int l, int position, uint32_t epoch, const 
     }
   }
   trace_sub<TR>(c, 2);
+  // The O projection has no exchange in front of it whose latency could hide the shared-memory reads of its weight
+  // tile (32 KB per CTA = 256 cycles of LDS bandwidth): move the A fragments into registers here, under the merge's
+  // barriers (the score loop's registers are dead now).
+  {
+    uint32_t tbo[4];
+    const uint32_t obase = smem_u32(c.ring + (size_t)(c.k % NSL) * SLOT2) + (uint32_t)a_row * 512u;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) tbo[t] = obase + (uint32_t)t * 8192u;
+    wait_full(c, c.k);
+    preload_a<4, 2, 4>(apre, tbo, c.warp, a_khalf, a_sw);
+  }
   // cross-warp merge: common max first, then plain sums in a fixed order
   if (c.lane == 0) {
     s_small[SS_M + c.warp * 2 + 0] = m0;
@@ -398,73 +493,6 @@ __device__ void phase_attn2(Ctx2& c, int l, int position, uint32_t epoch, const 
   consumer_bar();   // s_a complete; s_small / s_acc free again
 }
 
-// ---- tensor-core stages, specialised by phase shape (NT tiles, NK steps per warp, first PRE tiles preloaded) --------
-template <int NT, int NK, int PRE>
-__device__ __forceinline__ void preload_a(uint32_t (&apre)[16][4], const uint32_t (&tb)[4], int warp, int a_khalf, int a_sw) {
-  static_assert(PRE * NK <= 16, "preload registers");
-#pragma unroll
-  for (int t = 0; t < PRE; ++t)
-#pragma unroll
-    for (int jx = 0; jx < NK; ++jx)
-      ldsm4(apre[t * NK + jx], tb[t] + ((uint32_t)((((warp * NK + jx) * 2 + a_khalf) ^ a_sw)) << 4));
-}
-// acc[t] = tile t x activation slice of this warp.  `bvec`: bf16 vector in natural order; lane q4 owns the contiguous run
-// of 4 NK elements at  warp * 16 NK + q4 * 4 NK  (the weights are K-permuted to match, see pack_chunk2).
-template <int NT, int NK, int PRE>
-__device__ __forceinline__ void mma_tiles(float (&acc)[4][4], const uint32_t (&apre)[16][4], const uint32_t (&tb)[4], const uint8_t* bvec,
-                                          int ntiles, int warp, int q4, int a_khalf, int a_sw) {
-  uint32_t bfrag[NK][2];
-  const uint8_t* bp = bvec + warp * (32 * NK) + q4 * (8 * NK);
-  if (NK % 2 == 0) {
-#pragma unroll
-    for (int i = 0; i < NK / 2; ++i) {
-      const uint4 v = *reinterpret_cast<const uint4*>(bp + i * 16);
-      bfrag[2 * i][0] = v.x; bfrag[2 * i][1] = v.y; bfrag[2 * i + 1][0] = v.z; bfrag[2 * i + 1][1] = v.w;
-    }
-  } else {
-#pragma unroll
-    for (int jx = 0; jx < NK; ++jx) {
-      const uint2 v = *reinterpret_cast<const uint2*>(bp + jx * 8);
-      bfrag[jx][0] = v.x; bfrag[jx][1] = v.y;
-    }
-  }
-#pragma unroll
-  for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
-#pragma unroll
-  for (int t = 0; t < NT; ++t) {
-    if (t < PRE) {   // tiles below PRE always exist
-      if (NK >= 4) {
-        float acc2[4] = {0.f, 0.f, 0.f, 0.f};   // two accumulators halve the dependent HMMA chain
-#pragma unroll
-        for (int jx = 0; jx < NK; jx += 2) {
-          mma16816(acc[t], apre[t * NK + jx], bfrag[jx]);
-          if (jx + 1 < NK) mma16816(acc2, apre[t * NK + jx + 1], bfrag[jx + 1]);
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[t][e] += acc2[e];
-      } else {
-#pragma unroll
-        for (int jx = 0; jx < NK; ++jx) mma16816(acc[t], apre[t * NK + jx], bfrag[jx]);
-      }
-    } else if (t < ntiles) {
-      float acc2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int jb = 0; jb < NK; jb += 4) {
-        uint32_t afrag[4][4];
-#pragma unroll
-        for (int jx = 0; jx < 4; ++jx)
-          if (jb + jx < NK) ldsm4(afrag[jx], tb[t] + ((uint32_t)((((warp * NK + jb + jx) * 2 + a_khalf) ^ a_sw)) << 4));
-        if (jb + 0 < NK) mma16816(acc[t], afrag[0], bfrag[jb]);
-        if (jb + 1 < NK) mma16816(acc2, afrag[1], bfrag[jb + 1]);
-        if (jb + 2 < NK) mma16816(acc[t], afrag[2], bfrag[jb + 2]);
-        if (jb + 3 < NK) mma16816(acc2, afrag[3], bfrag[jb + 3]);
-      }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[t][e] += acc2[e];
-    }
-  }
-}
-
 // ---- main loop -----------------------------------------------------------------------------------------------------
 template <bool TR>
 __device__ void consumer_loop2(Ctx2& c) {
@@ -479,7 +507,6 @@ __device__ void consumer_loop2(Ctx2& c) {
   prod2_init(c, prod);
   if (c.warp == NCW - 1) prod2_issue(c, prod, NSL);
   KvRegs kv;
-  AttnPre pre = {{0.f, 0.f, 0.f, 0.f}};
   const int gi0 = c.tid * 4;
   // totals of this thread's accumulator words at the end of the previous launch
   u64 prevA[4], prevB[4];
@@ -528,6 +555,7 @@ __device__ void consumer_loop2(Ctx2& c) {
     consumer_bar();
 
     const int n_idx = L * PH_PER_LAYER + 2;
+    uint32_t apre[16][4];   // A fragments (weights) held in registers across an exchange wait
     for (int idx = 0; idx < n_idx; ++idx) {
       c.cur_idx = idx;
       trace_sub<TR>(c, 0);
@@ -536,7 +564,7 @@ __device__ void consumer_loop2(Ctx2& c) {
       const uint32_t epoch = (ebase + 1u + (uint32_t)l) & 0xffffu;
 
       if (kind == K2_ATTN) {
-        phase_attn2<TR>(c, l, position, epoch, item, kv, pre);
+        phase_attn2<TR>(c, l, position, epoch, item, kv, apre, a_row, a_khalf, a_sw);
         continue;
       }
       if (QMK_UNLIKELY(kind == K2_ARGMAX)) {
@@ -630,12 +658,13 @@ __device__ void consumer_loop2(Ctx2& c) {
       // ---- 2. shadow of the load latency: weights of this phase -> registers, norm weights, older KV rows ----
       uint2 wv = make_uint2(0, 0);
       if (norm) wv = *reinterpret_cast<const uint2*>(nw_ptr + c.tid * 8);
+      // Older KV rows of this CTA's attention item -> L2 now (fire and forget).  The register loads themselves are issued at
+      // the start of the attention phase: loads that miss L2 share hardware scoreboards with the exchange loads when
+      // they are in flight together, and the data check below would wait for them too.
       if (kind == K2_QKV) {
-        if (item.has) attn_prefetch2(c, l, position, item, 0, kv);
-        if (c.warp < 3) {
-          const uint2 nv = *reinterpret_cast<const uint2*>(p.aux_layers + ((size_t)l * 2) * AUX_BYTES + 2048 + (c.warp == 2 ? 256 : 0) + c.lane * 8);
-          pre.nw[0] = bf16_lo(nv.x); pre.nw[1] = bf16_hi(nv.x); pre.nw[2] = bf16_lo(nv.y); pre.nw[3] = bf16_hi(nv.y);
-        }
+        if (item.has) attn_l2_prefetch(c, l, position, item);
+        if (c.cta == ((l + 1) & (G2 - 1)) && c.tid < 40 && l + 1 < L)   // next layer's norm weights (one CTA per layer; 40 lines)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.aux_layers + ((size_t)(l + 1) * 2) * AUX_BYTES + c.tid * 128));
       }
       uint32_t tb[4];   // shared-memory address of this lane's ldmatrix row in tile t
 #pragma unroll
@@ -646,9 +675,8 @@ __device__ void consumer_loop2(Ctx2& c) {
       }
 #pragma unroll
       for (int sidx = 0; sidx < 3; ++sidx)
-        if (sidx < nst) wait_full(c, c.k + sidx);
-      uint32_t apre[16][4];
-      if (kind == K2_O) preload_a<4, 2, 4>(apre, tb, c.warp, a_khalf, a_sw);
+        if (sidx < nst && kind != K2_O) wait_full(c, c.k + sidx);
+      if (kind == K2_O) {}   // preloaded under the attention merge (phase_attn2)
       else if (kind == K2_DOWN) preload_a<4, 3, 4>(apre, tb, c.warp, a_khalf, a_sw);
       else preload_a<3, 8, 2>(apre, tb, c.warp, a_khalf, a_sw);   // QKV / head: both tiles; gate/up: tiles 0, 1
       trace_sub<TR>(c, 2);

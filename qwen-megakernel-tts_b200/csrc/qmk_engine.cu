@@ -125,10 +125,13 @@ extern "C" int qmk_engine_create(int device, int num_ctas, qmk_engine** out) {
   if (const char* env = getenv("QMK_NUM_CTAS")) {
     if (num_ctas <= 0) num_ctas = atoi(env);
   }
-  int version = 1;
+  // Kernel generation: 2 = group kernel (qmk_device2.cuh, 128 CTAs; default), 1 = row-split kernel (qmk_device.cuh, one CTA per
+  // SM; also the only one with the staged debugging mode).  QMK_ENGINE overrides; an explicit CTA count other than 128
+  // selects the row-split kernel.
+  int version = prop.multiProcessorCount >= qmk2::G2 ? 2 : 1;
   if (const char* env = getenv("QMK_ENGINE")) version = atoi(env);
   if (version != 1 && version != 2) return set_error(QMK_ERR_ARG, "QMK_ENGINE=%d: expected 1 or 2", version);
-  if (version == 2 && num_ctas > 0 && num_ctas != qmk2::G2) version = 1;   // an explicit CTA count selects the row-split kernel
+  if (version == 2 && num_ctas > 0 && num_ctas != qmk2::G2) version = 1;
   int G = num_ctas > 0 ? num_ctas : prop.multiProcessorCount;
   if (G > prop.multiProcessorCount) G = prop.multiProcessorCount;
   if (version == 2) {

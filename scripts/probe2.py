@@ -82,6 +82,18 @@ def trace2(dec, x, L):
         tot = np.mean(nxt - t[:, :, 0])
         tot_layer += tot
         print(f"  {names[ph]:5s} total {tot:7.0f} : " + "  ".join(parts))
+    # skew: per exchange, the wait (phase start -> data complete) of every CTA; the CTAs with the SHORTEST wait published last
+    smid = raw[:, n_idx, 1].astype(np.int64) if raw.shape[1] > n_idx else None
+    for ph, sub_done, nm in ((0, 3, "qkv-in (A)"), (1, 1, "attn-in (q/k/v)"), (3, 3, "gu-in (B)"), (4, 4, "down-in (m)")):
+        idxs = [l * 5 + ph for l in layers]
+        wait = raw[:, idxs, sub_done] - raw[:, idxs, 0]          # [G, layers]
+        per_cta = wait.mean(1)
+        order = np.argsort(per_cta)
+        print(f"  {nm:16s} wait over CTAs: min {per_cta.min():6.0f} p10 {np.percentile(per_cta,10):6.0f} median {np.median(per_cta):6.0f} "
+              f"p90 {np.percentile(per_cta,90):6.0f} max {per_cta.max():6.0f}; shortest (= last to publish): "
+              + " ".join(f"{int(cc)}({per_cta[cc]:.0f})" for cc in order[:8]))
+        grp = per_cta.reshape(8, 16).mean(1)
+        print("      per-group mean wait: " + " ".join(f"{v:.0f}" for v in grp))
     print(f"  per layer {tot_layer:.0f} cycles; kernel (cta 0) {raw[0, n_idx, 0] - raw[0, 0, 0]:.0f} cycles")
 
 

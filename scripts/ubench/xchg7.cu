@@ -51,6 +51,28 @@ __device__ __forceinline__ void red_gather(const P& p, u64* acc, int j, unsigned
   __syncthreads();
 }
 
+// variant: every CTA adds a partial to ALL 1024 words (128 adds per word): the down projection K-split per CTA
+__device__ __forceinline__ void red_gather_all(const P& p, u64* acc, unsigned use, float* s_vec, unsigned& chk) {
+  const int tid = threadIdx.x;
+  const int rot = (blockIdx.x * 8) & 1023;   // stagger the start word per CTA
+#pragma unroll
+  for (int e = 0; e < 4; ++e) red64(acc + ((tid + 256 * e + rot) & 1023), (1ull << 56) + (u64)(tid + 1));
+  spin(p.delay);
+  const unsigned want = (128u * use) & 0xffu;
+  u64 w[4];
+  for (unsigned sp = 0;; ++sp) {
+    if (sp > (1u << 14) || *(volatile unsigned*)p.sink == 0xdeadu) { p.sink[0] = 0xdeadu; break; }
+    ld2x64(acc + 4 * tid, w[0], w[1]);
+    ld2x64(acc + 4 * tid + 2, w[2], w[3]);
+    bool ok = true;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ok &= ((unsigned)((w[e] + (1ull << 55)) >> 56) & 0xffu) == want;
+    if (ok) break;
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { s_vec[4 * tid + e] = (float)(long long)(w[e] << 8); chk += (unsigned)w[e]; }
+  __syncthreads();
+}
 __device__ __forceinline__ void st32(unsigned* p, unsigned v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint4 ld128(const unsigned* p) {
   uint4 v; asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); return v; }
@@ -86,6 +108,17 @@ __global__ void __launch_bounds__(NT, 1) k_v2(P p) {
     if (p.mode == 0) {   // two accumulators alternate: a word may only be re-used after a full exchange on the other one
       spin(w);
       if (it & 1) red_gather(p, p.acc, j, ++use_a, s_vec, chk); else red_gather(p, p.acc + 1024, j, ++use_b, s_vec, chk);
+    } else if (p.mode == 3) {
+      spin(w);
+      if (it & 1) red_gather_all(p, p.acc, ++use_a, s_vec, chk); else red_gather_all(p, p.acc + 1024, ++use_b, s_vec, chk);
+    } else if (p.mode == 4) {   // layer shape with the CTA-local down: A(all-words), group, B(64 rows)
+      spin(w);
+      red_gather_all(p, p.acc, ++use_a, s_vec, chk);
+      spin(w);
+      ++ep; group_xchg(p, p.gb + (ep & 1) * 8192 + g * 512, j, ep & 0xffffu, chk);
+      spin(w);
+      red_gather(p, p.acc + 1024, j, ++use_b, s_vec, chk);
+      spin(w);
     } else if (p.mode == 1) {
       spin(w);
       ++ep;
@@ -122,10 +155,15 @@ int main() {
     long long mx = 0; for (auto v : h) mx = v > mx ? v : mx;
     unsigned flags[2]; CK(cudaMemcpy(flags, p.sink, 8, cudaMemcpyDeviceToHost));
     if (flags[0] == 0xdeadu || flags[1] == 0xdeadu) printf("TIMEOUT flags %x %x  ", flags[0], flags[1]);
-    const int per = (mode == 2) ? 4 : 1;
+    const int per = (mode == 2 || mode == 4) ? 4 : 1;
     printf("mode=%d gmap=%d delay=%4d cdelay=%4d work=%4d jitter=%4d : %8.1f cyc/round  net of work %8.1f\n", mode, gmap, delay, cdelay, work, jitter,
            (double)mx / p.iters, (double)mx / p.iters - per * (work + jitter / 2.0));
   };
+  for (int d : {0, 400, 800, 1200}) run(3, 0, d, 0, 0, 0);
+  for (int d : {400, 800}) run(3, 0, d, 0, 1000, 300);
+  for (int d : {400, 800}) run(4, 0, d, 300, 1000, 0);
+  for (int d : {400, 600}) run(2, 0, d, 300, 1000, 0);
+  return 0;
   for (int d : {0, 200, 400, 600, 800}) run(0, 0, d, 0, 0, 0);
   for (int d : {400, 600, 800}) run(0, 0, d, 0, 1000, 300);
   for (int gm : {0, 1}) for (int d : {0, 200, 400, 600}) run(1, gm, 0, d, 0, 0);

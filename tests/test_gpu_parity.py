@@ -96,6 +96,10 @@ def test_staged_mode_is_bit_identical_to_fused(gpu_weights, golden):
     g = golden["talker_config1"]
     emb = bf16_from_bits(g["prefill_bits"]).cuda()
     outs = []
+    probe = TTSDecoder(weights=gpu_weights, verbose=False, max_seq_len=64, num_layers=1)
+    if probe._lib.qmk_engine_num_ctas(probe._engine) == 128:
+        pytest.skip("the staged mode belongs to the row-split kernel (QMK_ENGINE=1); tests/test_gpu_engines.py runs it there")
+    del probe
     for mode in (0, 1):
         dec = TTSDecoder(weights=gpu_weights, verbose=False, max_seq_len=64, mode=mode, num_layers=6)
         run = []
