@@ -77,7 +77,10 @@ __device__ __forceinline__ void ld_acc2(const u64* p, u64& a, u64& b) {
 }
 __device__ __forceinline__ bool acc_done(u64 now, u64 prev) { return (uint32_t)(((now - prev) + (1ull << 55)) >> 56) == (uint32_t)NGRP; }
 __device__ __forceinline__ float acc_value(u64 now, u64 prev) {
-  return (float)(long long)((now - prev) - (u64)NGRP * CNT_ONE) * (1.0f / (float)(1 << FIX_SHIFT));
+  // signed 56-bit fixed point -> float through two 32-bit conversions (a 64-bit I2F is a multi-instruction slow path)
+  const u64 d = (now - prev) - (u64)NGRP * CNT_ONE;
+  const float hi = (float)(int)(uint32_t)(d >> 32), lo = (float)(uint32_t)d;
+  return fmaf(hi, 4294967296.0f, lo) * (1.0f / (float)(1 << FIX_SHIFT));
 }
 __device__ __forceinline__ u64 acc_word(float v) { return CNT_ONE + (u64)__float2ll_rn(v * (float)(1 << FIX_SHIFT)); }
 
@@ -117,17 +120,31 @@ __device__ __forceinline__ void prod2_init(Ctx2& c, Prod2& pr) {
   for (int st = 0; st < p.n_steps; ++st) pr.left += p.lay.L * ENT_PER_LAYER + head_tiles(p.steps[st].head);
   pr.layer_base = p.packed_layers + (size_t)c.cta * p.lay.L * LAYER_BYTES2;
 }
+// Weights are read exactly once per step and a step's weights exceed L2: stream them with an evict-first policy so
+// that they do not push out what IS re-used (KV rows, embedding tables, norm weights, the exchange words).
+__device__ __forceinline__ void tma_bulk_g2s_stream(void* dst_smem, const void* src_gmem, uint32_t bytes, u64* bar) {
+  u64 policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void prod2_tma(Ctx2& c, uint32_t k, const uint8_t* src, uint32_t bytes) {
   const int slot = k % NSL;
   if (c.p.delay_o_idle == -1) bytes = 16;   // experiment (QMK_POLL_DELAY_O=-1): no weight traffic, exchanges on an idle memory system
   mbar_arrive_expect_tx(&c.full[slot], bytes);
-  tma_bulk_g2s(c.ring + (size_t)slot * SLOT2, src, bytes, &c.full[slot]);
+  if (c.p.delay_o_idle == -2) tma_bulk_g2s(c.ring + (size_t)slot * SLOT2, src, bytes, &c.full[slot]);   // QMK_POLL_DELAY_O=-2: default L2 policy
+  else tma_bulk_g2s_stream(c.ring + (size_t)slot * SLOT2, src, bytes, &c.full[slot]);
 }
 __device__ __forceinline__ void prod2_issue(Ctx2& c, Prod2& pr, int n) {
   const Params& p = c.p;
   if (n > pr.left) n = pr.left;
   pr.left -= n;
-  for (; n > 0; --n, ++pr.k) {
+  // Called by warps 2..7 (the ones that neither finalise nor publish), all of which keep the cursor; stage i of the call
+  // is issued by warp 2 + i % 6, so that a three-stage refill costs one mbarrier + one bulk copy of latency instead of three.
+  for (int issuer = 2; n > 0; --n, ++pr.k, issuer = (issuer == NCW - 1) ? 2 : issuer + 1) {
     // skip steps without a head (their head phase has no stage)
     while (pr.l == p.lay.L && pr.e >= head_tiles(p.steps[pr.step].head)) {
       pr.l = 0; pr.e = 0; ++pr.step;
@@ -135,11 +152,11 @@ __device__ __forceinline__ void prod2_issue(Ctx2& c, Prod2& pr, int n) {
     }
     if (pr.l < p.lay.L) {
       const uint32_t off = pr.e < 6 ? (uint32_t)pr.e * SLOT2 : 6u * SLOT2 + (uint32_t)(pr.e - 6) * DOWN_SLOT;
-      if (c.lane == 0) prod2_tma(c, pr.k, pr.layer_base + off, pr.e < 6 ? SLOT2 : DOWN_SLOT);
+      if (c.lane == 0 && c.warp == issuer) prod2_tma(c, pr.k, pr.layer_base + off, pr.e < 6 ? SLOT2 : DOWN_SLOT);
       if (++pr.e == ENT_PER_LAYER) { pr.e = 0; ++pr.l; pr.layer_base += LAYER_BYTES2; }
     } else {
       const HeadDesc& h = p.steps[pr.step].head;
-      if (c.lane == 0) prod2_tma(c, pr.k, h.packed + ((size_t)c.cta * head_tiles(h) + pr.e) * SLOT2, SLOT2);
+      if (c.lane == 0 && c.warp == issuer) prod2_tma(c, pr.k, h.packed + ((size_t)c.cta * head_tiles(h) + pr.e) * SLOT2, SLOT2);
       ++pr.e;
     }
   }
@@ -501,11 +518,10 @@ __device__ void consumer_loop2(Ctx2& c) {
   uint32_t* const x_q = reinterpret_cast<uint32_t*>(c.xb + XB_Q) + c.g * 512;
   uint32_t* const x_m = reinterpret_cast<uint32_t*>(c.xb + XB_M) + c.g * 384;
   uint32_t* const x_logits = reinterpret_cast<uint32_t*>(c.xb + XB_LOGITS);
-  u64* const x_tok = reinterpret_cast<u64*>(c.xb + XB_TOKEN);
   u64* const accA = c.acc, * const accB = c.acc + 1024;
   Prod2 prod;
   prod2_init(c, prod);
-  if (c.warp == NCW - 1) prod2_issue(c, prod, NSL);
+  if (c.warp >= 2) prod2_issue(c, prod, NSL);
   KvRegs kv;
   const int gi0 = c.tid * 4;
   // totals of this thread's accumulator words at the end of the previous launch
@@ -515,6 +531,7 @@ __device__ void consumer_loop2(Ctx2& c) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) { prevA[e] = snap[gi0 + e]; prevB[e] = snap[1024 + gi0 + e]; }
   }
+  int next_token = 0;   // token selected at the end of the previous step of this launch
   float res[4] = {0.f, 0.f, 0.f, 0.f};   // residual stream, elements 4 tid .. 4 tid + 3 (every CTA holds all of it)
   // ldmatrix roles of this lane
   const int a_mi = c.lane >> 3;
@@ -532,16 +549,7 @@ __device__ void consumer_loop2(Ctx2& c) {
       in_token = *sd.token_ptr;
       in_token = in_token < 0 ? 0 : (in_token > sd.token ? sd.token : in_token);
     }
-    if (sd.in_mode == IN_TABLE_PREV) {
-      if (c.warp == 0) {
-        const long long t_ready = c.t_pub + c.s_delay[DL_TOKEN];
-        while (clock64() < t_ready) {
-        }
-        if (c.lane == 0) c.s_red[32] = __int_as_float((int)ll8_wait(c, x_tok + (step & 15), (ebase - 1u) & 0xffffu));
-      }
-      consumer_bar();
-      in_token = __float_as_int(c.s_red[32]);
-    }
+    if (sd.in_mode == IN_TABLE_PREV) in_token = next_token;   // selected by THIS CTA at the end of the previous step (see K2_ARGMAX)
     const __nv_bfloat16* x_in = (sd.in_mode == IN_TABLE_TOKEN || sd.in_mode == IN_TABLE_PREV)
                                     ? sd.in_table + (size_t)in_token * H
                                     : reinterpret_cast<const __nv_bfloat16*>(sd.in_vec);
@@ -568,7 +576,11 @@ __device__ void consumer_loop2(Ctx2& c) {
         continue;
       }
       if (QMK_UNLIKELY(kind == K2_ARGMAX)) {
-        if (c.cta != 0 || sd.head.rows <= 0) continue;
+        // Token selection.  Inside a multi-step launch EVERY CTA gathers the logits and selects the token itself
+        // (same words, same code, fixed summation orders -> the same token everywhere): the next step's input is
+        // known without a gather-to-one-CTA plus a broadcast, i.e. one exchange per step instead of two.  The last step
+        // of a launch is selected by CTA 0 alone.
+        if (sd.head.rows <= 0 || (c.cta != 0 && step + 1 >= p.n_steps)) continue;
         const int hrows = sd.head.rows;
         const uint32_t epoch_head = (ebase + (uint32_t)L + 1u) & 0xffffu;
         const bool sample = sd.select != 0 && hrows <= NCW * 2 * HD && (hrows % (NCT * 4)) == 0;
@@ -580,7 +592,7 @@ __device__ void consumer_loop2(Ctx2& c) {
         for (int i = c.tid * 4; i < hrows; i += NCT * 4) {
           const uint4 w = ll4_wait(c, x_logits + i, epoch_head, retried);
           const float4 v = make_float4(ll4_val(w.x), ll4_val(w.y), ll4_val(w.z), ll4_val(w.w));
-          if (sd.logits_out != nullptr) *reinterpret_cast<float4*>(sd.logits_out + i) = v;
+          if (sd.logits_out != nullptr && c.cta == 0) *reinterpret_cast<float4*>(sd.logits_out + i) = v;
           if (sample) *reinterpret_cast<float4*>(s_log + i) = v;
           const float v4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -608,16 +620,13 @@ __device__ void consumer_loop2(Ctx2& c) {
         if (sample)
           chosen = sample_token(s_log, reinterpret_cast<unsigned*>(c.s_part), c.s_red, c.tid, c.warp, c.lane, hrows,
                                 p.sample_top_k, p.sample_temperature, p.sample_seed, p.sample_counter, sd.group, best, best_i);
-        if (c.tid == 0) {
+        next_token = chosen;
+        if (p.forced_tokens != nullptr && sd.group >= 0) next_token = p.forced_tokens[sd.group];   // teacher forcing
+        if (c.cta == 0 && c.tid == 0) {
           const int st = *((volatile int*)p.status);
           const int out = (st != 0 || *c.s_abort) ? -1000 - st : chosen;
           if (sd.out_token != nullptr) *sd.out_token = out;
           if (sd.out_code != nullptr) *sd.out_code = (long long)out;
-          if (step + 1 < p.n_steps) {
-            int fed = chosen;
-            if (p.forced_tokens != nullptr && sd.group >= 0) fed = p.forced_tokens[sd.group];
-            ll8_st(x_tok + ((step + 1) & 15), (uint32_t)fed, epoch_head);
-          }
         }
         consumer_bar();
         continue;
@@ -673,9 +682,15 @@ __device__ void consumer_loop2(Ctx2& c) {
         const uint32_t toff = (kind == K2_O) ? (uint32_t)t * 8192u : (kind == K2_DOWN ? (uint32_t)(t & 1) * 12288u : 0u);
         tb[t] = smem_u32(c.ring + (size_t)((c.k + slot_i) % NSL) * SLOT2) + toff + (uint32_t)a_row * stride;
       }
-#pragma unroll
-      for (int sidx = 0; sidx < 3; ++sidx)
-        if (sidx < nst && kind != K2_O) wait_full(c, c.k + sidx);
+      if (kind != K2_O) {   // three phase tests back to back (their latencies overlap); a stage that is not resident yet is waited for
+        const uint32_t k0 = c.k, k1 = c.k + (nst > 1 ? 1 : 0), k2 = c.k + (nst > 2 ? 2 : 0);
+        const uint32_t ready = mbar_test_wait3(&c.full[k0 % NSL], (k0 / NSL) & 1u, &c.full[k1 % NSL], (k1 / NSL) & 1u,
+                                               &c.full[k2 % NSL], (k2 / NSL) & 1u);
+        if (QMK_UNLIKELY(ready != 7u)) {
+#pragma unroll 1
+          for (int sidx = 0; sidx < nst; ++sidx) wait_full(c, c.k + sidx);
+        }
+      }
       if (kind == K2_O) {}   // preloaded under the attention merge (phase_attn2)
       else if (kind == K2_DOWN) preload_a<4, 3, 4>(apre, tb, c.warp, a_khalf, a_sw);
       else preload_a<3, 8, 2>(apre, tb, c.warp, a_khalf, a_sw);   // QKV / head: both tiles; gate/up: tiles 0, 1
@@ -776,7 +791,7 @@ __device__ void consumer_loop2(Ctx2& c) {
       }
       consumer_bar();
       trace_sub<TR>(c, 6);
-      if (c.warp == NCW - 1) prod2_issue(c, prod, nst);
+      if (c.warp >= 2) prod2_issue(c, prod, nst);
 
       // ---- 5. finalize + publish ----
       if (kind == K2_QKV) {

@@ -23,7 +23,8 @@ _DIR = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_DIR)
 _CSRC = os.path.join(_ROOT, "csrc")
 _INCLUDE = os.path.join(os.path.dirname(_ROOT), "include")
-LIB_PATH = os.path.join(_DIR, "libqmk_b200.so")
+# QMK_LIB_PATH: load another build of the same ABI (A/B timing of kernel variants inside one GPU job)
+LIB_PATH = os.environ.get("QMK_LIB_PATH") or os.path.join(_DIR, "libqmk_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -97,6 +97,30 @@ def trace2(dec, x, L):
     print(f"  per layer {tot_layer:.0f} cycles; kernel (cta 0) {raw[0, n_idx, 0] - raw[0, 0, 0]:.0f} cycles")
 
 
+def trace_cp(cp, w, x):
+    """stamps of the LAST step of a fused code-predictor frame (the trace slots are overwritten step by step)"""
+    import ctypes
+    import numpy as np
+    lib, engine = cp._lib, cp._engine
+    L = 5
+    n_idx = L * 5 + 2
+    stride = (n_idx + 1) * 24
+    assert lib.qmk_engine_trace_enable(engine, stride) == 0
+    hid = x[0].float()
+    for sample in (False, True):
+        cp.predict(hid, 1335, w["embed_weight"], do_sample=sample, temperature=0.9, top_k=50)
+        G = lib.qmk_engine_num_ctas(engine)
+        buf = (ctypes.c_longlong * (G * stride))()
+        lib.qmk_engine_trace_read(engine, torch.cuda.current_stream().cuda_stream, buf, G * stride)
+        raw = np.frombuffer(buf, dtype=np.int64).reshape(G, n_idx + 1, 24).astype(np.float64)
+        st = raw[:, :, 0]
+        layer = (st[:, 25] - st[:, 5]).mean() / 4
+        print(f"  cp last step (sample={sample}): layer {layer:.0f} cycles; head phase {np.mean(st[:, 26] - st[:, 25]):.0f} "
+              f"(cta0 {st[0, 26] - st[0, 25]:.0f}); argmax phase cta0 {st[0, 27] - st[0, 26]:.0f}; "
+              f"head stamps cta0: " + " ".join(f"{raw[0, 25, s] - raw[0, 25, 0]:.0f}" for s in (1, 2, 3, 4, 5, 6, 8)))
+    lib.qmk_engine_trace_enable(engine, 0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--trace", action="store_true")
@@ -129,6 +153,7 @@ def main():
                 extra += f"  pos{pos}: {type(ex).__name__}"
         if args.trace and f[0] == "2":
             trace2(dec, x, args.layers)
+            trace_cp(cp, w, x)
         print(f"cfg={cfg:>16s} ctas={G}: talker {us:8.1f} us/step   cp step {us_cp:7.1f} us {extra}", flush=True)
         del dec, cp
 
