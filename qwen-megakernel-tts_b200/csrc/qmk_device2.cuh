@@ -276,7 +276,7 @@ __device__ __forceinline__ void attn_prefetch2(const Ctx2& c, int l, int positio
 // over this CTA's positions; cross-warp merge; (long context) cross-chunk merge through group-local LL8 words.
 // Result: bf16 a[256] of the group's two q heads in c.s_a (every CTA of the group holds the same values).
 template <bool TR>
-__device__ void phase_attn2(Ctx2& c, int l, int position, uint32_t epoch, const AttnItem2& it, KvRegs& kv, uint32_t (&apre)[16][4],
+__device__ void phase_attn2(Ctx2& c, int l, int position, uint32_t epoch, const AttnItem2& it, KvRegs& kv, Prod2& prod,
                             int a_row, int a_khalf, int a_sw) {
   const Params& p = c.p;
   const uint32_t* x_q = reinterpret_cast<const uint32_t*>(c.xb + XB_Q) + c.g * 512;
@@ -408,8 +408,9 @@ __device__ void phase_attn2(Ctx2& c, int l, int position, uint32_t epoch, const 
   // The O projection has no exchange in front of it whose latency could hide the shared-memory reads of its weight
   // tile (32 KB per CTA = 256 cycles of LDS bandwidth): move the A fragments into registers here, under the merge's
   // barriers (the score loop's registers are dead now).
+  uint32_t apre[16][4];
+  uint32_t tbo[4];
   {
-    uint32_t tbo[4];
     const uint32_t obase = smem_u32(c.ring + (size_t)(c.k % NSL) * SLOT2) + (uint32_t)a_row * 512u;
 #pragma unroll
     for (int t = 0; t < 4; ++t) tbo[t] = obase + (uint32_t)t * 8192u;
@@ -501,13 +502,35 @@ __device__ void phase_attn2(Ctx2& c, int l, int position, uint32_t epoch, const 
     }
   }
   trace_sub<TR>(c, 3);
-  // append the new K/V row (one CTA per group)
+  consumer_bar();   // s_a complete
+  // ---- O projection, K-split by group: rows 64 j .. 64 j + 63 of W_o x this group's 256 attention outputs.  It has no
+  //      exchange in front of it, so it runs here instead of as a phase of its own; the eight groups' partials of a row
+  //      meet in L2 (one fixed-point add per row). ----
+  {
+    float acc4[4][4];
+    mma_tiles<4, 2, 4>(acc4, apre, tbo, c.s_a, 4, c.warp, c.lane & 3, a_khalf, a_sw);
+    c.k += 1;
+    if ((c.lane & 3) == 0) {
+      const int g8 = c.lane >> 2;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        c.s_part[((t * 16 + g8) * NCW) + c.warp] = acc4[t][0];
+        c.s_part[((t * 16 + g8 + 8) * NCW) + c.warp] = acc4[t][2];
+      }
+    }
+    consumer_bar();
+    trace_sub<TR>(c, 4);
+    if (c.warp >= 2) prod2_issue(c, prod, 1);
+    if (c.tid < O_LOC) red_add64(c.acc + 1024 + O_LOC * c.j + c.tid, acc_word(item_sum(c.s_part, c.tid)));
+    c.t_pub = clock64();
+    trace_sub<TR>(c, 5);
+  }
+  // append the new K/V row (one CTA per group; off the critical path)
   if (c.j == 0 && c.tid < 128) {
     const size_t off = ((size_t)(l * NKVH + c.g) * p.max_seq + position) * HD + c.tid;
     p.k_cache[off] = __float2bfloat16_rn(s_small[SS_KN + c.tid]);
     p.v_cache[off] = __float2bfloat16_rn(s_small[SS_V + c.tid]);
   }
-  consumer_bar();   // s_a complete; s_small / s_acc free again
 }
 
 // ---- main loop -----------------------------------------------------------------------------------------------------
@@ -563,7 +586,6 @@ __device__ void consumer_loop2(Ctx2& c) {
     consumer_bar();
 
     const int n_idx = L * PH_PER_LAYER + 2;
-    uint32_t apre[16][4];   // A fragments (weights) held in registers across an exchange wait
     for (int idx = 0; idx < n_idx; ++idx) {
       c.cur_idx = idx;
       trace_sub<TR>(c, 0);
@@ -571,8 +593,9 @@ __device__ void consumer_loop2(Ctx2& c) {
       const int kind = idx < L * PH_PER_LAYER ? idx % PH_PER_LAYER : (idx == L * PH_PER_LAYER ? K2_HEAD : K2_ARGMAX);
       const uint32_t epoch = (ebase + 1u + (uint32_t)l) & 0xffffu;
 
+      if (kind == K2_O) continue;   // done inside phase_attn2
       if (kind == K2_ATTN) {
-        phase_attn2<TR>(c, l, position, epoch, item, kv, apre, a_row, a_khalf, a_sw);
+        phase_attn2<TR>(c, l, position, epoch, item, kv, prod, a_row, a_khalf, a_sw);
         continue;
       }
       if (QMK_UNLIKELY(kind == K2_ARGMAX)) {
@@ -640,7 +663,6 @@ __device__ void consumer_loop2(Ctx2& c) {
       int ntiles, nst;
       uint32_t stride;
       if (kind == K2_QKV) { ntiles = 2; nst = 2; stride = 2048; }
-      else if (kind == K2_O) { ntiles = 4; nst = 1; stride = 512; }
       else if (kind == K2_GU) { ntiles = 3; nst = 3; stride = 2048; }
       else if (kind == K2_DOWN) { ntiles = 4; nst = 2; stride = 768; }
       else { ntiles = (hrows_loc + 15) / 16; nst = ntiles; stride = 2048; }
@@ -654,7 +676,7 @@ __device__ void consumer_loop2(Ctx2& c) {
       // ---- 1. wait window, then issue the gather loads ----
       u64 now[4];
       uint4 mw = make_uint4(0, 0, 0, 0);
-      if (kind != K2_O && !from_input) {
+      if (!from_input) {
         wait_window(c, c.s_delay[dslot]);
         trace_sub<TR>(c, 1);
         if (norm) {
@@ -678,11 +700,11 @@ __device__ void consumer_loop2(Ctx2& c) {
       uint32_t tb[4];   // shared-memory address of this lane's ldmatrix row in tile t
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const int slot_i = (kind == K2_DOWN) ? (t >> 1) : (kind == K2_O ? 0 : (t < nst ? t : 0));
-        const uint32_t toff = (kind == K2_O) ? (uint32_t)t * 8192u : (kind == K2_DOWN ? (uint32_t)(t & 1) * 12288u : 0u);
+        const int slot_i = (kind == K2_DOWN) ? (t >> 1) : (t < nst ? t : 0);
+        const uint32_t toff = (kind == K2_DOWN) ? (uint32_t)(t & 1) * 12288u : 0u;
         tb[t] = smem_u32(c.ring + (size_t)((c.k + slot_i) % NSL) * SLOT2) + toff + (uint32_t)a_row * stride;
       }
-      if (kind != K2_O) {   // three phase tests back to back (their latencies overlap); a stage that is not resident yet is waited for
+      {   // three phase tests back to back (their latencies overlap); a stage that is not resident yet is waited for
         const uint32_t k0 = c.k, k1 = c.k + (nst > 1 ? 1 : 0), k2 = c.k + (nst > 2 ? 2 : 0);
         const uint32_t ready = mbar_test_wait3(&c.full[k0 % NSL], (k0 / NSL) & 1u, &c.full[k1 % NSL], (k1 / NSL) & 1u,
                                                &c.full[k2 % NSL], (k2 / NSL) & 1u);
@@ -691,8 +713,8 @@ __device__ void consumer_loop2(Ctx2& c) {
           for (int sidx = 0; sidx < nst; ++sidx) wait_full(c, c.k + sidx);
         }
       }
-      if (kind == K2_O) {}   // preloaded under the attention merge (phase_attn2)
-      else if (kind == K2_DOWN) preload_a<4, 3, 4>(apre, tb, c.warp, a_khalf, a_sw);
+      uint32_t apre[16][4];   // A fragments (weights) held in registers across the exchange wait
+      if (kind == K2_DOWN) preload_a<4, 3, 4>(apre, tb, c.warp, a_khalf, a_sw);
       else preload_a<3, 8, 2>(apre, tb, c.warp, a_khalf, a_sw);   // QKV / head: both tiles; gate/up: tiles 0, 1
       trace_sub<TR>(c, 2);
 
@@ -767,14 +789,13 @@ __device__ void consumer_loop2(Ctx2& c) {
         }
         gather_note(c, DL_DOWN, retried);
       }
-      __syncwarp();   // warp w consumes exactly the K slice its own lanes wrote (O: phase_attn2 ended with a CTA barrier)
+      __syncwarp();   // warp w consumes exactly the K slice its own lanes wrote 
       trace_sub<TR>(c, 4);
       if (kind == K2_HEAD && ntiles == 0) continue;   // step without an LM head: only the final norm / outputs
 
       // ---- 4. tensor-core stages ----
       float acc4[4][4];
-      if (kind == K2_O) mma_tiles<4, 2, 4>(acc4, apre, tb, c.s_a, 4, c.warp, q4, a_khalf, a_sw);
-      else if (kind == K2_DOWN) mma_tiles<4, 3, 4>(acc4, apre, tb, c.s_a, 4, c.warp, q4, a_khalf, a_sw);
+      if (kind == K2_DOWN) mma_tiles<4, 3, 4>(acc4, apre, tb, c.s_a, 4, c.warp, q4, a_khalf, a_sw);
       else mma_tiles<3, 8, 2>(acc4, apre, tb, c.s_vec, ntiles, c.warp, q4, a_khalf, a_sw);
       c.k += nst;
       if (TR) { if (__float_as_uint(acc4[0][0]) == 0x7fc12345u) c.s_red[40] = 1.f; }   // stamp 5 after the tensor-core results exist
@@ -812,10 +833,10 @@ __device__ void consumer_loop2(Ctx2& c) {
             ll4_st(x_m + M_LOC * c.j + (c.tid >> 1), sg * u, epoch);
           }
         }
-      } else if (kind == K2_O || kind == K2_DOWN) {
+      } else if (kind == K2_DOWN) {
         if (c.tid < O_LOC) {   // one fixed-point add per row: the eight groups' K-split partials meet in L2
           const float v = item_sum(c.s_part, c.tid);
-          red_add64((kind == K2_O ? accB : accA) + O_LOC * c.j + c.tid, acc_word(v));
+          red_add64(accA + O_LOC * c.j + c.tid, acc_word(v));
         }
       } else {   // head: logits as LL4 words for CTA 0
         if (c.tid < hrows_loc) ll4_st(x_logits + hrows_loc * c.cta + c.tid, item_sum(c.s_part, c.tid), (ebase + (uint32_t)L + 1u) & 0xffffu);
