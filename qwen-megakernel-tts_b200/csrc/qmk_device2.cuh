@@ -52,7 +52,8 @@ constexpr size_t XB_M = XB_Q + NGRP * 512 * 4;             // u32[8][384]
 constexpr size_t XB_LOGITS = XB_M + NGRP * 384 * 4;        // u32[3072]
 constexpr size_t XB_TOKEN = XB_LOGITS + MAX_HEAD_ROWS * 4; // u64[16]
 constexpr size_t XB_PART = XB_TOKEN + 16 * 8;              // u64[8][2][16][PART_STRIDE]
-constexpr size_t XBUF2_BYTES = XB_PART + (size_t)NGRP * 2 * S2_MAX * PART_STRIDE * 8;
+constexpr size_t XB_ROLE = XB_PART + (size_t)NGRP * 2 * S2_MAX * PART_STRIDE * 8;   // int[128]: blockIdx -> role (group * 16 + rank)
+constexpr size_t XBUF2_BYTES = XB_ROLE + G2 * 4;
 
 // shared memory
 constexpr int S2_RING = 0;
@@ -874,9 +875,11 @@ __device__ __forceinline__ void decode2_body(const Params& p) {
   c.tid = threadIdx.x;
   c.warp = threadIdx.x >> 5;
   c.lane = threadIdx.x & 31;
-  c.cta = blockIdx.x;
-  c.g = blockIdx.x / GSZ;
-  c.j = blockIdx.x % GSZ;
+  // Role of this CTA (which group, which rank): a host-built permutation (identity by default; see qmk_engine_create for the
+  // measured effect of SM-sorted groups).  Any permutation is correct; it only moves latency.
+  c.cta = reinterpret_cast<const int*>(p.xbuf + XB_ROLE)[blockIdx.x];
+  c.g = c.cta / GSZ;
+  c.j = c.cta % GSZ;
   c.k = 0;
   c.t0 = clock64();
   c.t_pub = c.t0;
@@ -890,6 +893,15 @@ __device__ __forceinline__ void decode2_body(const Params& p) {
   __syncthreads();
   consumer_loop2<TR>(c);
   __syncthreads();
+  if (TR && p.trace != nullptr && threadIdx.x == 0) {   // end stamp + the SM this CTA ran on
+    const int n_idx = p.lay.L * PH_PER_LAYER + 2;
+    if ((n_idx + 1) * TRACE_SUBS <= p.trace_stride) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.trace[(size_t)c.cta * p.trace_stride + n_idx * TRACE_SUBS + 0] = clock64();
+      p.trace[(size_t)c.cta * p.trace_stride + n_idx * TRACE_SUBS + 1] = (long long)smid;
+    }
+  }
   if (threadIdx.x >= DL_N && threadIdx.x < 3 * DL_N) p.delays[blockIdx.x * 3 * DL_N + threadIdx.x] = c.s_delay[threadIdx.x];
   if (*c.s_abort && threadIdx.x == 0) {
     const long long t = clock64();
@@ -900,6 +912,16 @@ __device__ __forceinline__ void decode2_body(const Params& p) {
 
 __global__ void __launch_bounds__(NTHREADS, 1) qmk2_decode_kernel(const __grid_constant__ Params p) { decode2_body<false>(p); }
 __global__ void __launch_bounds__(NTHREADS, 1) qmk2_decode_kernel_traced(const __grid_constant__ Params p) { decode2_body<true>(p); }
+
+// records the SM id of every CTA of a launch with the decode kernel's shape (grid 128, 256 threads, same shared memory)
+__global__ void __launch_bounds__(NTHREADS, 1) qmk2_probe_smid_kernel(int* out) {
+  extern __shared__ __align__(16) uint8_t smem_probe[];
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    out[blockIdx.x] = (int)smid + (smem_probe[0] & 0);
+  }
+}
 
 // ---- weight re-packing for the group layout -----------------------------------------------------------------------
 // 16-byte chunk `ch` of a packed row whose K block starts at 32-bit word `kw0` of the source row: slice w = ch / (2 nk),

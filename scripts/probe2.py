@@ -94,6 +94,8 @@ def trace2(dec, x, L):
               + " ".join(f"{int(cc)}({per_cta[cc]:.0f})" for cc in order[:8]))
         grp = per_cta.reshape(8, 16).mean(1)
         print("      per-group mean wait: " + " ".join(f"{v:.0f}" for v in grp))
+        if smid is not None and ph == 4:
+            print("      smid of CTA 0..127: " + " ".join(str(int(v)) for v in smid))
     print(f"  per layer {tot_layer:.0f} cycles; kernel (cta 0) {raw[0, n_idx, 0] - raw[0, 0, 0]:.0f} cycles")
 
 
