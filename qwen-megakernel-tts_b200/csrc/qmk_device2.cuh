@@ -64,7 +64,8 @@ constexpr int S2_SMALL = S2_ACC + NCW * 2 * HD * 4;  // float[1024] attention sc
 constexpr int S2_PART = S2_SMALL + 4096;           // float[64][8]
 constexpr int S2_RED = S2_PART + 64 * NCW * 4;     // float[64]
 constexpr int S2_BAR = S2_RED + 256;               // u64[8]
-constexpr int S2_MISC = S2_BAR + 64;               // abort, delays
+constexpr int S2_PREV = S2_BAR + 64;               // u64[2][1024]: totals of the accumulator words read last time (thread-private slots)
+constexpr int S2_MISC = S2_PREV + 2 * 1024 * 8;    // abort, delays
 constexpr int SMEM2_BYTES = S2_MISC + 256;
 static_assert(SMEM2_BYTES <= 232448, "shared memory budget");
 
@@ -89,6 +90,7 @@ struct Ctx2 : Ctx {
   uint8_t* s_a;      // bf16[384]
   u64* acc;          // [2][1024]
   uint8_t* xb;       // exchange buffer base
+  uint8_t* smem0;    // start of the CTA's shared memory
   int g, j;          // group (kv head), rank in group
   __device__ Ctx2(const Params& pp) : Ctx(pp) {}
 };
@@ -549,11 +551,12 @@ __device__ void consumer_loop2(Ctx2& c) {
   KvRegs kv;
   const int gi0 = c.tid * 4;
   // totals of this thread's accumulator words at the end of the previous launch
-  u64 prevA[4], prevB[4];
+  // (kept in shared memory, not in registers: 16 registers less across the whole kernel; they are read in the load shadow)
+  u64* const s_prev = reinterpret_cast<u64*>(c.smem0 + S2_PREV);
   {
     const u64* snap = reinterpret_cast<const u64*>(c.xb + XB_SNAP);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { prevA[e] = snap[gi0 + e]; prevB[e] = snap[1024 + gi0 + e]; }
+    for (int e = 0; e < 4; ++e) { s_prev[gi0 + e] = snap[gi0 + e]; s_prev[1024 + gi0 + e] = snap[1024 + gi0 + e]; }
   }
   int next_token = 0;   // token selected at the end of the previous step of this launch
   float res[4] = {0.f, 0.f, 0.f, 0.f};   // residual stream, elements 4 tid .. 4 tid + 3 (every CTA holds all of it)
@@ -744,8 +747,11 @@ __device__ void consumer_loop2(Ctx2& c) {
           }
         } else {
           u64 prev[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) prev[e] = useB ? prevB[e] : prevA[e];
+          {
+            const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(s_prev + (useB ? 1024 : 0) + gi0);
+            const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(s_prev + (useB ? 1024 : 0) + gi0 + 2);
+            prev[0] = q0.x; prev[1] = q0.y; prev[2] = q1.x; prev[3] = q1.y;
+          }
           if (QMK_UNLIKELY(!(acc_done(now[0], prev[0]) & acc_done(now[1], prev[1]) & acc_done(now[2], prev[2]) & acc_done(now[3], prev[3])))) {
             retried = true;
             acc_wait_slow(p.status, c.s_abort, c.t0, p.timeout_cycles, c.cta, idx, acc + gi0, prev[0], prev[1], prev[2], prev[3]);
@@ -756,8 +762,9 @@ __device__ void consumer_loop2(Ctx2& c) {
           for (int e = 0; e < 4; ++e) {
             const float o = bf16_round(acc_value(now[e], prev[e]));
             res[e] = p.residual_fp32 ? res[e] + o : bf16_round(res[e] + o);
-            if (useB) prevB[e] = now[e]; else prevA[e] = now[e];
           }
+          *reinterpret_cast<ulonglong2*>(s_prev + (useB ? 1024 : 0) + gi0) = make_ulonglong2(now[0], now[1]);
+          *reinterpret_cast<ulonglong2*>(s_prev + (useB ? 1024 : 0) + gi0 + 2) = make_ulonglong2(now[2], now[3]);
         }
         const float r0 = bf16_round(res[0]), r1 = bf16_round(res[1]), r2 = bf16_round(res[2]), r3 = bf16_round(res[3]);
         float ss = fmaf(r0, r0, r1 * r1) + fmaf(r2, r2, r3 * r3);
@@ -850,7 +857,7 @@ __device__ void consumer_loop2(Ctx2& c) {
   if (c.cta == 0) {
     u64* snap = reinterpret_cast<u64*>(c.xb + XB_SNAP);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { snap[gi0 + e] = prevA[e]; snap[1024 + gi0 + e] = prevB[e]; }
+    for (int e = 0; e < 4; ++e) { snap[gi0 + e] = s_prev[gi0 + e]; snap[1024 + gi0 + e] = s_prev[1024 + gi0 + e]; }
   }
 }
 
@@ -858,6 +865,7 @@ template <bool TR>
 __device__ __forceinline__ void decode2_body(const Params& p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctx2 c(p);
+  c.smem0 = smem;
   c.ring = smem + S2_RING;
   c.s_vec = smem + S2_VEC;
   c.s_a = smem + S2_A;
