@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError("qwen_megakernel: libqmk_b200.so is missing/stale and nvcc was not found")
-    cmd = [nvcc] + NVCC_FLAGS + ["-Xptxas", "-v"] * int(verbose) + [f"-I{_INCLUDE}", f"-I{_CSRC}", "-o", LIB_PATH] + srcs
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("QMK_NVCC_EXTRA", "").split() + ["-Xptxas", "-v"] * int(verbose) + [f"-I{_INCLUDE}", f"-I{_CSRC}", "-o", LIB_PATH] + srcs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")

@@ -24,6 +24,26 @@ def time_frames(cp, x, n=20):
     return None
 
 
+def time_steps_fixed(dec, x, pos=10, n=60, warm=10):
+    """talker step repeated at ONE position (short context: no split attention)"""
+    dec.reset()
+    for i in range(8):
+        dec.step_with_embed(x[i])
+    dec._hidden.copy_(x[0])
+    for _ in range(warm):
+        dec._position = pos
+        dec._launch(-1, dec._hidden.data_ptr())
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        dec._position = pos
+        dec._launch(-1, dec._hidden.data_ptr())
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n * 1e3
+
+
 def time_steps_at(dec, x, pos, n=40, warm=5):
     """talker step time with the KV cache filled up to `pos` (the step itself is repeated at that position)"""
     dec.reset()
@@ -147,7 +167,7 @@ def main():
         G = dec._lib.qmk_engine_num_ctas(dec._engine)
         us = time_steps(dec, x)
         us_cp = time_cp_steps(cp, x)
-        extra = ""
+        extra = f"  fixed pos10: {time_steps_fixed(dec, x):7.1f}"
         for pos in [int(v) for v in args.positions.split(",") if v]:
             try:
                 extra += f"  pos{pos}: {time_steps_at(dec, x, pos):7.1f}"
