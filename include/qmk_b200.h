@@ -68,7 +68,9 @@ int qmk_abi_version(void);
 const char* qmk_last_error(void);
 
 /* ---- engine ------------------------------------------------------------------------------------ */
-/* num_ctas = 0 -> one persistent CTA per SM of `device` (148 on B200). */
+/* num_ctas = 0 -> the default kernel generation for `device`: the group kernel (8 kv-head groups x 16 = 128 persistent CTAs,
+ * csrc/qmk_device2.cuh) when the device has >= 128 SMs, else the row-split kernel with one persistent CTA per SM (csrc/
+ * qmk_device.cuh).  An explicit num_ctas other than 128, or QMK_ENGINE=1, selects the row-split kernel. */
 int qmk_engine_create(int device, int num_ctas, qmk_engine** out);
 void qmk_engine_destroy(qmk_engine* e);
 int qmk_engine_num_ctas(const qmk_engine* e);
@@ -113,7 +115,8 @@ int64_t qmk_model_packed_bytes(const qmk_model* m);
  *   out_token (int32[1])        = argmax of head `head_index` (lowest index on ties); head_index < 0
  *                                 skips the LM head (code-predictor steps).
  * mode: 0 = fused persistent kernel (one cooperative launch), 1 = staged (one launch per phase; a
- * debugging/bisect mode that runs the same device code without inter-CTA waits).
+ * debugging/bisect mode of the row-split kernel that runs the same device code without inter-CTA waits; the group
+ * kernel ignores it and runs fused).
  * Asynchronous on `stream`. */
 int qmk_decode_step(qmk_model* m, int head_index, int input_token_id, const void* embed_weight,
                     const void* cos_table, const void* sin_table, void* k_cache, void* v_cache,

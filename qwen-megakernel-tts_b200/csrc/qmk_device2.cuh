@@ -50,8 +50,7 @@ constexpr size_t XB_LL = XB_SNAP + 2 * 1024 * 8;           // start of the epoch
 constexpr size_t XB_Q = XB_LL;                             // u32[8][512]   q0 | q1 | k | v of the group
 constexpr size_t XB_M = XB_Q + NGRP * 512 * 4;             // u32[8][384]
 constexpr size_t XB_LOGITS = XB_M + NGRP * 384 * 4;        // u32[3072]
-constexpr size_t XB_TOKEN = XB_LOGITS + MAX_HEAD_ROWS * 4; // u64[16]
-constexpr size_t XB_PART = XB_TOKEN + 16 * 8;              // u64[8][2][16][PART_STRIDE]
+constexpr size_t XB_PART = XB_LOGITS + MAX_HEAD_ROWS * 4;  // u64[8][2][16][PART_STRIDE]
 constexpr size_t XB_ROLE = XB_PART + (size_t)NGRP * 2 * S2_MAX * PART_STRIDE * 8;   // int[128]: blockIdx -> role (group * 16 + rank)
 constexpr size_t XBUF2_BYTES = XB_ROLE + G2 * 4;
 
