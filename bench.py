@@ -374,7 +374,17 @@ def main():
     barrier = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout during the first collective; stdout must carry ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
         barrier = lambda: (dist.barrier(), torch.cuda.synchronize())  # noqa: E731
 
     w_cpu = synthetic_tts_weights(seed=SEED, max_seq_len=MAX_SEQ)
