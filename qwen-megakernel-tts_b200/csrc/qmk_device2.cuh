@@ -680,30 +680,9 @@ __device__ void consumer_loop2(Ctx2& c) {
       const int dslot = kind == K2_GU ? DL_GU : (kind == K2_QKV ? DL_QKV : (kind == K2_DOWN ? DL_DOWN : DL_HEAD));
       const uint8_t* nw_ptr = (kind == K2_HEAD) ? sd.head.aux : p.aux_layers + ((size_t)l * 2 + (kind == K2_GU ? 1 : 0)) * AUX_BYTES;
 
-      // ---- 1. wait window, then issue the gather loads ----
-      u64 now[4];
-      uint4 mw = make_uint4(0, 0, 0, 0);
-      if (!from_input) {
-        wait_window(c, c.s_delay[dslot]);
-        trace_sub<TR>(c, 1);
-        if (norm) {
-          ld_acc2(acc + gi0, now[0], now[1]);
-          ld_acc2(acc + gi0 + 2, now[2], now[3]);
-        } else if (c.lane < 12) {   // down: warp w gathers its own K slice m[48 w .. 48 w + 48) of the group's 384 values
-          mw = ll4_ld4(x_m + c.warp * 48 + c.lane * 4);
-        }
-      }
-      // ---- 2. shadow of the load latency: weights of this phase -> registers, norm weights, older KV rows ----
-      uint2 wv = make_uint2(0, 0);
-      if (norm) wv = *reinterpret_cast<const uint2*>(nw_ptr + c.tid * 8);
-      // Older KV rows of this CTA's attention item -> L2 now (fire and forget).  The register loads themselves are issued at
-      // the start of the attention phase: loads that miss L2 share hardware scoreboards with the exchange loads when
-      // they are in flight together, and the data check below would wait for them too.
-      if (kind == K2_QKV) {
-        if (item.has) attn_l2_prefetch(c, l, position, item);
-        if (c.cta == ((l + 1) & (G2 - 1)) && c.tid < 40 && l + 1 < L)   // next layer's norm weights (one CTA per layer; 40 lines)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.aux_layers + ((size_t)(l + 1) * 2) * AUX_BYTES + c.tid * 128));
-      }
+      // ---- 1. weights of this phase -> registers, BEFORE the wait window: the warps that neither finalise nor publish sit
+      //         at the window's barrier for ~600 cycles anyway, and the 64-96 KB of shared-memory reads (500-750 cycles) would
+      //         otherwise outlast the round trip of the gather loads they are meant to hide behind ----
       uint32_t tb[4];   // shared-memory address of this lane's ldmatrix row in tile t
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -723,6 +702,30 @@ __device__ void consumer_loop2(Ctx2& c) {
       uint32_t apre[16][4];   // A fragments (weights) held in registers across the exchange wait
       if (kind == K2_DOWN) preload_a<4, 3, 4>(apre, tb, c.warp, a_khalf, a_sw);
       else preload_a<3, 8, 2>(apre, tb, c.warp, a_khalf, a_sw);   // QKV / head: both tiles; gate/up: tiles 0, 1
+      // ---- 2. wait window, then issue the gather loads ----
+      u64 now[4];
+      uint4 mw = make_uint4(0, 0, 0, 0);
+      if (!from_input) {
+        wait_window(c, c.s_delay[dslot]);
+        trace_sub<TR>(c, 1);
+        if (norm) {
+          ld_acc2(acc + gi0, now[0], now[1]);
+          ld_acc2(acc + gi0 + 2, now[2], now[3]);
+        } else if (c.lane < 12) {   // down: warp w gathers its own K slice m[48 w .. 48 w + 48) of the group's 384 values
+          mw = ll4_ld4(x_m + c.warp * 48 + c.lane * 4);
+        }
+      }
+      // shadow of the load latency: norm weights, L2 prefetches
+      uint2 wv = make_uint2(0, 0);
+      if (norm) wv = *reinterpret_cast<const uint2*>(nw_ptr + c.tid * 8);
+      // Older KV rows of this CTA's attention item -> L2 now (fire and forget).  The register loads themselves are issued at
+      // the start of the attention phase: loads that miss L2 share hardware scoreboards with the exchange loads when
+      // they are in flight together, and the data check below would wait for them too.
+      if (kind == K2_QKV) {
+        if (item.has) attn_l2_prefetch(c, l, position, item);
+        if (c.cta == ((l + 1) & (G2 - 1)) && c.tid < 40 && l + 1 < L)   // next layer's norm weights (one CTA per layer; 40 lines)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.aux_layers + ((size_t)(l + 1) * 2) * AUX_BYTES + c.tid * 128));
+      }
       trace_sub<TR>(c, 2);
 
       // ---- 3. data ----
