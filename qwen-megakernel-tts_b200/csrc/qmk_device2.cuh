@@ -47,12 +47,17 @@ constexpr u64 CNT_ONE = 1ull << 56;
 constexpr size_t XB_ACC = 0;                               // u64[2][1024]  accumulators A (h: down), B (h': O)
 constexpr size_t XB_SNAP = XB_ACC + 2 * 1024 * 8;          // u64[2][1024]  totals at the end of the previous launch
 constexpr size_t XB_LL = XB_SNAP + 2 * 1024 * 8;           // start of the epoch-tagged region (cleared on epoch wrap)
-constexpr size_t XB_Q = XB_LL;                             // u32[8][512]   q0 | q1 | k | v of the group
-constexpr size_t XB_M = XB_Q + NGRP * 512 * 4;             // u32[8][384]
-constexpr size_t XB_LOGITS = XB_M + NGRP * 384 * 4;        // u32[3072]
+// Group buffers (q0 | q1 | k | v: 512 LL4 words; m: 384) are placed by CALIBRATION: the latency of a group exchange depends on
+// where its 2 KB buffer lives in L2 (bimodal on B200: ~1950 vs ~2900 cycles per exchange, stable for an address), and the
+// slowest group gates the next grid-wide exchange.  The engine measures a pool of candidate slots once and gives every group
+// its two fastest (qmk2_calib_kernel; table behind the roles).
+constexpr int XP_CAND = 48, XP_WORDS = 512;
+constexpr size_t XB_POOL = XB_LL;                          // u32[48][512]
+constexpr size_t XB_LOGITS = XB_POOL + (size_t)XP_CAND * XP_WORDS * 4;   // u32[3072]
 constexpr size_t XB_PART = XB_LOGITS + MAX_HEAD_ROWS * 4;  // u64[8][2][16][PART_STRIDE]
 constexpr size_t XB_ROLE = XB_PART + (size_t)NGRP * 2 * S2_MAX * PART_STRIDE * 8;   // int[128]: blockIdx -> role (group * 16 + rank)
-constexpr size_t XBUF2_BYTES = XB_ROLE + G2 * 4;
+constexpr size_t XB_SLOTS = XB_ROLE + G2 * 4;                // int[8][2]: pool slot of the group's q/k/v buffer and of its m buffer
+constexpr size_t XBUF2_BYTES = XB_SLOTS + NGRP * 2 * 4;
 
 // shared memory
 constexpr int S2_RING = 0;
@@ -91,6 +96,7 @@ struct Ctx2 : Ctx {
   uint8_t* xb;       // exchange buffer base
   uint8_t* smem0;    // start of the CTA's shared memory
   int g, j;          // group (kv head), rank in group
+  int slot_q, slot_m;   // pool slots of the group's exchange buffers
   __device__ Ctx2(const Params& pp) : Ctx(pp) {}
 };
 
@@ -285,7 +291,7 @@ template <bool TR>
 __device__ void phase_attn2(Ctx2& c, int l, int position, uint32_t epoch, const AttnItem2& it, KvRegs& kv, Prod2& prod,
                             int a_row, int a_khalf, int a_sw) {
   const Params& p = c.p;
-  const uint32_t* x_q = reinterpret_cast<const uint32_t*>(c.xb + XB_Q) + c.g * 512;
+  const uint32_t* x_q = reinterpret_cast<const uint32_t*>(c.xb + XB_POOL) + (size_t)c.slot_q * XP_WORDS;
   u64* x_part = reinterpret_cast<u64*>(c.xb + XB_PART) + (size_t)c.g * 2 * S2_MAX * PART_STRIDE;
   float* s_small = c.s_small;
   __nv_bfloat16* s_a = reinterpret_cast<__nv_bfloat16*>(c.s_a);
@@ -544,8 +550,8 @@ template <bool TR>
 __device__ void consumer_loop2(Ctx2& c) {
   const Params& p = c.p;
   const int L = p.lay.L;
-  uint32_t* const x_q = reinterpret_cast<uint32_t*>(c.xb + XB_Q) + c.g * 512;
-  uint32_t* const x_m = reinterpret_cast<uint32_t*>(c.xb + XB_M) + c.g * 384;
+  uint32_t* const x_q = reinterpret_cast<uint32_t*>(c.xb + XB_POOL) + (size_t)c.slot_q * XP_WORDS;
+  uint32_t* const x_m = reinterpret_cast<uint32_t*>(c.xb + XB_POOL) + (size_t)c.slot_m * XP_WORDS;
   uint32_t* const x_logits = reinterpret_cast<uint32_t*>(c.xb + XB_LOGITS);
   u64* const accA = c.acc, * const accB = c.acc + 1024;
   Prod2 prod;
@@ -894,6 +900,8 @@ __device__ __forceinline__ void decode2_body(const Params& p) {
   c.cta = reinterpret_cast<const int*>(p.xbuf + XB_ROLE)[blockIdx.x];
   c.g = c.cta / GSZ;
   c.j = c.cta % GSZ;
+  c.slot_q = reinterpret_cast<const int*>(p.xbuf + XB_SLOTS)[2 * c.g];
+  c.slot_m = reinterpret_cast<const int*>(p.xbuf + XB_SLOTS)[2 * c.g + 1];
   c.k = 0;
   c.t0 = clock64();
   c.t_pub = c.t0;
@@ -926,6 +934,42 @@ __device__ __forceinline__ void decode2_body(const Params& p) {
 
 __global__ void __launch_bounds__(NTHREADS, 1) qmk2_decode_kernel(const __grid_constant__ Params p) { decode2_body<false>(p); }
 __global__ void __launch_bounds__(NTHREADS, 1) qmk2_decode_kernel_traced(const __grid_constant__ Params p) { decode2_body<true>(p); }
+
+// Calibration of the group-buffer placement: in step t group g exchanges `rounds` times through pool slot (t + 5 g) % 48
+// (all groups on different slots, like in the decode kernel); out[g][slot] = cycles.  A grid barrier separates the steps.
+__global__ void __launch_bounds__(NTHREADS, 1) qmk2_calib_kernel(uint32_t* pool, int rounds, const int* role, unsigned* bar, long long* out) {
+  extern __shared__ __align__(16) uint8_t smem_calib[];
+  const int cta = role[blockIdx.x], g = cta / GSZ, j = cta % GSZ, tid = threadIdx.x;
+  unsigned sink = 0;
+  for (int t = 0; t < XP_CAND; ++t) {
+    const int slot = (t + 5 * g) % XP_CAND;
+    uint32_t* buf = pool + (size_t)slot * XP_WORDS;
+    const long long t0 = clock64();
+    for (int r = 0; r < rounds; ++r) {
+      const uint32_t epoch = (uint32_t)(1 + t * rounds + r);
+      if (tid < 32) ll4_st(buf + 32 * j + tid, 1.0f, epoch);
+      if (tid < 128) {
+        uint4 w;
+        unsigned spins = 0;
+        do { w = ll4_ld4(buf + 4 * tid); } while (!ll4_ok(w, epoch) && ++spins < (1u << 10));
+        if (spins >= (1u << 10)) atomicAdd(bar + 1, 1u);   // give up (counted): a stuck poll must not hang engine creation
+        sink += w.x;
+      }
+      __syncthreads();
+    }
+    if (tid == 0 && j == 0) out[g * XP_CAND + slot] = clock64() - t0;
+    // grid barrier (all 128 CTAs are co-resident: cooperative launch)
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(bar, 1u);
+      unsigned spins = 0;
+      while (*((volatile unsigned*)bar) < (unsigned)(G2 * (t + 1)) && ++spins < (1u << 16)) {
+      }
+    }
+    __syncthreads();
+  }
+  if (sink == 0x12345u) smem_calib[0] = 1;
+}
 
 // records the SM id of every CTA of a launch with the decode kernel's shape (grid 128, 256 threads, same shared memory)
 __global__ void __launch_bounds__(NTHREADS, 1) qmk2_probe_smid_kernel(int* out) {

@@ -214,6 +214,66 @@ extern "C" int qmk_engine_create(int device, int num_ctas, qmk_engine** out) {
     }
     err = cudaMemcpy(e->xbuf + qmk2::XB_ROLE, role.data(), qmk2::G2 * sizeof(int), cudaMemcpyHostToDevice);
     e->roles = role;
+    // Placement of the groups' exchange buffers: default slots 2g, 2g+1; QMK_CALIBRATE=1 (default) measures the pool.
+    std::vector<int> slots(qmk2::NGRP * 2);
+    for (int g = 0; g < qmk2::NGRP; ++g) { slots[2 * g] = 2 * g; slots[2 * g + 1] = 2 * g + 1; }
+    int calibrate = 1;
+    if (const char* env = getenv("QMK_CALIBRATE")) calibrate = atoi(env);
+    if (err == cudaSuccess && calibrate) {
+      const int rounds = 40;
+      unsigned* d_bar = nullptr;
+      long long* d_out = nullptr;
+      std::vector<long long> t((size_t)qmk2::NGRP * qmk2::XP_CAND, 0);
+      cudaError_t ce = cudaMalloc(&d_bar, 2 * sizeof(unsigned));
+      if (ce == cudaSuccess) ce = cudaMemset(d_bar, 0, 2 * sizeof(unsigned));
+      if (ce == cudaSuccess) ce = cudaMalloc(&d_out, t.size() * sizeof(long long));
+      if (ce == cudaSuccess) ce = cudaMemset(d_out, 0, t.size() * sizeof(long long));
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(qmk2::qmk2_calib_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, qmk2::SMEM2_BYTES);
+      if (ce == cudaSuccess) {
+        uint32_t* pool = reinterpret_cast<uint32_t*>(e->xbuf + qmk2::XB_POOL);
+        const int* d_role = reinterpret_cast<const int*>(e->xbuf + qmk2::XB_ROLE);
+        int r = rounds;
+        void* cargs[] = {&pool, &r, &d_role, &d_bar, &d_out};
+        ce = cudaLaunchCooperativeKernel((const void*)qmk2::qmk2_calib_kernel, dim3(qmk2::G2), dim3(NTHREADS), cargs, qmk2::SMEM2_BYTES, 0);
+      }
+      unsigned h_bar[2] = {0, 0};
+      if (ce == cudaSuccess) ce = cudaMemcpy(t.data(), d_out, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      if (ce == cudaSuccess) ce = cudaMemcpy(h_bar, d_bar, sizeof(h_bar), cudaMemcpyDeviceToHost);
+      if (getenv("QMK_CALIBRATE_VERBOSE")) fprintf(stderr, "[qmk] calibration: %s, barrier count %u, abandoned polls %u\n", cudaGetErrorString(ce), h_bar[0], h_bar[1]);
+      if (ce == cudaSuccess && h_bar[1] != 0) ce = cudaErrorUnknown;   // unreliable measurement: keep the default slots
+      if (d_bar) cudaFree(d_bar);
+      if (d_out) cudaFree(d_out);
+      if (ce == cudaSuccess) {
+        // every group takes its two fastest slots that no other group has taken (groups in order of their best time)
+        std::vector<char> used(qmk2::XP_CAND, 0);
+        for (int g = 0; g < qmk2::NGRP; ++g) {
+          for (int which = 0; which < 2; ++which) {
+            int best = -1;
+            for (int c = 0; c < qmk2::XP_CAND; ++c)
+              if (!used[c] && t[(size_t)g * qmk2::XP_CAND + c] > 0 && (best < 0 || t[(size_t)g * qmk2::XP_CAND + c] < t[(size_t)g * qmk2::XP_CAND + best])) best = c;
+            if (best >= 0) { slots[2 * g + which] = best; used[best] = 1; }
+          }
+        }
+        bool ok = true;   // fall back to the default if a slot is duplicated (a measurement was missing)
+        std::vector<char> seen(qmk2::XP_CAND, 0);
+        for (int v : slots) { if (seen[v]) ok = false; seen[v] = 1; }
+        if (!ok) for (int g = 0; g < qmk2::NGRP; ++g) { slots[2 * g] = 2 * g; slots[2 * g + 1] = 2 * g + 1; }
+        if (getenv("QMK_CALIBRATE_VERBOSE")) {
+          for (int g = 0; g < qmk2::NGRP; ++g) {
+            long long mn = 1LL << 62, mx = 0;
+            for (int c = 0; c < qmk2::XP_CAND; ++c) { long long v = t[(size_t)g * qmk2::XP_CAND + c]; if (v > 0) { mn = v < mn ? v : mn; mx = v > mx ? v : mx; } }
+            fprintf(stderr, "[qmk] group %d: exchange cycles per round min %lld max %lld, chosen slots %d (%lld) %d (%lld)\n", g, mn / rounds,
+                    mx / rounds, slots[2 * g], t[(size_t)g * qmk2::XP_CAND + slots[2 * g]] / rounds, slots[2 * g + 1],
+                    t[(size_t)g * qmk2::XP_CAND + slots[2 * g + 1]] / rounds);
+          }
+        }
+      } else {
+        cudaGetLastError();
+      }
+      // the calibration left epoch-tagged words behind
+      if (err == cudaSuccess) err = cudaMemset(e->xbuf + qmk2::XB_LL, 0, qmk2::XB_ROLE - qmk2::XB_LL);
+    }
+    if (err == cudaSuccess) err = cudaMemcpy(e->xbuf + qmk2::XB_SLOTS, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice);
   }
   if (err != cudaSuccess) {
     if (e->xbuf) cudaFree(e->xbuf);
