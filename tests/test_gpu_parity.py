@@ -323,11 +323,12 @@ def test_upstream_decode_op_drop_in(gpu_weights, golden):
                                            L, S, S, 1.0 / 128 ** 0.5)       # position == max_seq_len
 
 
-@pytest.mark.parametrize("position", [59, 60, 61, 200, 1079, 1081, 1500, 2047])
+@pytest.mark.parametrize("position", [39, 40, 59, 60, 61, 79, 80, 81, 200, 639, 641, 1079, 1081, 1500, 2047])
 def test_long_context_attention_vs_oracle(gpu_weights, cpu_weights, position):
     """Split-KV / multi-round attention: fill both KV caches with the same random rows, then decode one
-    token at `position` with a 3-layer stack and compare with the oracle (edge cases around the 60-position
-    item size and the 18-way split cap at 1080)."""
+    token at `position` with a 3-layer stack and compare with the oracle.  Edge cases of both kernels: the group
+    kernel's second solo round (n = 41) and the switch to the 16-way split (n = 81, chunks longer than one round
+    from n = 641), the row-split kernel's 60-position item size and its 18-way split cap at 1080."""
     from oracle.tts_oracle import TalkerOracle, top2_margin
     from qwen_megakernel.model_tts import TTSDecoder
     from qwen_megakernel.synthetic import _normal_bf16, synthetic_inputs
