@@ -716,9 +716,9 @@ __device__ void consumer_loop2(Ctx2& c) {
       const int kind = idx < L * PH_PER_LAYER ? idx % PH_PER_LAYER : (idx == L * PH_PER_LAYER ? K2_HEAD : K2_ARGMAX);
       const uint32_t epoch = (ebase + 1u + (uint32_t)l) & 0xffffu;
 
-      if (kind == K2_O) continue;   // done inside phase_attn2
       if (kind == K2_ATTN) {
         phase_attn2<TR>(c, l, position, epoch, item, kv, prod, a_row, a_khalf, a_sw);
+        ++idx;   // the O projection (index K2_O) ran inside phase_attn2
         continue;
       }
       if (QMK_UNLIKELY(kind == K2_ARGMAX)) {
