@@ -944,32 +944,26 @@ __device__ void consumer_loop2(Ctx2& c) {
       trace_sub<TR>(c, 6);
       if (c.warp >= 2) prod2_issue(c, prod, nst);
 
-      // ---- 5. finalize + publish ----
-      if (kind == K2_QKV) {
-        if (c.tid < QKV_LOC) {   // local rows: 0..15 q (16 j + r of the head pair), 16..23 k, 24..31 v
-          const float v = item_sum(c.s_part, c.tid);
-          const int r = c.tid;
-          const int w = r < 16 ? GSZ * c.j + r : (r < 24 ? 256 + 8 * c.j + (r - 16) : 384 + 8 * c.j + (r - 24));
-          ll4_st(x_q + w, v, epoch);
-        }
-      } else if (kind == K2_GU) {
-        if (c.warp < 2) {   // gate in even lanes, up in the next lane
-          const bool mine = c.tid < GU_LOC;
-          const float v = mine ? item_sum(c.s_part, c.tid) : 0.f;
+      // ---- 5. finalize + publish: the cross-warp sum is common to all kinds (rows beyond the phase's count hold stale
+      //         partials and are not published), the kind only selects the tail ----
+      if (c.warp < 2) {
+        const float v = item_sum(c.s_part, c.tid);
+        if (kind == K2_DOWN) {          // one fixed-point add per row: the eight groups' K-split partials meet in L2
+          red_add64(accA + O_LOC * c.j + c.tid, acc_word(v));
+        } else if (kind == K2_GU) {     // gate in even lanes, up in the next lane
           const float u = bf16_round(__shfl_down_sync(0xffffffffu, v, 1));
-          if (mine && (c.tid & 1) == 0) {
+          if (c.tid < GU_LOC && (c.tid & 1) == 0) {
             const float gt = bf16_round(v);
             const float sg = bf16_round(__fdividef(gt, 1.0f + __expf(-gt)));
             ll4_st(x_m + M_LOC * c.j + (c.tid >> 1), sg * u, epoch);
           }
+        } else if (kind == K2_QKV) {    // local rows: 0..15 q (16 j + r of the head pair), 16..23 k, 24..31 v
+          const int r = c.tid;
+          const int w = r < 16 ? GSZ * c.j + r : (r < 24 ? 256 + 8 * c.j + (r - 16) : 384 + 8 * c.j + (r - 24));
+          if (r < QKV_LOC) ll4_st(x_q + w, v, epoch);
+        } else {                        // head: logits as LL4 words
+          if (c.tid < hrows_loc) ll4_st(x_logits + hrows_loc * c.cta + c.tid, v, (ebase + (uint32_t)L + 1u) & 0xffffu);
         }
-      } else if (kind == K2_DOWN) {
-        if (c.tid < O_LOC) {   // one fixed-point add per row: the eight groups' K-split partials meet in L2
-          const float v = item_sum(c.s_part, c.tid);
-          red_add64(accA + O_LOC * c.j + c.tid, acc_word(v));
-        }
-      } else {   // head: logits as LL4 words for CTA 0
-        if (c.tid < hrows_loc) ll4_st(x_logits + hrows_loc * c.cta + c.tid, item_sum(c.s_part, c.tid), (ebase + (uint32_t)L + 1u) & 0xffffu);
       }
       c.t_pub = clock64();
       trace_sub<TR>(c, 8);
