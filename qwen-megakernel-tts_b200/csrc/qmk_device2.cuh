@@ -340,6 +340,51 @@ __device__ void phase_attn2(Ctx2& c, int l, int position, uint32_t epoch, const 
   }
   const int len = it.has ? it.p1 - it.p0 : 0;
   const int nrounds = (len + ATT_ROUND - 1) / ATT_ROUND;
+  if (position < 2 * NCW) {
+    // Tiny context (every code-predictor step, the first talker steps): this warp owns positions w and w + 8 at most.
+    // Straight-line version of the loop below.
+    const int n = position + 1, pa = c.warp, pb = c.warp + NCW;
+    if (pa < n) {   // warp-uniform
+      const bool hb = pb < n;
+      float ka[4], kb[4], va[4], vb[4];
+      if (pa == position) {
+        const float4 kk = *reinterpret_cast<const float4*>(s_small + SS_KN + c.lane * 4), vv = *reinterpret_cast<const float4*>(s_small + SS_V + c.lane * 4);
+        ka[0] = kk.x; ka[1] = kk.y; ka[2] = kk.z; ka[3] = kk.w; va[0] = vv.x; va[1] = vv.y; va[2] = vv.z; va[3] = vv.w;
+      } else {
+        ka[0] = bf16_lo(kv.k[0].x); ka[1] = bf16_hi(kv.k[0].x); ka[2] = bf16_lo(kv.k[0].y); ka[3] = bf16_hi(kv.k[0].y);
+        va[0] = bf16_lo(kv.v[0].x); va[1] = bf16_hi(kv.v[0].x); va[2] = bf16_lo(kv.v[0].y); va[3] = bf16_hi(kv.v[0].y);
+      }
+      if (pb == position) {
+        const float4 kk = *reinterpret_cast<const float4*>(s_small + SS_KN + c.lane * 4), vv = *reinterpret_cast<const float4*>(s_small + SS_V + c.lane * 4);
+        kb[0] = kk.x; kb[1] = kk.y; kb[2] = kk.z; kb[3] = kk.w; vb[0] = vv.x; vb[1] = vv.y; vb[2] = vv.z; vb[3] = vv.w;
+      } else if (hb) {
+        kb[0] = bf16_lo(kv.k[1].x); kb[1] = bf16_hi(kv.k[1].x); kb[2] = bf16_lo(kv.k[1].y); kb[3] = bf16_hi(kv.k[1].y);
+        vb[0] = bf16_lo(kv.v[1].x); vb[1] = bf16_hi(kv.v[1].x); vb[2] = bf16_lo(kv.v[1].y); vb[3] = bf16_hi(kv.v[1].y);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { kb[e] = 0.f; vb[e] = 0.f; }
+      }
+      float d4[4] = {0.f, 0.f, 0.f, 0.f};   // {q0.ka, q0.kb, q1.ka, q1.kb}: same order as the general loop (sc[0], sc[1], sc[5], sc[6])
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        d4[0] = fmaf(q0[e], ka[e], d4[0]); d4[1] = fmaf(q0[e], kb[e], d4[1]);
+        d4[2] = fmaf(q1[e], ka[e], d4[2]); d4[3] = fmaf(q1[e], kb[e], d4[3]);
+      }
+      const float tot = warp_sum4(d4, c.lane);
+      const float s0a = __shfl_sync(0xffffffffu, tot, 0) * p.attn_scale, s0b = __shfl_sync(0xffffffffu, tot, 8) * p.attn_scale;
+      const float s1a = __shfl_sync(0xffffffffu, tot, 16) * p.attn_scale, s1b = __shfl_sync(0xffffffffu, tot, 24) * p.attn_scale;
+      m0 = hb ? fmaxf(s0a, s0b) : s0a;
+      m1 = hb ? fmaxf(s1a, s1b) : s1a;
+      const float e0a = __expf(s0a - m0), e0b = hb ? __expf(s0b - m0) : 0.f;
+      const float e1a = __expf(s1a - m1), e1b = hb ? __expf(s1b - m1) : 0.f;
+      l0 = e0a + e0b; l1 = e1a + e1b;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc0[e] = fmaf(e0b, vb[e], e0a * va[e]);
+        acc1[e] = fmaf(e1b, vb[e], e1a * va[e]);
+      }
+    }
+  } else
   for (int r = 0; r < nrounds; ++r) {
     if (r > 0) attn_prefetch2(c, l, position, it, r, kv);
     float sc[10];
