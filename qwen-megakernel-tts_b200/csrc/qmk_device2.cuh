@@ -894,15 +894,22 @@ __device__ void consumer_loop2(Ctx2& c) {
         bool retried = false;
         if (from_input) {
           if (sd.in_mode == IN_CODES_SUM) {
-            const uint2 v0 = *reinterpret_cast<const uint2*>(sd.in_table + (size_t)sd.codes[0] * H + gi0);
-            float e4[4] = {bf16_lo(v0.x), bf16_hi(v0.x), bf16_lo(v0.y), bf16_hi(v0.y)};
-#pragma unroll 1
-            for (int g = 0; g < 15; ++g) {
-              const uint2 v = *reinterpret_cast<const uint2*>(p.sum_tables[g] + (size_t)sd.codes[g + 1] * H + gi0);
-              e4[0] = bf16_round(e4[0] + bf16_lo(v.x)); e4[1] = bf16_round(e4[1] + bf16_hi(v.x));
-              e4[2] = bf16_round(e4[2] + bf16_lo(v.y)); e4[3] = bf16_round(e4[3] + bf16_hi(v.y));
-            }
+            // 16 code indices, then 16 embedding rows: two rounds of independent loads (a serial chain of 31 dependent
+            // global loads costs ~10 us per talker step), then the bf16 adds in the upstream order
+            long long code[16];
+#pragma unroll
+            for (int g = 0; g < 16; ++g) code[g] = sd.codes[g];
+            uint2 row[16];
+            row[0] = *reinterpret_cast<const uint2*>(sd.in_table + (size_t)code[0] * H + gi0);
+#pragma unroll
+            for (int g = 0; g < 15; ++g) row[g + 1] = *reinterpret_cast<const uint2*>(p.sum_tables[g] + (size_t)code[g + 1] * H + gi0);
             const uint2 vx = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(sd.in_vec) + gi0);
+            float e4[4] = {bf16_lo(row[0].x), bf16_hi(row[0].x), bf16_lo(row[0].y), bf16_hi(row[0].y)};
+#pragma unroll
+            for (int g = 1; g < 16; ++g) {
+              e4[0] = bf16_round(e4[0] + bf16_lo(row[g].x)); e4[1] = bf16_round(e4[1] + bf16_hi(row[g].x));
+              e4[2] = bf16_round(e4[2] + bf16_lo(row[g].y)); e4[3] = bf16_round(e4[3] + bf16_hi(row[g].y));
+            }
             res[0] = bf16_round(e4[0] + bf16_lo(vx.x)); res[1] = bf16_round(e4[1] + bf16_hi(vx.x));
             res[2] = bf16_round(e4[2] + bf16_lo(vx.y)); res[3] = bf16_round(e4[3] + bf16_hi(vx.y));
           } else if (sd.in_mode == IN_VEC_F32) {
