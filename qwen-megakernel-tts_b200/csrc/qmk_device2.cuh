@@ -744,6 +744,10 @@ __device__ void consumer_loop2(Ctx2& c) {
     const __nv_bfloat16* x_in = (sd.in_mode == IN_TABLE_TOKEN || sd.in_mode == IN_TABLE_PREV)
                                     ? sd.in_table + (size_t)in_token * H
                                     : reinterpret_cast<const __nv_bfloat16*>(sd.in_vec);
+    // the step's input row is requested before the RoPE row below, so that the two L2 / HBM round trips overlap
+    uint2 xin_pre = make_uint2(0, 0);
+    if (sd.in_mode == IN_TABLE_TOKEN || sd.in_mode == IN_TABLE_PREV || sd.in_mode == IN_VEC_BF16)
+      xin_pre = *reinterpret_cast<const uint2*>(x_in + gi0);
     const AttnItem2 item = attn_item2(position, c.j);
     const int hrows_loc = sd.head.rows > 0 ? sd.head.rows / G2 : 0;
     if (c.tid < 128) {  // RoPE row of this step
@@ -916,7 +920,7 @@ __device__ void consumer_loop2(Ctx2& c) {
             const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sd.in_vec) + gi0);
             res[0] = bf16_round(v.x); res[1] = bf16_round(v.y); res[2] = bf16_round(v.z); res[3] = bf16_round(v.w);
           } else {
-            const uint2 v = *reinterpret_cast<const uint2*>(x_in + gi0);
+            const uint2 v = xin_pre;
             res[0] = bf16_lo(v.x); res[1] = bf16_hi(v.x); res[2] = bf16_lo(v.y); res[3] = bf16_hi(v.y);
           }
         } else {
