@@ -10,9 +10,11 @@ allocated to 2048 positions, after the 8-step synthetic prefill + step(CODEC_BOS
 which contains configs[0] and configs[1] as its two halves; they are also timed separately below).
 
 Printed JSON (one line, rank 0):
-  value      codec frames/s, inputs resident in HBM, device-timed (CUDA events), max over ranks
-  e2e        same loop through the public API with the per-frame trailing-text embedding coming from pinned
-             host memory (H2D inside the timed region) and the frame's 16 codes + talker token read back (D2H)
+  value      codec frames/s, inputs resident in HBM, device-timed (CUDA events), max over ranks: the device-autonomous
+             frame loop (TTSDecoder.generate_frames -> qmk_generate_nosync)
+  e2e        same loop through the public API with the trailing-text embeddings coming from pinned host memory (H2D
+             inside the timed region) and every frame's 16 codes + talker token written to pinned host memory (D2H)
+  e2e_per_frame_api / e2e_dropin_loop / e2e_upstream_loop   the per-frame API in three control flows (see notes)
   roofline   qmk_decode_kernel in its talker configuration: algorithmic bytes per launch / mean launch time
   cpu_baseline  the CPU oracle port of the upstream PyTorch path, same frame loop, bounded sample
 `--impl reference` times that CPU port as the main line (rank 0 only under torchrun).
@@ -172,8 +174,7 @@ def cpu_frame_loop(weights_cpu, n_frames: int, warmup: int, budget_s: float, sam
 
 # ── GPU frame loop through the public API ──────────────────────────────────────────────────────────────
 class FrameLoop:
-    def __init__(self, weights_gpu, device, torch_glue=False):
-        self.torch_glue = torch_glue
+    def __init__(self, weights_gpu, device):
         from qwen_megakernel.model_tts import CodePredictorKernel, TTSDecoder
         from qwen_megakernel.synthetic import synthetic_inputs
         self.dev = device
@@ -181,35 +182,34 @@ class FrameLoop:
         self.talker = TTSDecoder(weights=weights_gpu, verbose=False, max_seq_len=MAX_SEQ, device=device)
         self.cp = CodePredictorKernel(weights_gpu, device=str(device))
         self.prefill = synthetic_inputs(99, N_PREFILL).to(device)
+        self.pad = synthetic_inputs(777, 1)[0].to(device)
         self.embed = weights_gpu["embed_weight"]
         self.cp_embeds = [weights_gpu["code_predictor"][f"codec_embedding.{g}.weight"] for g in range(15)]
         self.launches = 0
 
     def start_utterance(self):
+        """tts_engine.py:281-289: reset, 8 prefill steps, step(CODEC_BOS)."""
         self.talker.reset()
         for i in range(N_PREFILL):
             self.talker.step_with_embed(self.prefill[i])
         self.tok, self.hid = self.talker.step(CODEC_BOS)
+        self.launches += N_PREFILL + 1
         # device-resident (token, hidden) of the last talker step for the sync-free pipeline
         self.tok_dev, self.hid_dev = self.talker._out_token, self.talker._norm_out
 
     def frame_async(self, extra_bf16, sample=True):
-        """Same frame without a host round trip: predict() takes the talker's token from device memory and the talker
-        step returns device tensors; the host reads tokens / codes asynchronously (EOS would be seen one frame late)."""
-        if self.talker.position >= MAX_SEQ - 1:
-            self.start_utterance()
+        """One frame on the per-frame API without a host round trip: predict() takes the talker's token from device memory
+        and the talker step returns device tensors (two launches per frame)."""
         codes = self.cp.predict(self.hid_dev, self.tok_dev, self.embed, do_sample=sample, temperature=0.9, top_k=50)
         self.tok_dev, self.hid_dev = self.talker.step_with_codes(codes, self.cp_embeds, extra_bf16, sync=False)
         self.launches += 2
         return codes
 
-    def frame(self, extra_bf16, sample=True):
-        """tts_engine.py:306-335: predict -> embed sum -> step_with_embed."""
+    def frame(self, extra_bf16, sample=True, torch_glue=False):
+        """tts_engine.py:306-335 as written: predict -> embed sum -> step_with_embed, a Python int token per frame."""
         F = torch.nn.functional
-        if self.talker.position >= MAX_SEQ - 1:
-            self.start_utterance()
         codes = self.cp.predict(self.hid, self.tok, self.embed, do_sample=sample, temperature=0.9, top_k=50)
-        if self.torch_glue:      # the upstream caller's 32 torch launches (tts_engine.py:319-333)
+        if torch_glue:           # the upstream caller's 32 torch launches (tts_engine.py:319-333)
             e = F.embedding(codes[0:1], self.embed).squeeze(0)
             for g in range(15):
                 e = e + F.embedding(codes[g + 1:g + 2], self.cp_embeds[g]).squeeze(0)
@@ -217,53 +217,108 @@ class FrameLoop:
             self.tok, self.hid = self.talker.step_with_embed(e)
         else:                    # same sum evaluated inside the talker step's launch
             self.tok, self.hid = self.talker.step_with_codes(codes, self.cp_embeds, extra_bf16)
-        self.launches += 2          # one fused code-predictor frame launch + one talker step launch
+        self.launches += 2
         return codes
 
 
-def time_frames(loop: FrameLoop, n: int, warmup: int, trail_dev, trail_host=None, barrier=None, dropin=False):
-    """Returns elapsed ms for n frames (CUDA events on the current stream).
+def _median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2] if len(xs) % 2 else 0.5 * (xs[len(xs) // 2 - 1] + xs[len(xs) // 2])
 
-    dropin=False: the sync-free pipeline (frame_async).  With trail_host, every frame's input comes from pinned host
-    memory (H2D inside the timed region) and every frame's 16 codes + talker token are copied to pinned host memory
-    (D2H inside the timed region, read by the host after the final synchronise).
-    dropin=True: the upstream caller's control flow (tts_engine.py:301-335): step() returns a Python int, i.e. one
-    blocking device->host read per frame."""
-    loop.start_utterance()
-    step = loop.frame if dropin else loop.frame_async
-    for f in range(warmup):
-        step(trail_dev[f])
-    torch.cuda.synchronize()
-    if barrier:
-        barrier()
-    host_codes = torch.empty(n, 16, dtype=torch.int64).pin_memory() if trail_host is not None else None
-    host_tok = torch.empty(n, 1, dtype=torch.int32).pin_memory() if trail_host is not None else None
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = loop.launches
-    start.record()
-    sink = 0
-    for f in range(n):
-        if trail_host is None:
-            codes = step(trail_dev[warmup + f])
+
+def time_autonomous(loop: FrameLoop, K: int, trail_dev, trail_host, e2e: bool, reps: int, barrier=None):
+    """K frames per repetition through TTSDecoder.generate_frames (qmk_generate_nosync): the persistent kernel iterates
+    predict -> embedding sum -> talker step itself.  e2e: the utterance's trailing-text embeddings come from pinned host
+    memory (H2D inside the timed region) and the kernel writes every frame's codes / token / progress word straight into
+    pinned host memory (D2H inside the timed region), which the host reads after the final synchronise.
+    Returns (list of elapsed ms per repetition, launches per repetition)."""
+    times, sink = [], 0
+    launches = -(-K // 170)          # chained launches of <= 201 frames (16-bit epochs); see qmk_generate_nosync
+    for _ in range(reps):
+        loop.start_utterance()
+        torch.cuda.synchronize()
+        if barrier:
+            barrier()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        if e2e:
+            trail = trail_host[:K].to(loop.dev, non_blocking=True)
+            codes, tokens, state = loop.talker.generate_frames(loop.cp, K, trail, loop.pad, do_sample=True, temperature=0.9,
+                                                               top_k=50, eos_token=-1, host_visible=True, sync=False)
         else:
-            extra = trail_host[warmup + f].to(loop.dev, non_blocking=True)       # H2D of this frame's input
-            codes = step(extra)
-            if dropin:
-                sink += int(codes.cpu()[15])                                      # blocking D2H of this frame's result
+            codes, tokens, state = loop.talker.generate_frames(loop.cp, K, trail_dev[:K], loop.pad, do_sample=True,
+                                                               temperature=0.9, top_k=50, eos_token=-1, sync=False)
+        end.record()
+        n_done = loop.talker.finish_generate(state)
+        assert n_done == K, f"generate_frames produced {n_done} of {K} frames"
+        if e2e:
+            sink += int(codes[:, 15].sum()) + int(tokens.sum())
+        if barrier:
+            barrier()
+        times.append(start.elapsed_time(end))
+    return times, launches
+
+
+def time_frames(loop: FrameLoop, K: int, W: int, trail_dev, trail_host, mode: str, reps: int, barrier=None):
+    """K frames per repetition on the per-frame API.  mode: "async" (sync-free pipeline, device token), "dropin" (upstream
+    control flow: blocking Python int per frame, embedding sum inside the talker launch), "upstream" (dropin + the upstream
+    caller's 32 torch launches for the embedding sum).  With trail_host the frame's input comes from pinned host memory and
+    its 16 codes + token go back to pinned host memory inside the timed region."""
+    times, sink = [], 0
+    for _ in range(reps):
+        loop.start_utterance()
+        for f in range(W):
+            loop.frame_async(trail_dev[f]) if mode == "async" else loop.frame(trail_dev[f], torch_glue=(mode == "upstream"))
+        torch.cuda.synchronize()
+        if barrier:
+            barrier()
+        host_codes = torch.empty(K, 16, dtype=torch.int64).pin_memory()
+        host_tok = torch.empty(K, 1, dtype=torch.int32).pin_memory()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for f in range(K):
+            extra = trail_host[W + f].to(loop.dev, non_blocking=True) if trail_host is not None else trail_dev[W + f]
+            if mode == "async":
+                codes = loop.frame_async(extra)
+                if trail_host is not None:
+                    host_codes[f].copy_(codes, non_blocking=True)
+                    host_tok[f].copy_(loop.tok_dev, non_blocking=True)
             else:
-                host_codes[f].copy_(codes, non_blocking=True)                     # D2H of this frame's result
-                host_tok[f].copy_(loop.tok_dev, non_blocking=True)
+                codes = loop.frame(extra, torch_glue=(mode == "upstream"))
+                sink += int(codes.cpu()[15])                                      # blocking D2H of this frame's result
+        end.record()
+        torch.cuda.synchronize()
+        if mode == "async" and trail_host is not None:
+            sink += int(host_codes[:, 15].sum()) + int(host_tok.sum())
+        if barrier:
+            barrier()
+        times.append(start.elapsed_time(end))
+    return times
+
+
+def time_talker_at(loop: FrameLoop, position: int, n: int = 40, warmup: int = 5):
+    """Mean duration of one talker launch with `position` cached rows (the launch is repeated at the same position: the KV rows
+    it reads are whatever the cache holds, which does not change the work)."""
+    t = loop.talker
+    t._hidden.copy_(loop.prefill[0])
+    for _ in range(warmup):
+        t._position = position
+        t._launch(-1, t._hidden.data_ptr())
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(n):
+        t._position = position
+        t._launch(-1, t._hidden.data_ptr())
     end.record()
     torch.cuda.synchronize()
-    if host_codes is not None and not dropin:
-        sink += int(host_codes[:, 15].sum()) + int(host_tok.sum())
-    if barrier:
-        barrier()
-    return start.elapsed_time(end), loop.launches - l0
+    assert int(t._out_token.item()) >= 0, "talker kernel reported failure"
+    t.reset()
+    return start.elapsed_time(end) / n
 
 
 def time_talker_kernel(loop: FrameLoop, n: int = 50, warmup: int = 10):
-    """Mean duration of one talker launch of qmk_decode_kernel: n back-to-back launches, no host sync inside."""
+    """Mean duration of one talker launch over positions 18 .. 18 + n (the short-context end of the frame loop)."""
     t = loop.talker
     t.reset()
     for i in range(N_PREFILL):
@@ -279,22 +334,21 @@ def time_talker_kernel(loop: FrameLoop, n: int = 50, warmup: int = 10):
         t._launch(-1, t._hidden.data_ptr())
     end.record()
     torch.cuda.synchronize()
-    tok = int(t._out_token.item())
-    assert tok >= 0, "talker kernel reported failure"
+    assert int(t._out_token.item()) >= 0, "talker kernel reported failure"
     ms = start.elapsed_time(end) / n
     bytes_mean = sum(talker_bytes(p0 + i) for i in range(n)) / n
     return ms, bytes_mean
 
 
-def time_cp_frame(loop: FrameLoop, n: int = 30, warmup: int = 5):
+def time_cp_frame(loop: FrameLoop, n: int = 30, warmup: int = 5, sample: bool = False):
     hid = loop.hid if hasattr(loop, "hid") else torch.zeros(1024, device=loop.dev)
     for _ in range(warmup):
-        loop.cp.predict(hid, 1335, loop.embed, do_sample=False)
+        loop.cp.predict(hid, 1335, loop.embed, do_sample=sample)
     torch.cuda.synchronize()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for _ in range(n):
-        loop.cp.predict(hid, 1335, loop.embed, do_sample=False)
+        loop.cp.predict(hid, 1335, loop.embed, do_sample=sample)
     end.record()
     torch.cuda.synchronize()
     return start.elapsed_time(end) / n
@@ -322,45 +376,73 @@ def time_batched(weights_gpu, dev, batch: int, steps: int = 100, warmup: int = 1
     bytes_step = TALKER_STEP_BYTES + batch * sum(TALKER_KV_BYTES_PER_POS * (p + 2) for p in range(steps)) / steps
     del bd
     return {"streams": batch, "ms_per_step": ms, "stream_steps_per_s": batch * 1000.0 / ms,
-            "algorithmic_gbs": bytes_step / (ms * 1e-3) / 1e9, "launches_per_step": 6 * 28 + 3,
+            "algorithmic_gbs": bytes_step / (ms * 1e-3) / 1e9, "launches_per_step": 8 * 28 + 3,
             "note": "talker step for B streams: tcgen05/TMEM split-K GEMMs + fused epilogues, PDL chain; positions 0..%d" % steps}
+
+
+def pin_rank_to_cores(local_rank: int, world: int) -> list:
+    """Give every rank its own slice of the host cores (8 Python launchers otherwise migrate and share cores)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(world, 1))
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return mine
+    except Exception:
+        return []
+
+
+def gather_floats(x: float, world: int, dev) -> list:
+    if world == 1:
+        return [float(x)]
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [float(o[0]) for o in out]
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500, help="codec frames per utterance (BASELINE.json configs[2]: 500)")
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--min-seconds", type=float, default=0.6, help="every timed leg is repeated until it covers this much device time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--torch-glue", action="store_true",
-                    help="do the per-frame embedding sum with torch ops like upstream tts_engine.py instead of step_with_codes")
+    ap.add_argument("--no-batched", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     K, W = args.steps, max(args.warmup, 3 if args.impl == "b200" else 1)
-    config = {"workload": "qwen3-tts B=1 frame loop: code predictor (5L, 16 steps + 15 heads, top-k sampling) + "
-                          "talker (28L, hidden 1024, vocab 3072) step per frame; synthetic 8-step prefill; KV to 2048",
-              "frame_glue": "torch ops (upstream tts_engine.py:319-333)" if args.torch_glue else "fused into the talker launch (TTSDecoder.step_with_codes)",
-              "global_batch": world, "streams_per_gpu": 1, "kv_max_positions": MAX_SEQ,
+    if K + N_PREFILL + 1 + W > MAX_SEQ:
+        raise SystemExit(f"--steps {K}: an utterance must fit the {MAX_SEQ}-position KV cache")
+    # identical in both arms (the driver compares the dicts); implementation details live under "impl_detail"
+    config = {"workload": "qwen3-tts B=1 frame loop: code predictor (5L, 16 steps + 15 heads, top-k sampling T=0.9 k=50) + "
+                          "talker (28L, hidden 1024, vocab 3072) step per frame; synthetic 8-step prefill + step(CODEC_BOS); "
+                          "KV cache to 2048 positions",
+              "frames_per_utterance": K, "global_batch": world, "streams_per_gpu": 1, "kv_max_positions": MAX_SEQ,
               "parallelism": f"replicas x{world} (one engine per GPU, no collective on the path)",
               "l2_policy": "weights per step (887 MB talker / 157 MB code predictor x16) exceed the 126 MB L2; no flush needed"}
 
-    from qwen_megakernel.synthetic import synthetic_tts_weights, weights_to
+    from qwen_megakernel.synthetic import synthetic_inputs, synthetic_tts_weights, weights_to
 
     if args.impl == "reference":
         if rank != 0:
             return
         w = synthetic_tts_weights(seed=SEED, max_seq_len=MAX_SEQ)
-        budget = 150.0
-        config["frame_glue"] = "torch ops on the CPU (oracle port of tts_engine.py:319-333)"
-        fps, done, dt = cpu_frame_loop(w, K, W, budget)
+        # >= 6 s of CPU work regardless of --steps (a 20-frame sample is 2 s of a noisy host), bounded at 150 s
+        est = 10.0
+        n_frames = max(K, int(6.0 * est))
+        fps, done, dt = cpu_frame_loop(w, n_frames, W, 150.0)
         line = {"metric": METRIC, "value": fps, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": K,
                 "steps_timed": done, "warmup": W, "ms_per_step": 1000.0 / fps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+                "impl_detail": "oracle port of the upstream PyTorch path (validate_kernel.PyTorchTalkerReference + model_tts.CodePredictor + "
+                               "tts_engine.py:319-333 glue) on the host cores; the reference's own GPU path needs an sm_120a build",
                 "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                  "sample": f"{done} frames of the same loop in {dt:.1f} s (oracle/tts_oracle.py)"},
                 "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -369,6 +451,7 @@ def main():
         return
 
     assert torch.cuda.is_available(), "bench.py needs a GPU for --impl b200 (there is no CPU fallback)"
+    cores = pin_rank_to_cores(local_rank, world)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     barrier = None
@@ -389,29 +472,57 @@ def main():
 
     w_cpu = synthetic_tts_weights(seed=SEED, max_seq_len=MAX_SEQ)
     w_gpu = weights_to(w_cpu, str(dev))
-    from qwen_megakernel.synthetic import synthetic_inputs
     trail_cpu = synthetic_inputs(4321, K + W + 1)
     trail_dev = trail_cpu.to(dev)
     trail_host = trail_cpu.pin_memory()
-    loop = FrameLoop(w_gpu, dev, torch_glue=args.torch_glue)
+    loop = FrameLoop(w_gpu, dev)
 
-    # kernel-only legs (explain the headline): talker launch and code-predictor frame
+    # kernel-only legs (explain the headline): talker launch at the short-context end and at fixed depths, code-predictor frame
     talker_ms, talker_b = time_talker_kernel(loop)
+    by_pos = {}
+    for pos in (50, 500, 2047):
+        ms = time_talker_at(loop, pos)
+        by_pos[f"p{pos}"] = {"launch_us": ms * 1e3, "algorithmic_bytes": talker_bytes(pos),
+                             "achieved_gbs": talker_bytes(pos) / (ms * 1e-3) / 1e9}
     loop.start_utterance()
     cp_ms = time_cp_frame(loop)
+    cp_ms_sampled = time_cp_frame(loop, sample=True)
 
+    # repetitions: every leg covers >= --min-seconds of device time whatever --steps is
+    est_ms_frame = cp_ms_sampled + talker_ms * 1.25
+    reps = max(1, int(args.min_seconds * 1000.0 / (est_ms_frame * K) + 0.999))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, launches = time_frames(loop, K, W, trail_dev, None, barrier)
-    ms_e2e, _ = time_frames(loop, K, W, trail_dev, trail_host, barrier)
-    ms_dropin, _ = time_frames(loop, K, W, trail_dev, trail_host, barrier, dropin=True)
+    l0 = loop.launches
+    t_dev, launches_auto = time_autonomous(loop, K, trail_dev, trail_host, False, reps, barrier)
+    launches_value = loop.launches - l0 + launches_auto * reps
+    t_e2e, _ = time_autonomous(loop, K, trail_dev, trail_host, True, reps, barrier)
+    t_async = time_frames(loop, K, W, trail_dev, trail_host, "async", reps, barrier)
+    t_dropin = time_frames(loop, K, W, trail_dev, trail_host, "dropin", reps, barrier)
+    t_upstream = time_frames(loop, K, W, trail_dev, trail_host, "upstream", max(1, reps // 2), barrier)
     clocks = sampler.stop() if rank == 0 else {}
 
     from qwen_megakernel.replicas import combine
-    frames_dev, ms_dev = combine(K, ms_dev, device=dev)      # sum of frames over ranks, max of device time
-    frames_e2e, ms_e2e = combine(K, ms_e2e, device=dev)
-    frames_dropin, ms_dropin = combine(K, ms_dropin, device=dev)
+    def agg(times):
+        ms_local = _median(times)
+        frames, ms = combine(K, ms_local, device=dev)      # sum of frames over ranks, max over ranks of the (median) device time
+        return frames / (ms / 1000.0), ms, gather_floats(ms_local, world, dev)
+    value, ms_dev, per_rank = agg(t_dev)
+    e2e, ms_e2e, per_rank_e2e = agg(t_e2e)
+    v_async, _, _ = agg(t_async)
+    v_dropin, _, _ = agg(t_dropin)
+    v_upstream, _, _ = agg(t_upstream)
+
+    batched = None
+    if not args.no_batched:
+        batched = {}
+        for b in (16, 64):
+            r = time_batched(w_gpu, dev, b)
+            tot, ms_b = combine(r["stream_steps_per_s"], r["ms_per_step"], device=dev)   # replicas: sum of rates, max of step times
+            r["stream_steps_per_s_all_gpus"] = tot
+            r["ms_per_step_max_over_ranks"] = ms_b
+            batched[f"B{b}"] = r
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -420,33 +531,47 @@ def main():
     peak, peak_src = measured_peaks()
     n_ctas = loop.talker._lib.qmk_engine_num_ctas(loop.talker._engine)
     kernel_name = "qmk2_decode_kernel" if n_ctas == 128 else "qmk_decode_kernel"
-    config["engine"] = ("group kernel: 8 kv-head groups x 16 CTAs, K-split O/down reduced in L2" if n_ctas == 128
-                        else "row-split kernel: one CTA per SM")
-    value = frames_dev / (ms_dev / 1000.0)
-    e2e = frames_e2e / (ms_e2e / 1000.0)
     achieved = talker_b / (talker_ms * 1e-3) / 1e9
+    for v in by_pos.values():
+        v["frac"] = v["achieved_gbs"] / peak
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic", "config": config,
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2048, "d2h_bytes_per_step": 16 * 8 + 4,
-                "note": "public API, sync-free pipeline: input embedding from pinned host memory, codes + token copied to pinned "
-                        "host memory every frame"},
-        "e2e_dropin_loop": {"value": frames_dropin / (ms_dropin / 1000.0), "unit": UNIT,
+        "impl_detail": {"engine": ("group kernel: 8 kv-head groups x 16 CTAs, K-split O/down reduced in L2" if n_ctas == 128
+                                   else "row-split kernel: one CTA per SM"),
+                        "value_path": "TTSDecoder.generate_frames -> qmk_generate_nosync: the persistent kernel runs the whole frame loop "
+                                      "(predict + 16-way embedding sum + talker step per frame, device-side EOS flag), prefill + step(BOS) outside "
+                                      "the timed region",
+                        "timing": f"median of {reps} repetitions of the {K}-frame utterance per leg (CUDA events), max over ranks",
+                        "host_cores_of_rank0": len(cores)},
+        "reps": reps, "per_rank_ms": {"value": per_rank, "e2e": per_rank_e2e},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 2048, "d2h_bytes_per_step": 16 * 8 + 4 + 4,
+                "note": "public API (TTSDecoder.generate_frames, host_visible=True): the utterance's trailing-text embeddings are copied from "
+                        "pinned host memory inside the timed region (2048 B per frame), every frame's 16 codes + talker token + progress "
+                        "word are written by the kernel into pinned host memory and read by the host after the final synchronise"},
+        "e2e_per_frame_api": {"value": v_async, "unit": UNIT,
+                              "note": "two launches per frame (predict + step_with_codes, device token), input H2D / codes D2H per frame"},
+        "e2e_dropin_loop": {"value": v_dropin, "unit": UNIT,
                             "note": "upstream caller's control flow: step() returns a Python int (blocking D2H per frame)"},
-        "gpu_launches": launches,
+        "e2e_upstream_loop": {"value": v_upstream, "unit": UNIT,
+                              "note": "tts_engine.py:301-335 as written: blocking token per frame AND the caller's 32 torch launches for the embedding sum"},
+        "gpu_launches": launches_value,
         "roofline": {"bound": "hbm", "kernel": f"{kernel_name} (talker: 28 layers + LM head, one launch per step, {n_ctas} CTAs)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
-                     "traffic_source": f"profiles/{NCU_RAW} (ncu --set full, one talker launch, bytes)",
-                     "algorithmic_bytes_per_launch": talker_b, "launch_us": talker_ms * 1e3},
+                     "traffic_source": f"static: profiles/{NCU_RAW} (ncu --set full of one talker launch, committed; not measured in this run)",
+                     "algorithmic_bytes_per_launch": talker_b, "launch_us": talker_ms * 1e3,
+                     "positions": "18..68 (short-context end of the utterance); see roofline_by_position"},
+        "roofline_by_position": by_pos,
         "talker_steps_per_s": 1000.0 / talker_ms,
-        "cp_frame": {"ms": cp_ms, "frames_per_s": 1000.0 / cp_ms, "algorithmic_bytes": cp_frame_bytes(),
-                     "achieved_gbs": cp_frame_bytes() / (cp_ms * 1e-3) / 1e9, "note": "greedy predict(): one fused launch (16 steps + 15 heads + selection)"},
+        "cp_frame": {"ms": cp_ms, "ms_sampled": cp_ms_sampled, "frames_per_s": 1000.0 / cp_ms, "algorithmic_bytes": cp_frame_bytes(),
+                     "achieved_gbs": cp_frame_bytes() / (cp_ms * 1e-3) / 1e9, "frac": cp_frame_bytes() / (cp_ms * 1e-3) / 1e9 / peak,
+                     "note": "predict(): one fused launch (16 steps + 15 heads + selection); ms = greedy, ms_sampled = T 0.9 / top-k 50"},
         "clocks": clocks,
     }
-    if world == 1:
-        line["batched"] = {f"B{b}": time_batched(w_gpu, dev, b) for b in (16, 64)}
+    if batched is not None:
+        line["batched"] = batched
     if world == 1 and not args.no_cpu_baseline:
         fps, done, dt = cpu_frame_loop(w_cpu, 10_000, 1, args.cpu_budget)
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",

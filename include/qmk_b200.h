@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define QMK_ABI_VERSION 1
+#define QMK_ABI_VERSION 2
 
 /* Model constants (upstream kernel.cu:21-28, model_tts.py:19-34); compile-time in the kernel. */
 #define QMK_HIDDEN 1024
@@ -59,13 +59,16 @@ typedef struct LDGLayerWeights {
   const void* down_proj_weight;           /* [1024, 3072]  */
 } LDGLayerWeights;
 
-/* An engine owns one set of inter-SM exchange buffers: all launches on it (every model created on it) must be
- * ordered on ONE stream; use one engine per concurrent stream / per GPU. */
+/* An engine owns one set of inter-SM exchange buffers, so all launches on it (every model created on it) execute in
+ * submission order: a launch on a different stream than the engine's previous launch first waits (event) for everything
+ * submitted to that stream.  Use one engine per GPU, or one per stream if launches are meant to overlap. */
 typedef struct qmk_engine qmk_engine; /* per-device context: exchange buffers, watchdog word, epoch */
 typedef struct qmk_model qmk_model;   /* a layer stack re-packed into per-SM weight streams */
 
 int qmk_abi_version(void);
 const char* qmk_last_error(void);
+/* Hash of the sources this library was compiled from (csrc + include); the Python loader compares it with the tree. */
+const char* qmk_source_hash(void);
 
 /* ---- engine ------------------------------------------------------------------------------------ */
 /* num_ctas = 0 -> the default kernel generation for `device`: the group kernel (8 kv-head groups x 16 = 128 persistent CTAs,
@@ -102,6 +105,12 @@ int qmk_model_create(qmk_engine* e, const LDGLayerWeights* layers, int num_layer
 int qmk_model_add_head(qmk_model* m, const void* lm_head_weight, int rows, void* stream);
 /* Register the code-predictor embedding table of group g (bf16 [2048,1024]); used by qmk_cp_predict. */
 int qmk_model_set_group_embedding(qmk_model* m, int group, const void* embedding_weight);
+/* Multimodal RoPE (the talker of Qwen3-TTS is trained with mrope_section = [24, 20, 20]; upstream implements standard RoPE and
+ * documents the gap, README.md:208): rotary frequency i takes the cos/sin table row of the position of ITS axis
+ * (temporal / height / width).  section[3] must add up to 64; interleaved = 0: consecutive sections (Qwen2-VL
+ * apply_multimodal_rotary_pos_emb), 1: axes interleaved t,h,w,t,h,w.. (Qwen3-VL apply_interleaved_mrope).  section = NULL
+ * restores standard RoPE (the default).  The per-axis positions of a step are given to qmk_decode_step_mrope. */
+int qmk_model_set_mrope(qmk_model* m, const int32_t* section, int interleaved);
 void qmk_model_destroy(qmk_model* m);
 int64_t qmk_model_packed_bytes(const qmk_model* m);
 
@@ -123,15 +132,24 @@ int qmk_decode_step(qmk_model* m, int head_index, int input_token_id, const void
                     void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
                     int max_seq_len, float attn_scale, int mode, void* stream);
 
+/* Same step (fused mode) with separate RoPE positions: `position` is the KV row that is written / the last row attention reads,
+ * rope_pos[3] (HOST array) the table rows of the three M-RoPE axes (see qmk_model_set_mrope). */
+int qmk_decode_step_mrope(qmk_model* m, int head_index, int input_token_id, const void* embed_weight,
+                          const void* cos_table, const void* sin_table, void* k_cache, void* v_cache,
+                          void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
+                          const int32_t* rope_pos, int max_seq_len, float attn_scale, void* stream);
+
 /* Same step with the frame loop's embedding sum fused in front of it (upstream tts_engine.py:319-335):
  *   input = talker_embed[codes[0]] + sum_{g<15} group_embedding_tables[g][codes[g+1]] + extra_embed   (bf16 adds,
  *   upstream order), codes = the int64[16] device tensor predict() returned, extra_embed = the trailing-text or
- *   tts_pad embedding (bf16[1024], device).  group_embedding_tables is a HOST array of 15 device pointers.
+ *   tts_pad embedding (bf16[1024], device).  group_embedding_tables is a HOST array of 15 device pointers; talker_vocab /
+ *   group_vocab are the row counts of the tables (codes are clamped to them on the device: an aborted predict writes
+ *   negative sentinels).
  * Replaces 32 torch launches per frame; hidden_buffer is only written (last-layer output). */
 int qmk_decode_step_codes(qmk_model* m, int head_index, const int64_t* codes, const void* talker_embed_weight,
-                          const void* const* group_embedding_tables, const void* extra_embed_bf16,
-                          const void* cos_table, const void* sin_table, void* k_cache, void* v_cache,
-                          void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
+                          int talker_vocab, const void* const* group_embedding_tables, int group_vocab,
+                          const void* extra_embed_bf16, const void* cos_table, const void* sin_table, void* k_cache,
+                          void* v_cache, void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
                           int max_seq_len, float attn_scale, void* stream);
 
 /* ---- one code-predictor frame in ONE launch (replaces the 16-step loop of
@@ -156,6 +174,57 @@ int qmk_cp_predict_dev(qmk_model* m, const float* talker_hidden, const int32_t* 
                        const void* talker_embed_weight, const void* cos_table, const void* sin_table, void* k_cache,
                        void* v_cache, int max_seq_len, int do_sample, float temperature, int top_k, uint64_t seed,
                        uint64_t frame_counter, int64_t* out_codes, void* stream);
+
+/* ---- N codec frames without the host ------------------------------------------------
+ * Upstream analogue: launch_ldg_generate_nosync + ldg_update_step (kernel.cu:1555-1613, 1437-1448; op generate_nosync,
+ * torch_bindings.cpp:93-127) -- N steps queued with no host sync.  Here one persistent launch runs the whole upstream frame
+ * loop (tts_engine.py:301-335) n_frames times:
+ *     if token == eos_token: stop                      (device-side EOS flag, gen_state[1])
+ *     codes[f] = code_predictor.predict(hidden, token)  16 five-layer steps, 15 heads, greedy or top-k sampling
+ *     e = talker_embed[codes[0]] + sum_g group_table[g][codes[g+1]] + (trailing_text[offset + f] or pad_embed)
+ *     token, hidden = talker.step_with_embed(e)         at KV row position + f
+ * talker_token / talker_hidden are IN/OUT device buffers: the (int32 token, f32[1024] post-norm hidden) of the talker step
+ * that precedes the first frame, overwritten with the last frame's.  codes_out (int64[n_frames][16]), tokens_out
+ * (int32[n_frames], optional: the talker token produced by each frame) and gen_state (int32[4]: frames completed, EOS seen,
+ * last token, reserved) may be device memory or mapped pinned host memory (a host thread can then consume frames while the
+ * kernel is still generating: gen_state[0] is written after a frame's codes, behind a system-scope fence).
+ * n_frames = 1 is "one launch per frame".  Long runs are split into chained launches of a few hundred frames (16-bit epochs);
+ * once EOS was seen the remaining launches exit immediately.  reset_state = 1 zeroes gen_state first; with 0 a further call
+ * continues the same utterance (trailing-text index = trailing_offset + gen_state[0] + f). */
+typedef struct qmk_generate_args {
+  qmk_model* talker;
+  int32_t talker_head, talker_vocab;
+  const void* talker_embed_weight;   /* bf16 [talker_vocab, 1024] */
+  const void* talker_cos;
+  const void* talker_sin;
+  void* talker_k_cache;
+  void* talker_v_cache;
+  int32_t talker_max_seq, position;  /* KV row of the first frame's talker step */
+  const int32_t* rope_pos;           /* optional HOST int32[3]: M-RoPE positions of that step (advance by 1 per frame) */
+  void* hidden_buffer;               /* bf16[1024] out: last-layer output of the last talker step */
+  float* talker_hidden;              /* f32[1024] in/out */
+  int32_t* talker_token;             /* int32[1] in/out */
+  qmk_model* cp;                     /* code predictor: 15 heads + 14 group embeddings registered */
+  const void* cp_cos;
+  const void* cp_sin;
+  void* cp_k_cache;
+  void* cp_v_cache;
+  int32_t cp_max_seq, cp_vocab;
+  const void* const* group_embedding_tables;   /* HOST array of 15 device pointers, bf16 [cp_vocab, 1024] each */
+  int32_t n_frames, eos_token;       /* eos_token < 0: never stop early */
+  const void* trailing_text;         /* bf16 [n_trailing, 1024] or NULL */
+  int32_t n_trailing, trailing_offset;
+  const void* pad_embed;             /* bf16[1024] */
+  int32_t do_sample, top_k;
+  float temperature;
+  int32_t reset_state;
+  uint64_t seed, frame_counter;
+  int64_t* codes_out;
+  int32_t* tokens_out;
+  int32_t* gen_state;
+} qmk_generate_args;
+int qmk_generate_nosync(const qmk_generate_args* args, void* stream);
+int qmk_generate_args_size(void);   /* sizeof(qmk_generate_args) of this build (binding self-check) */
 
 /* ---- batched multi-stream decode (no upstream counterpart: upstream is strictly B = 1) ----
  * B = 16 .. 64 concurrent utterances, each numerically the B = 1 step (own position, own KV cache).  The projections
@@ -187,10 +256,21 @@ void launch_ldg_decode_direct(int input_token_id, int* output_token_id, const vo
                               void* g_mlp_intermediate, void* g_normalized, void* block_max_vals,
                               void* block_max_idxs, int num_layers, int position, int max_seq_len,
                               float attn_scale, void* stream);
-/* residual_fp32: see qmk_model_create.  lm_head_rows: 3072 (upstream compile-time LDG_VOCAB_SIZE) or 0
- * to skip the head (the code predictor passes an all-zero dummy table, model_tts.py:657-659). */
+/* How a blob is interpreted WITHOUT any extra call (so that upstream's classes run unchanged):
+ *   residual stream: num_layers == 5 -> bf16 (upstream PyTorch CodePredictor, model_tts.py:567-619), otherwise fp32
+ *                    (upstream PyTorchTalkerReference, validate_kernel.py:123-188);
+ *   LM head:         3072 rows (upstream compile-time LDG_VOCAB_SIZE, build_tts.py:47), unless the table is all zero -- the
+ *                    dummy the upstream CodePredictorKernel passes (model_tts.py:657-659) -- then the head is skipped and
+ *                    output_token is 0 (the argmax of all-zero logits).  Checked once per table (one reduction + sync).
+ * qmk_legacy_configure overrides either (-1 = keep the rule above; lm_head_rows 0 = never run a head).
+ * Caching: the re-packed copy is keyed by (device, blob address, num_layers) and the final-norm address.  Upstream reads the
+ * weights live on every call; if they change in place, or the blob's address is re-used, call qmk_legacy_invalidate (the
+ * Python op does it automatically when it sees a different blob tensor / version at a cached address). */
 int qmk_legacy_configure(const LDGLayerWeights* layer_weights, int residual_fp32, int lm_head_rows);
-int qmk_legacy_status(void);        /* status of the last launch_ldg_decode_direct call */
+int qmk_legacy_status(void);        /* host-side status of the last launch_ldg_decode_direct call */
+int qmk_legacy_sync_status(void* stream);   /* synchronise + return and clear the DEVICE-side status (watchdog) of the current device's legacy engine */
+void qmk_legacy_invalidate(const LDGLayerWeights* layer_weights);   /* drop the cached model of a blob (NULL: all) */
+int qmk_legacy_check_blob(const LDGLayerWeights* layer_weights, int num_layers, const uint64_t* host_blob);   /* 1 = cached copy was stale and has been dropped */
 void qmk_legacy_release(void);      /* drop cached engines / re-packed models */
 
 #ifdef __cplusplus

@@ -67,6 +67,29 @@ def _rope(t_bf16: torch.Tensor, cos_row: torch.Tensor, sin_row: torch.Tensor) ->
     return torch.cat([t1 * c - t2 * s, t2 * c + t1 * s], dim=-1)
 
 
+def mrope_axis_map(section, interleaved: bool = False) -> list:
+    """Axis (0 = temporal, 1 = height, 2 = width) of each of the 64 rotary frequencies under multimodal RoPE.
+
+    Third-party algorithm (the upstream repo implements standard RoPE only and documents M-RoPE as its gap,
+    README.md:208): HF transformers 5.5.0, ``models/qwen2_vl/modeling_qwen2_vl.py::apply_multimodal_rotary_pos_emb``
+    (chunked: ``cos.split(mrope_section * 2)``, chunk i takes axis i % 3) and
+    ``models/qwen3_vl/modeling_qwen3_vl.py::Qwen3VLTextRotaryEmbedding.apply_interleaved_mrope`` (interleaved: index
+    ``i`` with ``i % 3 == a`` and ``i < 3 * section[a]`` takes axis a for a = 1, 2; everything else axis 0).
+    Pinned by tests/golden/mrope.npz, generated from those two functions (tests/golden/make_golden_mrope.py)."""
+    assert sum(section) == HEAD_DIM // 2
+    if interleaved:
+        return [1 if (i % 3 == 1 and i < 3 * section[1]) else 2 if (i % 3 == 2 and i < 3 * section[2]) else 0
+                for i in range(HEAD_DIM // 2)]
+    return [0 if i < section[0] else 1 if i < section[0] + section[1] else 2 for i in range(HEAD_DIM // 2)]
+
+
+def mrope_rows(cos_table: torch.Tensor, sin_table: torch.Tensor, rope_pos, axis_map):
+    """cos / sin row [128] of one token whose three axes sit at positions ``rope_pos`` (halves duplicated like the tables)."""
+    idx = torch.tensor([rope_pos[a] for a in axis_map] * 2, dtype=torch.long)
+    col = torch.arange(HEAD_DIM)
+    return cos_table[idx, col], sin_table[idx, col]
+
+
 class LayerStackOracle:
     """N identical Qwen3 decoder layers + final RMSNorm with a bf16 KV cache (one token per call)."""
 
@@ -79,6 +102,7 @@ class LayerStackOracle:
         self.cos, self.sin = cos_table, sin_table
         self.max_seq = max_seq
         self.residual_fp32 = residual_fp32
+        self.mrope_axis = None          # list of 64 axes -> multimodal RoPE (see mrope_axis_map); None = standard RoPE
         dev = final_norm.device
         self.k_cache = torch.zeros(self.num_layers, NUM_KV_HEADS, max_seq, HEAD_DIM, dtype=BF16, device=dev)
         self.v_cache = torch.zeros_like(self.k_cache)
@@ -88,10 +112,16 @@ class LayerStackOracle:
         self.v_cache.zero_()
 
     @torch.no_grad()
-    def forward(self, x_bf16: torch.Tensor, pos: int) -> torch.Tensor:
-        """One decode step at position ``pos``; returns the post-final-norm hidden (bf16[1024])."""
+    def forward(self, x_bf16: torch.Tensor, pos: int, rope_pos=None) -> torch.Tensor:
+        """One decode step at position ``pos`` (KV row); returns the post-final-norm hidden (bf16[1024]).
+        ``rope_pos``: (t, h, w) positions of the three M-RoPE axes (default: ``pos`` on all of them)."""
         assert 0 <= pos < self.max_seq
-        cos_row, sin_row = self.cos[pos], self.sin[pos]
+        if self.mrope_axis is not None:
+            cos_row, sin_row = mrope_rows(self.cos, self.sin, rope_pos if rope_pos is not None else (pos, pos, pos),
+                                          self.mrope_axis)
+        else:
+            assert rope_pos is None or tuple(rope_pos) == (pos, pos, pos)
+            cos_row, sin_row = self.cos[pos], self.sin[pos]
         res = x_bf16.float() if self.residual_fp32 else x_bf16.to(BF16)
         for li, (w_in, wq, wk, wv, w_qn, w_kn, wo, w_post, wg, wu, wd) in enumerate(self.layers):
             n = _rmsnorm(res.to(BF16), w_in)
@@ -140,16 +170,19 @@ class TalkerOracle:
         self.stack.reset()
         self.position = 0
 
+    def set_mrope(self, section=(24, 20, 20), interleaved: bool = False):
+        self.stack.mrope_axis = None if section is None else mrope_axis_map(section, interleaved)
+
     @torch.no_grad()
-    def step_with_embed(self, embed_bf16: torch.Tensor):
-        hn = self.stack.forward(embed_bf16.to(BF16), self.position)
+    def step_with_embed(self, embed_bf16: torch.Tensor, rope_pos=None):
+        hn = self.stack.forward(embed_bf16.to(BF16), self.position, rope_pos)
         logits = _gemv(self.lm_head_weight, hn).float()        # bf16 logits widened (validate_kernel.py:197)
         self.last_logits = logits
         self.position += 1
         return int(logits.argmax()), hn.float()
 
-    def step(self, token_id: int):
-        return self.step_with_embed(self.embed_weight[token_id])
+    def step(self, token_id: int, rope_pos=None):
+        return self.step_with_embed(self.embed_weight[token_id], rope_pos)
 
 
 def select_token(logits_bf16: torch.Tensor, do_sample: bool, temperature: float, top_k: int,

@@ -57,13 +57,15 @@ __device__ __forceinline__ uint2 rmsnorm4(const float (&x)[4], const __nv_bfloat
 
 // ---- step input: embedding row or caller vector -> fp32 residual + layer-0 input norm -------------------------------
 // grid = B, block = 256
-__global__ void kb_input(const int* token_ids, const __nv_bfloat16* embed_table, const __nv_bfloat16* embeds, float* res,
+__global__ void kb_input(const int* token_ids, const __nv_bfloat16* embed_table, int vocab, const __nv_bfloat16* embeds, float* res,
                          const __nv_bfloat16* w_in, __nv_bfloat16* xn) {
   __shared__ float s_red[8];
   qmkb::pdl_wait();
   qmkb::pdl_launch_dependents();
   const int b = blockIdx.x, t = threadIdx.x;
-  const int tok = token_ids ? token_ids[b] : -1;
+  int tok = token_ids ? token_ids[b] : -1;
+  if (tok >= vocab) tok = vocab - 1;             // device-side ids are not trusted: clamp instead of reading out of bounds
+  if (tok < 0 && embeds == nullptr) tok = 0;     // sentinel without an embedding buffer
   const __nv_bfloat16* src = tok >= 0 ? embed_table + (size_t)tok * H : embeds + (size_t)b * H;
   const uint2 v = *reinterpret_cast<const uint2*>(src + t * 4);
   const float x[4] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y)};
@@ -113,7 +115,8 @@ __global__ void kb_qkv_attention(const float* partial, int splits, int B, const 
   qmkb::pdl_wait();
   qmkb::pdl_launch_dependents();
   const int b = blockIdx.x, g = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pos = positions[b];
+  int pos = positions[b];
+  pos = pos < 0 ? 0 : (pos >= max_seq ? max_seq - 1 : pos);   // a stream that ran past its cache keeps rewriting the last row
   const size_t base = (((size_t)b * L + layer) * NKVH + g) * max_seq * HD;
   if (warp < 4) {
     // warp 0, 1: q heads 2g, 2g+1; warp 2: k head g; warp 3: v head g
@@ -263,6 +266,17 @@ int fail(int code, const char* msg) {
 
 }  // namespace
 
+constexpr size_t PARTIAL_ELEMS = (size_t)2 * 1024 * 1024;   // fp32 split-K partials: max splits x B x rows = 4 x 64 x 6144
+
+struct BatchedDeviceGuard {
+  int prev = -1;
+  explicit BatchedDeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~BatchedDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 struct qmk_batched {
   int device = 0, L = 0, B = 0, max_seq = 0, head_rows = 0, residual_fp32 = 1;
   __nv_bfloat16 *w_qkv = nullptr, *w_gu = nullptr;           // [L][4096][1024], [L][6144][1024] (concatenated copies)
@@ -286,7 +300,11 @@ extern "C" int qmk_batched_create(int device, const LDGLayerWeights* layers_host
   if (batch < 16 || batch > MAX_N || batch % 16) return fail(QMK_ERR_ARG, "qmk_batched_create: batch must be 16, 32, 48 or 64");
   if (lm_head_rows % BM || lm_head_rows <= 0) return fail(QMK_ERR_ARG, "qmk_batched_create: lm_head_rows must be a multiple of 128");
   if (num_layers < 1 || max_seq_len < 1) return fail(QMK_ERR_ARG, "qmk_batched_create: bad num_layers / max_seq_len");
-  if (cudaSetDevice(device) != cudaSuccess) return fail(QMK_ERR_CUDA, "qmk_batched_create: cudaSetDevice failed");
+  if ((size_t)4 * batch * lm_head_rows > PARTIAL_ELEMS) return fail(QMK_ERR_ARG, "qmk_batched_create: lm_head_rows too large for the split-K partial buffer");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(QMK_ERR_ARG, "qmk_batched_create: bad device");
+  BatchedDeviceGuard guard(device);
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   if (prop.major != 10) return fail(QMK_ERR_UNSUPPORTED, "qmk_batched_create: tcgen05 needs an sm_100 device");
@@ -296,10 +314,10 @@ extern "C" int qmk_batched_create(int device, const LDGLayerWeights* layers_host
   h->final_norm = final_norm_weight; h->lm_head = lm_head_weight; h->embed = embed_weight; h->cos_t = cos_table; h->sin_t = sin_table;
   const size_t L = num_layers;
   bool ok = cudaMalloc(&h->w_qkv, L * QKV_ROWS * H * 2) == cudaSuccess && cudaMalloc(&h->w_gu, L * GU_ROWS * H * 2) == cudaSuccess &&
-            cudaMalloc(&h->res, (size_t)batch * H * 4) == cudaSuccess && cudaMalloc(&h->partial, (size_t)2 * 1024 * 1024 * sizeof(float)) == cudaSuccess  /* max splits x B x rows = 4 x 64 x 6144 */ &&
+            cudaMalloc(&h->res, (size_t)batch * H * 4) == cudaSuccess && cudaMalloc(&h->partial, PARTIAL_ELEMS * sizeof(float)) == cudaSuccess &&
             cudaMalloc(&h->xn, (size_t)batch * H * 2) == cudaSuccess &&
             cudaMalloc(&h->abuf, (size_t)batch * QSZ * 2) == cudaSuccess && cudaMalloc(&h->mbuf, (size_t)batch * INTER * 2) == cudaSuccess;
-  if (!ok) { delete h; return fail(QMK_ERR_CUDA, "qmk_batched_create: allocation failed"); }
+  if (!ok) { qmk_batched_destroy(h); return fail(QMK_ERR_CUDA, "qmk_batched_create: allocation failed"); }
   for (int l = 0; l < num_layers; ++l) {
     const LDGLayerWeights& w = layers_host[l];
     auto cp = [&](const void* src, __nv_bfloat16* dst, size_t rows) {
@@ -318,16 +336,16 @@ extern "C" int qmk_batched_create(int device, const LDGLayerWeights* layers_host
     rc |= make_tensor_map(&m, w.o_proj_weight, H, QSZ, BM); h->map_o.push_back(m);
     rc |= make_tensor_map(&m, h->w_gu + (size_t)l * GU_ROWS * H, GU_ROWS, H, BM); h->map_gu.push_back(m);
     rc |= make_tensor_map(&m, w.down_proj_weight, H, INTER, BM); h->map_down.push_back(m);
-    if (rc) { delete h; return fail(QMK_ERR_CUDA, "qmk_batched_create: cuTensorMapEncodeTiled failed"); }
+    if (rc) { qmk_batched_destroy(h); return fail(QMK_ERR_CUDA, "qmk_batched_create: cuTensorMapEncodeTiled failed"); }
   }
   int rc = make_tensor_map(&h->map_head, lm_head_weight, lm_head_rows, H, BM);
   rc |= make_tensor_map(&h->map_x1024, h->xn, batch, H, batch);
   rc |= make_tensor_map(&h->map_x2048, h->abuf, batch, QSZ, batch);
   rc |= make_tensor_map(&h->map_x3072, h->mbuf, batch, INTER, batch);
-  if (rc) { delete h; return fail(QMK_ERR_CUDA, "qmk_batched_create: cuTensorMapEncodeTiled failed"); }
+  if (rc) { qmk_batched_destroy(h); return fail(QMK_ERR_CUDA, "qmk_batched_create: cuTensorMapEncodeTiled failed"); }
   if (cudaFuncSetAttribute(qmk_bgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
       cudaDeviceSynchronize() != cudaSuccess) {
-    delete h;
+    qmk_batched_destroy(h);
     return fail(QMK_ERR_CUDA, "qmk_batched_create: kernel setup failed");
   }
   *out = h;
@@ -336,7 +354,7 @@ extern "C" int qmk_batched_create(int device, const LDGLayerWeights* layers_host
 
 extern "C" void qmk_batched_destroy(qmk_batched* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  BatchedDeviceGuard guard(h->device);
   cudaDeviceSynchronize();
   cudaFree(h->w_qkv); cudaFree(h->w_gu); cudaFree(h->res); cudaFree(h->partial);
   cudaFree(h->xn); cudaFree(h->abuf); cudaFree(h->mbuf);
@@ -344,6 +362,7 @@ extern "C" void qmk_batched_destroy(qmk_batched* h) {
 }
 
 // Every kernel of the step chain is launched with programmatic stream serialization (PDL).
+static thread_local cudaError_t g_launch_err = cudaSuccess;   // first failed launch of the current step
 template <typename... KArgs, typename... Args>
 static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
@@ -356,7 +375,8 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e;
 }
 static void gemm(qmk_batched* h, const CUtensorMap& mw, const CUtensorMap& mx, int M, int K, int splits, cudaStream_t st) {
   qmkb::BgemmArgs a{h->partial, M, h->B, K, splits};
@@ -371,13 +391,15 @@ extern "C" int qmk_batched_step(qmk_batched* h, const int32_t* token_ids, const 
   if (!h || !positions || !k_cache || !v_cache || !tokens_out) return fail(QMK_ERR_ARG, "qmk_batched_step: null argument");
   if (!token_ids && !embeds) return fail(QMK_ERR_ARG, "qmk_batched_step: neither token ids nor embeddings given");
   cudaStream_t st = (cudaStream_t)stream;
+  BatchedDeviceGuard guard(h->device);
+  g_launch_err = cudaSuccess;
   const int B = h->B, L = h->L;
   const float scale = 0.08838834764831845f;
   __nv_bfloat16* kc = reinterpret_cast<__nv_bfloat16*>(k_cache);
   __nv_bfloat16* vc = reinterpret_cast<__nv_bfloat16*>(v_cache);
   const __nv_bfloat16* cos_t = reinterpret_cast<const __nv_bfloat16*>(h->cos_t);
   const __nv_bfloat16* sin_t = reinterpret_cast<const __nv_bfloat16*>(h->sin_t);
-  launch_pdl(kb_input, dim3(B), dim3(256), 0, st, (const int*)token_ids, reinterpret_cast<const __nv_bfloat16*>(h->embed),
+  launch_pdl(kb_input, dim3(B), dim3(256), 0, st, (const int*)token_ids, reinterpret_cast<const __nv_bfloat16*>(h->embed), h->head_rows,
              reinterpret_cast<const __nv_bfloat16*>(embeds), h->res, reinterpret_cast<const __nv_bfloat16*>(h->ln_in[0]), h->xn);
   for (int l = 0; l < L; ++l) {
     gemm(h, h->map_qkv[l], h->map_x1024, QKV_ROWS, H, 4, st);                       // 32 tiles x 4 K-slices
@@ -397,7 +419,7 @@ extern "C" int qmk_batched_step(qmk_batched* h, const int32_t* token_ids, const 
   }
   gemm(h, h->map_head, h->map_x1024, h->head_rows, H, 4, st);
   launch_pdl(kb_head_epilogue, dim3(B), dim3(256), 0, st, (const float*)h->partial, 4, B, h->head_rows, (int*)tokens_out, (int*)positions);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(QMK_ERR_CUDA, cudaGetErrorString(e));
+  cudaError_t e = g_launch_err != cudaSuccess ? g_launch_err : cudaGetLastError();
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(QMK_ERR_CUDA, cudaGetErrorString(e)); }
   return QMK_OK;
 }

@@ -52,7 +52,7 @@ constexpr int ATT_ROUND = NCW * ATT_PER_WARP;  // 40 cached positions per round 
 constexpr int S_MAX = 18;                      // max KV splits per kv head (8 * 18 = 144 CTAs)
 constexpr int PART_STRIDE = 132;               // u64 words per (q head, split) partial: m, l, acc[128], pad
 constexpr int MAX_HEAD_ROWS = 3072;
-constexpr int MAX_STEPS = 16;
+constexpr int MAX_STEPS = 17;              // a code-predictor frame (16 steps) + the talker step of the same frame
 constexpr float EPS = 1e-6f;
 
 enum Phase { PH_QKV = 0, PH_ATTN = 1, PH_O = 2, PH_GU = 3, PH_DOWN = 4, PH_PER_LAYER = 5 };
@@ -86,7 +86,8 @@ struct HeadDesc {
   int segs_max;
 };
 
-enum InMode { IN_TABLE_TOKEN = 0, IN_VEC_BF16 = 1, IN_TABLE_PREV = 2, IN_VEC_F32 = 3, IN_CODES_SUM = 4 };
+enum InMode { IN_TABLE_TOKEN = 0, IN_VEC_BF16 = 1, IN_TABLE_PREV = 2, IN_VEC_F32 = 3, IN_CODES_SUM = 4,
+              IN_PREV_NORM = 5 };   // group kernel only: the previous step's post-final-norm hidden (kept on chip)
 struct StepDesc {
   const __nv_bfloat16* in_table;  // IN_TABLE_TOKEN: row `token`; IN_TABLE_PREV: row = token selected by the previous step
   const void* in_vec;             // IN_VEC_BF16: bf16[1024]; IN_VEC_F32: f32[1024] (rounded to bf16 on load)
@@ -98,11 +99,47 @@ struct StepDesc {
   HeadDesc head;
   int select;                     // 0 = argmax, 1 = temperature / top-k / multinomial (Params::sample_*)
   int group;                      // code-predictor group of this head (index into forced_tokens), or -1
+  int model;                      // group kernel: index into Params::models (0 = the launch's primary model)
+  int in_mode_next;               // group kernel, frame loop: input mode of this step in frames after the first (-1 = in_mode)
+  int pos_per_frame;              // group kernel, frame loop: position / rope_pos advance by this much per frame
+  int rope_pos[3];                // RoPE table rows of the three M-RoPE axes (standard RoPE: all = position)
+  int epoch_off;                  // group kernel: epochs used by the steps before this one (sum of L + 2)
   int* out_token;                 // int32[1] (head.rows > 0) or null
   long long* out_code;            // int64[1] or null
   float* logits_out;              // f32[head.rows] or null
   float* out_norm;                // f32[1024] post-final-norm hidden (bf16-rounded values) or null
   __nv_bfloat16* hidden_out;      // bf16[1024] last-layer output or null
+};
+
+// A second (or first) layer stack a step can run on: the group kernel executes a whole codec frame -- 16 code-predictor
+// steps and the talker step -- in one launch, so a launch carries two models.  models[0] mirrors the fields below.
+struct ModelDesc {
+  const uint8_t* packed_layers;
+  const uint8_t* aux_layers;
+  const __nv_bfloat16* cos_t;
+  const __nv_bfloat16* sin_t;
+  __nv_bfloat16* k_cache;
+  __nv_bfloat16* v_cache;
+  int max_seq;
+  int L;
+  int residual_fp32;
+  unsigned long long rope_axis[2]; // M-RoPE: 2 bits per rotary frequency index 0..63 = axis (0..2) whose position that frequency
+                                   // uses (StepDesc::rope_pos); all zero = standard RoPE
+};
+// Device-autonomous frame loop (group kernel): the launch repeats its step program `n_frames` times without the host
+// (upstream analogue: launch_ldg_generate_nosync, kernel.cu:1555-1613).  Frame f: stop if the talker's last token is EOS;
+// code-predictor steps write codes_out[f][0..15]; the talker step (pos_per_frame = 1) runs at position + f on
+// embed-sum(codes) + (f0 + f < n_trailing ? trailing[f0 + f] : pad_embed) and writes tokens_out[f].
+struct FrameLoop {
+  int n_frames;                    // 0 = plain launch (no loop)
+  int eos_token;                   // < 0: never stop early
+  const __nv_bfloat16* trailing;   // bf16[n_trailing][1024] or null
+  int n_trailing, trailing_offset;
+  const __nv_bfloat16* pad_embed;  // bf16[1024]
+  long long* codes_out;            // int64[n_frames][16]
+  int* tokens_out;                 // int32[n_frames] or null: talker token produced by frame f
+  int* gen_state;                  // int32[4] {frames done (cumulative over chained launches), eos seen, last token, -}
+  int epochs_per_frame;            // sum of L + 2 over the step program
 };
 
 struct Params {
@@ -136,6 +173,9 @@ struct Params {
   const int* code0_ptr;            // optional: code0 comes from device memory (the talker's out_token)
   long long* code0_out;            // optional: receives code0 (the talker's token, first entry of the frame's codes)
   int code0;
+  ModelDesc models[2];
+  FrameLoop frames;
+  int sum_rows0, sum_rows;         // IN_CODES_SUM clamp bounds: rows of the talker table / of the 15 group tables
   int n_steps;
   StepDesc steps[MAX_STEPS];
 };

@@ -121,12 +121,17 @@ struct Prod2 {
   uint32_t k;
   int left;
 };
+__device__ __forceinline__ const uint8_t* model_layers(const Params& p, int cta, int step) {
+  const ModelDesc& md = p.models[p.steps[step].model];
+  return md.packed_layers + (size_t)cta * md.L * LAYER_BYTES2;
+}
 __device__ __forceinline__ int head_tiles(const HeadDesc& h) { return h.rows > 0 ? (h.rows / G2 + 15) / 16 : 0; }
 __device__ __forceinline__ void prod2_init(Ctx2& c, Prod2& pr) {
   const Params& p = c.p;
   pr.step = 0; pr.l = 0; pr.e = 0; pr.k = 0; pr.left = 0;
-  for (int st = 0; st < p.n_steps; ++st) pr.left += p.lay.L * ENT_PER_LAYER + head_tiles(p.steps[st].head);
-  pr.layer_base = p.packed_layers + (size_t)c.cta * p.lay.L * LAYER_BYTES2;
+  for (int st = 0; st < p.n_steps; ++st) pr.left += p.models[p.steps[st].model].L * ENT_PER_LAYER + head_tiles(p.steps[st].head);
+  if (p.frames.n_frames > 1) pr.left *= p.frames.n_frames;   // the frame loop repeats the step program
+  pr.layer_base = model_layers(p, c.cta, 0);
 }
 // Weights are read exactly once per step and a step's weights exceed L2: stream them with an evict-first policy so
 // that they do not push out what IS re-used (KV rows, embedding tables, norm weights, the exchange words).
@@ -153,12 +158,13 @@ __device__ __forceinline__ void prod2_issue(Ctx2& c, Prod2& pr, int n) {
   // Called by warps 2..7 (the ones that neither finalise nor publish), all of which keep the cursor; stage i of the call
   // is issued by warp 2 + i % 6, so that a three-stage refill costs one mbarrier + one bulk copy of latency instead of three.
   for (int issuer = 2; n > 0; --n, ++pr.k, issuer = (issuer == NCW - 1) ? 2 : issuer + 1) {
-    // skip steps without a head (their head phase has no stage)
-    while (pr.l == p.lay.L && pr.e >= head_tiles(p.steps[pr.step].head)) {
-      pr.l = 0; pr.e = 0; ++pr.step;
-      pr.layer_base = p.packed_layers + (size_t)c.cta * p.lay.L * LAYER_BYTES2;
+    // skip steps without a head (their head phase has no stage); after the last step the program restarts (next frame)
+    while (pr.l == p.models[p.steps[pr.step].model].L && pr.e >= head_tiles(p.steps[pr.step].head)) {
+      pr.l = 0; pr.e = 0;
+      if (++pr.step == p.n_steps) pr.step = 0;
+      pr.layer_base = model_layers(p, c.cta, pr.step);
     }
-    if (pr.l < p.lay.L) {
+    if (pr.l < p.models[p.steps[pr.step].model].L) {
       const uint32_t off = pr.e < 6 ? (uint32_t)pr.e * SLOT2 : 6u * SLOT2 + (uint32_t)(pr.e - 6) * DOWN_SLOT;
       if (c.lane == 0 && c.warp == issuer) prod2_tma(c, pr.k, pr.layer_base + off, pr.e < 6 ? SLOT2 : DOWN_SLOT);
       if (++pr.e == ENT_PER_LAYER) { pr.e = 0; ++pr.l; pr.layer_base += LAYER_BYTES2; }
@@ -259,8 +265,7 @@ __device__ __forceinline__ AttnItem2 attn_item2(int position, int j) {
   it.p1 = it.p0 + C < n ? it.p0 + C : n;
   return it;
 }
-__device__ __forceinline__ void attn_l2_prefetch(const Ctx2& c, int l, int position, const AttnItem2& it) {
-  const Params& p = c.p;
+__device__ __forceinline__ void attn_l2_prefetch(const Ctx2& c, const ModelDesc& p, int l, int position, const AttnItem2& it) {
   const size_t base = ((size_t)(l * NKVH + c.g) * p.max_seq) * HD;
   for (int i = c.tid; i < (it.p1 - it.p0) * 4; i += NCT) {   // (row, K|V, half row): 128-byte lines
     const int pos = it.p0 + (i >> 2);
@@ -270,8 +275,7 @@ __device__ __forceinline__ void attn_l2_prefetch(const Ctx2& c, int l, int posit
     }
   }
 }
-__device__ __forceinline__ void attn_prefetch2(const Ctx2& c, int l, int position, const AttnItem2& it, int round, KvRegs& r) {
-  const Params& p = c.p;
+__device__ __forceinline__ void attn_prefetch2(const Ctx2& c, const ModelDesc& p, int l, int position, const AttnItem2& it, int round, KvRegs& r) {
   const size_t base = ((size_t)(l * NKVH + c.g) * p.max_seq) * HD;
 #pragma unroll
   for (int i = 0; i < ATT_PER_WARP; ++i) {
@@ -288,7 +292,7 @@ __device__ __forceinline__ void attn_prefetch2(const Ctx2& c, int l, int positio
 // over this CTA's positions; cross-warp merge; (long context) cross-chunk merge through group-local LL8 words.
 // Result: bf16 a[256] of the group's two q heads in c.s_a (every CTA of the group holds the same values).
 template <bool TR>
-__device__ void phase_attn2(Ctx2& c, int l, int position, uint32_t epoch, const AttnItem2& it, KvRegs& kv, Prod2& prod,
+__device__ void phase_attn2(Ctx2& c, const ModelDesc& md, int l, int position, uint32_t epoch, const AttnItem2& it, KvRegs& kv, Prod2& prod,
                             int a_row, int a_khalf, int a_sw) {
   const Params& p = c.p;
   const uint32_t* x_q = reinterpret_cast<const uint32_t*>(c.xb + XB_POOL) + (size_t)c.slot_q * XP_WORDS;
@@ -297,9 +301,9 @@ __device__ void phase_attn2(Ctx2& c, int l, int position, uint32_t epoch, const 
   __nv_bfloat16* s_a = reinterpret_cast<__nv_bfloat16*>(c.s_a);
 
   bool retried = false;
-  if (it.has) attn_prefetch2(c, l, position, it, 0, kv);   // L2 hits (prefetched during the QKV phase)
+  if (it.has) attn_prefetch2(c, md, l, position, it, 0, kv);   // L2 hits (prefetched during the QKV phase)
   uint2 nw_raw = make_uint2(0, 0);
-  if (c.warp < 3) nw_raw = *reinterpret_cast<const uint2*>(p.aux_layers + ((size_t)l * 2) * AUX_BYTES + 2048 + (c.warp == 2 ? 256 : 0) + c.lane * 8);
+  if (c.warp < 3) nw_raw = *reinterpret_cast<const uint2*>(md.aux_layers + ((size_t)l * 2) * AUX_BYTES + 2048 + (c.warp == 2 ? 256 : 0) + c.lane * 8);
   wait_window(c, c.s_delay[DL_ATTN]);
   if (c.warp < 4) {
     const uint4 w = ll4_wait(c, x_q + c.warp * HD + c.lane * 4, epoch, retried);
@@ -386,7 +390,7 @@ __device__ void phase_attn2(Ctx2& c, int l, int position, uint32_t epoch, const 
     }
   } else
   for (int r = 0; r < nrounds; ++r) {
-    if (r > 0) attn_prefetch2(c, l, position, it, r, kv);
+    if (r > 0) attn_prefetch2(c, md, l, position, it, r, kv);
     float sc[10];
     const int pos_first = it.p0 + r * ATT_ROUND + c.warp;
     if (pos_first < it.p1) {  // warp-uniform
@@ -582,11 +586,15 @@ __device__ void phase_attn2(Ctx2& c, int l, int position, uint32_t epoch, const 
     c.t_pub = clock64();
     trace_sub<TR>(c, 5);
   }
-  // append the new K/V row (one CTA per group; off the critical path)
+  // Append the new K/V row (one CTA per group; off the critical path).  Memory-model ordering for readers in LATER steps of
+  // the same launch: the fence makes these stores precede this CTA's next strong write (its down-projection red.add, which
+  // every CTA gathers) -- release pattern; a reader executes a fence at the start of the next step, after it has observed
+  // that word -- acquire pattern.  The fence's latency falls into the wait window of the gate/up exchange.
   if (c.j == 0 && c.tid < 128) {
-    const size_t off = ((size_t)(l * NKVH + c.g) * p.max_seq + position) * HD + c.tid;
-    p.k_cache[off] = __float2bfloat16_rn(s_small[SS_KN + c.tid]);
-    p.v_cache[off] = __float2bfloat16_rn(s_small[SS_V + c.tid]);
+    const size_t off = ((size_t)(l * NKVH + c.g) * md.max_seq + position) * HD + c.tid;
+    md.k_cache[off] = __float2bfloat16_rn(s_small[SS_KN + c.tid]);
+    md.v_cache[off] = __float2bfloat16_rn(s_small[SS_V + c.tid]);
+    __threadfence();
   }
 }
 
@@ -704,15 +712,25 @@ __device__ __noinline__ int sample_token2(const float* s_log, unsigned* hist, fl
 template <bool TR>
 __device__ void consumer_loop2(Ctx2& c) {
   const Params& p = c.p;
-  const int L = p.lay.L;
   uint32_t* const x_q = reinterpret_cast<uint32_t*>(c.xb + XB_POOL) + (size_t)c.slot_q * XP_WORDS;
   uint32_t* const x_m = reinterpret_cast<uint32_t*>(c.xb + XB_POOL) + (size_t)c.slot_m * XP_WORDS;
   uint32_t* const x_logits = reinterpret_cast<uint32_t*>(c.xb + XB_LOGITS);
   u64* const accA = c.acc, * const accB = c.acc + 1024;
+  // Frame loop (device-autonomous generation): a chained launch whose predecessor already saw EOS does nothing at all
+  // (checked before the first weight copy is issued, so there is nothing to drain).
+  // Loop state that is touched once per frame lives in shared memory, not in registers (the kernel sits at the register limit).
+  int* const s_frames_base = reinterpret_cast<int*>(c.smem0 + S2_MISC + 192);
+  if (p.frames.n_frames > 0 && p.frames.gen_state != nullptr) {
+    if (p.frames.gen_state[1] != 0) return;
+    if (c.tid == 0) *s_frames_base = p.frames.gen_state[0];
+  } else if (c.tid == 0) {
+    *s_frames_base = 0;
+  }
   Prod2 prod;
   prod2_init(c, prod);
   if (c.warp >= 2) prod2_issue(c, prod, NSL);
   KvRegs kv;
+#define QMK2_S_CODES (reinterpret_cast<int*>(c.smem0 + S2_MISC + 128))   /* int[16]: the codes of the current frame, selected by this CTA */
   const int gi0 = c.tid * 4;
   // totals of this thread's accumulator words at the end of the previous launch
   // (kept in shared memory, not in registers: 16 registers less across the whole kernel; they are read in the load shadow)
@@ -730,30 +748,66 @@ __device__ void consumer_loop2(Ctx2& c) {
   const int a_sw = a_row & 7, a_khalf = a_mi >> 1;
   const int g8 = c.lane >> 2, q4 = c.lane & 3;
 
-  if (c.cta == 0 && c.tid == 0 && p.code0_out != nullptr) *p.code0_out = (long long)(p.code0_ptr ? *p.code0_ptr : p.code0);
+  int frame = 0;
+  for (; frame < (p.frames.n_frames > 0 ? p.frames.n_frames : 1); ++frame) {
+  if (p.frames.n_frames > 0) {
+    // ---- frame prologue: EOS check on the token every CTA selected itself (first frame: the preceding launch's token) ----
+    int tok0 = next_token;
+    if (frame == 0) {
+      tok0 = p.code0_ptr ? *p.code0_ptr : p.code0;
+      const int hi = p.sum_rows0 - 1;
+      tok0 = tok0 < 0 ? 0 : (tok0 > hi ? hi : tok0);
+      next_token = tok0;
+    }
+    if (p.frames.eos_token >= 0 && tok0 == p.frames.eos_token) break;
+    if (c.tid == 0) QMK2_S_CODES[0] = tok0;
+    if (c.cta == 0 && c.tid == 0 && p.frames.codes_out != nullptr) p.frames.codes_out[(size_t)frame * 16] = (long long)tok0;
+    c.t0 = clock64();   // the watchdog budget is per frame
+  } else if (c.cta == 0 && c.tid == 0 && p.code0_out != nullptr) {
+    *p.code0_out = (long long)(p.code0_ptr ? *p.code0_ptr : p.code0);
+  }
   for (int step = 0; step < p.n_steps; ++step) {
     const StepDesc& sd = p.steps[step];
-    const uint32_t ebase = p.epoch_base + (uint32_t)step * (uint32_t)(L + 2);
-    const int position = sd.position;
+    const ModelDesc& md = p.models[sd.model];
+    const int L = md.L;
+    // epochs ebase + 1 .. ebase + L + 1 belong to this step
+    const uint32_t ebase = p.epoch_base + (uint32_t)frame * (uint32_t)p.frames.epochs_per_frame + (uint32_t)sd.epoch_off;
+    const int fadv = frame * sd.pos_per_frame;
+    const int position = sd.position + fadv;
+    const int in_mode = (frame > 0 && sd.in_mode_next >= 0) ? sd.in_mode_next : sd.in_mode;
     int in_token = sd.token;
-    if (sd.in_mode == IN_TABLE_TOKEN && sd.token_ptr != nullptr) {
+    if (in_mode == IN_TABLE_TOKEN && sd.token_ptr != nullptr) {
       in_token = *sd.token_ptr;
       in_token = in_token < 0 ? 0 : (in_token > sd.token ? sd.token : in_token);
     }
-    if (sd.in_mode == IN_TABLE_PREV) in_token = next_token;   // selected by THIS CTA at the end of the previous step (see K2_ARGMAX)
-    const __nv_bfloat16* x_in = (sd.in_mode == IN_TABLE_TOKEN || sd.in_mode == IN_TABLE_PREV)
+    if (in_mode == IN_TABLE_PREV) {   // selected by THIS CTA at the end of an earlier step of this launch (see K2_ARGMAX)
+      in_token = next_token;
+      in_token = in_token < 0 ? 0 : ((sd.token > 0 && in_token > sd.token) ? sd.token : in_token);   // sd.token = last row of the table
+    }
+    // frame loop: the talker step's extra embedding is this frame's trailing-text row, or the pad embedding after the text
+    const void* in_vec = sd.in_vec;
+    if (p.frames.n_frames > 0 && sd.pos_per_frame != 0) {
+      const int ti = p.frames.trailing_offset + *s_frames_base + frame;
+      in_vec = (p.frames.trailing != nullptr && ti < p.frames.n_trailing) ? (const void*)(p.frames.trailing + (size_t)ti * H) : (const void*)p.frames.pad_embed;
+    }
+    const __nv_bfloat16* x_in = (in_mode == IN_TABLE_TOKEN || in_mode == IN_TABLE_PREV)
                                     ? sd.in_table + (size_t)in_token * H
-                                    : reinterpret_cast<const __nv_bfloat16*>(sd.in_vec);
+                                    : reinterpret_cast<const __nv_bfloat16*>(in_vec);
     // the step's input row is requested before the RoPE row below, so that the two L2 / HBM round trips overlap
     uint2 xin_pre = make_uint2(0, 0);
-    if (sd.in_mode == IN_TABLE_TOKEN || sd.in_mode == IN_TABLE_PREV || sd.in_mode == IN_VEC_BF16)
+    if (in_mode == IN_TABLE_TOKEN || in_mode == IN_TABLE_PREV || in_mode == IN_VEC_BF16)
       xin_pre = *reinterpret_cast<const uint2*>(x_in + gi0);
+    else if (in_mode == IN_PREV_NORM)   // this thread's own four elements of the previous step's normalised hidden
+      xin_pre = *reinterpret_cast<const uint2*>(c.s_vec + gi0 * 2);
     const AttnItem2 item = attn_item2(position, c.j);
     const int hrows_loc = sd.head.rows > 0 ? sd.head.rows / G2 : 0;
-    if (c.tid < 128) {  // RoPE row of this step
+    // KV rows appended by other CTAs in earlier steps of this launch: acquire side of the ordering described in phase_attn2
+    if (step > 0 || frame > 0) __threadfence();
+    if (c.tid < 128) {  // RoPE row of this step; with M-RoPE every rotary frequency takes the table row of its axis' position
       const int d = c.tid & 63;
-      const __nv_bfloat16* t = (c.tid < 64) ? p.cos_t : p.sin_t;
-      c.s_small[SS_CS + c.tid] = __bfloat162float(t[(size_t)position * HD + d]);
+      const int axis = (int)((md.rope_axis[d >> 5] >> (2 * (d & 31))) & 3ull);
+      const __nv_bfloat16* t = (c.tid < 64) ? md.cos_t : md.sin_t;
+      c.s_small[SS_CS + c.tid] = __bfloat162float(t[(size_t)(sd.rope_pos[axis] + fadv) * HD + d]);
     }
     consumer_bar();
 
@@ -766,7 +820,7 @@ __device__ void consumer_loop2(Ctx2& c) {
       const uint32_t epoch = (ebase + 1u + (uint32_t)l) & 0xffffu;
 
       if (kind == K2_ATTN) {
-        phase_attn2<TR>(c, l, position, epoch, item, kv, prod, a_row, a_khalf, a_sw);
+        phase_attn2<TR>(c, md, l, position, epoch, item, kv, prod, a_row, a_khalf, a_sw);
         ++idx;   // the O projection (index K2_O) ran inside phase_attn2
         continue;
       }
@@ -775,7 +829,7 @@ __device__ void consumer_loop2(Ctx2& c) {
         // (same words, same code, fixed summation orders -> the same token everywhere): the next step's input is
         // known without a gather-to-one-CTA plus a broadcast, i.e. one exchange per step instead of two.  The last step
         // of a launch is selected by CTA 0 alone.
-        if (sd.head.rows <= 0 || (c.cta != 0 && step + 1 >= p.n_steps)) continue;
+        if (sd.head.rows <= 0 || (c.cta != 0 && step + 1 >= p.n_steps && frame + 1 >= p.frames.n_frames)) continue;
         const int hrows = sd.head.rows;
         const uint32_t epoch_head = (ebase + (uint32_t)L + 1u) & 0xffffu;
         const bool sample = sd.select != 0 && hrows <= NCW * 2 * HD && (hrows % (NCT * 4)) == 0;
@@ -811,17 +865,24 @@ __device__ void consumer_loop2(Ctx2& c) {
           const int oi = __float_as_int(c.s_red[w * 2 + 1]);
           if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
         }
+        if (QMK_UNLIKELY(best_i == 0x7fffffff)) best_i = 0;   // all-NaN logits: never hand an out-of-range index to a table lookup
         int chosen = best_i;
         if (sample)
           chosen = sample_token2(s_log, reinterpret_cast<unsigned*>(c.s_part), c.s_red, c.tid, c.warp, c.lane, hrows,
-                                p.sample_top_k, p.sample_temperature, p.sample_seed, p.sample_counter, sd.group, best, best_i);
+                                p.sample_top_k, p.sample_temperature, p.sample_seed, p.sample_counter + (unsigned long long)frame, sd.group, best, best_i);
         next_token = chosen;
         if (p.forced_tokens != nullptr && sd.group >= 0) next_token = p.forced_tokens[sd.group];   // teacher forcing
+        if (c.tid == 0 && sd.group >= 0) QMK2_S_CODES[sd.group + 1] = chosen;
         if (c.cta == 0 && c.tid == 0) {
           const int st = *((volatile int*)p.status);
           const int out = (st != 0 || *c.s_abort) ? -1000 - st : chosen;
           if (sd.out_token != nullptr) *sd.out_token = out;
-          if (sd.out_code != nullptr) *sd.out_code = (long long)out;
+          if (p.frames.n_frames > 0) {
+            if (sd.group >= 0 && p.frames.codes_out != nullptr) p.frames.codes_out[(size_t)frame * 16 + sd.group + 1] = (long long)out;
+            if (sd.pos_per_frame != 0 && p.frames.tokens_out != nullptr) p.frames.tokens_out[frame] = out;
+          } else if (sd.out_code != nullptr) {
+            *sd.out_code = (long long)out;
+          }
         }
         consumer_bar();
         continue;
@@ -843,7 +904,7 @@ __device__ void consumer_loop2(Ctx2& c) {
       const bool useB = (kind == K2_GU);
       u64* const acc = useB ? accB : accA;
       const int dslot = kind == K2_GU ? DL_GU : (kind == K2_QKV ? DL_QKV : (kind == K2_DOWN ? DL_DOWN : DL_HEAD));
-      const uint8_t* nw_ptr = (kind == K2_HEAD) ? sd.head.aux : p.aux_layers + ((size_t)l * 2 + (kind == K2_GU ? 1 : 0)) * AUX_BYTES;
+      const uint8_t* nw_ptr = (kind == K2_HEAD) ? sd.head.aux : md.aux_layers + ((size_t)l * 2 + (kind == K2_GU ? 1 : 0)) * AUX_BYTES;
 
       // ---- 1. weights of this phase -> registers, BEFORE the wait window: the warps that neither finalise nor publish sit
       //         at the window's barrier for ~600 cycles anyway, and the 64-96 KB of shared-memory reads (500-750 cycles) would
@@ -887,9 +948,9 @@ __device__ void consumer_loop2(Ctx2& c) {
       // the start of the attention phase: loads that miss L2 share hardware scoreboards with the exchange loads when
       // they are in flight together, and the data check below would wait for them too.
       if (kind == K2_QKV) {
-        if (item.has) attn_l2_prefetch(c, l, position, item);
+        if (item.has) attn_l2_prefetch(c, md, l, position, item);
         if (c.cta == ((l + 1) & (G2 - 1)) && c.tid < 40 && l + 1 < L)   // next layer's norm weights (one CTA per layer; 40 lines)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.aux_layers + ((size_t)(l + 1) * 2) * AUX_BYTES + c.tid * 128));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(md.aux_layers + ((size_t)(l + 1) * 2) * AUX_BYTES + c.tid * 128));
       }
       trace_sub<TR>(c, 2);
 
@@ -897,17 +958,23 @@ __device__ void consumer_loop2(Ctx2& c) {
       if (norm) {
         bool retried = false;
         if (from_input) {
-          if (sd.in_mode == IN_CODES_SUM) {
+          if (in_mode == IN_CODES_SUM) {
             // 16 code indices, then 16 embedding rows: two rounds of independent loads (a serial chain of 31 dependent
-            // global loads costs ~10 us per talker step), then the bf16 adds in the upstream order
-            long long code[16];
+            // global loads costs ~10 us per talker step), then the bf16 adds in the upstream order.  The indices come from
+            // device memory (a preceding launch's codes) or, inside the frame loop, from this CTA's own selections; they are
+            // clamped to the tables' rows (an aborted predecessor writes negative sentinels).
+            int code[16];
 #pragma unroll
-            for (int g = 0; g < 16; ++g) code[g] = sd.codes[g];
+            for (int g = 0; g < 16; ++g) {
+              const int v = sd.codes != nullptr ? (int)sd.codes[g] : QMK2_S_CODES[g];
+              const int hi = (g == 0 ? p.sum_rows0 : p.sum_rows) - 1;
+              code[g] = v < 0 ? 0 : (v > hi ? hi : v);
+            }
             uint2 row[16];
             row[0] = *reinterpret_cast<const uint2*>(sd.in_table + (size_t)code[0] * H + gi0);
 #pragma unroll
             for (int g = 0; g < 15; ++g) row[g + 1] = *reinterpret_cast<const uint2*>(p.sum_tables[g] + (size_t)code[g + 1] * H + gi0);
-            const uint2 vx = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(sd.in_vec) + gi0);
+            const uint2 vx = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(in_vec) + gi0);
             float e4[4] = {bf16_lo(row[0].x), bf16_hi(row[0].x), bf16_lo(row[0].y), bf16_hi(row[0].y)};
 #pragma unroll
             for (int g = 1; g < 16; ++g) {
@@ -916,8 +983,8 @@ __device__ void consumer_loop2(Ctx2& c) {
             }
             res[0] = bf16_round(e4[0] + bf16_lo(vx.x)); res[1] = bf16_round(e4[1] + bf16_hi(vx.x));
             res[2] = bf16_round(e4[2] + bf16_lo(vx.y)); res[3] = bf16_round(e4[3] + bf16_hi(vx.y));
-          } else if (sd.in_mode == IN_VEC_F32) {
-            const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sd.in_vec) + gi0);
+          } else if (in_mode == IN_VEC_F32) {
+            const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in_vec) + gi0);
             res[0] = bf16_round(v.x); res[1] = bf16_round(v.y); res[2] = bf16_round(v.z); res[3] = bf16_round(v.w);
           } else {
             const uint2 v = xin_pre;
@@ -939,7 +1006,7 @@ __device__ void consumer_loop2(Ctx2& c) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float o = bf16_round(acc_value(now[e], prev[e]));
-            res[e] = p.residual_fp32 ? res[e] + o : bf16_round(res[e] + o);
+            res[e] = md.residual_fp32 ? res[e] + o : bf16_round(res[e] + o);
           }
           *reinterpret_cast<ulonglong2*>(s_prev + (useB ? 1024 : 0) + gi0) = make_ulonglong2(now[0], now[1]);
           *reinterpret_cast<ulonglong2*>(s_prev + (useB ? 1024 : 0) + gi0 + 2) = make_ulonglong2(now[2], now[3]);
@@ -1024,6 +1091,21 @@ __device__ void consumer_loop2(Ctx2& c) {
       c.t_pub = clock64();
       trace_sub<TR>(c, 8);
     }
+  }
+  if (p.frames.n_frames > 0 && c.cta == 0 && c.tid == 0 && p.frames.gen_state != nullptr) {
+    // progress word for a polling host (the buffers may be mapped host memory): codes and tokens first, then the count
+    __threadfence_system();
+    *((volatile int*)p.frames.gen_state) = *s_frames_base + frame + 1;
+    ((volatile int*)p.frames.gen_state)[2] = next_token;
+  }
+  }
+  if (p.frames.n_frames > 0 && frame < p.frames.n_frames) {
+    // EOS: the weight copies already issued for the next frame must land before the CTA may exit
+    consumer_bar();
+    if (c.warp >= 2) {
+      for (uint32_t k = c.k; k != prod.k; ++k) wait_full(c, k);
+    }
+    if (c.cta == 0 && c.tid == 0 && p.frames.gen_state != nullptr) ((volatile int*)p.frames.gen_state)[1] = 1;
   }
   // totals for the next launch
   if (c.cta == 0) {

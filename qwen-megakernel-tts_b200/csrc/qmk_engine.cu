@@ -78,6 +78,12 @@ struct qmk_engine {
   uint32_t epoch = 0;
   long long timeout_cycles = 4000000000LL;  // ~2 s at 1.9 GHz
   std::mutex mu;
+  // Stream hand-over: all launches of an engine share one set of exchange words, cumulative accumulator totals and one epoch
+  // counter, so they must execute in submission order.  The engine remembers the stream of its latest launch; a launch on a
+  // different stream first waits (event) for everything submitted to the previous one.
+  cudaStream_t last_stream = nullptr;
+  bool has_last_stream = false;
+  cudaEvent_t handover = nullptr;
 };
 
 struct qmk_model {
@@ -90,9 +96,16 @@ struct qmk_model {
   int64_t packed_bytes = 0;
   std::vector<qmk_head> heads;
   const void* group_embed[QMK_CP_GROUPS] = {nullptr};
+  unsigned long long rope_axis[2] = {0ull, 0ull};   // M-RoPE axis of every rotary frequency (2 bits each); 0 = standard RoPE
 };
 
 extern "C" int qmk_abi_version(void) { return QMK_ABI_VERSION; }
+#ifndef QMK_SRC_HASH
+#define QMK_SRC_HASH "unknown"
+#endif
+// The marker makes the hash readable from the file without loading the library (build_tts.library_hash).
+static const char g_src_hash_marker[] = "QMK_SRC_HASH:" QMK_SRC_HASH;
+extern "C" const char* qmk_source_hash(void) { return g_src_hash_marker + 13; }
 extern "C" const char* qmk_last_error(void) { return g_last_error.c_str(); }
 
 static Layout make_layout(int G, int L) {
@@ -296,6 +309,7 @@ extern "C" void qmk_engine_destroy(qmk_engine* e) {
   cudaFree(e->delays);
   cudaFree(e->status_dev);
   if (e->trace_dev) cudaFree(e->trace_dev);
+  if (e->handover) cudaEventDestroy(e->handover);
   delete e;
 }
 
@@ -444,6 +458,22 @@ extern "C" void qmk_model_destroy(qmk_model* m) {
 
 extern "C" int64_t qmk_model_packed_bytes(const qmk_model* m) { return m ? m->packed_bytes : 0; }
 
+// Called with e->mu held, before anything is enqueued for a launch on `st`.
+static int order_after_previous_stream(qmk_engine* e, cudaStream_t st) {
+  if (e->has_last_stream && e->last_stream != st) {
+    if (!e->handover) QMK_CUDA(cudaEventCreateWithFlags(&e->handover, cudaEventDisableTiming));
+    cudaError_t err = cudaEventRecord(e->handover, e->last_stream);
+    if (err == cudaSuccess) err = cudaStreamWaitEvent(st, e->handover, 0);
+    if (err != cudaSuccess) {   // the previous stream no longer exists: its work is ordered by a device-wide wait
+      cudaGetLastError();
+      QMK_CUDA(cudaDeviceSynchronize());
+    }
+  }
+  e->last_stream = st;
+  e->has_last_stream = true;
+  return QMK_OK;
+}
+
 static int launch_slice(qmk_engine* e, Params& p, int begin, int end, cudaStream_t st) {
   p.phase_begin = begin;
   p.phase_end = end;
@@ -460,10 +490,47 @@ static int launch_slice(qmk_engine* e, Params& p, int begin, int end, cudaStream
 }
 
 // Fields shared by every launch of `m` on its engine.
+static void fill_model(ModelDesc& d, const qmk_model* m, const void* cos_table, const void* sin_table, void* k_cache,
+                       void* v_cache, int max_seq_len) {
+  d.packed_layers = m->packed_layers;
+  d.aux_layers = m->aux_layers;
+  d.cos_t = reinterpret_cast<const __nv_bfloat16*>(cos_table);
+  d.sin_t = reinterpret_cast<const __nv_bfloat16*>(sin_table);
+  d.k_cache = reinterpret_cast<__nv_bfloat16*>(k_cache);
+  d.v_cache = reinterpret_cast<__nv_bfloat16*>(v_cache);
+  d.max_seq = max_seq_len;
+  d.L = m->lay.L;
+  d.residual_fp32 = m->residual_fp32;
+  d.rope_axis[0] = m->rope_axis[0];
+  d.rope_axis[1] = m->rope_axis[1];
+}
+static void init_step(StepDesc& sd, int position) {
+  sd.position = position;
+  sd.rope_pos[0] = sd.rope_pos[1] = sd.rope_pos[2] = position;
+  sd.model = 0;
+  sd.in_mode_next = -1;
+  sd.pos_per_frame = 0;
+  sd.epoch_off = 0;
+  sd.group = -1;
+}
+// Epoch offsets of a finished step program (every step uses L + 2 epochs of its model).
+static uint32_t finish_program(Params& p) {
+  uint32_t off = 0;
+  for (int s = 0; s < p.n_steps; ++s) {
+    p.steps[s].epoch_off = (int)off;
+    off += (uint32_t)p.models[p.steps[s].model].L + 2u;
+  }
+  p.frames.epochs_per_frame = (int)off;
+  return off;
+}
 static void fill_common(Params& p, qmk_model* m, const void* cos_table, const void* sin_table, void* k_cache,
                         void* v_cache, int max_seq_len, float attn_scale) {
   qmk_engine* e = m->e;
   memset(&p, 0, sizeof(p));
+  fill_model(p.models[0], m, cos_table, sin_table, k_cache, v_cache, max_seq_len);
+  p.models[1] = p.models[0];
+  p.sum_rows0 = p.sum_rows = 1;
+  for (int s = 0; s < MAX_STEPS; ++s) init_step(p.steps[s], 0);
   p.lay = m->lay;
   p.packed_layers = m->packed_layers;
   p.aux_layers = m->aux_layers;
@@ -510,10 +577,10 @@ static int reserve_epochs(qmk_engine* e, uint32_t need, cudaStream_t st, uint32_
 }
 
 static int decode_step_impl(qmk_model* m, int head_index, int input_token_id, const void* embed_weight,
-                            const int64_t* codes, const void* const* group_tables, const void* extra_bf16,
-                            const void* cos_table, const void* sin_table, void* k_cache, void* v_cache,
+                            const int64_t* codes, const void* const* group_tables, int talker_vocab, int group_vocab,
+                            const void* extra_bf16, const void* cos_table, const void* sin_table, void* k_cache, void* v_cache,
                             void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
-                            int max_seq_len, float attn_scale, int mode, void* stream) {
+                            const int32_t* rope_pos, int max_seq_len, float attn_scale, int mode, void* stream) {
   if (!m) return set_error(QMK_ERR_ARG, "qmk_decode_step: model is null");
   if (!cos_table || !sin_table || !k_cache || !v_cache || !hidden_buffer)
     return set_error(QMK_ERR_ARG, "qmk_decode_step: null table / cache / hidden_buffer pointer");
@@ -523,14 +590,24 @@ static int decode_step_impl(qmk_model* m, int head_index, int input_token_id, co
   if (head_index >= (int)m->heads.size()) return set_error(QMK_ERR_ARG, "qmk_decode_step: head index %d not registered", head_index);
   if (head_index >= 0 && !out_token) return set_error(QMK_ERR_ARG, "qmk_decode_step: out_token is null");
   qmk_engine* e = m->e;
+  if (rope_pos) {
+    if (e->version != 2) return set_error(QMK_ERR_UNSUPPORTED, "M-RoPE positions need the group kernel");
+    for (int a = 0; a < 3; ++a)
+      if (rope_pos[a] < 0) return set_error(QMK_ERR_ARG, "qmk_decode_step_mrope: negative rope position");
+  }
+  if (codes && (talker_vocab < 1 || group_vocab < 1)) return set_error(QMK_ERR_ARG, "qmk_decode_step_codes: table row counts must be positive");
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
   std::lock_guard<std::mutex> lock(e->mu);
+  int rc = order_after_previous_stream(e, st);
+  if (rc != QMK_OK) return rc;
 
   Params p;
   fill_common(p, m, cos_table, sin_table, k_cache, v_cache, max_seq_len, attn_scale);
   p.n_steps = 1;
   StepDesc& sd = p.steps[0];
+  init_step(sd, position);
+  if (rope_pos) { sd.rope_pos[0] = rope_pos[0]; sd.rope_pos[1] = rope_pos[1]; sd.rope_pos[2] = rope_pos[2]; }
   sd.in_table = reinterpret_cast<const __nv_bfloat16*>(embed_weight);
   sd.in_vec = hidden_buffer;
   sd.in_mode = input_token_id >= 0 ? IN_TABLE_TOKEN : IN_VEC_BF16;
@@ -540,15 +617,15 @@ static int decode_step_impl(qmk_model* m, int head_index, int input_token_id, co
     sd.codes = reinterpret_cast<const long long*>(codes);
     sd.in_vec = extra_bf16;
     for (int g = 0; g < 15; ++g) p.sum_tables[g] = reinterpret_cast<const __nv_bfloat16*>(group_tables[g]);
+    p.sum_rows0 = talker_vocab;
+    p.sum_rows = group_vocab;
   }
-  sd.position = position;
   set_head(sd, m, head_index);
-  sd.group = -1;
   sd.out_token = out_token;
   sd.out_norm = normalized_out;
   sd.hidden_out = reinterpret_cast<__nv_bfloat16*>(hidden_buffer);
 
-  int rc = reserve_epochs(e, (uint32_t)m->lay.L + 2u, st, &p.epoch_base);
+  rc = reserve_epochs(e, finish_program(p), st, &p.epoch_base);
   if (rc != QMK_OK) return rc;
 
   const int n_idx = m->lay.L * PH_PER_LAYER + 2;
@@ -564,59 +641,62 @@ extern "C" int qmk_decode_step(qmk_model* m, int head_index, int input_token_id,
                                const void* cos_table, const void* sin_table, void* k_cache, void* v_cache,
                                void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
                                int max_seq_len, float attn_scale, int mode, void* stream) {
-  return decode_step_impl(m, head_index, input_token_id, embed_weight, nullptr, nullptr, nullptr, cos_table, sin_table,
-                          k_cache, v_cache, hidden_buffer, normalized_out, out_token, position, max_seq_len, attn_scale,
-                          mode, stream);
+  return decode_step_impl(m, head_index, input_token_id, embed_weight, nullptr, nullptr, 0, 0, nullptr, cos_table, sin_table,
+                          k_cache, v_cache, hidden_buffer, normalized_out, out_token, position, nullptr, max_seq_len,
+                          attn_scale, mode, stream);
+}
+
+extern "C" int qmk_decode_step_mrope(qmk_model* m, int head_index, int input_token_id, const void* embed_weight,
+                                     const void* cos_table, const void* sin_table, void* k_cache, void* v_cache,
+                                     void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
+                                     const int32_t* rope_pos, int max_seq_len, float attn_scale, void* stream) {
+  if (!rope_pos) return set_error(QMK_ERR_ARG, "qmk_decode_step_mrope: rope_pos is null");
+  return decode_step_impl(m, head_index, input_token_id, embed_weight, nullptr, nullptr, 0, 0, nullptr, cos_table, sin_table,
+                          k_cache, v_cache, hidden_buffer, normalized_out, out_token, position, rope_pos, max_seq_len,
+                          attn_scale, 0, stream);
+}
+
+// Axis map of multimodal RoPE.  Chunked (Qwen2-VL `apply_multimodal_rotary_pos_emb`: the 64 rotary frequencies are cut into
+// consecutive sections of section[0], section[1], section[2] entries that take the temporal / height / width position) or
+// interleaved (Qwen3-VL `apply_interleaved_mrope`: frequency i < 3 section[a] with i % 3 == a takes axis a = 1, 2; the rest axis 0).
+extern "C" int qmk_model_set_mrope(qmk_model* m, const int32_t* section, int interleaved) {
+  if (!m) return set_error(QMK_ERR_ARG, "qmk_model_set_mrope: model is null");
+  m->rope_axis[0] = m->rope_axis[1] = 0ull;
+  if (!section) return QMK_OK;   // back to standard RoPE
+  if (m->e->version != 2) return set_error(QMK_ERR_UNSUPPORTED, "M-RoPE needs the group kernel");
+  if (section[0] < 0 || section[1] < 0 || section[2] < 0 || section[0] + section[1] + section[2] != HD / 2)
+    return set_error(QMK_ERR_ARG, "qmk_model_set_mrope: sections %d + %d + %d must add up to %d", section[0], section[1], section[2], HD / 2);
+  for (int i = 0; i < HD / 2; ++i) {
+    unsigned long long axis;
+    if (interleaved) axis = (i % 3 == 1 && i < 3 * section[1]) ? 1ull : ((i % 3 == 2 && i < 3 * section[2]) ? 2ull : 0ull);
+    else axis = i < section[0] ? 0ull : (i < section[0] + section[1] ? 1ull : 2ull);
+    m->rope_axis[i >> 5] |= axis << (2 * (i & 31));
+  }
+  return QMK_OK;
 }
 
 extern "C" int qmk_decode_step_codes(qmk_model* m, int head_index, const int64_t* codes, const void* talker_embed_weight,
-                                     const void* const* group_embedding_tables, const void* extra_embed_bf16,
-                                     const void* cos_table, const void* sin_table, void* k_cache, void* v_cache,
-                                     void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
+                                     int talker_vocab, const void* const* group_embedding_tables, int group_vocab,
+                                     const void* extra_embed_bf16, const void* cos_table, const void* sin_table, void* k_cache,
+                                     void* v_cache, void* hidden_buffer, float* normalized_out, int32_t* out_token, int position,
                                      int max_seq_len, float attn_scale, void* stream) {
   if (!codes || !talker_embed_weight || !group_embedding_tables || !extra_embed_bf16)
     return set_error(QMK_ERR_ARG, "qmk_decode_step_codes: null argument");
   for (int g = 0; g < 15; ++g)
     if (!group_embedding_tables[g]) return set_error(QMK_ERR_ARG, "qmk_decode_step_codes: group table %d is null", g);
-  return decode_step_impl(m, head_index, -1, talker_embed_weight, codes, group_embedding_tables, extra_embed_bf16,
-                          cos_table, sin_table, k_cache, v_cache, hidden_buffer, normalized_out, out_token, position,
-                          max_seq_len, attn_scale, 0, stream);
+  return decode_step_impl(m, head_index, -1, talker_embed_weight, codes, group_embedding_tables, talker_vocab, group_vocab,
+                          extra_embed_bf16, cos_table, sin_table, k_cache, v_cache, hidden_buffer, normalized_out, out_token,
+                          position, nullptr, max_seq_len, attn_scale, 0, stream);
 }
 
-static int cp_predict_impl(qmk_model* m, const float* talker_hidden, int first_codebook_token,
-                           const int32_t* first_token_dev, int talker_vocab, const void* talker_embed_weight,
-                           const void* cos_table, const void* sin_table, void* k_cache, void* v_cache, int max_seq_len,
-                           int do_sample, float temperature, int top_k, uint64_t seed, uint64_t frame_counter,
-                           const int32_t* forced_tokens, int64_t* out_codes, float* logits_out, float* hidden_out,
-                           void* stream) {
-  if (!m || !talker_hidden || !talker_embed_weight || !cos_table || !sin_table || !k_cache || !v_cache || !out_codes)
-    return set_error(QMK_ERR_ARG, "qmk_cp_predict: null argument");
-  if (max_seq_len < QMK_CP_GROUPS + 1) return set_error(QMK_ERR_ARG, "qmk_cp_predict: max_seq_len %d < 16", max_seq_len);
-  if (!first_token_dev && first_codebook_token < 0) return set_error(QMK_ERR_ARG, "qmk_cp_predict: negative first token");
-  if (first_token_dev && talker_vocab < 1) return set_error(QMK_ERR_ARG, "qmk_cp_predict_dev: talker_vocab must be positive");
-  if ((int)m->heads.size() < QMK_CP_GROUPS) return set_error(QMK_ERR_ARG, "qmk_cp_predict: %d group heads registered, need 15", (int)m->heads.size());
-  for (int g = 0; g < QMK_CP_GROUPS - 1; ++g)
-    if (!m->group_embed[g]) return set_error(QMK_ERR_ARG, "qmk_cp_predict: group embedding %d not set", g);
-  const bool sample = do_sample && temperature > 0.f;
-  qmk_engine* e = m->e;
-  DeviceGuard guard(e->device);
-  cudaStream_t st = (cudaStream_t)stream;
-  std::lock_guard<std::mutex> lock(e->mu);
-
-  Params p;
-  fill_common(p, m, cos_table, sin_table, k_cache, v_cache, max_seq_len, 0.08838834764831845f /* 1/sqrt(128) */);
-  p.n_steps = QMK_CP_GROUPS + 1;
-  p.sample_temperature = sample ? temperature : 1.0f;
-  p.sample_top_k = top_k;
-  p.sample_seed = seed;
-  p.sample_counter = frame_counter;
-  p.forced_tokens = forced_tokens;
-  p.code0_out = reinterpret_cast<long long*>(out_codes);
-  p.code0 = first_codebook_token;
-  p.code0_ptr = first_token_dev;
-  for (int s = 0; s < p.n_steps; ++s) {
+// Step program of one code-predictor frame on model slot `mi` (16 steps, 15 heads; upstream model_tts.py:742-773).
+static void fill_cp_steps(Params& p, int mi, qmk_model* m, const float* talker_hidden, int first_codebook_token,
+                          const int32_t* first_token_dev, int talker_vocab, const void* talker_embed_weight, bool sample,
+                          int64_t* out_codes, float* logits_out, float* hidden_out) {
+  for (int s = 0; s < QMK_CP_GROUPS + 1; ++s) {
     StepDesc& sd = p.steps[s];
-    sd.position = s;
+    init_step(sd, s);
+    sd.model = mi;
     sd.group = s - 1;
     if (s == 0) {           // the talker's hidden state (upstream model_tts.py:745)
       sd.in_mode = IN_VEC_F32;
@@ -631,15 +711,58 @@ static int cp_predict_impl(qmk_model* m, const float* talker_hidden, int first_c
       } else {              // embedding of the previous group's code (model_tts.py:768-770)
         sd.in_mode = IN_TABLE_PREV;
         sd.in_table = reinterpret_cast<const __nv_bfloat16*>(m->group_embed[s - 2]);
+        sd.token = m->heads[s - 2].rows - 1;   // clamp bound: the previous head's vocabulary = rows of its embedding table
       }
       set_head(sd, m, s - 1);
       sd.select = sample ? 1 : 0;
-      sd.out_code = reinterpret_cast<long long*>(out_codes) + s;
+      sd.out_code = out_codes ? reinterpret_cast<long long*>(out_codes) + s : nullptr;
       sd.logits_out = logits_out ? logits_out + (size_t)(s - 1) * m->heads[s - 1].rows : nullptr;
       sd.out_norm = hidden_out ? hidden_out + (size_t)(s - 1) * H : nullptr;
     }
   }
-  int rc = reserve_epochs(e, (uint32_t)p.n_steps * ((uint32_t)m->lay.L + 2u), st, &p.epoch_base);
+}
+static int check_cp_model(const qmk_model* m, const char* who) {
+  if ((int)m->heads.size() < QMK_CP_GROUPS) return set_error(QMK_ERR_ARG, "%s: %d group heads registered, need 15", who, (int)m->heads.size());
+  for (int g = 0; g < QMK_CP_GROUPS - 1; ++g)
+    if (!m->group_embed[g]) return set_error(QMK_ERR_ARG, "%s: group embedding %d not set", who, g);
+  return QMK_OK;
+}
+
+static int cp_predict_impl(qmk_model* m, const float* talker_hidden, int first_codebook_token,
+                           const int32_t* first_token_dev, int talker_vocab, const void* talker_embed_weight,
+                           const void* cos_table, const void* sin_table, void* k_cache, void* v_cache, int max_seq_len,
+                           int do_sample, float temperature, int top_k, uint64_t seed, uint64_t frame_counter,
+                           const int32_t* forced_tokens, int64_t* out_codes, float* logits_out, float* hidden_out,
+                           void* stream) {
+  if (!m || !talker_hidden || !talker_embed_weight || !cos_table || !sin_table || !k_cache || !v_cache || !out_codes)
+    return set_error(QMK_ERR_ARG, "qmk_cp_predict: null argument");
+  if (max_seq_len < QMK_CP_GROUPS + 1) return set_error(QMK_ERR_ARG, "qmk_cp_predict: max_seq_len %d < 16", max_seq_len);
+  if (!first_token_dev && first_codebook_token < 0) return set_error(QMK_ERR_ARG, "qmk_cp_predict: negative first token");
+  if (first_token_dev && talker_vocab < 1) return set_error(QMK_ERR_ARG, "qmk_cp_predict_dev: talker_vocab must be positive");
+  int rc = check_cp_model(m, "qmk_cp_predict");
+  if (rc != QMK_OK) return rc;
+  const bool sample = do_sample && temperature > 0.f;
+  qmk_engine* e = m->e;
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> lock(e->mu);
+  rc = order_after_previous_stream(e, st);
+  if (rc != QMK_OK) return rc;
+
+  Params p;
+  fill_common(p, m, cos_table, sin_table, k_cache, v_cache, max_seq_len, 0.08838834764831845f /* 1/sqrt(128) */);
+  p.n_steps = QMK_CP_GROUPS + 1;
+  p.sample_temperature = sample ? temperature : 1.0f;
+  p.sample_top_k = top_k;
+  p.sample_seed = seed;
+  p.sample_counter = frame_counter;
+  p.forced_tokens = forced_tokens;
+  p.code0_out = reinterpret_cast<long long*>(out_codes);
+  p.code0 = first_codebook_token;
+  p.code0_ptr = first_token_dev;
+  fill_cp_steps(p, 0, m, talker_hidden, first_codebook_token, first_token_dev, talker_vocab, talker_embed_weight, sample, out_codes,
+                logits_out, hidden_out);
+  rc = reserve_epochs(e, finish_program(p), st, &p.epoch_base);
   if (rc != QMK_OK) return rc;
   return launch_slice(e, p, 0, m->lay.L * PH_PER_LAYER + 2, st);
 }
@@ -665,39 +788,185 @@ extern "C" int qmk_cp_predict_dev(qmk_model* m, const float* talker_hidden, cons
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Device-autonomous frame loop: N codec frames (code-predictor frame + embedding sum + talker step each) with no host
+// round trip, EOS detected on the device.  Upstream analogue: launch_ldg_generate_nosync (kernel.cu:1555-1613) with
+// ldg_update_step (:1437-1448) between steps; here the loop lives inside the persistent kernel.
+// ---------------------------------------------------------------------------------------------------
+extern "C" int qmk_generate_args_size(void) { return (int)sizeof(qmk_generate_args); }
+
+extern "C" int qmk_generate_nosync(const qmk_generate_args* a, void* stream) {
+  if (!a) return set_error(QMK_ERR_ARG, "qmk_generate_nosync: args is null");
+  qmk_model* tk = a->talker;
+  qmk_model* cp = a->cp;
+  if (!tk || !cp) return set_error(QMK_ERR_ARG, "qmk_generate_nosync: model is null");
+  if (tk->e != cp->e) return set_error(QMK_ERR_ARG, "qmk_generate_nosync: both models must live on the same engine");
+  qmk_engine* e = tk->e;
+  if (e->version != 2) return set_error(QMK_ERR_UNSUPPORTED, "qmk_generate_nosync needs the group kernel");
+  if (!a->talker_embed_weight || !a->talker_cos || !a->talker_sin || !a->talker_k_cache || !a->talker_v_cache || !a->hidden_buffer ||
+      !a->talker_hidden || !a->talker_token || !a->cp_cos || !a->cp_sin || !a->cp_k_cache || !a->cp_v_cache ||
+      !a->group_embedding_tables || !a->pad_embed || !a->codes_out || !a->gen_state)
+    return set_error(QMK_ERR_ARG, "qmk_generate_nosync: null pointer argument");
+  if (a->talker_head < 0 || a->talker_head >= (int)tk->heads.size()) return set_error(QMK_ERR_ARG, "qmk_generate_nosync: talker head %d not registered", a->talker_head);
+  int rc = check_cp_model(cp, "qmk_generate_nosync");
+  if (rc != QMK_OK) return rc;
+  for (int g = 0; g < 15; ++g)
+    if (!a->group_embedding_tables[g]) return set_error(QMK_ERR_ARG, "qmk_generate_nosync: group table %d is null", g);
+  if (a->n_frames < 1) return set_error(QMK_ERR_ARG, "qmk_generate_nosync: n_frames %d", a->n_frames);
+  if (a->position < 0 || a->position + a->n_frames > a->talker_max_seq)
+    return set_error(QMK_ERR_ARG, "qmk_generate_nosync: positions %d .. %d exceed max_seq_len %d", a->position, a->position + a->n_frames - 1, a->talker_max_seq);
+  if (a->cp_max_seq < QMK_CP_GROUPS + 1) return set_error(QMK_ERR_ARG, "qmk_generate_nosync: cp_max_seq %d < 16", a->cp_max_seq);
+  if (a->talker_vocab < 1 || a->cp_vocab < 1) return set_error(QMK_ERR_ARG, "qmk_generate_nosync: vocab sizes must be positive");
+  if (a->n_trailing < 0 || a->trailing_offset < 0 || (a->n_trailing > 0 && !a->trailing_text)) return set_error(QMK_ERR_ARG, "qmk_generate_nosync: bad trailing text");
+  const bool sample = a->do_sample && a->temperature > 0.f;
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> lock(e->mu);
+  rc = order_after_previous_stream(e, st);
+  if (rc != QMK_OK) return rc;
+  if (a->reset_state) QMK_CUDA(cudaMemsetAsync(a->gen_state, 0, 4 * sizeof(int32_t), st));
+
+  const uint32_t epochs_per_frame = (uint32_t)(QMK_CP_GROUPS + 1) * ((uint32_t)cp->lay.L + 2u) + (uint32_t)tk->lay.L + 2u;
+  int max_chunk = (int)(0x7000u / epochs_per_frame);   // 16-bit epochs: a launch must not wrap (the buffer is cleared between launches)
+  if (max_chunk < 1) return set_error(QMK_ERR_UNSUPPORTED, "qmk_generate_nosync: a frame needs %u epochs", epochs_per_frame);
+  if (const char* env = getenv("QMK_FRAMES_PER_LAUNCH")) { int v = atoi(env); if (v >= 1 && v < max_chunk) max_chunk = v; }
+  for (int done = 0; done < a->n_frames;) {
+    const int chunk = std::min(max_chunk, a->n_frames - done);
+    Params p;
+    fill_common(p, tk, a->talker_cos, a->talker_sin, a->talker_k_cache, a->talker_v_cache, a->talker_max_seq, 0.08838834764831845f);
+    fill_model(p.models[1], cp, a->cp_cos, a->cp_sin, a->cp_k_cache, a->cp_v_cache, a->cp_max_seq);
+    p.n_steps = QMK_CP_GROUPS + 2;
+    p.sample_temperature = sample ? a->temperature : 1.0f;
+    p.sample_top_k = a->top_k;
+    p.sample_seed = a->seed;
+    p.sample_counter = a->frame_counter + (uint64_t)done;
+    p.code0_ptr = a->talker_token;
+    fill_cp_steps(p, 1, cp, a->talker_hidden, 0, a->talker_token, a->talker_vocab, a->talker_embed_weight, sample, nullptr, nullptr, nullptr);
+    p.steps[0].in_mode_next = IN_PREV_NORM;    // later frames: the talker's hidden state never leaves the chip
+    p.steps[1].in_mode_next = IN_TABLE_PREV;   // ... nor does its token
+    StepDesc& sd = p.steps[QMK_CP_GROUPS + 1];
+    init_step(sd, a->position + done);
+    if (a->rope_pos) for (int x = 0; x < 3; ++x) sd.rope_pos[x] = a->rope_pos[x] + done;
+    sd.model = 0;
+    sd.pos_per_frame = 1;
+    sd.in_mode = IN_CODES_SUM;                 // codes == null: the codes this CTA selected itself
+    sd.in_table = reinterpret_cast<const __nv_bfloat16*>(a->talker_embed_weight);
+    sd.in_vec = a->pad_embed;
+    for (int g = 0; g < 15; ++g) p.sum_tables[g] = reinterpret_cast<const __nv_bfloat16*>(a->group_embedding_tables[g]);
+    p.sum_rows0 = a->talker_vocab;
+    p.sum_rows = a->cp_vocab;
+    set_head(sd, tk, a->talker_head);
+    sd.out_token = a->talker_token;
+    sd.out_norm = a->talker_hidden;
+    sd.hidden_out = reinterpret_cast<__nv_bfloat16*>(a->hidden_buffer);
+    p.frames.n_frames = chunk;
+    p.frames.eos_token = a->eos_token;
+    p.frames.trailing = reinterpret_cast<const __nv_bfloat16*>(a->trailing_text);
+    p.frames.n_trailing = a->n_trailing;
+    p.frames.trailing_offset = a->trailing_offset;
+    p.frames.pad_embed = reinterpret_cast<const __nv_bfloat16*>(a->pad_embed);
+    p.frames.codes_out = reinterpret_cast<long long*>(a->codes_out) + (size_t)done * 16;
+    p.frames.tokens_out = a->tokens_out ? a->tokens_out + done : nullptr;
+    p.frames.gen_state = a->gen_state;
+    if (finish_program(p) != epochs_per_frame) return set_error(QMK_ERR_ARG, "qmk_generate_nosync: internal epoch accounting");
+    rc = reserve_epochs(e, epochs_per_frame * (uint32_t)chunk, st, &p.epoch_base);
+    if (rc != QMK_OK) return rc;
+    rc = launch_slice(e, p, 0, tk->lay.L * PH_PER_LAYER + 2, st);
+    if (rc != QMK_OK) return rc;
+    done += chunk;
+  }
+  return QMK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // upstream-compatible entry (kernel.cu:1485-1513).  Process-wide cache: device -> engine,
 // (device, blob pointer, num_layers) -> re-packed model.
 // ---------------------------------------------------------------------------------------------------
 namespace {
 struct LegacyCfg {
-  int residual_fp32 = 1;
-  int lm_head_rows = 3072;
+  int residual_fp32 = -1;   // -1 = infer from num_layers (see launch_ldg_decode_direct)
+  int lm_head_rows = -1;    // -1 = 3072 unless the head table is all zero (upstream's dummy), 0 = skip
 };
 struct LegacyModel {
   qmk_model* m = nullptr;
   const void* final_norm = nullptr;
-  std::map<const void*, int> heads;
+  int residual_fp32 = 1;
+  std::vector<uint64_t> blob;            // host copy of the 11 * L pointers the model was packed from
+  std::map<const void*, int> heads;      // LM-head table -> head index (-1: all-zero dummy table, no head)
 };
 std::mutex g_legacy_mu;
 std::map<int, qmk_engine*> g_engines;
 std::map<std::tuple<int, const void*, int>, LegacyModel> g_models;
 std::map<const void*, LegacyCfg> g_cfg;
 int g_legacy_status = QMK_OK;
+
+// 1 if the bf16 table is entirely zero (upstream's CodePredictorKernel passes torch.zeros as LM head, model_tts.py:657-659)
+__global__ void qmk_any_nonzero_kernel(const uint4* p, size_t n16, int* flag) {
+  int nz = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = p[i];
+    nz |= (v.x | v.y | v.z | v.w) != 0u;
+  }
+  if (nz) *flag = 1;
+}
+int table_is_zero(const void* table, size_t bytes, cudaStream_t st, bool* out) {
+  int* d_flag = nullptr;
+  int h_flag = 0;
+  QMK_CUDA(cudaMalloc(&d_flag, sizeof(int)));
+  cudaError_t err = cudaMemsetAsync(d_flag, 0, sizeof(int), st);
+  if (err == cudaSuccess) {
+    qmk_any_nonzero_kernel<<<148, 256, 0, st>>>(reinterpret_cast<const uint4*>(table), bytes / 16, d_flag);
+    err = cudaGetLastError();
+  }
+  if (err == cudaSuccess) err = cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+  cudaFree(d_flag);
+  if (err != cudaSuccess) return set_error(QMK_ERR_CUDA, "table_is_zero: %s", cudaGetErrorString(err));
+  *out = h_flag == 0;
+  return QMK_OK;
+}
 }  // namespace
 
 extern "C" int qmk_legacy_configure(const LDGLayerWeights* layer_weights, int residual_fp32, int lm_head_rows) {
   if (!layer_weights) return set_error(QMK_ERR_ARG, "qmk_legacy_configure: null blob");
-  if (lm_head_rows != 0 && (lm_head_rows < 64 || lm_head_rows > MAX_HEAD_ROWS))
+  if (lm_head_rows > 0 && (lm_head_rows < 64 || lm_head_rows > MAX_HEAD_ROWS))
     return set_error(QMK_ERR_ARG, "qmk_legacy_configure: lm_head_rows %d", lm_head_rows);
   std::lock_guard<std::mutex> lock(g_legacy_mu);
   LegacyCfg c;
-  c.residual_fp32 = residual_fp32 ? 1 : 0;
-  c.lm_head_rows = lm_head_rows;
+  c.residual_fp32 = residual_fp32 < 0 ? -1 : (residual_fp32 ? 1 : 0);
+  c.lm_head_rows = lm_head_rows < 0 ? -1 : lm_head_rows;
   g_cfg[layer_weights] = c;
   return QMK_OK;
 }
 
 extern "C" int qmk_legacy_status(void) { return g_legacy_status; }
+
+// Drop the re-packed copy of one blob (all devices): call after the weights behind it changed, or when the blob's
+// address may be re-used by another model.  Null drops every cached model but keeps the engines.
+extern "C" void qmk_legacy_invalidate(const LDGLayerWeights* layer_weights) {
+  std::lock_guard<std::mutex> lock(g_legacy_mu);
+  for (auto it = g_models.begin(); it != g_models.end();) {
+    if (!layer_weights || std::get<1>(it->first) == (const void*)layer_weights) {
+      qmk_model_destroy(it->second.m);
+      it = g_models.erase(it);
+    } else {
+      ++it;
+    }
+  }
+  if (layer_weights) g_cfg.erase(layer_weights); else g_cfg.clear();
+}
+
+// Synchronise `stream` and return + clear the device-side status of the legacy engine of the current device
+// (QMK_OK or QMK_ERR_KERNEL): what qmk_engine_sync_status is for engines the caller owns.
+extern "C" int qmk_legacy_sync_status(void* stream) {
+  std::lock_guard<std::mutex> lock(g_legacy_mu);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return set_error(QMK_ERR_CUDA, "qmk_legacy_sync_status: no CUDA device");
+  auto it = g_engines.find(dev);
+  if (it == g_engines.end()) return QMK_OK;
+  const int rc = qmk_engine_sync_status(it->second, stream, nullptr);
+  g_legacy_status = rc;
+  return rc;
+}
 
 extern "C" void qmk_legacy_release(void) {
   std::lock_guard<std::mutex> lock(g_legacy_mu);
@@ -722,6 +991,10 @@ extern "C" void launch_ldg_decode_direct(int input_token_id, int* output_token_i
     g_legacy_status = set_error(QMK_ERR_CUDA, "launch_ldg_decode_direct: no CUDA device");
     return;
   }
+  if (!layer_weights || num_layers < 1 || num_layers > 1024) {
+    g_legacy_status = set_error(QMK_ERR_ARG, "launch_ldg_decode_direct: bad layer blob / num_layers %d", num_layers);
+    return;
+  }
   qmk_engine*& e = g_engines[dev];
   if (!e) {
     int rc = qmk_engine_create(dev, 0, &e);
@@ -735,34 +1008,65 @@ extern "C" void launch_ldg_decode_direct(int input_token_id, int* output_token_i
   LegacyCfg cfg;
   auto ci = g_cfg.find(layer_weights);
   if (ci != g_cfg.end()) cfg = ci->second;
+  // Which upstream PyTorch path a blob is judged against: the 5-layer stack is the code predictor (bf16 residual stream,
+  // model_tts.py:567-619), anything else the talker (fp32 residual, validate_kernel.py:123-188); qmk_legacy_configure overrides.
+  const int residual_fp32 = cfg.residual_fp32 >= 0 ? cfg.residual_fp32 : (num_layers == 5 ? 0 : 1);
   LegacyModel& lm = g_models[std::make_tuple(dev, (const void*)layer_weights, num_layers)];
-  if (!lm.m || lm.final_norm != final_norm_weight) {
+  if (!lm.m || lm.final_norm != final_norm_weight || lm.residual_fp32 != residual_fp32) {
     if (lm.m) qmk_model_destroy(lm.m);
     lm = LegacyModel();
-    int rc = qmk_model_create(e, layer_weights, num_layers, final_norm_weight, cfg.residual_fp32, stream, &lm.m);
+    int rc = qmk_model_create(e, layer_weights, num_layers, final_norm_weight, residual_fp32, stream, &lm.m);
+    if (rc == QMK_OK) {   // remember which pointers were packed (the create call has synchronised the stream already)
+      lm.blob.resize((size_t)num_layers * 11);
+      if (cudaMemcpy(lm.blob.data(), layer_weights, lm.blob.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = set_error(QMK_ERR_CUDA, "launch_ldg_decode_direct: blob copy failed");
+    }
     if (rc != QMK_OK) {
+      if (lm.m) qmk_model_destroy(lm.m);
+      g_models.erase(std::make_tuple(dev, (const void*)layer_weights, num_layers));
       g_legacy_status = rc;
       fprintf(stderr, "[qmk] %s\n", qmk_last_error());
       return;
     }
     lm.final_norm = final_norm_weight;
+    lm.residual_fp32 = residual_fp32;
   }
   int head = -1;
-  if (cfg.lm_head_rows > 0) {
+  if (cfg.lm_head_rows != 0 && lm_head_weight) {
     auto hi = lm.heads.find(lm_head_weight);
     if (hi == lm.heads.end()) {
-      int rc = qmk_model_add_head(lm.m, lm_head_weight, cfg.lm_head_rows, stream);
-      if (rc < 0) {
+      const int rows = cfg.lm_head_rows > 0 ? cfg.lm_head_rows : 3072;   // upstream compile-time LDG_VOCAB_SIZE (build_tts.py:47)
+      bool zero = false;
+      int rc = cfg.lm_head_rows > 0 ? QMK_OK : table_is_zero(lm_head_weight, (size_t)rows * H * 2, (cudaStream_t)stream, &zero);
+      if (rc == QMK_OK && zero) rc = -1;   // dummy table: no head; the argmax of all-zero logits is token 0
+      else if (rc == QMK_OK) rc = qmk_model_add_head(lm.m, lm_head_weight, rows, stream);
+      if (rc < 0 && !zero) {
         g_legacy_status = rc;
         fprintf(stderr, "[qmk] %s\n", qmk_last_error());
         return;
       }
-      hi = lm.heads.emplace(lm_head_weight, rc).first;
+      hi = lm.heads.emplace(lm_head_weight, zero ? -1 : rc).first;
     }
     head = hi->second;
   }
+  if (head < 0 && output_token_id) cudaMemsetAsync(output_token_id, 0, sizeof(int), (cudaStream_t)stream);
   g_legacy_status = qmk_decode_step(lm.m, head, input_token_id, embed_weight, cos_table, sin_table, k_cache, v_cache,
                                     hidden_buffer, reinterpret_cast<float*>(g_normalized), output_token_id, position,
                                     max_seq_len, attn_scale, 0, stream);
   if (g_legacy_status != QMK_OK) fprintf(stderr, "[qmk] %s\n", qmk_last_error());
+}
+
+// Compare the blob a cached model was packed from with the caller's current blob (HOST copy of the 11 * L pointers):
+// returns 1 if they differ (the model is dropped and re-packed on the next call), 0 if equal or unknown.  The Python op
+// calls this with the blob tensor's identity / version so that a recycled allocator address cannot alias a stale model.
+extern "C" int qmk_legacy_check_blob(const LDGLayerWeights* layer_weights, int num_layers, const uint64_t* host_blob) {
+  if (!layer_weights || !host_blob) return 0;
+  std::lock_guard<std::mutex> lock(g_legacy_mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto it = g_models.find(std::make_tuple(dev, (const void*)layer_weights, num_layers));
+  if (it == g_models.end() || it->second.blob.empty()) return 0;
+  if (memcmp(it->second.blob.data(), host_blob, it->second.blob.size() * 8) == 0) return 0;
+  qmk_model_destroy(it->second.m);
+  g_models.erase(it);
+  return 1;
 }

@@ -12,10 +12,13 @@ raises.
 from __future__ import annotations
 
 import ctypes
+import glob
+import hashlib
 import os
 import shutil
 import subprocess
 import threading
+import weakref
 
 import torch
 
@@ -43,18 +46,47 @@ def _nvcc() -> str | None:
     return cand if os.path.exists(cand) else shutil.which("nvcc")
 
 
+def source_files() -> list[str]:
+    """Every file the library is compiled from: csrc/*.cu, csrc/*.cuh, include/*.h."""
+    return sorted(glob.glob(os.path.join(_CSRC, "*.cu")) + glob.glob(os.path.join(_CSRC, "*.cuh")) +
+                  glob.glob(os.path.join(_INCLUDE, "*.h")))
+
+
+def source_hash() -> str:
+    """Content hash of the sources (and the compiler flags); compiled into the library as qmk_source_hash()."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + os.environ.get("QMK_NVCC_EXTRA", "").split()).encode())
+    for path in source_files():
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def library_hash(path: str = LIB_PATH) -> str | None:
+    """The source hash a built library carries, read from the file WITHOUT loading it (a dlopen here would pin the old
+    image in the process and a rebuild would then be invisible); None if the file predates the hash."""
+    import re
+    try:
+        with open(path, "rb") as f:
+            m = re.search(rb"QMK_SRC_HASH:([0-9a-f]{16})", f.read())
+    except OSError:
+        return None
+    return m.group(1).decode() if m else None
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/qmk_engine.cu -> libqmk_b200.so (cross-compiles without a GPU)."""
+    """Compile csrc/*.cu -> libqmk_b200.so (cross-compiles without a GPU).
+
+    Staleness is decided by CONTENT: the library carries the hash of the sources it was compiled from and is rebuilt
+    whenever that differs from the tree (an edited header can no longer leave a stale binary behind)."""
     srcs = [os.path.join(_CSRC, "qmk_engine.cu"), os.path.join(_CSRC, "qmk_batched.cu")]
-    deps = srcs + [os.path.join(_CSRC, "qmk_device.cuh"), os.path.join(_CSRC, "qmk_bgemm.cuh"),
-                   os.path.join(_INCLUDE, "qmk_b200.h")]
-    if not force and os.path.exists(LIB_PATH):
-        if all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps if os.path.exists(d)):
-            return LIB_PATH
+    want = source_hash()
+    if not force and os.path.exists(LIB_PATH) and library_hash(LIB_PATH) == want:
+        return LIB_PATH
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError("qwen_megakernel: libqmk_b200.so is missing/stale and nvcc was not found")
-    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("QMK_NVCC_EXTRA", "").split() + ["-Xptxas", "-v"] * int(verbose) + [f"-I{_INCLUDE}", f"-I{_CSRC}", "-o", LIB_PATH] + srcs
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("QMK_NVCC_EXTRA", "").split() + ["-Xptxas", "-v"] * int(verbose) + [f'-DQMK_SRC_HASH="{want}"', f"-I{_INCLUDE}", f"-I{_CSRC}", "-o", LIB_PATH] + srcs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
@@ -69,6 +101,7 @@ _vp, _i32, _f32, _u64, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, cty
 SIGNATURES = {
     "qmk_abi_version": (_i32, []),
     "qmk_last_error": (ctypes.c_char_p, []),
+    "qmk_source_hash": (ctypes.c_char_p, []),
     "qmk_engine_create": (_i32, [_i32, _i32, ctypes.POINTER(_vp)]),
     "qmk_engine_destroy": (None, [_vp]),
     "qmk_engine_num_ctas": (_i32, [_vp]),
@@ -79,11 +112,16 @@ SIGNATURES = {
     "qmk_model_create": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, ctypes.POINTER(_vp)]),
     "qmk_model_add_head": (_i32, [_vp, _vp, _i32, _vp]),
     "qmk_model_set_group_embedding": (_i32, [_vp, _i32, _vp]),
+    "qmk_model_set_mrope": (_i32, [_vp, ctypes.POINTER(ctypes.c_int32), _i32]),
     "qmk_model_destroy": (None, [_vp]),
     "qmk_model_packed_bytes": (_i64, [_vp]),
     "qmk_decode_step": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _vp]),
-    "qmk_decode_step_codes": (_i32, [_vp, _i32, _vp, _vp, ctypes.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
-                                     _i32, _f32, _vp]),
+    "qmk_decode_step_mrope": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
+                                     ctypes.POINTER(ctypes.c_int32), _i32, _f32, _vp]),
+    "qmk_decode_step_codes": (_i32, [_vp, _i32, _vp, _vp, _i32, ctypes.POINTER(_vp), _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                     _i32, _i32, _f32, _vp]),
+    "qmk_generate_nosync": (_i32, [_vp, _vp]),
+    "qmk_generate_args_size": (_i32, []),
     "qmk_cp_predict": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _u64, _u64, _vp,
                               _vp, _vp, _vp, _vp]),
     "qmk_cp_predict_dev": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, _u64, _u64, _vp, _vp]),
@@ -95,6 +133,9 @@ SIGNATURES = {
                                         _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
     "qmk_legacy_configure": (_i32, [_vp, _i32, _i32]),
     "qmk_legacy_status": (_i32, []),
+    "qmk_legacy_sync_status": (_i32, [_vp]),
+    "qmk_legacy_invalidate": (None, [_vp]),
+    "qmk_legacy_check_blob": (_i32, [_vp, _i32, _vp]),
     "qmk_legacy_release": (None, []),
 }
 
@@ -113,6 +154,23 @@ def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
 
 class NativeError(RuntimeError):
     pass
+
+
+class GenerateArgs(ctypes.Structure):
+    """Mirror of ``qmk_generate_args`` (include/qmk_b200.h)."""
+    _fields_ = [
+        ("talker", _vp), ("talker_head", ctypes.c_int32), ("talker_vocab", ctypes.c_int32),
+        ("talker_embed_weight", _vp), ("talker_cos", _vp), ("talker_sin", _vp), ("talker_k_cache", _vp),
+        ("talker_v_cache", _vp), ("talker_max_seq", ctypes.c_int32), ("position", ctypes.c_int32),
+        ("rope_pos", ctypes.POINTER(ctypes.c_int32)), ("hidden_buffer", _vp), ("talker_hidden", _vp),
+        ("talker_token", _vp), ("cp", _vp), ("cp_cos", _vp), ("cp_sin", _vp), ("cp_k_cache", _vp), ("cp_v_cache", _vp),
+        ("cp_max_seq", ctypes.c_int32), ("cp_vocab", ctypes.c_int32), ("group_embedding_tables", ctypes.POINTER(_vp)),
+        ("n_frames", ctypes.c_int32), ("eos_token", ctypes.c_int32), ("trailing_text", _vp),
+        ("n_trailing", ctypes.c_int32), ("trailing_offset", ctypes.c_int32), ("pad_embed", _vp),
+        ("do_sample", ctypes.c_int32), ("top_k", ctypes.c_int32), ("temperature", ctypes.c_float),
+        ("reset_state", ctypes.c_int32), ("seed", ctypes.c_uint64), ("frame_counter", ctypes.c_uint64),
+        ("codes_out", _vp), ("tokens_out", _vp), ("gen_state", _vp),
+    ]
 
 
 def check(lib, rc: int, what: str):
@@ -158,6 +216,7 @@ def _decode_op(output_token, input_token_id, embed_weight, layer_weights_packed,
         raise ValueError("decode: hidden_buffer / normalized must have 1024 elements")
     if not (0 <= int(position) < int(max_seq_len)):
         raise ValueError(f"decode: position {position} outside [0, {max_seq_len})")
+    _revalidate_blob(lib, layer_weights_packed, int(num_layers))
     with torch.cuda.device(hidden_buffer.device):
         stream = torch.cuda.current_stream().cuda_stream
         lib.launch_ldg_decode_direct(
@@ -172,6 +231,23 @@ def _decode_op(output_token, input_token_id, embed_weight, layer_weights_packed,
         raise NativeError(f"decode: {lib.qmk_last_error().decode()} (code {rc})")
 
 
+# The C entry caches the re-packed weights by blob ADDRESS; torch's caching allocator re-uses addresses.  Remember which
+# tensor (identity + in-place version) was seen at an address; when another one shows up there, compare the pointer table
+# it holds with the one the cached model was packed from and drop the model if they differ.
+_blob_seen: dict = {}
+
+
+def _revalidate_blob(lib, blob: torch.Tensor, num_layers: int) -> None:
+    key = (blob.device.index, blob.data_ptr(), num_layers)
+    ent = _blob_seen.get(key)
+    if ent is not None and ent[0]() is blob and ent[1] == blob._version:
+        return
+    if ent is not None:     # same address, different tensor or modified in place: one D2H copy of 88 bytes per layer
+        host = blob.cpu().contiguous()
+        lib.qmk_legacy_check_blob(blob.data_ptr(), num_layers, host.data_ptr())
+    _blob_seen[key] = (weakref.ref(blob), blob._version)
+
+
 class _Extension:
     """What ``get_extension()`` returns: the loaded C-ABI library plus the registered torch op."""
 
@@ -179,6 +255,13 @@ class _Extension:
         self.lib = lib
         self.decode = torch.ops.qwen_megakernel_C.decode
         self.path = LIB_PATH
+
+    def sync_status(self) -> None:
+        """Synchronise the current stream and raise if a ``decode`` launch since the last call failed on the device
+        (watchdog); clears the condition so that later calls work again."""
+        rc = self.lib.qmk_legacy_sync_status(torch.cuda.current_stream().cuda_stream)
+        if rc < 0:
+            raise NativeError(f"decode: {self.lib.qmk_last_error().decode()} (code {rc})")
 
 
 _ext = None
@@ -192,7 +275,7 @@ def get_extension():
             return _ext
         path = build()
         _lib = load_library(path)
-        if _lib.qmk_abi_version() != 1:
+        if _lib.qmk_abi_version() != 2:
             raise RuntimeError("qwen_megakernel: ABI version mismatch between Python layer and libqmk_b200.so")
         _op_lib = torch.library.Library("qwen_megakernel_C", "DEF")
         _op_lib.define(DECODE_SCHEMA)

@@ -160,7 +160,12 @@ def _require_cuda_bf16(t: torch.Tensor, n: int, what: str) -> None:
 
 
 class _Native:
-    """Process-wide handle on libqmk_b200.so plus one engine per CUDA device."""
+    """Process-wide handle on libqmk_b200.so plus one engine per CUDA device.
+
+    Every ``TTSDecoder`` / ``CodePredictorKernel`` on a device shares that device's engine (exchange words, accumulator
+    totals, epoch counter), so their launches execute in submission order: the C layer makes a launch on a different
+    CUDA stream wait for the engine's previous stream (include/qmk_b200.h).  Launches from several host threads are
+    serialised by the engine's mutex; they never overlap on the GPU."""
 
     _engines: dict = {}
 
@@ -217,6 +222,7 @@ class TTSDecoder:
         self._weights = weights
         self._position = 0
         self._mode = mode
+        self._mrope_delta = None
         self._max_seq = int(max_seq_len)
         # num_layers is a runtime parameter of the kernel (upstream passes 28 or 5, model_tts.py:278,724)
         self._num_layers = int(num_layers) if num_layers is not None else len(weights["layer_weights"]) // 11
@@ -266,16 +272,43 @@ class TTSDecoder:
         except Exception:
             pass
 
-    def _launch(self, token_id: int, input_ptr: int) -> None:
+    def _launch(self, token_id: int, input_ptr: int, rope_pos=None) -> None:
         from .build_tts import check
         if self._position >= self._max_seq:
             raise IndexError(f"KV cache is full (position {self._position} == max_seq_len)")
-        check(self._lib, self._lib.qmk_decode_step(
-            self._model, self._head, token_id, self._embed_weight.data_ptr(), self._cos_table.data_ptr(),
-            self._sin_table.data_ptr(), self._k_cache.data_ptr(), self._v_cache.data_ptr(), input_ptr,
-            self._norm_out.data_ptr(), self._out_token.data_ptr(), self._position, self._max_seq,
-            self._attn_scale, self._mode, _stream_ptr(self.device)), "qmk_decode_step")
+        if rope_pos is None and self._mrope_delta is not None:
+            rope_pos = tuple(self._position + d for d in self._mrope_delta)
+        if rope_pos is not None:
+            rp = (ctypes.c_int32 * 3)(*[int(v) for v in rope_pos])
+            if min(rp) < 0 or max(rp) >= self._cos_table.shape[0]:
+                raise ValueError(f"rope_pos {tuple(rp)} outside the RoPE tables")
+            check(self._lib, self._lib.qmk_decode_step_mrope(
+                self._model, self._head, token_id, self._embed_weight.data_ptr(), self._cos_table.data_ptr(),
+                self._sin_table.data_ptr(), self._k_cache.data_ptr(), self._v_cache.data_ptr(), input_ptr,
+                self._norm_out.data_ptr(), self._out_token.data_ptr(), self._position, rp, self._max_seq,
+                self._attn_scale, _stream_ptr(self.device)), "qmk_decode_step_mrope")
+        else:
+            check(self._lib, self._lib.qmk_decode_step(
+                self._model, self._head, token_id, self._embed_weight.data_ptr(), self._cos_table.data_ptr(),
+                self._sin_table.data_ptr(), self._k_cache.data_ptr(), self._v_cache.data_ptr(), input_ptr,
+                self._norm_out.data_ptr(), self._out_token.data_ptr(), self._position, self._max_seq,
+                self._attn_scale, self._mode, _stream_ptr(self.device)), "qmk_decode_step")
         self._position += 1
+
+    def set_mrope(self, section=(24, 20, 20), interleaved: bool = False, delta=(0, 0, 0)) -> None:
+        """Switch the talker to multimodal RoPE (upstream's documented gap, README.md:208: the checkpoint is trained with
+        ``mrope_section = [24, 20, 20]`` while upstream's kernel applies standard RoPE).  Rotary frequency ``i`` then takes
+        the cos/sin row of the position of its axis (temporal / height / width).  ``delta``: per-axis offset added to the
+        sequence position when ``step`` / ``step_with_embed`` are called without explicit ``rope_pos`` (text-only TTS
+        uses the same position on all three axes, i.e. ``(0, 0, 0)``).  ``section=None`` restores standard RoPE."""
+        from .build_tts import check
+        if section is None:
+            check(self._lib, self._lib.qmk_model_set_mrope(self._model, None, 0), "qmk_model_set_mrope")
+            self._mrope_delta = None
+            return
+        sec = (ctypes.c_int32 * 3)(*[int(v) for v in section])
+        check(self._lib, self._lib.qmk_model_set_mrope(self._model, sec, int(bool(interleaved))), "qmk_model_set_mrope")
+        self._mrope_delta = tuple(int(v) for v in delta)
 
     def _finish(self) -> tuple[int, torch.Tensor]:
         hidden = self._norm_out.clone()
@@ -284,15 +317,16 @@ class TTSDecoder:
             _Native.raise_kernel_status(self.device, "TTSDecoder.step")
         return token, hidden
 
-    def step(self, token_id: int) -> tuple[int, torch.Tensor]:
-        """Decode one token via embedding lookup. Returns (next_token, hidden_state_f32)."""
+    def step(self, token_id: int, *, rope_pos=None) -> tuple[int, torch.Tensor]:
+        """Decode one token via embedding lookup. Returns (next_token, hidden_state_f32).
+        ``rope_pos``: optional (t, h, w) M-RoPE positions of this step (after ``set_mrope``)."""
         token_id = int(token_id)
         if not 0 <= token_id < VOCAB_SIZE:
             raise ValueError(f"token id {token_id} outside [0, {VOCAB_SIZE})")
-        self._launch(token_id, self._hidden.data_ptr())
+        self._launch(token_id, self._hidden.data_ptr(), rope_pos)
         return self._finish()
 
-    def step_with_embed(self, embed_bf16: torch.Tensor) -> tuple[int, torch.Tensor]:
+    def step_with_embed(self, embed_bf16: torch.Tensor, *, rope_pos=None) -> tuple[int, torch.Tensor]:
         """Decode from a precomputed bf16[1024] embedding (upstream sentinel path, token_id = -1)."""
         if embed_bf16.dtype != torch.bfloat16:
             embed_bf16 = embed_bf16.to(torch.bfloat16)
@@ -301,7 +335,7 @@ class TTSDecoder:
             embed_bf16 = embed_bf16.to(self.device)
         _require_cuda_bf16(embed_bf16.contiguous(), HIDDEN_SIZE, "step_with_embed(embed_bf16)")
         self._hidden.copy_(embed_bf16)
-        self._launch(EMBED_FROM_BUFFER, self._hidden.data_ptr())
+        self._launch(EMBED_FROM_BUFFER, self._hidden.data_ptr(), rope_pos)
         return self._finish()
 
     def step_with_codes(self, codes: torch.Tensor, code_embeddings, extra_embed_bf16: torch.Tensor, *, sync: bool = True):
@@ -329,12 +363,110 @@ class TTSDecoder:
         tables = (ctypes.c_void_p * 15)(*[t.data_ptr() for t in code_embeddings])
         codes = codes.contiguous()
         check(self._lib, self._lib.qmk_decode_step_codes(
-            self._model, self._head, codes.data_ptr(), self._embed_weight.data_ptr(), tables, extra.data_ptr(),
+            self._model, self._head, codes.data_ptr(), self._embed_weight.data_ptr(), int(self._embed_weight.shape[0]),
+            tables, int(min(t.shape[0] for t in code_embeddings)), extra.data_ptr(),
             self._cos_table.data_ptr(), self._sin_table.data_ptr(), self._k_cache.data_ptr(), self._v_cache.data_ptr(),
             self._hidden.data_ptr(), self._norm_out.data_ptr(), self._out_token.data_ptr(), self._position,
             self._max_seq, self._attn_scale, _stream_ptr(self.device)), "qmk_decode_step_codes")
         self._position += 1
         return self._finish() if sync else (self._out_token, self._norm_out)
+
+    def generate_frames(self, code_predictor: "CodePredictorKernel", n_frames: int, trailing_text=None,
+                        pad_embed_bf16: Optional[torch.Tensor] = None, *, do_sample: bool = True,
+                        temperature: float = 0.9, top_k: int = 50, eos_token: int = CODEC_EOS, trailing_offset: int = 0,
+                        host_visible: bool = False, sync: bool = True):
+        """Up to ``n_frames`` codec frames of the upstream loop (tts_engine.py:301-335) WITHOUT the host in it: the
+        persistent kernel itself iterates ``predict -> 16-way embedding sum + trailing text -> talker step``, checks EOS on
+        the device and stops there (``qmk_generate_nosync``; upstream analogue: ``generate_nosync``).  Must follow a talker
+        step (``step(CODEC_BOS)`` in the upstream flow): the loop starts from that step's token and hidden state.
+
+        ``trailing_text``: bf16[T, 1024] embeddings added to frame ``trailing_offset + f`` while it lasts, afterwards
+        ``pad_embed_bf16`` (the tts_pad embedding).  ``host_visible=True`` puts codes / tokens / progress word into pinned
+        host memory that the kernel writes directly, so another host thread can consume frames while generation runs
+        (``state[0]`` = frames finished).  ``sync=True`` waits and returns ``(codes[n_done, 16], tokens[n_done], n_done)``
+        with ``position`` advanced by ``n_done``; ``sync=False`` returns ``(codes, tokens, state)`` buffers immediately --
+        call ``finish_generate(state)`` before the next talker step."""
+        from .build_tts import GenerateArgs, check
+        cp = code_predictor
+        n_frames = int(n_frames)
+        if n_frames < 1:
+            raise ValueError("n_frames must be >= 1")
+        if cp.device != self.device:
+            raise ValueError("talker and code predictor must live on the same device")
+        if self._position + n_frames > self._max_seq:
+            raise IndexError(f"{n_frames} frames from position {self._position} exceed max_seq_len {self._max_seq}")
+        dev = self.device
+        with torch.cuda.device(dev):
+            if pad_embed_bf16 is None:
+                pad_embed_bf16 = torch.zeros(HIDDEN_SIZE, dtype=torch.bfloat16, device=dev)
+            pad = pad_embed_bf16.to(dev, torch.bfloat16).reshape(-1).contiguous()
+            _require_cuda_bf16(pad, HIDDEN_SIZE, "generate_frames(pad_embed_bf16)")
+            trail, n_trail = None, 0
+            if trailing_text is not None and trailing_text.numel() > 0:
+                trail = trailing_text.to(dev, torch.bfloat16).reshape(-1, HIDDEN_SIZE).contiguous()
+                n_trail = trail.shape[0]
+            if host_visible:
+                codes = torch.zeros(n_frames, NUM_CODE_GROUPS, dtype=torch.int64).pin_memory()
+                tokens = torch.zeros(n_frames, dtype=torch.int32).pin_memory()
+                state = torch.zeros(4, dtype=torch.int32).pin_memory()
+            else:
+                codes = torch.zeros(n_frames, NUM_CODE_GROUPS, dtype=torch.int64, device=dev)
+                tokens = torch.zeros(n_frames, dtype=torch.int32, device=dev)
+                state = torch.zeros(4, dtype=torch.int32, device=dev)
+            tables = (ctypes.c_void_p * 15)(*[t.data_ptr() for t in cp.codec_embeddings])
+            rope = None
+            if self._mrope_delta is not None:
+                rope = (ctypes.c_int32 * 3)(*[self._position + d for d in self._mrope_delta])
+            cp._frame_counter += 1
+            a = GenerateArgs(
+                talker=self._model, talker_head=self._head, talker_vocab=int(self._embed_weight.shape[0]),
+                talker_embed_weight=self._embed_weight.data_ptr(), talker_cos=self._cos_table.data_ptr(),
+                talker_sin=self._sin_table.data_ptr(), talker_k_cache=self._k_cache.data_ptr(),
+                talker_v_cache=self._v_cache.data_ptr(), talker_max_seq=self._max_seq, position=self._position,
+                rope_pos=rope, hidden_buffer=self._hidden.data_ptr(), talker_hidden=self._norm_out.data_ptr(),
+                talker_token=self._out_token.data_ptr(), cp=cp._model, cp_cos=cp._cos_table.data_ptr(),
+                cp_sin=cp._sin_table.data_ptr(), cp_k_cache=cp._k_cache.data_ptr(), cp_v_cache=cp._v_cache.data_ptr(),
+                cp_max_seq=cp._max_seq, cp_vocab=CODE_PREDICTOR_VOCAB, group_embedding_tables=tables,
+                n_frames=n_frames, eos_token=int(eos_token), trailing_text=trail.data_ptr() if trail is not None else None,
+                n_trailing=n_trail, trailing_offset=int(trailing_offset), pad_embed=pad.data_ptr(),
+                do_sample=int(bool(do_sample) and temperature > 0), top_k=int(top_k), temperature=float(temperature),
+                reset_state=1, seed=torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, frame_counter=cp._frame_counter,
+                codes_out=codes.data_ptr(), tokens_out=tokens.data_ptr(), gen_state=state.data_ptr())
+            check(self._lib, self._lib.qmk_generate_nosync(ctypes.byref(a), _stream_ptr(dev)), "qmk_generate_nosync")
+            cp._frame_counter += n_frames
+            cp._position = NUM_CODE_GROUPS
+            self._gen_keep = (a, tables, rope, pad, trail, codes, tokens, state)   # buffers the queued launches still use
+            self._gen_pending = n_frames
+            if not sync:
+                return codes, tokens, state
+            n_done = self.finish_generate(state)
+            return codes[:n_done], tokens[:n_done], n_done
+
+    def finish_generate(self, state: torch.Tensor) -> int:
+        """Wait for a ``generate_frames(sync=False)`` run; advances ``position`` by the frames it produced and returns
+        their number (fewer than requested if the talker emitted EOS)."""
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream().synchronize()
+        st = state.cpu().tolist()
+        n_done = int(st[0])
+        if n_done < 0 or n_done > getattr(self, "_gen_pending", 0):
+            raise RuntimeError(f"generate_frames: inconsistent progress word {st}")
+        if int(self._out_token.item()) < 0:
+            _Native.raise_kernel_status(self.device, "TTSDecoder.generate_frames")
+        self._position += n_done
+        self._gen_pending = 0
+        self._gen_keep = None
+        return n_done
+
+    def frame(self, code_predictor: "CodePredictorKernel", extra_embed_bf16: torch.Tensor, *, do_sample: bool = True,
+              temperature: float = 0.9, top_k: int = 50, eos_token: int = CODEC_EOS):
+        """ONE launch for one frame of the upstream loop (predict + embedding sum + talker step), with the device-side
+        EOS flag: returns ``(codes int64[16] or None if the preceding token was EOS, next_token, hidden)``."""
+        codes, tokens, n = self.generate_frames(code_predictor, 1, None, extra_embed_bf16, do_sample=do_sample,
+                                                temperature=temperature, top_k=top_k, eos_token=eos_token)
+        if n == 0:
+            return None, int(eos_token), self._norm_out.clone()
+        return codes[0], int(tokens[0].item()), self._norm_out.clone()
 
     def reset(self):
         """New utterance.  O(1): rows beyond ``position`` are never read."""

@@ -14,6 +14,10 @@ qwen-megakernel-tts_b200/qwen_megakernel/synthetic.py.  Outputs (committed):
   tests/golden/talker_mixed.npz     BOS + 39 steps alternating caller embeddings / token feedback
   tests/golden/cp_config2.npz       code-predictor frames, greedy        (BASELINE.json configs[1])
   tests/golden/meta.json            torch version, cpu capability, weights fingerprint
+  tests/golden/frame_loop.npz       (``--only frames``) the full frame loop of tts_engine.py:246-335, greedy: 8 prefill
+                                    steps, step(CODEC_BOS), then N_FRAMES x {CodePredictor.predict, 16-way embedding sum +
+                                    trailing text / pad, step_with_embed}: talker positions run to 8 + N_FRAMES, i.e. past
+                                    the attention boundaries at 40 / 80 cached positions at full depth (28 layers)
 Hidden states are stored as bf16 bit patterns (uint16); logits margins as float32.
 """
 
@@ -37,6 +41,8 @@ SEED_PREFILL = 99
 N_PREFILL, N_DECODE = 8, 50
 N_CP_FRAMES = 6
 N_MIXED = 40
+N_FRAMES, N_TRAILING = 112, 40
+SEED_TRAILING, SEED_PAD = 4321, 777
 
 
 def _load_synth():
@@ -51,6 +57,76 @@ def bf16_bits(t: torch.Tensor) -> np.ndarray:
     return t.to(torch.bfloat16).contiguous().view(torch.int16).numpy().astype(np.uint16)
 
 
+def cp_frame_replay(cp, w, talker_hidden, first_token):
+    """One greedy frame through the upstream CodePredictor's own layer methods, recording what predict() hides:
+    per-group tokens, top-2 margins and post-norm hidden states."""
+    cp._reset_cache()
+    first_embed = w["embed_weight"][first_token]
+    h = torch.stack([talker_hidden.to(torch.bfloat16), first_embed], 0).unsqueeze(0)
+    for li, lw in enumerate(cp.layers):
+        h = cp._layer_prefill(h, lw, li, seq_len=2)
+    last = cp._rms_norm(h, cp.final_norm)[:, -1:, :]
+    toks, mar, hid_bits = [], [], []
+    pos = 2
+    for g in range(cp.num_groups):
+        logits = torch.nn.functional.linear(last, cp.lm_heads[g]).reshape(-1).float()
+        t2 = torch.topk(logits, 2).values
+        tok = int(logits.argmax())
+        toks.append(tok)
+        mar.append(float(t2[0] - t2[1]))
+        hid_bits.append(bf16_bits(last.reshape(-1)))
+        if g < cp.num_groups - 1:
+            h = cp.codec_embeddings[g][tok].view(1, 1, -1)
+            for li, lw in enumerate(cp.layers):
+                h = cp._layer_decode(h, lw, li, pos)
+            last = cp._rms_norm(h, cp.final_norm)
+            pos += 1
+    return toks, mar, hid_bits
+
+
+def make_frame_loop(synth, ref_vk, ref_mt, w):
+    """tts_engine.py:281-335 with the upstream reference classes (greedy), synthetic prefill / trailing text."""
+    ref = ref_vk.PyTorchTalkerReference(w, device="cpu")
+    cp = ref_mt.CodePredictor(w, device="cpu")
+    prefill = synth.synthetic_inputs(SEED_PREFILL, N_PREFILL)
+    trailing = synth.synthetic_inputs(SEED_TRAILING, N_TRAILING)
+    pad = synth.synthetic_inputs(SEED_PAD, 1)[0]
+    cp_embeds = [w["code_predictor"][f"codec_embedding.{g}.weight"] for g in range(15)]
+    ref.reset()
+    for i in range(N_PREFILL):
+        ref.step_with_embed(prefill[i])
+    tok, hid = ref.step(CODEC_BOS)
+    rec = dict(codes=[], cp_margins=[], talker_tokens=[], talker_margins=[], talker_hidden=[], in_hidden=[bf16_bits(hid)],
+               in_token=tok)
+    for f in range(N_FRAMES):
+        toks, mar, _ = cp_frame_replay(cp, w, hid, tok)
+        want = cp.predict(hid, tok, w["embed_weight"], do_sample=False)
+        assert want.tolist() == [tok] + toks
+        codes = [tok] + toks
+        e = torch.nn.functional.embedding(torch.tensor(codes[0:1]), w["embed_weight"]).squeeze(0)
+        for g in range(15):
+            e = e + torch.nn.functional.embedding(torch.tensor(codes[g + 1:g + 2]), cp_embeds[g]).squeeze(0)
+        e = e + (trailing[f].to(torch.bfloat16) if f < N_TRAILING else pad)
+        tok, hid = ref.step_with_embed(e)
+        logits = torch.nn.functional.linear(hid.to(torch.bfloat16), w["lm_head_weight"]).float()
+        t2 = torch.topk(logits, 2).values
+        assert int(logits.argmax()) == tok
+        rec["codes"].append(codes); rec["cp_margins"].append(mar); rec["talker_tokens"].append(tok)
+        rec["talker_margins"].append(float(t2[0] - t2[1])); rec["talker_hidden"].append(bf16_bits(hid))
+        if f % 10 == 0:
+            print("frame", f, codes[:4], "->", tok, flush=True)
+    np.savez_compressed(
+        os.path.join(HERE, "frame_loop.npz"),
+        prefill_bits=bf16_bits(prefill), trailing_bits=bf16_bits(trailing), pad_bits=bf16_bits(pad),
+        first_token=np.int32(rec["in_token"]), first_hidden_bits=rec["in_hidden"][0],
+        codes=np.array(rec["codes"], np.int32), cp_margins=np.array(rec["cp_margins"], np.float32),
+        talker_tokens=np.array(rec["talker_tokens"], np.int32), talker_margins=np.array(rec["talker_margins"], np.float32),
+        talker_hidden_bits=np.stack(rec["talker_hidden"]),
+    )
+    print("wrote frame_loop.npz:", N_FRAMES, "frames; min cp margin", float(np.min(rec["cp_margins"])),
+          "min talker margin", min(rec["talker_margins"]))
+
+
 def main():
     warnings.filterwarnings("ignore", category=UserWarning)
     torch.manual_seed(0)
@@ -63,6 +139,9 @@ def main():
     w = synth.synthetic_tts_weights(seed=SEED_WEIGHTS)
     fp = synth.weights_fingerprint(w)
     print("weights fingerprint", fp)
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "frames":
+        make_frame_loop(synth, ref_vk, ref_mt, w)
+        return
 
     # ── config 1: talker ────────────────────────────────────────────────────────────────────
     ref = ref_vk.PyTorchTalkerReference(w, device="cpu")

@@ -25,7 +25,26 @@ def test_library_builds_and_exports_header_symbols():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in qmk_b200.h but not exported"
         assert n in build_tts.SIGNATURES, f"{n} has no ctypes signature"
-    assert lib.qmk_abi_version() == 1
+    assert lib.qmk_abi_version() == 2
+
+
+def test_library_is_never_stale():
+    """The library carries the hash of the sources it was compiled from; build() rebuilds on any difference (every csrc/*.cu,
+    csrc/*.cuh and include/*.h is hashed, so an edited kernel header cannot leave a stale binary behind)."""
+    from qwen_megakernel import build_tts
+    path = build_tts.build()
+    names = {os.path.basename(f) for f in build_tts.source_files()}
+    assert {"qmk_engine.cu", "qmk_batched.cu", "qmk_device.cuh", "qmk_device2.cuh", "qmk_bgemm.cuh", "qmk_b200.h"} <= names
+    assert build_tts.library_hash(path) == build_tts.source_hash()
+
+
+def test_generate_args_mirror_matches_the_c_struct():
+    """ctypes mirror of qmk_generate_args: same size as the C struct the library was compiled with."""
+    import ctypes
+    from qwen_megakernel import build_tts
+    lib = build_tts.load_library(build_tts.build())
+    assert lib.qmk_generate_args_size() == ctypes.sizeof(build_tts.GenerateArgs)
+    assert lib.qmk_generate_nosync(None, None) == -1          # null args: QMK_ERR_ARG, no GPU touched
 
 
 def test_import_does_not_load_native_code():

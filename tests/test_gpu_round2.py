@@ -1,0 +1,369 @@
+"""GPU parity tests added in round 2 (through the C ABI): full-depth long-context decode, the frame loop at depth against
+fixtures recorded from the upstream classes, teacher-forced sampling, the upstream op in its code-predictor configuration,
+the device-autonomous frame loop (qmk_generate_nosync), M-RoPE, stream hand-over and the legacy cache.
+Rule and tolerances: tests/parity.py."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, bf16_from_bits
+from parity import assert_parity, compare
+
+pytestmark = pytest.mark.gpu
+CODEC_BOS = 2149
+
+
+@pytest.fixture(scope="module")
+def talker(gpu_weights):
+    from qwen_megakernel.model_tts import TTSDecoder
+    return TTSDecoder(weights=gpu_weights, verbose=False, max_seq_len=2048)
+
+
+@pytest.fixture(scope="module")
+def cp_kernel(gpu_weights):
+    from qwen_megakernel.model_tts import CodePredictorKernel
+    return CodePredictorKernel(gpu_weights, device="cuda")
+
+
+@pytest.fixture(scope="module")
+def frame_golden():
+    return np.load(os.path.join(GOLDEN, "frame_loop.npz"))
+
+
+# ---- config 3 at depth ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("position", [80, 81, 640, 641, 2046, 2047])
+def test_talker_full_depth_long_context_vs_oracle(talker, gpu_weights, cpu_weights, position):
+    """All 28 layers AND the group-split attention together (every bench frame beyond position 80 runs this): both KV caches
+    hold the same rows for positions < p, then one (or two) tokens are decoded at p with the full stack."""
+    from oracle.tts_oracle import TalkerOracle, top2_margin
+    from qwen_megakernel.synthetic import _normal_bf16, synthetic_inputs
+    L, S = 28, 2048
+    orc = TalkerOracle(cpu_weights, max_seq=S)
+    kfill = _normal_bf16((L, 8, position, 128), 1.0, 7, 300 + position)
+    vfill = _normal_bf16((L, 8, position, 128), 1.0, 7, 5300 + position)
+    orc.stack.k_cache[:, :, :position] = kfill; orc.stack.v_cache[:, :, :position] = vfill
+    talker._k_cache[:, :, :position] = kfill.cuda(); talker._v_cache[:, :, :position] = vfill.cuda()
+    orc.position = position; talker._position = position
+    x = synthetic_inputs(7000 + position, 2)
+    rt, rm, rh, toks, hids = [], [], [], [], []
+    for i in range(2 if position + 1 < S else 1):
+        t0, h0 = orc.step_with_embed(x[i]); t1, h1 = talker.step_with_embed(x[i].cuda())
+        rt.append(t0); rm.append(top2_margin(orc.last_logits)); rh.append(h0); toks.append(t1); hids.append(h1.cpu())
+    assert_parity(compare(f"28-layer long-context pos {position}", toks, hids, rt, rm, rh))
+    kd = (talker._k_cache[:, :, position].float().cpu() - orc.stack.k_cache[:, :, position].float()).abs().max()
+    assert kd <= 0.07, kd
+    talker.reset()
+
+
+def test_frame_loop_at_depth_vs_reference_golden(talker, cp_kernel, gpu_weights, frame_golden):
+    """112 frames of the upstream frame loop (tts_engine.py:281-335, greedy) recorded from the UPSTREAM classes, replayed
+    teacher-forced: every frame the kernel gets the reference's codes; talker positions run 9 .. 120 at full depth."""
+    g = frame_golden
+    prefill = bf16_from_bits(g["prefill_bits"]).cuda()
+    trailing = bf16_from_bits(g["trailing_bits"]).cuda()
+    pad = bf16_from_bits(g["pad_bits"]).cuda()
+    emb = gpu_weights["embed_weight"]
+    talker.reset()
+    for i in range(prefill.shape[0]):
+        talker.step_with_embed(prefill[i])
+    tok, hid = talker.step(CODEC_BOS)
+    ref_first_h = bf16_from_bits(g["first_hidden_bits"]).float()
+    assert float((hid.cpu() - ref_first_h).abs().max() / ref_first_h.abs().max()) <= 2e-2
+    n = g["codes"].shape[0]
+    toks, hids, cp_bad = [], [], []
+    hid_ref, tok_ref = ref_first_h, int(g["first_token"])
+    for f in range(n):
+        codes_ref = g["codes"][f]
+        forced = torch.tensor(np.asarray(codes_ref[1:]), dtype=torch.int32).cuda()
+        out = cp_kernel.predict(hid_ref.cuda(), tok_ref, emb, do_sample=False, forced_tokens=forced).cpu().tolist()
+        for grp in range(15):
+            if out[grp + 1] != int(codes_ref[grp + 1]) and float(g["cp_margins"][f][grp]) > 1e-2:
+                cp_bad.append((f, grp, out[grp + 1], int(codes_ref[grp + 1]), float(g["cp_margins"][f][grp])))
+        extra = trailing[f] if f < trailing.shape[0] else pad
+        t, h = talker.step_with_codes(torch.tensor(np.asarray(codes_ref), dtype=torch.int64).cuda(), cp_kernel.codec_embeddings, extra)
+        toks.append(t); hids.append(h.cpu())
+        tok_ref, hid_ref = int(g["talker_tokens"][f]), bf16_from_bits(g["talker_hidden_bits"][f]).float()
+    assert not cp_bad, f"code-predictor mismatches at reference margin > 1e-2: {cp_bad[:5]}"
+    ref_h = [bf16_from_bits(b).float() for b in g["talker_hidden_bits"]]
+    assert_parity(compare("frame loop at depth (talker)", toks, hids, g["talker_tokens"], g["talker_margins"], ref_h))
+    assert talker.position == prefill.shape[0] + 1 + n
+
+
+def test_sampled_frame_teacher_forced_logits_vs_oracle(cp_kernel, gpu_weights, cpu_weights):
+    """Sampling path at the bench's settings (T = 0.9, top_k = 50): the oracle samples a frame, its tokens are forced into
+    the kernel's sampling launch, and the 15 logit vectors the kernel sampled FROM must equal the oracle's (bf16 tolerance);
+    the kernel's own draws must lie in the oracle's top-50 set (ties kept, model_tts.py:756-762)."""
+    from oracle.tts_oracle import CodePredictorOracle
+    from qwen_megakernel.synthetic import synthetic_inputs
+    cpo = CodePredictorOracle(cpu_weights)
+    for seed in (21, 22):
+        th = synthetic_inputs(500 + seed, 1)[0].float()
+        rec = []
+        ref = cpo.predict(th, 40 + seed, cpu_weights["embed_weight"], do_sample=True, temperature=0.9, top_k=50,
+                          generator=torch.Generator().manual_seed(seed), record=rec)
+        forced = ref[1:].to(torch.int32).cuda()
+        out, logits, hidden = cp_kernel.predict(th.cuda(), 40 + seed, gpu_weights["embed_weight"], do_sample=True,
+                                                temperature=0.9, top_k=50, forced_tokens=forced, return_debug=True)
+        out = out.cpu().tolist()
+        for grp in range(15):
+            lo, lk = rec[grp]["logits"], logits[grp].cpu()
+            rel = float((lk - lo).abs().max() / lo.abs().max())
+            assert rel <= 2e-2, f"group {grp}: logits max rel err {rel}"
+            kth = float(torch.topk(lo, 50).values[-1])
+            assert float(lo[out[grp + 1]]) >= kth - 2 * 0.0079 * max(1.0, abs(kth)), \
+                f"group {grp}: sampled token {out[grp + 1]} outside the oracle's top-50 (logit {float(lo[out[grp + 1]])} < {kth})"
+            hrel = float((hidden[grp].cpu() - rec[grp]["hidden"]).abs().max() / rec[grp]["hidden"].abs().max())
+            assert hrel <= 2e-2
+
+
+def test_upstream_decode_op_code_predictor_config(gpu_weights, golden):
+    """torch.ops.qwen_megakernel_C.decode driven exactly like upstream CodePredictorKernel._step_with_embed
+    (model_tts.py:711-727: num_layers = 5, max_seq 64, all-zero dummy embed / LM-head tables, token -1) with NO extra
+    configuration call: the 5-layer blob must get the code predictor's bf16 residual stream and the dummy head must be
+    skipped.  Hidden states vs the upstream CodePredictor fixtures, tokens via the upstream torch glue (:752-764)."""
+    from qwen_megakernel.build_tts import get_extension
+    from qwen_megakernel.model_tts import _LAYER_FIELDS, _pack_layer_weights, _rope_tables
+    ext = get_extension()
+    cp = gpu_weights["code_predictor"]
+    lw = [cp[f"layers.{i}.{f}"].contiguous() for i in range(5) for f in _LAYER_FIELDS]
+    blob = _pack_layer_weights(lw, 5)
+    dev = "cuda"
+    f32 = dict(dtype=torch.float32, device=dev)
+    dummy_head = torch.zeros(3072, 1024, dtype=torch.bfloat16, device=dev)
+    dummy_embed = torch.zeros(3072, 1024, dtype=torch.bfloat16, device=dev)
+    cos, sin = _rope_tables(64, dev)
+    k_cache = torch.zeros(5, 8, 64, 128, dtype=torch.bfloat16, device=dev)
+    v_cache = torch.zeros_like(k_cache)
+    hidden = torch.empty(1024, dtype=torch.bfloat16, device=dev)
+    act, res, q, k, v = (torch.empty(1024, **f32), torch.empty(1024, **f32), torch.empty(2048, **f32),
+                         torch.empty(1024, **f32), torch.empty(1024, **f32))
+    attn_out, mlp, norm_out = torch.empty(2048, **f32), torch.empty(3072, **f32), torch.empty(1024, **f32)
+    bmv, bmi = torch.empty(4096, **f32), torch.empty(4096, dtype=torch.int32, device=dev)
+    out_token = torch.full((1,), -7, dtype=torch.int32, device=dev)
+    heads = [cp[f"lm_head.{g}.weight"] for g in range(15)]
+    embeds = [cp[f"codec_embedding.{g}.weight"] for g in range(15)]
+    state = {"pos": 0}
+
+    def step(e):
+        hidden.copy_(e)
+        torch.ops.qwen_megakernel_C.decode(out_token, -1, dummy_embed, blob, cp["norm.weight"], dummy_head, cos, sin, k_cache,
+                                           v_cache, hidden, act, res, q, k, v, attn_out, mlp, norm_out, bmv, bmi,
+                                           5, state["pos"], 64, 1.0 / 128 ** 0.5)
+        state["pos"] += 1
+
+    g = golden["cp_config2"]
+    for f in range(2):
+        state["pos"] = 0
+        step(bf16_from_bits(g["talker_hidden_bits"][f]).cuda())
+        step(gpu_weights["embed_weight"][int(g["first_tokens"][f])])
+        toks, hids = [], []
+        for grp in range(15):
+            logits = torch.nn.functional.linear(norm_out.to(torch.bfloat16).unsqueeze(0), heads[grp]).squeeze(0)
+            toks.append(int(logits.argmax()))
+            hids.append(norm_out.clone().cpu())
+            if grp < 14:
+                step(embeds[grp][int(g["tokens"][f][grp])])
+        assert int(out_token.item()) == 0, "dummy all-zero LM head: the argmax of all-zero logits is token 0"
+        ref_h = [bf16_from_bits(b).float() for b in g["hidden_bits"][f]]
+        assert_parity(compare(f"decode-op (5 layers) cp frame {f}", toks, hids, g["tokens"][f], g["margins"][f], ref_h))
+    ext.sync_status()
+
+
+# ---- device-autonomous frame loop -------------------------------------------------------------------
+def _sync_loop(talker, cp_kernel, emb, n, trailing, pad, do_sample, eos=None, counter0=100):
+    """The upstream control flow (tts_engine.py:301-335) on the per-frame API."""
+    talker.reset()
+    cp_kernel._frame_counter = counter0
+    tok, hid = talker.step(CODEC_BOS)
+    frames, toks = [], [tok]
+    for f in range(n):
+        if eos is not None and tok == eos:
+            break
+        codes = cp_kernel.predict(hid, tok, emb, do_sample=do_sample, temperature=0.9, top_k=50)
+        extra = trailing[f] if f < trailing.shape[0] else pad
+        tok, hid = talker.step_with_codes(codes, cp_kernel.codec_embeddings, extra)
+        frames.append(codes.cpu().tolist()); toks.append(tok)
+    return frames, toks, hid.cpu(), talker.position
+
+
+@pytest.mark.parametrize("do_sample,chunk,host_visible", [(False, 0, False), (True, 0, True), (False, 5, False)])
+def test_generate_frames_equals_synchronous_loop(talker, cp_kernel, gpu_weights, monkeypatch, do_sample, chunk, host_visible):
+    """ONE persistent launch (or a chain of launches of `chunk` frames) runs predict -> embedding sum -> talker step for 12
+    frames without the host; frames, talker tokens, final hidden state and KV rows must equal the synchronous loop bit for bit
+    (same device code, same counter-based sampler)."""
+    from qwen_megakernel.synthetic import synthetic_inputs
+    torch.manual_seed(1234)
+    emb = gpu_weights["embed_weight"]
+    trailing = synthetic_inputs(606, 5).cuda()
+    pad = synthetic_inputs(607, 1)[0].cuda()
+    n = 12
+    frames, toks, hid, pos = _sync_loop(talker, cp_kernel, emb, n, trailing, pad, do_sample)
+    k_ref = talker._k_cache[:, :, :pos].clone()
+    if chunk:
+        monkeypatch.setenv("QMK_FRAMES_PER_LAUNCH", str(chunk))
+    talker.reset()
+    cp_kernel._frame_counter = 100
+    talker.step(CODEC_BOS)
+    codes, tokens, n_done = talker.generate_frames(cp_kernel, n, trailing, pad, do_sample=do_sample, temperature=0.9, top_k=50,
+                                                   eos_token=-1, host_visible=host_visible)
+    assert n_done == n and talker.position == pos
+    assert codes.cpu().tolist() == frames
+    assert tokens.cpu().tolist() == toks[1:]
+    assert torch.equal(talker._norm_out.cpu(), hid)
+    assert torch.equal(talker._k_cache[:, :, :pos], k_ref)
+    # the ordinary per-step API continues from the state the loop left behind
+    t_a, _ = talker.step(toks[-1])
+    assert 0 <= t_a < 3072
+
+
+def test_generate_frames_stops_at_eos_on_the_device(talker, cp_kernel, gpu_weights, monkeypatch):
+    """Device-side EOS flag: with eos_token set to a token the greedy run produces, the loop must stop in front of exactly the
+    frame the upstream host loop would stop at (tts_engine.py:302), also across chained launches, and report it."""
+    from qwen_megakernel.synthetic import synthetic_inputs
+    emb = gpu_weights["embed_weight"]
+    trailing = synthetic_inputs(616, 3).cuda()
+    pad = synthetic_inputs(617, 1)[0].cuda()
+    frames, toks, _, _ = _sync_loop(talker, cp_kernel, emb, 10, trailing, pad, False)
+    stop = next(i for i in range(3, 10) if toks[i] not in toks[:i])     # a token that first appears at index i >= 3
+    eos = toks[stop]
+    ref_frames, ref_toks, hid, pos = _sync_loop(talker, cp_kernel, emb, 10, trailing, pad, False, eos=eos)
+    assert len(ref_frames) == stop
+    for chunk in (0, 2):
+        if chunk:
+            monkeypatch.setenv("QMK_FRAMES_PER_LAUNCH", str(chunk))
+        talker.reset()
+        talker.step(CODEC_BOS)
+        codes, tokens, state = talker.generate_frames(cp_kernel, 10, trailing, pad, do_sample=False, eos_token=eos, sync=False)
+        n_done = talker.finish_generate(state)
+        st = state.cpu().tolist()
+        assert n_done == stop and st[1] == 1 and st[2] == eos, st
+        assert codes[:n_done].cpu().tolist() == ref_frames
+        assert talker.position == pos and torch.equal(talker._norm_out.cpu(), hid)
+    # EOS as the very first token: zero frames, nothing written
+    talker.reset()
+    t0, _ = talker.step(CODEC_BOS)
+    codes, tokens, n_done = talker.generate_frames(cp_kernel, 4, None, pad, do_sample=False, eos_token=t0)
+    assert n_done == 0 and talker.position == 1
+
+
+def test_frame_is_one_launch_with_eos_flag(talker, cp_kernel, gpu_weights):
+    from qwen_megakernel.synthetic import synthetic_inputs
+    emb = gpu_weights["embed_weight"]
+    extra = synthetic_inputs(626, 3).cuda()
+    frames, toks, hid, _ = _sync_loop(talker, cp_kernel, emb, 3, extra, extra[0], False)
+    talker.reset()
+    talker.step(CODEC_BOS)
+    for f in range(3):
+        codes, tok, h = talker.frame(cp_kernel, extra[f], do_sample=False)
+        assert codes.cpu().tolist() == frames[f] and tok == toks[f + 1]
+    assert torch.equal(h.cpu(), hid)
+    codes, tok, _ = talker.frame(cp_kernel, extra[0], do_sample=False, eos_token=toks[3])
+    assert codes is None
+
+
+# ---- M-RoPE ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("interleaved", [False, True])
+def test_mrope_vs_oracle(gpu_weights, cpu_weights, interleaved):
+    """mrope_section [24, 20, 20] with DIFFERENT positions on the three axes (what distinguishes M-RoPE from RoPE) on a
+    6-layer talker, against the oracle whose row selection is pinned to HF transformers' functions (tests/golden/mrope.npz)."""
+    from oracle.tts_oracle import TalkerOracle, top2_margin
+    from qwen_megakernel.model_tts import TTSDecoder
+    from qwen_megakernel.synthetic import synthetic_inputs
+    L = 6
+    wc = dict(cpu_weights); wc["layer_weights"] = cpu_weights["layer_weights"][:11 * L]
+    wg = dict(gpu_weights); wg["layer_weights"] = gpu_weights["layer_weights"][:11 * L]
+    orc = TalkerOracle(wc, max_seq=256)
+    dec = TTSDecoder(weights=wg, verbose=False, max_seq_len=256, num_layers=L)
+    orc.set_mrope((24, 20, 20), interleaved)
+    dec.set_mrope((24, 20, 20), interleaved)
+    x = synthetic_inputs(888, 10)
+    rope = [(i, (3 * i) % 7, 2 * i + 1) for i in range(10)]
+    rt, rm, rh, toks, hids = [], [], [], [], []
+    for i in range(10):
+        t0, h0 = orc.step_with_embed(x[i], rope_pos=rope[i]); t1, h1 = dec.step_with_embed(x[i].cuda(), rope_pos=rope[i])
+        rt.append(t0); rm.append(top2_margin(orc.last_logits)); rh.append(h0); toks.append(t1); hids.append(h1.cpu())
+    assert_parity(compare(f"m-rope interleaved={interleaved}", toks, hids, rt, rm, rh))
+    kd = (dec._k_cache[:, :, :10].float().cpu() - orc.stack.k_cache[:, :, :10].float()).abs().max()
+    assert kd <= 0.07, kd
+    # the positions matter: standard RoPE on the same inputs gives different keys
+    dec2 = TTSDecoder(weights=wg, verbose=False, max_seq_len=256, num_layers=L)
+    for i in range(10):
+        dec2.step_with_embed(x[i].cuda())
+    assert not torch.equal(dec2._k_cache[:, :, :10], dec._k_cache[:, :, :10])
+
+
+def test_mrope_with_equal_axes_is_standard_rope(talker, gpu_weights):
+    """Text-only TTS puts the same position on all three axes: M-RoPE must then be bit-identical to standard RoPE."""
+    from qwen_megakernel.synthetic import synthetic_inputs
+    x = synthetic_inputs(889, 6).cuda()
+    talker.reset()
+    a = [talker.step_with_embed(x[i]) for i in range(6)]
+    talker.set_mrope((24, 20, 20))
+    try:
+        talker.reset()
+        b = [talker.step_with_embed(x[i]) for i in range(6)]
+    finally:
+        talker.set_mrope(None)
+    assert [t for t, _ in a] == [t for t, _ in b]
+    assert all(torch.equal(h0, h1) for (_, h0), (_, h1) in zip(a, b))
+
+
+# ---- boundary hardening -------------------------------------------------------------------------------------------------------
+def test_engine_orders_launches_across_streams(talker, cp_kernel, gpu_weights):
+    """All decoders of a device share one engine (exchange words, totals, epochs): launches issued on different CUDA streams
+    must still execute in submission order (event hand-over in the C layer), giving the single-stream result."""
+    from qwen_megakernel.synthetic import synthetic_inputs
+    emb = gpu_weights["embed_weight"]
+    extra = synthetic_inputs(636, 6).cuda()
+    ref_frames, ref_toks, _, _ = _sync_loop(talker, cp_kernel, emb, 6, extra, extra[0], False)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    talker.reset()
+    with torch.cuda.stream(s1):
+        tok, hid = talker.step(CODEC_BOS)
+    frames, toks = [], [tok]
+    for f in range(6):
+        with torch.cuda.stream(s2 if f % 2 == 0 else s1):
+            s_cur = torch.cuda.current_stream()
+            s_cur.wait_stream(s1); s_cur.wait_stream(s2)      # tensor-level dependencies are the caller's job ...
+            codes = cp_kernel.predict(hid, tok, emb, do_sample=False)
+        with torch.cuda.stream(s1 if f % 2 == 0 else s2):      # ... the engine's own state is ordered by the library
+            torch.cuda.current_stream().wait_stream(s1); torch.cuda.current_stream().wait_stream(s2)
+            tok, hid = talker.step_with_codes(codes, cp_kernel.codec_embeddings, extra[f])
+        frames.append(codes.cpu().tolist()); toks.append(tok)
+    torch.cuda.synchronize()
+    assert frames == ref_frames and toks == ref_toks
+
+
+def test_legacy_cache_notices_a_changed_blob(gpu_weights):
+    """The upstream-compatible entry caches the re-packed weights by blob address.  Overwriting the blob IN PLACE with another
+    model's pointers (what a recycled allocator address amounts to) must re-pack instead of decoding with the old weights."""
+    from qwen_megakernel.build_tts import get_extension
+    from qwen_megakernel.model_tts import _pack_layer_weights
+    get_extension()
+    w = gpu_weights
+    L, S, dev = 2, 64, "cuda"
+    f32 = dict(dtype=torch.float32, device=dev)
+    blob = _pack_layer_weights(w["layer_weights"][:22], L)
+    other = _pack_layer_weights(w["layer_weights"][22:44], L)
+    k_cache = torch.zeros(L, 8, S, 128, dtype=torch.bfloat16, device=dev); v_cache = torch.zeros_like(k_cache)
+    hidden = torch.empty(1024, dtype=torch.bfloat16, device=dev)
+    scr = [torch.empty(n, **f32) for n in (1024, 1024, 2048, 1024, 1024, 2048, 3072)]
+    norm_out, bmv = torch.empty(1024, **f32), torch.empty(4096, **f32)
+    bmi = torch.empty(4096, dtype=torch.int32, device=dev)
+    out_token = torch.empty(1, dtype=torch.int32, device=dev)
+
+    def run(b):
+        torch.ops.qwen_megakernel_C.decode(out_token, 77, w["embed_weight"], b, w["final_norm_weight"], w["lm_head_weight"],
+                                           w["cos_table"], w["sin_table"], k_cache, v_cache, hidden, *scr, norm_out, bmv, bmi,
+                                           L, 0, S, 1.0 / 128 ** 0.5)
+        return norm_out.clone()
+
+    h_a = run(blob)
+    h_b = run(other)
+    assert not torch.equal(h_a, h_b)
+    blob.copy_(other)                      # same address, different model
+    assert torch.equal(run(blob), h_b)
