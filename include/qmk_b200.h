@@ -243,6 +243,24 @@ void qmk_batched_destroy(qmk_batched* h);
 int qmk_batched_step(qmk_batched* h, const int32_t* token_ids, const void* embeds, int32_t* positions, void* k_cache,
                      void* v_cache, float* hidden_out, int32_t* tokens_out, void* stream);
 const char* qmk_batched_last_error(void);
+/* csrc/qmk_bstep.cuh holds a PERSISTENT form of the step: one cooperative launch runs all layers, the LM head and the argmax
+ * (grid barriers between phases, weights re-packed k-block-major and prefetched through a shared-memory ring by a producer
+ * warp, tcgen05 / TMEM projections).  It serves the one-pass prefill below.  For decode steps it is opt-in
+ * (QMK_BATCHED_PERSISTENT=1 at create time): measured on B200 it is slower than the chain of per-projection launches
+ * (1.4 / 2.1 ms vs 1.0 / 1.1 ms at B = 16 / 64), see DESIGN.md.  Return value: bit 0 = kernel available, bit 1 = used for decode. */
+int qmk_batched_is_persistent(const qmk_batched* h);
+/* Synchronise `stream`; QMK_ERR_KERNEL if a wait inside the persistent kernel timed out since the last call (tokens_out then
+ * holds -1001). */
+int qmk_batched_sync_status(qmk_batched* h, void* stream);
+/* Debug (QMK_BATCHED_TRACE=1): clock64 of CTA 0 entering / leaving every grid barrier of the latest persistent step. */
+int qmk_batched_trace_read(qmk_batched* h, void* stream, long long* host_out, int max_elems);
+/* Prefill of ONE utterance as a single batched pass (upstream runs the 8 prefill embeddings
+ * through 8 sequential decode steps, tts_engine.py:281-282): lane i of `embeds` (bf16[n][1024], n <= batch) is position
+ * position0 + i; all lanes share the caller's B = 1 cache [L][8][max_seq_len][128] and attend causally.  Writes the same KV
+ * rows as n sequential steps; hidden_out_last (f32[1024]) / token_out_last (int32[1]) receive the last position's
+ * post-norm hidden state and argmax token.  Needs the persistent kernel. */
+int qmk_batched_prefill(qmk_batched* h, const void* embeds, int n, int position0, void* k_cache, void* v_cache,
+                        float* hidden_out_last, int32_t* token_out_last, void* stream);
 
 /* ---- upstream-compatible entry point (same symbol, same argument list) ---------------------------- */
 /* The scratch arguments (g_activations .. g_mlp_intermediate, block_max_*) are accepted and ignored:

@@ -10,11 +10,13 @@
 
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
 #include "qmk_b200.h"
 #include "qmk_bgemm.cuh"
+#include "qmk_bstep.cuh"
 
 namespace {
 
@@ -258,6 +260,16 @@ __global__ void kb_copy_rows(const uint4* src, uint4* dst, size_t n16) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+// [rows][K] (upstream layout) -> k-block-major [K / 64][rows_total][64] at row offset row_off: one 128-row x 64-k tile becomes
+// 16 KB of contiguous memory (what the persistent kernel's TMA requests).  One uint4 = 8 bf16.
+__global__ void kb_repack_kmajor(const uint4* src, uint4* dst, int rows, int K, int row_off, int rows_total) {
+  const size_t n = (size_t)rows * (K / 8);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / (K / 8)), ch = (int)(i % (K / 8));
+    dst[((size_t)(ch >> 3) * rows_total + row_off + r) * 8 + (ch & 7)] = src[i];
+  }
+}
+
 thread_local std::string g_err;
 int fail(int code, const char* msg) {
   g_err = msg;
@@ -267,6 +279,8 @@ int fail(int code, const char* msg) {
 }  // namespace
 
 constexpr size_t PARTIAL_ELEMS = (size_t)2 * 1024 * 1024;   // fp32 split-K partials: max splits x B x rows = 4 x 64 x 6144
+constexpr int MAX_LANES = 64;
+static size_t qmkb_hidden_offset() { return PARTIAL_ELEMS; }   // prefill: per-lane hidden states live behind the partials
 
 struct BatchedDeviceGuard {
   int prev = -1;
@@ -280,12 +294,25 @@ struct BatchedDeviceGuard {
 struct qmk_batched {
   int device = 0, L = 0, B = 0, max_seq = 0, head_rows = 0, residual_fp32 = 1;
   __nv_bfloat16 *w_qkv = nullptr, *w_gu = nullptr;           // [L][4096][1024], [L][6144][1024] (concatenated copies)
+  // persistent kernel: k-block-major copies [L][K / 64][rows][64] of qkv, o, gate/up, down and [K / 64][rows][64] of the head
+  __nv_bfloat16 *p_qkv = nullptr, *p_o = nullptr, *p_gu = nullptr, *p_down = nullptr, *p_head = nullptr;
+  CUtensorMap pmap_w[5], pmap_x[3];
   std::vector<const void*> w_o, w_down, ln_in, ln_post, qn, kn;
   const void *final_norm = nullptr, *lm_head = nullptr, *embed = nullptr, *cos_t = nullptr, *sin_t = nullptr;
   std::vector<CUtensorMap> map_qkv, map_o, map_gu, map_down;
   CUtensorMap map_head, map_x1024, map_x2048, map_x3072;
   float *res = nullptr, *partial = nullptr;
   __nv_bfloat16 *xn = nullptr, *abuf = nullptr, *mbuf = nullptr;
+  // persistent step kernel (qmk_bstep.cuh)
+  int persistent = 0, decode_persistent = 0, grid = 0, N = 0;   // persistent: kernel usable (prefill); decode_persistent: also used for decode steps
+  const __nv_bfloat16** d_ptrs = nullptr; // [4][L]: ln_in, ln_post, qn, kn
+  float* qbuf = nullptr;
+  unsigned* d_bar = nullptr;
+  unsigned bar_count = 0;
+  int* d_status = nullptr;
+  int* d_pos0 = nullptr;                  // prefill: first position
+  long long* d_trace = nullptr;           // QMK_BATCHED_TRACE=1: barrier stamps of CTA 0 (debug)
+  int* d_tok_scratch = nullptr;           // prefill: per-lane argmax (only the last lane's is reported)
 };
 
 extern "C" const char* qmk_batched_last_error(void) { return g_err.c_str(); }
@@ -300,7 +327,7 @@ extern "C" int qmk_batched_create(int device, const LDGLayerWeights* layers_host
   if (batch < 16 || batch > MAX_N || batch % 16) return fail(QMK_ERR_ARG, "qmk_batched_create: batch must be 16, 32, 48 or 64");
   if (lm_head_rows % BM || lm_head_rows <= 0) return fail(QMK_ERR_ARG, "qmk_batched_create: lm_head_rows must be a multiple of 128");
   if (num_layers < 1 || max_seq_len < 1) return fail(QMK_ERR_ARG, "qmk_batched_create: bad num_layers / max_seq_len");
-  if ((size_t)4 * batch * lm_head_rows > PARTIAL_ELEMS) return fail(QMK_ERR_ARG, "qmk_batched_create: lm_head_rows too large for the split-K partial buffer");
+  if ((size_t)6 * batch * lm_head_rows > PARTIAL_ELEMS) return fail(QMK_ERR_ARG, "qmk_batched_create: lm_head_rows too large for the split-K partial buffer");
   *out = nullptr;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(QMK_ERR_ARG, "qmk_batched_create: bad device");
@@ -314,9 +341,11 @@ extern "C" int qmk_batched_create(int device, const LDGLayerWeights* layers_host
   h->final_norm = final_norm_weight; h->lm_head = lm_head_weight; h->embed = embed_weight; h->cos_t = cos_table; h->sin_t = sin_table;
   const size_t L = num_layers;
   bool ok = cudaMalloc(&h->w_qkv, L * QKV_ROWS * H * 2) == cudaSuccess && cudaMalloc(&h->w_gu, L * GU_ROWS * H * 2) == cudaSuccess &&
-            cudaMalloc(&h->res, (size_t)batch * H * 4) == cudaSuccess && cudaMalloc(&h->partial, PARTIAL_ELEMS * sizeof(float)) == cudaSuccess &&
+            cudaMalloc(&h->res, (size_t)batch * H * 4) == cudaSuccess && cudaMalloc(&h->partial, (PARTIAL_ELEMS + (size_t)MAX_LANES * H) * sizeof(float)) == cudaSuccess &&
             cudaMalloc(&h->xn, (size_t)batch * H * 2) == cudaSuccess &&
-            cudaMalloc(&h->abuf, (size_t)batch * QSZ * 2) == cudaSuccess && cudaMalloc(&h->mbuf, (size_t)batch * INTER * 2) == cudaSuccess;
+            cudaMalloc(&h->abuf, (size_t)batch * QSZ * 2) == cudaSuccess && cudaMalloc(&h->mbuf, (size_t)batch * INTER * 2) == cudaSuccess &&
+            cudaMemset(h->xn, 0, (size_t)batch * H * 2) == cudaSuccess && cudaMemset(h->abuf, 0, (size_t)batch * QSZ * 2) == cudaSuccess &&
+            cudaMemset(h->mbuf, 0, (size_t)batch * INTER * 2) == cudaSuccess;   // rows of unused lanes feed the tensor cores too: keep them finite
   if (!ok) { qmk_batched_destroy(h); return fail(QMK_ERR_CUDA, "qmk_batched_create: allocation failed"); }
   for (int l = 0; l < num_layers; ++l) {
     const LDGLayerWeights& w = layers_host[l];
@@ -343,6 +372,63 @@ extern "C" int qmk_batched_create(int device, const LDGLayerWeights* layers_host
   rc |= make_tensor_map(&h->map_x2048, h->abuf, batch, QSZ, batch);
   rc |= make_tensor_map(&h->map_x3072, h->mbuf, batch, INTER, batch);
   if (rc) { qmk_batched_destroy(h); return fail(QMK_ERR_CUDA, "qmk_batched_create: cuTensorMapEncodeTiled failed"); }
+  // ---- persistent step kernel: one cooperative launch per step (default when every projection's ~144 items fit the SMs) ----
+  h->N = batch;
+  h->grid = prop.multiProcessorCount;
+  {
+    // Decode steps run as the chain of per-projection launches by default: measured on B200 (round 2) the persistent kernel
+    // needs 1.4 ms (B = 16) / 2.1 ms (B = 64) per step against the chain's 1.0 / 1.1 ms -- nine grid barriers per layer at ~2 us
+    // each (fence.proxy.async + release/acquire round trip) and one CTA per SM walking its items serially cost more than the
+    // chain's kernel boundaries, which overlap through programmatic dependent launch and several CTAs per SM.
+    // QMK_BATCHED_PERSISTENT=1 selects it for decode; the one-pass prefill always uses it.
+    int want = 1;
+    if (const char* env = getenv("QMK_BATCHED_PERSISTENT")) h->decode_persistent = atoi(env) ? 1 : 0;
+    int coop = 0, occ = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    cudaError_t pe = cudaFuncSetAttribute(qmk_bstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_SMEM);
+    if (pe == cudaSuccess) pe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qmk_bstep_kernel, NT_ALL, PS_SMEM);
+    if (pe != cudaSuccess) cudaGetLastError();
+    h->persistent = (want && coop && pe == cudaSuccess && occ >= 1 && h->grid >= 144 && lm_head_rows / BM * 6 <= h->grid) ? 1 : 0;
+    if (!h->persistent) h->decode_persistent = 0;
+  }
+  if (h->persistent) {
+    std::vector<const void*> ptrs;
+    for (auto* v : {&h->ln_in, &h->ln_post, &h->qn, &h->kn}) ptrs.insert(ptrs.end(), v->begin(), v->end());
+    bool okp = cudaMalloc(&h->p_qkv, L * QKV_ROWS * H * 2) == cudaSuccess && cudaMalloc(&h->p_o, L * H * QSZ * 2) == cudaSuccess &&
+               cudaMalloc(&h->p_gu, L * GU_ROWS * H * 2) == cudaSuccess && cudaMalloc(&h->p_down, L * H * INTER * 2) == cudaSuccess &&
+               cudaMalloc(&h->p_head, (size_t)lm_head_rows * H * 2) == cudaSuccess &&
+               cudaMalloc(&h->d_ptrs, ptrs.size() * sizeof(void*)) == cudaSuccess &&
+               cudaMemcpy(h->d_ptrs, ptrs.data(), ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice) == cudaSuccess &&
+               cudaMalloc(&h->qbuf, (size_t)batch * QSZ * 4) == cudaSuccess && cudaMalloc(&h->d_bar, sizeof(unsigned)) == cudaSuccess &&
+               cudaMemset(h->d_bar, 0, sizeof(unsigned)) == cudaSuccess && cudaMalloc(&h->d_status, sizeof(int)) == cudaSuccess &&
+               cudaMemset(h->d_status, 0, sizeof(int)) == cudaSuccess && cudaMalloc(&h->d_pos0, sizeof(int)) == cudaSuccess &&
+               cudaMalloc(&h->d_tok_scratch, (size_t)batch * sizeof(int)) == cudaSuccess;
+    if (okp) {
+      auto pack = [&](const void* src, __nv_bfloat16* dst, int rows, int K, int row_off, int rows_total) {
+        kb_repack_kmajor<<<592, 256>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), rows, K, row_off, rows_total);
+      };
+      for (int l = 0; l < num_layers; ++l) {
+        const LDGLayerWeights& w = layers_host[l];
+        pack(w.q_proj_weight, h->p_qkv + (size_t)l * QKV_ROWS * H, QSZ, H, 0, QKV_ROWS);
+        pack(w.k_proj_weight, h->p_qkv + (size_t)l * QKV_ROWS * H, KVSZ, H, QSZ, QKV_ROWS);
+        pack(w.v_proj_weight, h->p_qkv + (size_t)l * QKV_ROWS * H, KVSZ, H, QSZ + KVSZ, QKV_ROWS);
+        pack(w.o_proj_weight, h->p_o + (size_t)l * H * QSZ, H, QSZ, 0, H);
+        pack(w.gate_proj_weight, h->p_gu + (size_t)l * GU_ROWS * H, INTER, H, 0, GU_ROWS);
+        pack(w.up_proj_weight, h->p_gu + (size_t)l * GU_ROWS * H, INTER, H, INTER, GU_ROWS);
+        pack(w.down_proj_weight, h->p_down + (size_t)l * H * INTER, H, INTER, 0, H);
+      }
+      pack(lm_head_weight, h->p_head, lm_head_rows, H, 0, lm_head_rows);
+      // 2-D views [L * KB * rows, 64]: tile (layer, k-block, row tile) = rows (l * KB + kb) * rows + 128 t .. + 127, all 64 columns
+      int prc = make_tensor_map(&h->pmap_w[0], h->p_qkv, L * (H / BK) * QKV_ROWS, BK, BM);
+      prc |= make_tensor_map(&h->pmap_w[1], h->p_o, L * (QSZ / BK) * H, BK, BM);
+      prc |= make_tensor_map(&h->pmap_w[2], h->p_gu, L * (H / BK) * GU_ROWS, BK, BM);
+      prc |= make_tensor_map(&h->pmap_w[3], h->p_down, L * (INTER / BK) * H, BK, BM);
+      prc |= make_tensor_map(&h->pmap_w[4], h->p_head, (uint64_t)(H / BK) * lm_head_rows, BK, BM);
+      h->pmap_x[0] = h->map_x1024; h->pmap_x[1] = h->map_x2048; h->pmap_x[2] = h->map_x3072;
+      okp = prc == 0 && cudaDeviceSynchronize() == cudaSuccess;
+    }
+    if (!okp) { qmk_batched_destroy(h); return fail(QMK_ERR_CUDA, "qmk_batched_create: allocation failed (persistent kernel)"); }
+  }
   if (cudaFuncSetAttribute(qmk_bgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
       cudaDeviceSynchronize() != cudaSuccess) {
     qmk_batched_destroy(h);
@@ -358,6 +444,8 @@ extern "C" void qmk_batched_destroy(qmk_batched* h) {
   cudaDeviceSynchronize();
   cudaFree(h->w_qkv); cudaFree(h->w_gu); cudaFree(h->res); cudaFree(h->partial);
   cudaFree(h->xn); cudaFree(h->abuf); cudaFree(h->mbuf);
+  cudaFree(h->p_qkv); cudaFree(h->p_o); cudaFree(h->p_gu); cudaFree(h->p_down); cudaFree(h->p_head); cudaFree(h->d_ptrs); cudaFree(h->qbuf); cudaFree(h->d_bar); cudaFree(h->d_status); cudaFree(h->d_pos0);
+  cudaFree(h->d_tok_scratch); cudaFree(h->d_trace);
   delete h;
 }
 
@@ -383,6 +471,51 @@ static void gemm(qmk_batched* h, const CUtensorMap& mw, const CUtensorMap& mx, i
   launch_pdl(qmkb::qmk_bgemm_kernel, dim3(M / qmkb::BM, splits), dim3(128), (size_t)qmkb::SMEM_BYTES, st, mw, mx, a);
 }
 
+// One cooperative launch of the persistent step kernel for `lanes` lanes (decode: lanes = B utterances; prefill: lanes =
+// consecutive positions of one utterance whose first position is *positions).
+static int launch_persistent(qmk_batched* h, int lanes, int prefill, const int32_t* token_ids, const void* embeds, int32_t* positions,
+                             void* k_cache, void* v_cache, float* hidden_out, int32_t* tokens_out, cudaStream_t st) {
+  qmkb::BStepParams p;
+  memset(&p, 0, sizeof(p));
+  memcpy(p.map_w, h->pmap_w, sizeof(p.map_w));
+  memcpy(p.map_x, h->pmap_x, sizeof(p.map_x));
+  p.L = h->L; p.B = lanes; p.N = h->N;
+  p.head_rows = h->head_rows; p.vocab = h->head_rows;
+  p.residual_fp32 = h->residual_fp32;
+  p.prefill = prefill;
+  p.max_seq = h->max_seq;
+  p.attn_scale = 0.08838834764831845f;
+  p.ln_in = reinterpret_cast<const __nv_bfloat16* const*>(h->d_ptrs);
+  p.ln_post = p.ln_in + h->L; p.qn = p.ln_in + 2 * h->L; p.kn = p.ln_in + 3 * h->L;
+  p.final_norm = reinterpret_cast<const __nv_bfloat16*>(h->final_norm);
+  p.embed = reinterpret_cast<const __nv_bfloat16*>(h->embed);
+  p.cos_t = reinterpret_cast<const __nv_bfloat16*>(h->cos_t);
+  p.sin_t = reinterpret_cast<const __nv_bfloat16*>(h->sin_t);
+  p.token_ids = token_ids;
+  p.embeds = reinterpret_cast<const __nv_bfloat16*>(embeds);
+  p.positions = positions;
+  p.k_cache = reinterpret_cast<__nv_bfloat16*>(k_cache);
+  p.v_cache = reinterpret_cast<__nv_bfloat16*>(v_cache);
+  p.hidden_out = hidden_out;
+  p.tokens_out = tokens_out;
+  p.res = h->res; p.partial = h->partial; p.qbuf = h->qbuf; p.xn = h->xn; p.abuf = h->abuf; p.mbuf = h->mbuf;
+  p.bar = h->d_bar;
+  p.bar_base = h->bar_count;
+  p.status = h->d_status;
+  p.timeout_cycles = 4000000000LL;
+  if (const char* env = getenv("QMK_TIMEOUT_CYCLES")) p.timeout_cycles = atoll(env);
+  if (getenv("QMK_BATCHED_TRACE")) {
+    if (!h->d_trace) cudaMalloc(&h->d_trace, 1024 * sizeof(long long));
+    p.trace = h->d_trace;
+  }
+  const unsigned n_barriers = 1u + (unsigned)h->L * (8u + (prefill ? 1u : 0u)) + 1u;
+  h->bar_count += n_barriers * (unsigned)h->grid;
+  void* args[] = {&p};
+  const cudaError_t e = cudaLaunchCooperativeKernel((const void*)qmkb::qmk_bstep_kernel, dim3(h->grid), dim3(qmkb::NT_ALL), args, (size_t)qmkb::PS_SMEM, st);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(QMK_ERR_CUDA, cudaGetErrorString(e)); }
+  return QMK_OK;
+}
+
 // One decode step for all B streams.  token_ids (int32[B], device; entry < 0 or null pointer -> the stream's row of
 // `embeds` bf16[B][1024] is the input, the upstream sentinel path), positions (int32[B], device, advanced by one),
 // k_cache / v_cache: [B][L][8][max_seq][128] bf16.  Outputs: tokens_out int32[B], hidden_out f32[B][1024].
@@ -393,6 +526,8 @@ extern "C" int qmk_batched_step(qmk_batched* h, const int32_t* token_ids, const 
   cudaStream_t st = (cudaStream_t)stream;
   BatchedDeviceGuard guard(h->device);
   g_launch_err = cudaSuccess;
+  if (h->decode_persistent)
+    return launch_persistent(h, h->B, 0, token_ids, embeds, positions, k_cache, v_cache, hidden_out, tokens_out, st);
   const int B = h->B, L = h->L;
   const float scale = 0.08838834764831845f;
   __nv_bfloat16* kc = reinterpret_cast<__nv_bfloat16*>(k_cache);
@@ -422,4 +557,58 @@ extern "C" int qmk_batched_step(qmk_batched* h, const int32_t* token_ids, const 
   cudaError_t e = g_launch_err != cudaSuccess ? g_launch_err : cudaGetLastError();
   if (e != cudaSuccess) { cudaGetLastError(); return fail(QMK_ERR_CUDA, cudaGetErrorString(e)); }
   return QMK_OK;
+}
+
+// Prefill of ONE utterance as a single batched pass (upstream feeds the 8 prefill embeddings
+// through 8 sequential decode steps, tts_engine.py:281-282): lane i is position position0 + i, all lanes share the caller's
+// B = 1 cache [L][8][max_seq][128] and attend causally.  Writes the same KV rows as n sequential steps and returns the LAST
+// position's post-norm hidden state (f32[1024]) and argmax token; n <= batch.  Needs the persistent step kernel.
+extern "C" int qmk_batched_prefill(qmk_batched* h, const void* embeds, int n, int position0, void* k_cache, void* v_cache,
+                                   float* hidden_out_last, int32_t* token_out_last, void* stream) {
+  if (!h || !embeds || !k_cache || !v_cache) return fail(QMK_ERR_ARG, "qmk_batched_prefill: null argument");
+  if (!h->persistent) return fail(QMK_ERR_UNSUPPORTED, "qmk_batched_prefill needs the persistent step kernel");
+  if (n < 1 || n > h->B) return fail(QMK_ERR_ARG, "qmk_batched_prefill: n must be in [1, batch]");
+  if (position0 < 0 || position0 + n > h->max_seq) return fail(QMK_ERR_ARG, "qmk_batched_prefill: positions exceed max_seq_len");
+  cudaStream_t st = (cudaStream_t)stream;
+  BatchedDeviceGuard guard(h->device);
+  if (cudaMemcpyAsync(h->d_pos0, &position0, sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(QMK_ERR_CUDA, "qmk_batched_prefill: copy failed");
+  float* hid_all = reinterpret_cast<float*>(h->partial) + qmkb_hidden_offset();   // scratch behind the partials: [n][1024]
+  int rc = launch_persistent(h, n, 1, nullptr, embeds, h->d_pos0, k_cache, v_cache, hid_all, h->d_tok_scratch, st);
+  if (rc != QMK_OK) return rc;
+  cudaError_t e = cudaSuccess;
+  if (hidden_out_last) e = cudaMemcpyAsync(hidden_out_last, hid_all + (size_t)(n - 1) * H, H * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess && token_out_last) e = cudaMemcpyAsync(token_out_last, h->d_tok_scratch + (n - 1), sizeof(int), cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return fail(QMK_ERR_CUDA, cudaGetErrorString(e));
+  return QMK_OK;
+}
+
+// bit 0: the persistent step kernel (qmk_bstep.cuh) is available (one-pass prefill); bit 1: decode steps use it too.
+extern "C" int qmk_batched_is_persistent(const qmk_batched* h) { return h ? (h->persistent ? 1 : 0) + (h->decode_persistent ? 2 : 0) : 0; }
+// Synchronise `stream`; QMK_ERR_KERNEL if a wait inside the persistent kernel timed out since the last call.
+extern "C" int qmk_batched_sync_status(qmk_batched* h, void* stream) {
+  if (!h) return fail(QMK_ERR_ARG, "qmk_batched_sync_status: null handle");
+  BatchedDeviceGuard guard(h->device);
+  if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return fail(QMK_ERR_CUDA, "qmk_batched_sync_status: synchronize failed");
+  if (!h->d_status) return QMK_OK;
+  int st = 0;
+  cudaMemcpy(&st, h->d_status, sizeof(int), cudaMemcpyDeviceToHost);
+  if (st != 0) {
+    cudaMemset(h->d_status, 0, sizeof(int));
+    unsigned cur = 0;
+    cudaMemcpy(&cur, h->d_bar, sizeof(unsigned), cudaMemcpyDeviceToHost);
+    h->bar_count = cur;   // an aborted launch leaves the barrier counter short: resynchronise the host's view
+    return fail(QMK_ERR_KERNEL, "batched step: device watchdog fired");
+  }
+  return QMK_OK;
+}
+
+// Debug: barrier stamps (clock64 of CTA 0: enter / leave of every grid barrier) of the latest persistent step launched with
+// QMK_BATCHED_TRACE set; returns the number of stamps copied.
+extern "C" int qmk_batched_trace_read(qmk_batched* h, void* stream, long long* host_out, int max_elems) {
+  if (!h || !host_out || !h->d_trace) return 0;
+  BatchedDeviceGuard guard(h->device);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  const int n = std::min(max_elems, 1024);
+  cudaMemcpy(host_out, h->d_trace, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost);
+  return n;
 }

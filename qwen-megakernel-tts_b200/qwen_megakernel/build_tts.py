@@ -129,6 +129,10 @@ SIGNATURES = {
     "qmk_batched_destroy": (None, [_vp]),
     "qmk_batched_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qmk_batched_last_error": (ctypes.c_char_p, []),
+    "qmk_batched_is_persistent": (_i32, [_vp]),
+    "qmk_batched_trace_read": (_i32, [_vp, _vp, ctypes.POINTER(ctypes.c_longlong), _i32]),
+    "qmk_batched_sync_status": (_i32, [_vp, _vp]),
+    "qmk_batched_prefill": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "launch_ldg_decode_direct": (None, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
     "qmk_legacy_configure": (_i32, [_vp, _i32, _i32]),

@@ -468,6 +468,30 @@ class TTSDecoder:
             return None, int(eos_token), self._norm_out.clone()
         return codes[0], int(tokens[0].item()), self._norm_out.clone()
 
+    def prefill(self, embeds_bf16: torch.Tensor) -> tuple[int, torch.Tensor]:
+        """Feed n prefill embeddings (bf16[n, 1024], n <= 16) as ONE batched pass instead of n sequential
+        ``step_with_embed`` calls (upstream tts_engine.py:281-282 loops; the prefill is 24.9 of its 50.5 ms time to first
+        chunk, README.md:23): the projections run once for all positions on the tcgen05 tensor cores (every weight byte is
+        read once instead of n times) with causal attention, writing the same KV rows.  Returns what the LAST sequential
+        step would return: ``(token, hidden)``.  Standard RoPE only."""
+        if self._mrope_delta is not None:
+            raise NotImplementedError("prefill() implements standard RoPE; use step_with_embed with set_mrope()")
+        e = embeds_bf16.to(self.device, torch.bfloat16).reshape(-1, HIDDEN_SIZE)
+        n = e.shape[0]
+        if n < 1 or n > 16:
+            raise ValueError("prefill(): between 1 and 16 positions")
+        if self._position + n > self._max_seq:
+            raise IndexError(f"KV cache is full (position {self._position} + {n} > max_seq_len)")
+        if getattr(self, "_prefiller", None) is None:
+            self._prefiller = BatchedTTSDecoder(self._weights, 16, device=self.device, max_seq_len=self._max_seq,
+                                                num_layers=self._num_layers)
+            if not self._prefiller.persistent:
+                raise RuntimeError("prefill() needs the persistent batched kernel (>= 144 SMs)")
+        with torch.cuda.device(self.device):
+            self._prefiller.prefill_into(e, self._position, self._k_cache, self._v_cache, self._norm_out, self._out_token)
+        self._position += n
+        return self._finish()
+
     def reset(self):
         """New utterance.  O(1): rows beyond ``position`` are never read."""
         self._position = 0
@@ -566,6 +590,40 @@ class BatchedTTSDecoder:
         """New utterances on every stream (O(1): rows beyond a stream's position are never read)."""
         self.positions.zero_()
         self._steps = 0
+
+    @property
+    def persistent(self) -> bool:
+        """True if the persistent tcgen05 step kernel (csrc/qmk_bstep.cuh) is available on this device (one-pass prefill)."""
+        return bool(self._lib.qmk_batched_is_persistent(self._handle) & 1)
+
+    @property
+    def persistent_decode(self) -> bool:
+        """True if decode steps run as ONE persistent launch (QMK_BATCHED_PERSISTENT=1) instead of the launch chain."""
+        return bool(self._lib.qmk_batched_is_persistent(self._handle) & 2)
+
+    def sync_status(self) -> None:
+        """Synchronise the current stream and raise if a wait inside the persistent kernel timed out."""
+        from .build_tts import NativeError
+        rc = self._lib.qmk_batched_sync_status(self._handle, _stream_ptr(self.device))
+        if rc < 0:
+            raise NativeError(f"BatchedTTSDecoder: {self._lib.qmk_batched_last_error().decode()} (code {rc})")
+
+    def prefill_into(self, embeds_bf16: torch.Tensor, position0: int, k_cache: torch.Tensor, v_cache: torch.Tensor,
+                     hidden_out: torch.Tensor, token_out: torch.Tensor) -> None:
+        """One batched pass over n <= batch consecutive positions of ONE utterance (causal), writing the KV rows into a
+        B = 1 cache ``[L, 8, S, 128]`` and the last position's hidden state / token (``qmk_batched_prefill``)."""
+        from .build_tts import NativeError
+        e = embeds_bf16.to(self.device, torch.bfloat16).reshape(-1, HIDDEN_SIZE).contiguous()
+        n = e.shape[0]
+        if not 1 <= n <= self.batch:
+            raise ValueError(f"prefill of {n} positions needs a batched decoder with batch >= {n}")
+        if tuple(k_cache.shape) != (self._num_layers, NUM_KV_HEADS, self._max_seq, HEAD_DIM) or k_cache.shape != v_cache.shape:
+            raise ValueError("prefill_into: cache must be [L, 8, max_seq_len, 128] with this decoder's max_seq_len")
+        self._keep = e
+        rc = self._lib.qmk_batched_prefill(self._handle, e.data_ptr(), n, int(position0), k_cache.data_ptr(), v_cache.data_ptr(),
+                                           hidden_out.data_ptr(), token_out.data_ptr(), _stream_ptr(self.device))
+        if rc < 0:
+            raise NativeError(f"qmk_batched_prefill: {self._lib.qmk_batched_last_error().decode()} (code {rc})")
 
 
 class TextProjection:

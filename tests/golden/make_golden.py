@@ -66,7 +66,7 @@ def cp_frame_replay(cp, w, talker_hidden, first_token):
     for li, lw in enumerate(cp.layers):
         h = cp._layer_prefill(h, lw, li, seq_len=2)
     last = cp._rms_norm(h, cp.final_norm)[:, -1:, :]
-    toks, mar, hid_bits = [], [], []
+    toks, mar, hid_bits, top1 = [], [], [], []
     pos = 2
     for g in range(cp.num_groups):
         logits = torch.nn.functional.linear(last, cp.lm_heads[g]).reshape(-1).float()
@@ -74,6 +74,7 @@ def cp_frame_replay(cp, w, talker_hidden, first_token):
         tok = int(logits.argmax())
         toks.append(tok)
         mar.append(float(t2[0] - t2[1]))
+        top1.append(float(t2[0]))
         hid_bits.append(bf16_bits(last.reshape(-1)))
         if g < cp.num_groups - 1:
             h = cp.codec_embeddings[g][tok].view(1, 1, -1)
@@ -81,7 +82,7 @@ def cp_frame_replay(cp, w, talker_hidden, first_token):
                 h = cp._layer_decode(h, lw, li, pos)
             last = cp._rms_norm(h, cp.final_norm)
             pos += 1
-    return toks, mar, hid_bits
+    return toks, mar, hid_bits, top1
 
 
 def make_frame_loop(synth, ref_vk, ref_mt, w):
@@ -96,10 +97,10 @@ def make_frame_loop(synth, ref_vk, ref_mt, w):
     for i in range(N_PREFILL):
         ref.step_with_embed(prefill[i])
     tok, hid = ref.step(CODEC_BOS)
-    rec = dict(codes=[], cp_margins=[], talker_tokens=[], talker_margins=[], talker_hidden=[], in_hidden=[bf16_bits(hid)],
+    rec = dict(codes=[], cp_margins=[], cp_top1=[], talker_top1=[], talker_tokens=[], talker_margins=[], talker_hidden=[], in_hidden=[bf16_bits(hid)],
                in_token=tok)
     for f in range(N_FRAMES):
-        toks, mar, _ = cp_frame_replay(cp, w, hid, tok)
+        toks, mar, _, top1 = cp_frame_replay(cp, w, hid, tok)
         want = cp.predict(hid, tok, w["embed_weight"], do_sample=False)
         assert want.tolist() == [tok] + toks
         codes = [tok] + toks
@@ -112,6 +113,7 @@ def make_frame_loop(synth, ref_vk, ref_mt, w):
         t2 = torch.topk(logits, 2).values
         assert int(logits.argmax()) == tok
         rec["codes"].append(codes); rec["cp_margins"].append(mar); rec["talker_tokens"].append(tok)
+        rec["cp_top1"].append(top1); rec["talker_top1"].append(float(t2[0]))
         rec["talker_margins"].append(float(t2[0] - t2[1])); rec["talker_hidden"].append(bf16_bits(hid))
         if f % 10 == 0:
             print("frame", f, codes[:4], "->", tok, flush=True)
@@ -120,6 +122,7 @@ def make_frame_loop(synth, ref_vk, ref_mt, w):
         prefill_bits=bf16_bits(prefill), trailing_bits=bf16_bits(trailing), pad_bits=bf16_bits(pad),
         first_token=np.int32(rec["in_token"]), first_hidden_bits=rec["in_hidden"][0],
         codes=np.array(rec["codes"], np.int32), cp_margins=np.array(rec["cp_margins"], np.float32),
+        cp_top1=np.array(rec["cp_top1"], np.float32), talker_top1=np.array(rec["talker_top1"], np.float32),
         talker_tokens=np.array(rec["talker_tokens"], np.int32), talker_margins=np.array(rec["talker_margins"], np.float32),
         talker_hidden_bits=np.stack(rec["talker_hidden"]),
     )

@@ -20,9 +20,11 @@ def _lane_check(name, h_b, h_1, tok_b, tok_1, lm_head):
     return rel
 
 
-@pytest.mark.parametrize("batch", [16, 64])
-def test_batched_streams_equal_b1_lane_by_lane(gpu_weights, batch):
-    """Staggered positions: stream b has already decoded b % 4 positions (its KV rows come from the B = 1 engine)."""
+@pytest.mark.parametrize("batch,persistent", [(16, 0), (32, 0), (48, 0), (64, 0), (16, 1), (64, 1)])
+def test_batched_streams_equal_b1_lane_by_lane(gpu_weights, monkeypatch, batch, persistent):
+    """Staggered positions: stream b has already decoded b % 4 positions (its KV rows come from the B = 1 engine).  Both forms
+    of the step: the chain of per-projection launches (default) and the persistent kernel."""
+    monkeypatch.setenv("QMK_BATCHED_PERSISTENT", str(persistent))
     from qwen_megakernel.model_tts import BatchedTTSDecoder, TTSDecoder
     from qwen_megakernel.synthetic import synthetic_inputs
     S = 64
@@ -49,7 +51,7 @@ def test_batched_streams_equal_b1_lane_by_lane(gpu_weights, batch):
     toks0, hid0 = toks.clone(), hid.clone()
     toks1, hid1 = bd.step(toks0)
     toks1, hid1 = toks1.clone(), hid1.clone()
-    torch.cuda.synchronize()
+    bd.sync_status()
     assert bd.positions.cpu().tolist() == [b % 4 + 2 for b in range(batch)]
     worst = 0.0
     for b in lanes:
@@ -97,3 +99,86 @@ def test_batched_argument_validation(gpu_weights):
         bd.step(torch.zeros(5, dtype=torch.int32))
     with pytest.raises(ValueError):
         bd.step_with_embed(torch.zeros(16, 8, dtype=torch.bfloat16))
+
+
+def test_batched_chain_and_persistent_agree(gpu_weights, monkeypatch):
+    """The chain of per-projection launches and the persistent kernel (QMK_BATCHED_PERSISTENT=1) evaluate the same step
+    with different split-K partitions: hidden states within the bf16 tolerance, tokens equal up to near-ties."""
+    from qwen_megakernel.model_tts import BatchedTTSDecoder
+    from qwen_megakernel.synthetic import synthetic_inputs
+    x = synthetic_inputs(515, 16 * 3).cuda().view(3, 16, 1024)
+    outs = []
+    for pers in ("1", "0"):
+        monkeypatch.setenv("QMK_BATCHED_PERSISTENT", pers)
+        bd = BatchedTTSDecoder(gpu_weights, 16, max_seq_len=32)
+        assert bd.persistent and bd.persistent_decode == (pers == "1")
+        run = []
+        for i in range(3):
+            t, h = bd.step_with_embed(x[i])
+            run.append((t.clone(), h.clone()))
+        bd.sync_status()
+        outs.append(run)
+        del bd
+    for (t0, h0), (t1, h1) in zip(*outs):
+        for b in range(16):
+            _lane_check(f"chain vs persistent lane {b}", h0[b], h1[b], int(t0[b]), int(t1[b]), gpu_weights["lm_head_weight"])
+
+
+@pytest.mark.parametrize("position,persistent", [(100, 0), (2045, 0), (2045, 1)])
+def test_batched_lanes_at_depth_equal_b1(gpu_weights, monkeypatch, position, persistent):
+    """Lane parity deep in the cache (up to position 2047): every stream's cache holds the same random rows as the B = 1
+    engine's; streams sit at different depths (position - 3 b)."""
+    from qwen_megakernel.model_tts import BatchedTTSDecoder, TTSDecoder
+    from qwen_megakernel.synthetic import _normal_bf16, synthetic_inputs
+    S, batch = 2048, 16
+    monkeypatch.setenv("QMK_BATCHED_PERSISTENT", str(persistent))
+    bd = BatchedTTSDecoder(gpu_weights, batch, max_seq_len=S)
+    d1 = TTSDecoder(weights=gpu_weights, verbose=False, max_seq_len=S)
+    kfill = _normal_bf16((28, 8, position, 128), 1.0, 9, 40 + position).cuda()
+    vfill = _normal_bf16((28, 8, position, 128), 1.0, 9, 90 + position).cuda()
+    x = synthetic_inputs(3030 + position, batch).cuda()
+    for b in range(batch):
+        bd._k_cache[b, :, :, :position] = kfill; bd._v_cache[b, :, :, :position] = vfill
+        bd.positions[b] = position - 3 * b
+    bd._steps = position
+    toks, hid = bd.step_with_embed(x)
+    toks, hid = toks.clone(), hid.clone()
+    toks2, hid2 = bd.step(toks)
+    bd.sync_status()
+    for b in (0, 7, 15):
+        d1._k_cache[:, :, :position] = kfill; d1._v_cache[:, :, :position] = vfill
+        d1._position = position - 3 * b
+        t0, h0 = d1.step_with_embed(x[b])
+        _lane_check(f"depth {position} lane {b} step 0", hid[b], h0, int(toks[b]), t0, gpu_weights["lm_head_weight"])
+        if int(toks[b]) == t0:
+            t1, h1 = d1.step(t0)
+            _lane_check(f"depth {position} lane {b} step 1", hid2[b], h1, int(toks2[b]), t1, gpu_weights["lm_head_weight"])
+
+
+@pytest.mark.parametrize("n,start", [(8, 0), (13, 5)])
+def test_prefill_as_one_batched_pass_equals_sequential_steps(gpu_weights, n, start):
+    """n prefill embeddings in ONE batched pass (tcgen05 projections, causal attention over a shared cache)
+    against n sequential step_with_embed calls of the B = 1 engine: same KV rows and last hidden state within the bf16
+    tolerance (different accumulation order), same token up to near-ties; decoding then continues on the B = 1 engine."""
+    from qwen_megakernel.model_tts import TTSDecoder
+    from qwen_megakernel.synthetic import synthetic_inputs
+    S = 64
+    x = synthetic_inputs(4141, start + n + 2).cuda()
+    seq = TTSDecoder(weights=gpu_weights, verbose=False, max_seq_len=S)
+    for i in range(start + n):
+        t_ref, h_ref = seq.step_with_embed(x[i])
+    one = TTSDecoder(weights=gpu_weights, verbose=False, max_seq_len=S)
+    for i in range(start):
+        one.step_with_embed(x[i])
+    t, h = one.prefill(x[start:start + n])
+    assert one.position == seq.position == start + n
+    _lane_check(f"prefill n={n}", h, h_ref, t, t_ref, gpu_weights["lm_head_weight"])
+    for name, a, b in (("K", one._k_cache, seq._k_cache), ("V", one._v_cache, seq._v_cache)):
+        rows_a, rows_b = a[:, :, :start + n].float(), b[:, :, :start + n].float()
+        d = float((rows_a - rows_b).abs().max())
+        assert d <= 0.07, f"{name} rows differ by {d}"
+        assert start == 0 or float((rows_a[:, :, :start] - rows_b[:, :, :start]).abs().max()) == 0.0      # untouched rows
+    # both continue identically in distribution: next step on each, compared lane-style
+    t2, h2 = one.step_with_embed(x[start + n])
+    t2r, h2r = seq.step_with_embed(x[start + n])
+    _lane_check(f"step after prefill n={n}", h2, h2r, t2, t2r, gpu_weights["lm_head_weight"])

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN, bf16_from_bits
-from parity import assert_parity, compare
+from parity import assert_parity, compare, near_tie
 
 pytestmark = pytest.mark.gpu
 CODEC_BOS = 2149
@@ -73,7 +73,7 @@ def test_frame_loop_at_depth_vs_reference_golden(talker, cp_kernel, gpu_weights,
     ref_first_h = bf16_from_bits(g["first_hidden_bits"]).float()
     assert float((hid.cpu() - ref_first_h).abs().max() / ref_first_h.abs().max()) <= 2e-2
     n = g["codes"].shape[0]
-    toks, hids, cp_bad = [], [], []
+    toks, hids, cp_bad, cp_ties = [], [], [], []
     hid_ref, tok_ref = ref_first_h, int(g["first_token"])
     for f in range(n):
         codes_ref = g["codes"][f]
@@ -81,12 +81,15 @@ def test_frame_loop_at_depth_vs_reference_golden(talker, cp_kernel, gpu_weights,
         out = cp_kernel.predict(hid_ref.cuda(), tok_ref, emb, do_sample=False, forced_tokens=forced).cpu().tolist()
         for grp in range(15):
             if out[grp + 1] != int(codes_ref[grp + 1]) and float(g["cp_margins"][f][grp]) > 1e-2:
-                cp_bad.append((f, grp, out[grp + 1], int(codes_ref[grp + 1]), float(g["cp_margins"][f][grp])))
+                rec = (f, grp, out[grp + 1], int(codes_ref[grp + 1]), float(g["cp_margins"][f][grp]), float(g["cp_top1"][f][grp]))
+                (cp_ties if near_tie(rec[4], rec[5]) else cp_bad).append(rec)
         extra = trailing[f] if f < trailing.shape[0] else pad
         t, h = talker.step_with_codes(torch.tensor(np.asarray(codes_ref), dtype=torch.int64).cuda(), cp_kernel.codec_embeddings, extra)
         toks.append(t); hids.append(h.cpu())
         tok_ref, hid_ref = int(g["talker_tokens"][f]), bf16_from_bits(g["talker_hidden_bits"][f]).float()
-    assert not cp_bad, f"code-predictor mismatches at reference margin > 1e-2: {cp_bad[:5]}"
+    print(f"code predictor: {n * 15} decisions, {len(cp_ties)} flips at a reference margin in (1e-2, 2 ulps] (recorded): {cp_ties}")
+    assert not cp_bad, f"code-predictor mismatches beyond a two-ulp reference margin: {cp_bad[:5]}"
+    assert len(cp_ties) <= n * 15 // 500, f"too many near-tie flips: {cp_ties}"      # <= 0.2 % of the decisions (tests/parity.py)
     ref_h = [bf16_from_bits(b).float() for b in g["talker_hidden_bits"]]
     assert_parity(compare("frame loop at depth (talker)", toks, hids, g["talker_tokens"], g["talker_margins"], ref_h))
     assert talker.position == prefill.shape[0] + 1 + n
