@@ -380,6 +380,31 @@ def time_batched(weights_gpu, dev, batch: int, steps: int = 100, warmup: int = 1
             "note": "talker step for B streams: tcgen05/TMEM split-K GEMMs + fused epilogues, PDL chain; positions 0..%d" % steps}
 
 
+def time_batched_frames(weights_gpu, dev, batch: int, frames: int = 20, warmup: int = 3, max_seq: int = 512):
+    """BASELINE.json configs[3]-[4] in codec frames/s: B concurrent utterances through the whole frame loop (batched
+    code-predictor frame with top-k sampling + 16-way embedding sum + batched talker step per frame), no host sync inside."""
+    from qwen_megakernel.model_tts import BatchedFrameLoop
+    from qwen_megakernel.synthetic import synthetic_inputs
+    loop = BatchedFrameLoop(weights_gpu, batch, device=dev, max_seq_len=max_seq)
+    pre = synthetic_inputs(99, N_PREFILL * batch).to(dev).view(N_PREFILL, batch, 1024)
+    extra = synthetic_inputs(4321, batch).to(dev)
+    loop.start(pre)
+    for _ in range(warmup):
+        loop.frame(extra)
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(frames):
+        loop.frame(extra)
+    end.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(end) / frames
+    del loop
+    return {"ms_per_frame_all_streams": ms, "codec_frames_per_s": batch * 1000.0 / ms,
+            "launches_per_frame": 16 * (8 * 5 + 1) + 15 * 2 + 1 + (8 * 28 + 3),
+            "note": "BatchedFrameLoop.frame: 16 batched code-predictor steps + 15 heads (T 0.9 / top-k 50) + embedding sum + talker step"}
+
+
 def pin_rank_to_cores(local_rank: int, world: int) -> list:
     """Give every rank its own slice of the host cores (8 Python launchers otherwise migrate and share cores)."""
     try:
@@ -522,6 +547,9 @@ def main():
             tot, ms_b = combine(r["stream_steps_per_s"], r["ms_per_step"], device=dev)   # replicas: sum of rates, max of step times
             r["stream_steps_per_s_all_gpus"] = tot
             r["ms_per_step_max_over_ranks"] = ms_b
+            fr = time_batched_frames(w_gpu, dev, b)
+            fr["codec_frames_per_s_all_gpus"], fr["ms_per_frame_max_over_ranks"] = combine(fr["codec_frames_per_s"], fr["ms_per_frame_all_streams"], device=dev)
+            r["frame_loop"] = fr
             batched[f"B{b}"] = r
     if rank != 0:
         if world > 1:

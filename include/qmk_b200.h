@@ -243,6 +243,36 @@ void qmk_batched_destroy(qmk_batched* h);
 int qmk_batched_step(qmk_batched* h, const int32_t* token_ids, const void* embeds, int32_t* positions, void* k_cache,
                      void* v_cache, float* hidden_out, int32_t* tokens_out, void* stream);
 const char* qmk_batched_last_error(void);
+
+/* ---- batched code-predictor frame / batched frame loop (BASELINE.json configs[3], [4] in codec frames/s) -------------------
+ * A code-predictor stack is a qmk_batched with num_layers = 5, residual_fp32 = 0, its group heads registered with
+ * qmk_batched_add_head and its steps issued with qmk_batched_step_ex (input table per step, fp32 input for step 0, head
+ * index or none, greedy or temperature / top-k / multinomial selection with the B = 1 engine's sampler, int64 code outputs). */
+typedef struct qmk_batched_step_args {
+  const int32_t* token_ids;     /* int32[B] or NULL; entry < 0 takes the stream's row of embeds_bf16 */
+  const void* token_table;      /* bf16 [table_rows, 1024] the ids index; NULL = the create-time embedding table */
+  int32_t table_rows;
+  const void* embeds_bf16;      /* bf16[B][1024] or NULL */
+  const float* embeds_f32;      /* f32[B][1024] or NULL: rounded to bf16 on load (takes precedence) */
+  int32_t* positions;           /* int32[B], advanced by one */
+  void* k_cache;
+  void* v_cache;
+  float* hidden_out;            /* f32[B][1024] or NULL */
+  int32_t head;                 /* -1: no LM head; 0: the create-time head; n >= 1: n-th qmk_batched_add_head */
+  int32_t do_sample, top_k, group;
+  float temperature;
+  uint64_t seed, counter;       /* stream b draws like a B = 1 engine seeded seed + b * 0x632BE59BD9B4E019 at frame `counter` */
+  int32_t* tokens_out;          /* int32[B] (head >= 0) */
+  int64_t* codes_out;           /* optional: codes_out[b * codes_stride + codes_col] = token */
+  int32_t codes_stride, codes_col;
+} qmk_batched_step_args;
+int qmk_batched_add_head(qmk_batched* h, const void* lm_head_weight, int rows);
+int qmk_batched_step_ex(qmk_batched* h, const qmk_batched_step_args* args, void* stream);
+/* out[b] = talker_embed[codes[b][0]] + sum_g group_tables[g][codes[b][g+1]] + extra[b * extra_stride]  (bf16 adds, upstream order:
+ * tts_engine.py:319-333 for B streams).  codes: int64[B][16]; group_tables: HOST array of 15 device pointers. */
+int qmk_batched_embed_sum(int batch, const int64_t* codes, const void* talker_embed, int talker_rows,
+                          const void* const* group_tables, int group_rows, const void* extra_bf16, int extra_stride,
+                          void* out_bf16, void* stream);
 /* csrc/qmk_bstep.cuh holds a PERSISTENT form of the step: one cooperative launch runs all layers, the LM head and the argmax
  * (grid barriers between phases, weights re-packed k-block-major and prefetched through a shared-memory ring by a producer
  * warp, tcgen05 / TMEM projections).  It serves the one-pass prefill below.  For decode steps it is opt-in

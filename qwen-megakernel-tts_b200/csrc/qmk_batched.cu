@@ -17,6 +17,7 @@
 #include "qmk_b200.h"
 #include "qmk_bgemm.cuh"
 #include "qmk_bstep.cuh"
+#include "qmk_sample.cuh"
 
 namespace {
 
@@ -59,18 +60,24 @@ __device__ __forceinline__ uint2 rmsnorm4(const float (&x)[4], const __nv_bfloat
 
 // ---- step input: embedding row or caller vector -> fp32 residual + layer-0 input norm -------------------------------
 // grid = B, block = 256
-__global__ void kb_input(const int* token_ids, const __nv_bfloat16* embed_table, int vocab, const __nv_bfloat16* embeds, float* res,
-                         const __nv_bfloat16* w_in, __nv_bfloat16* xn) {
+__global__ void kb_input(const int* token_ids, const __nv_bfloat16* embed_table, int vocab, const __nv_bfloat16* embeds,
+                         const float* embeds_f32, float* res, const __nv_bfloat16* w_in, __nv_bfloat16* xn) {
   __shared__ float s_red[8];
   qmkb::pdl_wait();
   qmkb::pdl_launch_dependents();
   const int b = blockIdx.x, t = threadIdx.x;
-  int tok = token_ids ? token_ids[b] : -1;
-  if (tok >= vocab) tok = vocab - 1;             // device-side ids are not trusted: clamp instead of reading out of bounds
-  if (tok < 0 && embeds == nullptr) tok = 0;     // sentinel without an embedding buffer
-  const __nv_bfloat16* src = tok >= 0 ? embed_table + (size_t)tok * H : embeds + (size_t)b * H;
-  const uint2 v = *reinterpret_cast<const uint2*>(src + t * 4);
-  const float x[4] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y)};
+  float x[4];
+  if (embeds_f32 != nullptr) {      // fp32 vector rounded to bf16 on load (the talker's hidden state entering the code predictor)
+    const float4 v = *reinterpret_cast<const float4*>(embeds_f32 + (size_t)b * H + t * 4);
+    x[0] = bf16_round(v.x); x[1] = bf16_round(v.y); x[2] = bf16_round(v.z); x[3] = bf16_round(v.w);
+  } else {
+    int tok = token_ids ? token_ids[b] : -1;
+    if (tok >= vocab) tok = vocab - 1;             // device-side ids are not trusted: clamp instead of reading out of bounds
+    if (tok < 0 && embeds == nullptr) tok = 0;     // sentinel without an embedding buffer
+    const __nv_bfloat16* src = tok >= 0 ? embed_table + (size_t)tok * H : embeds + (size_t)b * H;
+    const uint2 v = *reinterpret_cast<const uint2*>(src + t * 4);
+    x[0] = bf16_lo(v.x); x[1] = bf16_hi(v.x); x[2] = bf16_lo(v.y); x[3] = bf16_hi(v.y);
+  }
   *reinterpret_cast<float4*>(res + (size_t)b * H + t * 4) = make_float4(x[0], x[1], x[2], x[3]);
   *reinterpret_cast<uint2*>(xn + (size_t)b * H + t * 4) = rmsnorm4(x, w_in, s_red);
 }
@@ -78,7 +85,7 @@ __global__ void kb_input(const int* token_ids, const __nv_bfloat16* embed_table,
 // ---- O / down epilogue: split-K sum -> bf16 -> residual -> next RMSNorm ----------------------------------------------
 // grid = B, block = 256.  partial: [splits][B][1024].  hidden_out (optional, final norm only): f32[B][1024]
 __global__ void kb_resid_norm(const float* partial, int splits, int B, float* res, int residual_fp32,
-                              const __nv_bfloat16* w_norm, __nv_bfloat16* xn, float* hidden_out) {
+                              const __nv_bfloat16* w_norm, __nv_bfloat16* xn, float* hidden_out, int* advance_positions) {
   __shared__ float s_red[8];
   qmkb::pdl_wait();
   qmkb::pdl_launch_dependents();
@@ -100,6 +107,7 @@ __global__ void kb_resid_norm(const float* partial, int splits, int B, float* re
   *reinterpret_cast<uint2*>(xn + (size_t)b * H + t * 4) = n;
   if (hidden_out)
     *reinterpret_cast<float4*>(hidden_out + (size_t)b * H + t * 4) = make_float4(bf16_lo(n.x), bf16_hi(n.x), bf16_lo(n.y), bf16_hi(n.y));
+  if (advance_positions != nullptr && t == 0) advance_positions[b] += 1;   // a step without an LM head ends here
 }
 
 // ---- QKV epilogue + decode attention, one CTA per (stream, kv head) --------------------------------------------------
@@ -223,20 +231,34 @@ __global__ void kb_gu_epilogue(const float* partial, int splits, int B, __nv_bfl
   *reinterpret_cast<uint2*>(m_out + (size_t)b * INTER + j) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
 }
 
-// ---- LM head epilogue: bf16 logits, argmax with lowest index on ties; advances the stream's position ----------------
-// grid = B, block = 256; partial: [splits][B][rows]
-__global__ void kb_head_epilogue(const float* partial, int splits, int B, int rows, int* tokens_out, int* positions) {
+// ---- LM head epilogue: bf16 logits; argmax (lowest index on ties) or temperature / top-k / multinomial (the B = 1 engine's
+//      sampler, csrc/qmk_sample.cuh; stream b draws from the generator of a B = 1 engine seeded seed + b * 0x632BE59BD9B4E019);
+//      advances the stream's position ------------------------------------------------------------------------------------
+// grid = B, block = 256; partial: [splits][B][rows]; codes_out (optional): int64, element b * codes_stride + codes_col
+struct HeadSelect {
+  int do_sample, top_k, group;
+  float temperature;
+  unsigned long long seed, counter;
+  long long* codes_out;
+  int codes_stride, codes_col;
+};
+__global__ void kb_head_epilogue(const float* partial, int splits, int B, int rows, int* tokens_out, int* positions, HeadSelect sel) {
   __shared__ float s_v[8];
   __shared__ int s_i[8];
+  __shared__ float s_log[2048];
+  __shared__ unsigned s_hist[512];
+  __shared__ float s_red[64];
   qmkb::pdl_wait();
   qmkb::pdl_launch_dependents();
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool sample = sel.do_sample && rows <= 2048 && rows % 256 == 0;
   float best = -INFINITY;
   int best_i = 0x7fffffff;
-  for (int r = threadIdx.x; r < rows; r += 256) {
+  for (int r = tid; r < rows; r += 256) {
     float acc = 0.f;
     for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * B + b) * rows + r];
     const float v = bf16_round(acc);
+    if (sample) s_log[r] = v;
     if (v > best) { best = v; best_i = r; }
   }
 #pragma unroll
@@ -245,14 +267,49 @@ __global__ void kb_head_epilogue(const float* partial, int splits, int B, int ro
     const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
     if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
   }
-  if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = best_i; }
+  if (lane == 0) { s_v[warp] = best; s_i[warp] = best_i; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w)
-      if (s_v[w] > best || (s_v[w] == best && s_i[w] < best_i)) { best = s_v[w]; best_i = s_i[w]; }
-    tokens_out[b] = best_i;
+#pragma unroll
+  for (int w = 0; w < 8; ++w)
+    if (s_v[w] > best || (s_v[w] == best && s_i[w] < best_i)) { best = s_v[w]; best_i = s_i[w]; }
+  if (best_i == 0x7fffffff) best_i = 0;
+  int chosen = best_i;
+  if (sample)
+    chosen = qmk2::sample_token2(s_log, s_hist, s_red, tid, warp, lane, rows, sel.top_k, sel.temperature,
+                                 sel.seed + (unsigned long long)b * 0x632BE59BD9B4E019ull, sel.counter, sel.group, best, best_i);
+  if (tid == 0) {
+    tokens_out[b] = chosen;
+    if (sel.codes_out != nullptr) sel.codes_out[(size_t)b * sel.codes_stride + sel.codes_col] = (long long)chosen;
     positions[b] += 1;
   }
+}
+
+// ---- frame loop glue for B streams (upstream tts_engine.py:319-333 per stream): e[b] = talker_embed[codes[b][0]] +
+//      sum_g group_table[g][codes[b][g + 1]] + extra[b]   (bf16 adds in the upstream order); grid = B, block = 256 -------------
+struct GroupTables { const __nv_bfloat16* t[15]; };
+__global__ void kb_embed_sum(const long long* codes, const __nv_bfloat16* talker_embed, int rows0, GroupTables gt, int rows,
+                             const __nv_bfloat16* extra, int extra_stride, __nv_bfloat16* out) {
+  const int b = blockIdx.x, t = threadIdx.x;
+  int code[16];
+#pragma unroll
+  for (int g = 0; g < 16; ++g) {
+    const int v = (int)codes[(size_t)b * 16 + g], hi = (g == 0 ? rows0 : rows) - 1;
+    code[g] = v < 0 ? 0 : (v > hi ? hi : v);
+  }
+  uint2 row[16];
+  row[0] = *reinterpret_cast<const uint2*>(talker_embed + (size_t)code[0] * H + t * 4);
+#pragma unroll
+  for (int g = 0; g < 15; ++g) row[g + 1] = *reinterpret_cast<const uint2*>(gt.t[g] + (size_t)code[g + 1] * H + t * 4);
+  const uint2 vx = *reinterpret_cast<const uint2*>(extra + (size_t)b * extra_stride + t * 4);
+  float e4[4] = {bf16_lo(row[0].x), bf16_hi(row[0].x), bf16_lo(row[0].y), bf16_hi(row[0].y)};
+#pragma unroll
+  for (int g = 1; g < 16; ++g) {
+    e4[0] = bf16_round(e4[0] + bf16_lo(row[g].x)); e4[1] = bf16_round(e4[1] + bf16_hi(row[g].x));
+    e4[2] = bf16_round(e4[2] + bf16_lo(row[g].y)); e4[3] = bf16_round(e4[3] + bf16_hi(row[g].y));
+  }
+  const uint32_t o0 = bf16_bits(e4[0] + bf16_lo(vx.x)) | (bf16_bits(e4[1] + bf16_hi(vx.x)) << 16);
+  const uint32_t o1 = bf16_bits(e4[2] + bf16_lo(vx.y)) | (bf16_bits(e4[3] + bf16_hi(vx.y)) << 16);
+  *reinterpret_cast<uint2*>(out + (size_t)b * H + t * 4) = make_uint2(o0, o1);
 }
 
 // concatenate row blocks of two / three [rows, K] matrices into one (one-time, at model creation)
@@ -301,6 +358,8 @@ struct qmk_batched {
   const void *final_norm = nullptr, *lm_head = nullptr, *embed = nullptr, *cos_t = nullptr, *sin_t = nullptr;
   std::vector<CUtensorMap> map_qkv, map_o, map_gu, map_down;
   CUtensorMap map_head, map_x1024, map_x2048, map_x3072;
+  std::vector<CUtensorMap> extra_head_maps;                  // heads registered with qmk_batched_add_head (index 1, 2, ...)
+  std::vector<int> extra_head_rows;
   float *res = nullptr, *partial = nullptr;
   __nv_bfloat16 *xn = nullptr, *abuf = nullptr, *mbuf = nullptr;
   // persistent step kernel (qmk_bstep.cuh)
@@ -516,6 +575,98 @@ static int launch_persistent(qmk_batched* h, int lanes, int prefill, const int32
   return QMK_OK;
 }
 
+// One decode step for all B streams (the chain of per-projection launches).
+static int chain_step(qmk_batched* h, const qmk_batched_step_args* a, cudaStream_t st) {
+  const int B = h->B, L = h->L;
+  const float scale = 0.08838834764831845f;
+  __nv_bfloat16* kc = reinterpret_cast<__nv_bfloat16*>(a->k_cache);
+  __nv_bfloat16* vc = reinterpret_cast<__nv_bfloat16*>(a->v_cache);
+  const __nv_bfloat16* cos_t = reinterpret_cast<const __nv_bfloat16*>(h->cos_t);
+  const __nv_bfloat16* sin_t = reinterpret_cast<const __nv_bfloat16*>(h->sin_t);
+  const __nv_bfloat16* table = reinterpret_cast<const __nv_bfloat16*>(a->token_table ? a->token_table : h->embed);
+  const int table_rows = a->token_table ? a->table_rows : h->head_rows;
+  int head_rows = 0;
+  const CUtensorMap* head_map = nullptr;
+  if (a->head == 0) { head_rows = h->head_rows; head_map = &h->map_head; }
+  else if (a->head > 0) { head_rows = h->extra_head_rows[a->head - 1]; head_map = &h->extra_head_maps[a->head - 1]; }
+  launch_pdl(kb_input, dim3(B), dim3(256), 0, st, (const int*)a->token_ids, table, table_rows,
+             reinterpret_cast<const __nv_bfloat16*>(a->embeds_bf16), (const float*)a->embeds_f32, h->res,
+             reinterpret_cast<const __nv_bfloat16*>(h->ln_in[0]), h->xn);
+  for (int l = 0; l < L; ++l) {
+    gemm(h, h->map_qkv[l], h->map_x1024, QKV_ROWS, H, 4, st);                       // 32 tiles x 4 K-slices
+    launch_pdl(kb_qkv_attention, dim3(B, NKVH), dim3(256), 0, st, (const float*)h->partial, 4, B, (const int*)a->positions,
+               reinterpret_cast<const __nv_bfloat16*>(h->qn[l]), reinterpret_cast<const __nv_bfloat16*>(h->kn[l]), cos_t, sin_t,
+               kc, vc, h->abuf, l, L, h->max_seq, scale);
+    gemm(h, h->map_o[l], h->map_x2048, H, QSZ, 16, st);                              // 8 tiles x 16 K-slices
+    launch_pdl(kb_resid_norm, dim3(B), dim3(256), 0, st, (const float*)h->partial, 16, B, h->res, h->residual_fp32,
+               reinterpret_cast<const __nv_bfloat16*>(h->ln_post[l]), h->xn, (float*)nullptr, (int*)nullptr);
+    gemm(h, h->map_gu[l], h->map_x1024, GU_ROWS, H, 4, st);                          // 48 tiles x 4 K-slices
+    launch_pdl(kb_gu_epilogue, dim3(B, 3), dim3(256), 0, st, (const float*)h->partial, 4, B, h->mbuf);
+    gemm(h, h->map_down[l], h->map_x3072, H, INTER, 16, st);                         // 8 tiles x 16 K-slices
+    const bool last = (l == L - 1);
+    launch_pdl(kb_resid_norm, dim3(B), dim3(256), 0, st, (const float*)h->partial, 16, B, h->res, h->residual_fp32,
+               reinterpret_cast<const __nv_bfloat16*>(last ? h->final_norm : h->ln_in[l + 1]), h->xn,
+               last ? a->hidden_out : (float*)nullptr, (last && head_map == nullptr) ? (int*)a->positions : (int*)nullptr);
+  }
+  if (head_map != nullptr) {
+    gemm(h, *head_map, h->map_x1024, head_rows, H, 4, st);
+    HeadSelect sel;
+    sel.do_sample = (a->do_sample && a->temperature > 0.f) ? 1 : 0;
+    sel.top_k = a->top_k; sel.group = a->group; sel.temperature = sel.do_sample ? a->temperature : 1.0f;
+    sel.seed = a->seed; sel.counter = a->counter;
+    sel.codes_out = reinterpret_cast<long long*>(a->codes_out); sel.codes_stride = a->codes_stride; sel.codes_col = a->codes_col;
+    launch_pdl(kb_head_epilogue, dim3(B), dim3(256), 0, st, (const float*)h->partial, 4, B, head_rows, (int*)a->tokens_out,
+               (int*)a->positions, sel);
+  }
+  cudaError_t e = g_launch_err != cudaSuccess ? g_launch_err : cudaGetLastError();
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(QMK_ERR_CUDA, cudaGetErrorString(e)); }
+  return QMK_OK;
+}
+
+// Register a further LM head (bf16 [rows, 1024], rows % 128 == 0): returns its index (1, 2, ...; 0 is the create-time head).
+extern "C" int qmk_batched_add_head(qmk_batched* h, const void* lm_head_weight, int rows) {
+  if (!h || !lm_head_weight) return fail(QMK_ERR_ARG, "qmk_batched_add_head: null argument");
+  if (rows <= 0 || rows % qmkb::BM || (size_t)6 * h->B * rows > PARTIAL_ELEMS) return fail(QMK_ERR_ARG, "qmk_batched_add_head: bad row count");
+  CUtensorMap m;
+  if (qmkb::make_tensor_map(&m, lm_head_weight, rows, H, qmkb::BM)) return fail(QMK_ERR_CUDA, "qmk_batched_add_head: cuTensorMapEncodeTiled failed");
+  h->extra_head_maps.push_back(m);
+  h->extra_head_rows.push_back(rows);
+  return (int)h->extra_head_maps.size();
+}
+
+// General step (the code predictor's steps need more than qmk_batched_step offers: an input table per step, fp32 inputs, a head
+// index or none, sampling, int64 code outputs).  Always the chain of launches.
+extern "C" int qmk_batched_step_ex(qmk_batched* h, const qmk_batched_step_args* a, void* stream) {
+  if (!h || !a || !a->positions || !a->k_cache || !a->v_cache) return fail(QMK_ERR_ARG, "qmk_batched_step_ex: null argument");
+  if (!a->token_ids && !a->embeds_bf16 && !a->embeds_f32) return fail(QMK_ERR_ARG, "qmk_batched_step_ex: no input given");
+  if (a->head > (int)h->extra_head_maps.size()) return fail(QMK_ERR_ARG, "qmk_batched_step_ex: head index not registered");
+  if (a->head >= 0 && !a->tokens_out) return fail(QMK_ERR_ARG, "qmk_batched_step_ex: tokens_out is null");
+  if (a->token_table && a->table_rows < 1) return fail(QMK_ERR_ARG, "qmk_batched_step_ex: table_rows must be positive");
+  BatchedDeviceGuard guard(h->device);
+  g_launch_err = cudaSuccess;
+  return chain_step(h, a, (cudaStream_t)stream);
+}
+
+// 16-way embedding sum of the frame loop for B streams: out[b] = talker_embed[codes[b][0]] + sum_g tables[g][codes[b][g+1]] +
+// extra[b * extra_stride ..] (extra_stride = 0: one vector for all streams).  group_tables: HOST array of 15 device pointers.
+extern "C" int qmk_batched_embed_sum(int batch, const int64_t* codes, const void* talker_embed, int talker_rows,
+                                     const void* const* group_tables, int group_rows, const void* extra_bf16, int extra_stride,
+                                     void* out_bf16, void* stream) {
+  if (batch < 1 || !codes || !talker_embed || !group_tables || !extra_bf16 || !out_bf16 || talker_rows < 1 || group_rows < 1)
+    return fail(QMK_ERR_ARG, "qmk_batched_embed_sum: bad argument");
+  GroupTables gt;
+  for (int g = 0; g < 15; ++g) {
+    if (!group_tables[g]) return fail(QMK_ERR_ARG, "qmk_batched_embed_sum: null group table");
+    gt.t[g] = reinterpret_cast<const __nv_bfloat16*>(group_tables[g]);
+  }
+  kb_embed_sum<<<batch, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(codes), reinterpret_cast<const __nv_bfloat16*>(talker_embed),
+                                                        talker_rows, gt, group_rows, reinterpret_cast<const __nv_bfloat16*>(extra_bf16),
+                                                        extra_stride, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(QMK_ERR_CUDA, cudaGetErrorString(e));
+  return QMK_OK;
+}
+
 // One decode step for all B streams.  token_ids (int32[B], device; entry < 0 or null pointer -> the stream's row of
 // `embeds` bf16[B][1024] is the input, the upstream sentinel path), positions (int32[B], device, advanced by one),
 // k_cache / v_cache: [B][L][8][max_seq][128] bf16.  Outputs: tokens_out int32[B], hidden_out f32[B][1024].
@@ -528,35 +679,11 @@ extern "C" int qmk_batched_step(qmk_batched* h, const int32_t* token_ids, const 
   g_launch_err = cudaSuccess;
   if (h->decode_persistent)
     return launch_persistent(h, h->B, 0, token_ids, embeds, positions, k_cache, v_cache, hidden_out, tokens_out, st);
-  const int B = h->B, L = h->L;
-  const float scale = 0.08838834764831845f;
-  __nv_bfloat16* kc = reinterpret_cast<__nv_bfloat16*>(k_cache);
-  __nv_bfloat16* vc = reinterpret_cast<__nv_bfloat16*>(v_cache);
-  const __nv_bfloat16* cos_t = reinterpret_cast<const __nv_bfloat16*>(h->cos_t);
-  const __nv_bfloat16* sin_t = reinterpret_cast<const __nv_bfloat16*>(h->sin_t);
-  launch_pdl(kb_input, dim3(B), dim3(256), 0, st, (const int*)token_ids, reinterpret_cast<const __nv_bfloat16*>(h->embed), h->head_rows,
-             reinterpret_cast<const __nv_bfloat16*>(embeds), h->res, reinterpret_cast<const __nv_bfloat16*>(h->ln_in[0]), h->xn);
-  for (int l = 0; l < L; ++l) {
-    gemm(h, h->map_qkv[l], h->map_x1024, QKV_ROWS, H, 4, st);                       // 32 tiles x 4 K-slices
-    launch_pdl(kb_qkv_attention, dim3(B, NKVH), dim3(256), 0, st, (const float*)h->partial, 4, B, (const int*)positions,
-               reinterpret_cast<const __nv_bfloat16*>(h->qn[l]), reinterpret_cast<const __nv_bfloat16*>(h->kn[l]), cos_t, sin_t,
-               kc, vc, h->abuf, l, L, h->max_seq, scale);
-    gemm(h, h->map_o[l], h->map_x2048, H, QSZ, 16, st);                              // 8 tiles x 16 K-slices
-    launch_pdl(kb_resid_norm, dim3(B), dim3(256), 0, st, (const float*)h->partial, 16, B, h->res, h->residual_fp32,
-               reinterpret_cast<const __nv_bfloat16*>(h->ln_post[l]), h->xn, (float*)nullptr);
-    gemm(h, h->map_gu[l], h->map_x1024, GU_ROWS, H, 4, st);                          // 48 tiles x 4 K-slices
-    launch_pdl(kb_gu_epilogue, dim3(B, 3), dim3(256), 0, st, (const float*)h->partial, 4, B, h->mbuf);
-    gemm(h, h->map_down[l], h->map_x3072, H, INTER, 16, st);                         // 8 tiles x 16 K-slices
-    const bool last = (l == L - 1);
-    launch_pdl(kb_resid_norm, dim3(B), dim3(256), 0, st, (const float*)h->partial, 16, B, h->res, h->residual_fp32,
-               reinterpret_cast<const __nv_bfloat16*>(last ? h->final_norm : h->ln_in[l + 1]), h->xn,
-               last ? hidden_out : (float*)nullptr);
-  }
-  gemm(h, h->map_head, h->map_x1024, h->head_rows, H, 4, st);
-  launch_pdl(kb_head_epilogue, dim3(B), dim3(256), 0, st, (const float*)h->partial, 4, B, h->head_rows, (int*)tokens_out, (int*)positions);
-  cudaError_t e = g_launch_err != cudaSuccess ? g_launch_err : cudaGetLastError();
-  if (e != cudaSuccess) { cudaGetLastError(); return fail(QMK_ERR_CUDA, cudaGetErrorString(e)); }
-  return QMK_OK;
+  qmk_batched_step_args a;
+  memset(&a, 0, sizeof(a));
+  a.token_ids = token_ids; a.embeds_bf16 = embeds; a.positions = positions; a.k_cache = k_cache; a.v_cache = v_cache;
+  a.hidden_out = hidden_out; a.tokens_out = tokens_out; a.head = 0; a.group = -1;
+  return chain_step(h, &a, st);
 }
 
 // Prefill of ONE utterance as a single batched pass (upstream feeds the 8 prefill embeddings

@@ -129,6 +129,9 @@ SIGNATURES = {
     "qmk_batched_destroy": (None, [_vp]),
     "qmk_batched_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qmk_batched_last_error": (ctypes.c_char_p, []),
+    "qmk_batched_add_head": (_i32, [_vp, _vp, _i32]),
+    "qmk_batched_step_ex": (_i32, [_vp, _vp, _vp]),
+    "qmk_batched_embed_sum": (_i32, [_i32, _vp, _vp, _i32, ctypes.POINTER(_vp), _i32, _vp, _i32, _vp, _vp]),
     "qmk_batched_is_persistent": (_i32, [_vp]),
     "qmk_batched_trace_read": (_i32, [_vp, _vp, ctypes.POINTER(ctypes.c_longlong), _i32]),
     "qmk_batched_sync_status": (_i32, [_vp, _vp]),
@@ -158,6 +161,17 @@ def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
 
 class NativeError(RuntimeError):
     pass
+
+
+class BatchedStepArgs(ctypes.Structure):
+    """Mirror of ``qmk_batched_step_args`` (include/qmk_b200.h)."""
+    _fields_ = [
+        ("token_ids", _vp), ("token_table", _vp), ("table_rows", ctypes.c_int32), ("embeds_bf16", _vp), ("embeds_f32", _vp),
+        ("positions", _vp), ("k_cache", _vp), ("v_cache", _vp), ("hidden_out", _vp), ("head", ctypes.c_int32),
+        ("do_sample", ctypes.c_int32), ("top_k", ctypes.c_int32), ("group", ctypes.c_int32), ("temperature", ctypes.c_float),
+        ("seed", ctypes.c_uint64), ("counter", ctypes.c_uint64), ("tokens_out", _vp), ("codes_out", _vp),
+        ("codes_stride", ctypes.c_int32), ("codes_col", ctypes.c_int32),
+    ]
 
 
 class GenerateArgs(ctypes.Structure):

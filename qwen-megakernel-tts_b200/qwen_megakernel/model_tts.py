@@ -626,6 +626,140 @@ class BatchedTTSDecoder:
             raise NativeError(f"qmk_batched_prefill: {self._lib.qmk_batched_last_error().decode()} (code {rc})")
 
 
+class BatchedCodePredictor:
+    """The code predictor for B concurrent streams (BASELINE.json configs[3]-[4] in codec frames/s; no upstream counterpart):
+    one frame = 16 five-layer batched steps (tcgen05 projections, every weight byte read once for all streams) + the 15 group
+    heads with greedy or temperature / top-k / multinomial selection on the device.  Lane b is numerically the B = 1
+    ``CodePredictorKernel`` (bf16 residual stream, same rounding points) and, when sampling, draws like a B = 1 engine seeded
+    ``seed + b * 0x632BE59BD9B4E019``."""
+
+    def __init__(self, weights: dict, batch: int, *, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedCodePredictor needs a CUDA device (sm_100a); there is no CPU fallback")
+        dev = torch.device(device if device is not None else "cuda")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        from .build_tts import NativeError
+        self.device, self.batch = dev, int(batch)
+        cp = weights["code_predictor"]
+        self.num_groups = NUM_CODE_GROUPS - 1
+        self._layer_weights = [cp[f"layers.{i}.{f}"].contiguous() for i in range(CODE_PREDICTOR_LAYERS) for f in _LAYER_FIELDS]
+        _check_layer_tensors(self._layer_weights, CODE_PREDICTOR_LAYERS, dev)
+        self._final_norm = cp["norm.weight"].contiguous()
+        self.codec_embeddings = [cp[f"codec_embedding.{g}.weight"].contiguous() for g in range(self.num_groups)]
+        self.lm_heads = [cp[f"lm_head.{g}.weight"].contiguous() for g in range(self.num_groups)]
+        self._max_seq = 64
+        self._cos, self._sin = _rope_tables(self._max_seq, dev)
+        self._lib = _Native.lib()
+        host_blob = (ctypes.c_void_p * (11 * CODE_PREDICTOR_LAYERS))(*[t.data_ptr() for t in self._layer_weights])
+        h = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            rc = self._lib.qmk_batched_create(
+                dev.index, host_blob, CODE_PREDICTOR_LAYERS, self._final_norm.data_ptr(), self.lm_heads[0].data_ptr(),
+                CODE_PREDICTOR_VOCAB, self.codec_embeddings[0].data_ptr(), self._cos.data_ptr(), self._sin.data_ptr(), 0,
+                self.batch, self._max_seq, ctypes.byref(h))
+            if rc < 0:
+                raise NativeError(f"qmk_batched_create: {self._lib.qmk_batched_last_error().decode()} (code {rc})")
+            self._handle = h
+            for g in range(1, self.num_groups):
+                rc = self._lib.qmk_batched_add_head(self._handle, self.lm_heads[g].data_ptr(), CODE_PREDICTOR_VOCAB)
+                if rc != g:
+                    raise NativeError(f"qmk_batched_add_head: {self._lib.qmk_batched_last_error().decode()} (code {rc})")
+            B = self.batch
+            self._k_cache = torch.zeros(B, CODE_PREDICTOR_LAYERS, NUM_KV_HEADS, self._max_seq, HEAD_DIM, dtype=torch.bfloat16, device=dev)
+            self._v_cache = torch.zeros_like(self._k_cache)
+            self._positions = torch.zeros(B, dtype=torch.int32, device=dev)
+            self._tokens = torch.zeros(B, dtype=torch.int32, device=dev)
+        self._frame_counter = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                self._lib.qmk_batched_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    def _step(self, **kw):
+        from .build_tts import BatchedStepArgs, NativeError
+        kw.setdefault("group", -1)
+        kw.setdefault("head", -1)
+        a = BatchedStepArgs(positions=self._positions.data_ptr(), k_cache=self._k_cache.data_ptr(), v_cache=self._v_cache.data_ptr(), **kw)
+        rc = self._lib.qmk_batched_step_ex(self._handle, ctypes.byref(a), _stream_ptr(self.device))
+        if rc < 0:
+            raise NativeError(f"qmk_batched_step_ex: {self._lib.qmk_batched_last_error().decode()} (code {rc})")
+
+    @torch.no_grad()
+    def predict(self, talker_hidden: torch.Tensor, first_tokens: torch.Tensor, talker_embed_weight: torch.Tensor,
+                do_sample: bool = True, temperature: float = 0.9, top_k: int = 50) -> torch.Tensor:
+        """All 16 codebook groups of one frame for every stream: int64[B, 16] on the device = [first_token, g0..g14].
+        ``talker_hidden``: f32[B, 1024]; ``first_tokens``: int32[B] (device; the talker's tokens).  Asynchronous."""
+        B = self.batch
+        hid = talker_hidden.to(self.device, torch.float32).reshape(B, HIDDEN_SIZE).contiguous()
+        tok = first_tokens.to(self.device, torch.int32).reshape(B).contiguous()
+        sample = bool(do_sample) and temperature > 0
+        with torch.cuda.device(self.device):
+            codes = torch.empty(B, NUM_CODE_GROUPS, dtype=torch.int64, device=self.device)
+            codes[:, 0] = tok
+            self._positions.zero_()
+            self._frame_counter += 1
+            sel = dict(do_sample=int(sample), top_k=int(top_k), temperature=float(temperature),
+                       seed=torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, counter=self._frame_counter,
+                       tokens_out=self._tokens.data_ptr(), codes_out=codes.data_ptr(), codes_stride=NUM_CODE_GROUPS)
+            self._step(embeds_f32=hid.data_ptr())                                     # position 0: the talker's hidden state
+            self._keep = (hid, tok, codes)
+            for g in range(self.num_groups):                                          # position 1 + g: head g
+                if g == 0:
+                    src = dict(token_ids=tok.data_ptr(), token_table=talker_embed_weight.data_ptr(),
+                               table_rows=int(talker_embed_weight.shape[0]))
+                else:
+                    src = dict(token_ids=self._tokens.data_ptr(), token_table=self.codec_embeddings[g - 1].data_ptr(),
+                               table_rows=CODE_PREDICTOR_VOCAB)
+                kw = dict(sel, **src)
+                kw.update(head=g, group=g, codes_col=g + 1)
+                self._step(**kw)
+        return codes
+
+
+class BatchedFrameLoop:
+    """The upstream frame loop (tts_engine.py:301-335) for B concurrent utterances on one GPU: per frame one batched
+    code-predictor frame, the 16-way embedding sum for every stream and one batched talker step -- all asynchronous on the
+    device (tokens and hidden states never visit the host)."""
+
+    def __init__(self, weights: dict, batch: int, *, device=None, max_seq_len: int = 2048):
+        self.talker = BatchedTTSDecoder(weights, batch, device=device, max_seq_len=max_seq_len)
+        self.cp = BatchedCodePredictor(weights, batch, device=self.talker.device)
+        self.device, self.batch = self.talker.device, int(batch)
+        self._embed = weights["embed_weight"]
+        self._tables = (ctypes.c_void_p * 15)(*[t.data_ptr() for t in self.cp.codec_embeddings])
+        self._e = torch.zeros(batch, HIDDEN_SIZE, dtype=torch.bfloat16, device=self.device)
+        self.tokens = self.hidden = None
+
+    def start(self, prefill_bf16: torch.Tensor, bos_token: int = CODEC_BOS):
+        """``prefill_bf16``: bf16[n, B, 1024] prefill embeddings (n steps for every stream), then step(bos)."""
+        self.talker.reset()
+        for i in range(prefill_bf16.shape[0]):
+            self.talker.step_with_embed(prefill_bf16[i])
+        tok = torch.full((self.batch,), int(bos_token), dtype=torch.int32, device=self.device)
+        self.tokens, self.hidden = self.talker.step(tok)
+
+    def frame(self, extra_bf16: torch.Tensor, do_sample: bool = True, temperature: float = 0.9, top_k: int = 50) -> torch.Tensor:
+        """One codec frame for every stream; ``extra_bf16``: bf16[B, 1024] (per-stream trailing-text / pad embedding) or
+        bf16[1024] (same for all).  Returns codes int64[B, 16] (device)."""
+        from .build_tts import NativeError
+        codes = self.cp.predict(self.hidden, self.tokens, self._embed, do_sample, temperature, top_k)
+        extra = extra_bf16.to(self.device, torch.bfloat16).contiguous()
+        stride = HIDDEN_SIZE if extra.dim() == 2 else 0
+        rc = self.talker._lib.qmk_batched_embed_sum(self.batch, codes.data_ptr(), self._embed.data_ptr(), int(self._embed.shape[0]),
+                                                    self._tables, CODE_PREDICTOR_VOCAB, extra.data_ptr(), stride, self._e.data_ptr(),
+                                                    _stream_ptr(self.device))
+        if rc < 0:
+            raise NativeError(f"qmk_batched_embed_sum: {self.talker._lib.qmk_batched_last_error().decode()} (code {rc})")
+        self._keep = extra
+        self.tokens, self.hidden = self.talker.step_with_embed(self._e)
+        return codes
+
+
 class TextProjection:
     """text ids -> talker hidden size: embedding(151936 -> 2048) -> fc1 + SiLU -> fc2 (-> 1024).
 

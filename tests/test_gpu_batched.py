@@ -182,3 +182,75 @@ def test_prefill_as_one_batched_pass_equals_sequential_steps(gpu_weights, n, sta
     t2, h2 = one.step_with_embed(x[start + n])
     t2r, h2r = seq.step_with_embed(x[start + n])
     _lane_check(f"step after prefill n={n}", h2, h2r, t2, t2r, gpu_weights["lm_head_weight"])
+
+
+def test_batched_code_predictor_frame_equals_b1_lane_by_lane(gpu_weights):
+    """The batched code-predictor frame (16 steps x 16 streams, greedy): every stream's codes equal the B = 1
+    CodePredictorKernel's up to the first group whose B = 1 top-2 margin is inside the tie rule."""
+    from qwen_megakernel.model_tts import BatchedCodePredictor, CodePredictorKernel
+    from qwen_megakernel.synthetic import synthetic_inputs
+    B = 16
+    bcp = BatchedCodePredictor(gpu_weights, B)
+    cp1 = CodePredictorKernel(gpu_weights, device="cuda")
+    hid = synthetic_inputs(5151, B).float().cuda()
+    toks = torch.tensor([(131 * b + 7) % 3072 for b in range(B)], dtype=torch.int32, device="cuda")
+    for rep in range(2):                                              # second frame: positions / caches are reset correctly
+        codes = bcp.predict(hid, toks, gpu_weights["embed_weight"], do_sample=False).cpu()
+        for b in range(B):
+            ref, logits, _ = cp1.predict(hid[b], int(toks[b]), gpu_weights["embed_weight"], do_sample=False, return_debug=True)
+            ref = ref.cpu().tolist()
+            assert int(codes[b, 0]) == ref[0]
+            for g in range(15):
+                if int(codes[b, g + 1]) != ref[g + 1]:
+                    top2 = torch.topk(logits[g], 2).values
+                    assert float(top2[0] - top2[1]) <= MARGIN_RULE, f"stream {b} group {g}: {int(codes[b, g + 1])} vs {ref[g + 1]}"
+                    break
+
+
+def test_batched_code_predictor_sampling_stays_in_top_k(gpu_weights):
+    from qwen_megakernel.model_tts import BatchedCodePredictor, CodePredictorKernel
+    from qwen_megakernel.synthetic import synthetic_inputs
+    B = 16
+    torch.manual_seed(99)
+    bcp = BatchedCodePredictor(gpu_weights, B)
+    cp1 = CodePredictorKernel(gpu_weights, device="cuda")
+    hid = synthetic_inputs(5252, B).float().cuda()
+    toks = torch.tensor([(17 * b + 3) % 3072 for b in range(B)], dtype=torch.int32, device="cuda")
+    a = bcp.predict(hid, toks, gpu_weights["embed_weight"], do_sample=True, temperature=0.9, top_k=50).cpu()
+    b2 = bcp.predict(hid, toks, gpu_weights["embed_weight"], do_sample=True, temperature=0.9, top_k=50).cpu()
+    assert not torch.equal(a, b2), "two sampled frames are identical"
+    assert len({tuple(r.tolist()) for r in a[:, 1:]}) > 1, "all streams drew the same codes"
+    assert int(a.min()) >= 0 and int(a[:, 1:].max()) < 2048
+    for b in (0, 5, 11):                                              # group 0 of a stream: inside the top-50 of the B = 1 logits
+        _, logits, _ = cp1.predict(hid[b], int(toks[b]), gpu_weights["embed_weight"], do_sample=False, return_debug=True)
+        kth = float(torch.topk(logits[0], 50).values[-1])
+        assert float(logits[0][int(a[b, 1])]) >= kth - 0.02
+
+
+def test_batched_frame_loop_equals_b1_loop(gpu_weights):
+    """B = 16 concurrent utterances (greedy) against the B = 1 engine's loop on three of them, two frames deep."""
+    from qwen_megakernel.model_tts import BatchedFrameLoop, CodePredictorKernel, TTSDecoder
+    from qwen_megakernel.synthetic import synthetic_inputs
+    B, S = 16, 64
+    loop = BatchedFrameLoop(gpu_weights, B, max_seq_len=S)
+    prefill = synthetic_inputs(6161, 3 * B).cuda().view(3, B, 1024)
+    extra = synthetic_inputs(6262, 2 * B).cuda().view(2, B, 1024)
+    loop.start(prefill)
+    frames = [loop.frame(extra[f], do_sample=False).clone() for f in range(2)]
+    torch.cuda.synchronize()
+    d1 = TTSDecoder(weights=gpu_weights, verbose=False, max_seq_len=S)
+    cp1 = CodePredictorKernel(gpu_weights, device="cuda")
+    for b in (0, 6, 15):
+        d1.reset()
+        for i in range(3):
+            d1.step_with_embed(prefill[i, b])
+        tok, hid = d1.step(CODEC_BOS)
+        for f in range(2):
+            ref, logits, _ = cp1.predict(hid, tok, gpu_weights["embed_weight"], do_sample=False, return_debug=True)
+            got = frames[f][b].cpu().tolist()
+            ref_l = ref.cpu().tolist()
+            if got != ref_l:                                          # allowed only at a near-tie; the streams diverge afterwards
+                g = next(i for i in range(16) if got[i] != ref_l[i])
+                assert g >= 1 and float(torch.topk(logits[g - 1], 2).values[0] - torch.topk(logits[g - 1], 2).values[1]) <= MARGIN_RULE
+                break
+            tok, hid = d1.step_with_codes(ref, cp1.codec_embeddings, extra[f, b])
