@@ -249,7 +249,10 @@ struct AttnItem2 {
   int S, p0, p1;
   bool has;
 };
-constexpr int ATT_SOLO_ROUNDS = 2;
+#ifndef QMK_ATT_SOLO_ROUNDS
+#define QMK_ATT_SOLO_ROUNDS 2
+#endif
+constexpr int ATT_SOLO_ROUNDS = QMK_ATT_SOLO_ROUNDS;
 __device__ __forceinline__ AttnItem2 attn_item2(int position, int j) {
   AttnItem2 it;
   const int n = position + 1;
@@ -269,7 +272,13 @@ __device__ __forceinline__ AttnItem2 attn_item2(int position, int j) {
 // Cached K/V rows are read with strong loads (see the append at the end of phase_attn2); like .cg they bypass L1.
 __device__ __forceinline__ uint2 ld_strong_u2(const void* p) {
   uint2 v;
+#ifdef QMK_EXP_KV_LD_CG
+  asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+#elif defined(QMK_EXP_KV_LD_NOCLOBBER)
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+#else
   asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+#endif
   return v;
 }
 __device__ __forceinline__ void attn_l2_prefetch(const Ctx2& c, const ModelDesc& p, int l, int position, const AttnItem2& it) {
@@ -397,7 +406,7 @@ __device__ void phase_attn2(Ctx2& c, const ModelDesc& md, int l, int position, u
     }
   } else
   for (int r = 0; r < nrounds; ++r) {
-    if (r > 0) attn_prefetch2(c, md, l, position, it, r, kv);
+    if (r > 0) attn_prefetch2(c, md, l, position, it, r, kv);   // (double-buffering the rows in registers spills: +15 us per step, measured twice)
     float sc[10];
     const int pos_first = it.p0 + r * ATT_ROUND + c.warp;
     if (pos_first < it.p1) {  // warp-uniform
@@ -598,7 +607,11 @@ __device__ void phase_attn2(Ctx2& c, const ModelDesc& md, int l, int position, u
   // step of the same launch is ordered after its OWN store by the CTA barriers in between, and whatever other store to that
   // address it observes instead carries the identical value -- no fence, no flag and no reliance on timing.  (A single writer
   // per group would need a release fence in front of its next publish, i.e. on the layer's critical path: +16 us per step.)
+#ifdef QMK_EXP_KV_ONE_WRITER
+  if (c.j == 0 && c.tid < 64) {
+#else
   if (c.tid < 64) {
+#endif
     const size_t off = ((size_t)(l * NKVH + c.g) * md.max_seq + position) * HD + c.tid * 2;
     const uint32_t kw = bf16_bits(s_small[SS_KN + c.tid * 2]) | (bf16_bits(s_small[SS_KN + c.tid * 2 + 1]) << 16);
     const uint32_t vw = bf16_bits(s_small[SS_V + c.tid * 2]) | (bf16_bits(s_small[SS_V + c.tid * 2 + 1]) << 16);

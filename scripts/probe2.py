@@ -64,6 +64,9 @@ def time_steps_at(dec, x, pos, n=40, warm=5):
     return a.elapsed_time(b) / n * 1e3
 
 
+TRACE_POS = -1
+
+
 def trace2(dec, x, L):
     """per-phase critical-path stamps of thread 0 of every CTA (group kernel)"""
     import ctypes
@@ -75,6 +78,9 @@ def trace2(dec, x, L):
     dec.reset()
     for i in range(12):
         dec.step_with_embed(x[i % 8])
+    if TRACE_POS >= 0:                      # the traced launch is the last one: put it at the requested depth
+        dec._position = TRACE_POS
+        dec.step_with_embed(x[0])
     G = lib.qmk_engine_num_ctas(engine)
     buf = (ctypes.c_longlong * (G * stride))()
     lib.qmk_engine_trace_read(engine, torch.cuda.current_stream().cuda_stream, buf, G * stride)
@@ -149,7 +155,10 @@ def main():
     ap.add_argument("--configs", default="1;2")
     ap.add_argument("--layers", type=int, default=28)
     ap.add_argument("--positions", default="300")
+    ap.add_argument("--trace-pos", type=int, default=-1)
     args = ap.parse_args()
+    global TRACE_POS
+    TRACE_POS = args.trace_pos
     torch.cuda.set_device(0)
     w = weights_to(synthetic_tts_weights(max_seq_len=2048, num_layers=args.layers), "cuda")
     x = synthetic_inputs(99, 16).cuda()
