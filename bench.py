@@ -72,7 +72,7 @@ def measured_peaks() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-NCU_RAW = "r01_ncu_group_raw.csv"   # ncu --set full of one talker launch of the default (group) kernel
+NCU_RAW = "r02_ncu_b1_raw.csv"   # ncu --set full: launch 0 = one talker launch of the default (group) kernel
 
 
 def ncu_traffic_bytes():
