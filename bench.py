@@ -405,6 +405,30 @@ def time_batched_frames(weights_gpu, dev, batch: int, frames: int = 20, warmup: 
             "note": "BatchedFrameLoop.frame: 16 batched code-predictor steps + 15 heads (T 0.9 / top-k 50) + embedding sum + talker step"}
 
 
+def time_upstream_kernel_subprocess(limit_s: float = 60.0) -> dict:
+    """Launch times of the unmodified upstream kernel (oracle/ref_kernel.py) measured in a child process."""
+    lib = os.path.join(REPO, "oracle", "_ref", "libref_kernel_sm100a.so")
+    if not os.path.exists(lib):
+        return {"available": False, "why": "oracle/_ref/libref_kernel_sm100a.so not built (needs the reference tree at build time)"}
+    code = ("import sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r); import torch\n"
+            "from oracle import ref_kernel\n"
+            "from qwen_megakernel.synthetic import synthetic_inputs, synthetic_tts_weights, weights_to\n"
+            "w = weights_to(synthetic_tts_weights(seed=%d, max_seq_len=%d), 'cuda'); x = synthetic_inputs(99, %d).cuda()\n"
+            "t, c = ref_kernel.time_upstream_kernel(w, x); print(json.dumps({'talker_step_us': t, 'cp_step_us': c}))\n"
+            % (REPO, PKG_ROOT, SEED, MAX_SEQ, N_PREFILL))
+    try:
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=limit_s)
+        d = json.loads(out.stdout.strip().splitlines()[-1])
+        d.update(available=True, frame_us_kernels_only=d["talker_step_us"] + 16 * d["cp_step_us"],
+                 note="upstream csrc/kernel.cu (decode kernel + LM-head kernel + memset per step) recompiled with -gencode "
+                      "arch=compute_100a,code=sm_100a and upstream's build_tts.py flags; same weights, positions 18..68")
+        return d
+    except subprocess.TimeoutExpired:
+        return {"available": False, "why": f"upstream kernel hung (> {limit_s:.0f} s): its grid barrier deadlocks intermittently on B200"}
+    except Exception as ex:  # noqa: BLE001
+        return {"available": False, "why": f"{type(ex).__name__}: {ex}"}
+
+
 def pin_rank_to_cores(local_rank: int, world: int) -> list:
     """Give every rank its own slice of the host cores (8 Python launchers otherwise migrate and share cores)."""
     try:
@@ -437,6 +461,8 @@ def main():
     ap.add_argument("--min-seconds", type=float, default=0.6, help="every timed leg is repeated until it covers this much device time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
+    ap.add_argument("--upstream-kernel", action="store_true",
+                    help="also time upstream's kernel.cu built for sm_100a (oracle/_ref; child process with a time limit)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -556,6 +582,14 @@ def main():
             dist.destroy_process_group()
         return
 
+    # GPU-side reference point (opt-in, --upstream-kernel): upstream's own kernel.cu compiled for sm_100a (oracle/Makefile ->
+    # oracle/_ref/*.so, built from the reference tree in the build container).  On B200 that kernel deadlocks intermittently in
+    # its grid barrier (2 of 5 attempts hung on the first launch in round 2), so it runs in a child process with a time limit
+    # and never in the default (driver) run.
+    upstream_kernel = {"available": False, "why": "not requested (--upstream-kernel)"}
+    if args.upstream_kernel:
+        upstream_kernel = time_upstream_kernel_subprocess()
+
     peak, peak_src = measured_peaks()
     n_ctas = loop.talker._lib.qmk_engine_num_ctas(loop.talker._engine)
     kernel_name = "qmk2_decode_kernel" if n_ctas == 128 else "qmk_decode_kernel"
@@ -596,6 +630,7 @@ def main():
         "cp_frame": {"ms": cp_ms, "ms_sampled": cp_ms_sampled, "frames_per_s": 1000.0 / cp_ms, "algorithmic_bytes": cp_frame_bytes(),
                      "achieved_gbs": cp_frame_bytes() / (cp_ms * 1e-3) / 1e9, "frac": cp_frame_bytes() / (cp_ms * 1e-3) / 1e9 / peak,
                      "note": "predict(): one fused launch (16 steps + 15 heads + selection); ms = greedy, ms_sampled = T 0.9 / top-k 50"},
+        "upstream_kernel_sm100a": upstream_kernel,
         "clocks": clocks,
     }
     if batched is not None:
