@@ -296,6 +296,36 @@ def time_frames(loop: FrameLoop, K: int, W: int, trail_dev, trail_host, mode: st
     return times
 
 
+def time_prefill(loop: FrameLoop, reps: int = 5):
+    """The 8-step prefill of an utterance (tts_engine.py:281-282): upstream's loop of sequential step_with_embed calls against
+    TTSDecoder.prefill (one batched tcgen05 pass, qmk_batched_prefill); then time to the first codec frame (prefill +
+    step(CODEC_BOS) + one predict).  Wall-clock ms around a final synchronise (these are latency numbers)."""
+    t = loop.talker
+    out = {}
+    for name in ("sequential", "one_pass"):
+        best = 1e9
+        for _ in range(reps + 1):
+            t.reset()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if name == "sequential":
+                for i in range(N_PREFILL):
+                    t.step_with_embed(loop.prefill[i])
+            else:
+                t.prefill(loop.prefill)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            tok, hid = t.step(CODEC_BOS)
+            codes = loop.cp.predict(hid, tok, loop.embed, do_sample=True, temperature=0.9, top_k=50)
+            codes.cpu()
+            t2 = time.perf_counter()
+            best = min(best, (t1 - t0) * 1e3)
+            out[f"first_frame_ms_{name}"] = min(out.get(f"first_frame_ms_{name}", 1e9), (t2 - t0) * 1e3)
+        out[f"prefill_ms_{name}"] = best
+    t.reset()
+    return out
+
+
 def time_talker_at(loop: FrameLoop, position: int, n: int = 40, warmup: int = 5):
     """Mean duration of one talker launch with `position` cached rows (the launch is repeated at the same position: the KV rows
     it reads are whatever the cache holds, which does not change the work)."""
@@ -535,6 +565,7 @@ def main():
         ms = time_talker_at(loop, pos)
         by_pos[f"p{pos}"] = {"launch_us": ms * 1e3, "algorithmic_bytes": talker_bytes(pos),
                              "achieved_gbs": talker_bytes(pos) / (ms * 1e-3) / 1e9}
+    prefill = time_prefill(loop)
     loop.start_utterance()
     cp_ms = time_cp_frame(loop)
     cp_ms_sampled = time_cp_frame(loop, sample=True)
@@ -630,6 +661,8 @@ def main():
         "cp_frame": {"ms": cp_ms, "ms_sampled": cp_ms_sampled, "frames_per_s": 1000.0 / cp_ms, "algorithmic_bytes": cp_frame_bytes(),
                      "achieved_gbs": cp_frame_bytes() / (cp_ms * 1e-3) / 1e9, "frac": cp_frame_bytes() / (cp_ms * 1e-3) / 1e9 / peak,
                      "note": "predict(): one fused launch (16 steps + 15 heads + selection); ms = greedy, ms_sampled = T 0.9 / top-k 50"},
+        "prefill": dict(prefill, note="8 prefill embeddings: sequential step_with_embed calls (upstream's loop, one blocking token read each) vs "
+                                      "TTSDecoder.prefill (one batched tcgen05 pass); first_frame = prefill + step(BOS) + predict + codes on the host"),
         "upstream_kernel_sm100a": upstream_kernel,
         "clocks": clocks,
     }

@@ -348,6 +348,7 @@ __device__ void phase_attn2(Ctx2& c, const ModelDesc& md, int l, int position, u
     }
   }
   gather_bar(c, DL_ATTN, retried);
+  if (c.tid == 0) c.s_delay[2 * DL_N + DL_ATTN] += (int)((clock64() - c.t_pub) >> 4);   // in-situ cost of this group's q/k/v buffer (autotuner)
   trace_sub<TR>(c, 1);
 
   float q0[4], q1[4], acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
@@ -953,6 +954,7 @@ __device__ void consumer_loop2(Ctx2& c) {
           *reinterpret_cast<uint2*>(c.s_a + (c.warp * 48 + c.lane * 4) * 2) = make_uint2((mw.x & 0xffffu) | (mw.y << 16), (mw.z & 0xffffu) | (mw.w << 16));
         }
         gather_note(c, DL_DOWN, retried);
+        if (c.tid == 0) c.s_delay[2 * DL_N + DL_DOWN] += (int)((clock64() - c.t_pub) >> 4);   // ... and of its m buffer
       }
       __syncwarp();   // warp w consumes exactly the K slice its own lanes wrote 
       trace_sub<TR>(c, 4);
