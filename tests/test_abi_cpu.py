@@ -126,3 +126,32 @@ def test_pack_layer_weights_blob_cpu():
     assert blob.dtype == torch.uint8 and blob.numel() == 2 * 88
     ptrs = struct.unpack("22Q", bytes(blob.tolist()))
     assert list(ptrs) == [t.data_ptr() for t in ts]
+
+
+def test_entry_points_reject_null_arguments_without_a_gpu():
+    """Argument validation happens before any CUDA call: null handles / pointers give QMK_ERR_ARG (-1) on a CPU-only host."""
+    from qwen_megakernel import build_tts
+    lib = build_tts.load_library(build_tts.build())
+    assert lib.qmk_model_set_mrope(None, None, 0) == -1
+    assert lib.qmk_decode_step(None, 0, 0, None, None, None, None, None, None, None, None, 0, 1, 0.0, 0, None) == -1
+    assert lib.qmk_decode_step_mrope(None, 0, 0, None, None, None, None, None, None, None, None, 0, None, 1, 0.0, None) == -1
+    assert lib.qmk_cp_predict(None, None, 0, None, None, None, None, None, 64, 0, 1.0, 0, 0, 0, None, None, None, None, None) == -1
+    assert lib.qmk_batched_step_ex(None, None, None) == -1
+    assert lib.qmk_batched_prefill(None, None, 1, 0, None, None, None, None, None) == -1
+    assert lib.qmk_batched_add_head(None, None, 128) == -1
+    assert lib.qmk_batched_embed_sum(0, None, None, 0, None, 0, None, 0, None, None) == -1
+    assert b"null" in lib.qmk_last_error() or b"null" in lib.qmk_batched_last_error()
+    assert lib.qmk_legacy_check_blob(None, 5, None) == 0
+    lib.qmk_legacy_invalidate(None)                     # no cached models: a no-op
+
+
+def test_ctypes_mirrors_have_the_header_field_order():
+    """GenerateArgs / BatchedStepArgs mirror the C structs field by field (names in header order)."""
+    import re
+    from qwen_megakernel import build_tts
+    text = open(os.path.join(REPO, "include", "qmk_b200.h")).read()
+    for cname, mirror in (("qmk_generate_args", build_tts.GenerateArgs), ("qmk_batched_step_args", build_tts.BatchedStepArgs)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), text, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        c_names = re.findall(r"(\w+)\s*(?:,|$)", " , ".join(re.sub(r"^[\w\s\*]*?([\w]+(?:\s*,\s*\w+)*)$", r"\1", d.strip().replace("*", " ")) for d in body.split(";") if d.strip()))
+        assert [n for n, _ in mirror._fields_] == c_names, (cname, c_names)

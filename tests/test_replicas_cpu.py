@@ -32,7 +32,10 @@ def _worker(rank, world, port, out):
         mine = assign(utts, world, rank)
         units, ms = combine(len(mine) * 10, 100.0 + 50.0 * rank)      # rank 1 is the slow one
         dist.barrier()
-        out.put((rank, mine, units, ms, throughput(len(mine) * 10, 100.0 + 50.0 * rank)))
+        import bench                                                   # the bench's own helpers on the same process group
+        per_rank = bench.gather_floats(100.0 + 50.0 * rank, world, torch.device("cpu"))
+        cores = bench.pin_rank_to_cores(rank, world)
+        out.put((rank, mine, units, ms, throughput(len(mine) * 10, 100.0 + 50.0 * rank), per_rank, cores))
     finally:
         dist.destroy_process_group()
 
@@ -50,7 +53,19 @@ def test_two_rank_gloo_aggregate():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, m0, u0, t0, f0), (r1, m1, u1, t1, f1) = res
+    (r0, m0, u0, t0, f0, pr0, c0), (r1, m1, u1, t1, f1, pr1, c1) = res
     assert sorted(m0 + m1) == list(range(11)) and not set(m0) & set(m1)
     assert u0 == u1 == 110.0 and t0 == t1 == 150.0          # sum of units, max of time
     assert abs(f0 - 110.0 / 0.150) < 1e-6 and f0 == f1
+    assert pr0 == pr1 == [100.0, 150.0]                      # every rank's own time travels with the line (bench.per_rank_ms)
+    assert c0 and c1 and (len(c0) == 1 or not set(c0) & set(c1))   # ranks are pinned to disjoint host cores
+
+
+def test_bench_median_and_reference_config_match():
+    """bench.py helpers that need no GPU: the median over repetitions, and the two arms print IDENTICAL config dicts."""
+    import bench
+    assert bench._median([3.0, 1.0, 2.0]) == 2.0 and bench._median([4.0, 1.0, 2.0, 3.0]) == 2.5
+    assert bench.talker_bytes(0) == 887_228_928 + 2 * 114_688 and bench.cp_frame_bytes() == 2_583_052_288
+    src = open(bench.__file__).read()
+    assert src.count('"frames_per_utterance": K') == 1 and "config[\"" not in src.split("def main()")[1], \
+        "config must be built once and never edited per arm (the driver compares the two arms' dicts)"
