@@ -390,24 +390,30 @@ def time_batched(weights_gpu, dev, batch: int, steps: int = 100, warmup: int = 1
     from qwen_megakernel.model_tts import BatchedTTSDecoder
     bd = BatchedTTSDecoder(weights_gpu, batch, device=dev, max_seq_len=max_seq)
     tok = torch.full((batch,), CODEC_BOS, dtype=torch.int32, device=dev)
-    for _ in range(warmup):
-        t, _ = bd.step(tok)
-        tok.copy_(t)
+    def run(step_fn, n):
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(n):
+            t, _ = step_fn(tok)
+            tok.copy_(t)
+        end.record()
+        torch.cuda.synchronize()
+        return start.elapsed_time(end) / n
+    run(bd.step, warmup)
     bd.reset()
-    torch.cuda.synchronize()
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    start.record()
-    for _ in range(steps):
-        t, _ = bd.step(tok)
-        tok.copy_(t)
-    end.record()
-    torch.cuda.synchronize()
-    ms = start.elapsed_time(end) / steps
+    ms_launches = run(bd.step, steps)                 # 227 launches issued by the host per step
+    bd.reset()
+    run(bd.step_graph, max(warmup, 3))                # first call plain, second captures
+    bd.reset()
+    ms = run(bd.step_graph, steps)                    # the same launches replayed from a CUDA graph
     bytes_step = TALKER_STEP_BYTES + batch * sum(TALKER_KV_BYTES_PER_POS * (p + 2) for p in range(steps)) / steps
     del bd
     return {"streams": batch, "ms_per_step": ms, "stream_steps_per_s": batch * 1000.0 / ms,
             "algorithmic_gbs": bytes_step / (ms * 1e-3) / 1e9, "launches_per_step": 8 * 28 + 3,
-            "note": "talker step for B streams: tcgen05/TMEM split-K GEMMs + fused epilogues, PDL chain; positions 0..%d" % steps}
+            "ms_per_step_host_launches": ms_launches,
+            "note": "talker step for B streams: tcgen05/TMEM split-K GEMMs + fused epilogues, PDL chain replayed from a CUDA "
+                    "graph (BatchedTTSDecoder.step_graph; ms_per_step_host_launches = the same kernels launched one by one); "
+                    "positions 0..%d" % steps}
 
 
 def time_batched_frames(weights_gpu, dev, batch: int, frames: int = 20, warmup: int = 3, max_seq: int = 512):
@@ -432,7 +438,8 @@ def time_batched_frames(weights_gpu, dev, batch: int, frames: int = 20, warmup: 
     del loop
     return {"ms_per_frame_all_streams": ms, "codec_frames_per_s": batch * 1000.0 / ms,
             "launches_per_frame": 16 * (8 * 5 + 1) + 15 * 2 + 1 + (8 * 28 + 3),
-            "note": "BatchedFrameLoop.frame: 16 batched code-predictor steps + 15 heads (T 0.9 / top-k 50) + embedding sum + talker step"}
+            "note": "BatchedFrameLoop.frame: 16 batched code-predictor steps + 15 heads (T 0.9 / top-k 50) + embedding sum + talker "
+                    "step, one CUDA-graph replay per frame"}
 
 
 def time_upstream_kernel_subprocess(limit_s: float = 60.0) -> dict:

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define QMK_ABI_VERSION 2
+#define QMK_ABI_VERSION 3
 
 /* Model constants (upstream kernel.cu:21-28, model_tts.py:19-34); compile-time in the kernel. */
 #define QMK_HIDDEN 1024
@@ -265,6 +265,8 @@ typedef struct qmk_batched_step_args {
   int32_t* tokens_out;          /* int32[B] (head >= 0) */
   int64_t* codes_out;           /* optional: codes_out[b * codes_stride + codes_col] = token */
   int32_t codes_stride, codes_col;
+  const uint64_t* counter_ptr;  /* optional (ABI 3): device word added to `counter` when the kernel runs -- a CUDA graph captured
+                                   from these calls draws fresh numbers on every replay (qmk_batched_counter_add advances it) */
 } qmk_batched_step_args;
 int qmk_batched_add_head(qmk_batched* h, const void* lm_head_weight, int rows);
 int qmk_batched_step_ex(qmk_batched* h, const qmk_batched_step_args* args, void* stream);
@@ -273,6 +275,11 @@ int qmk_batched_step_ex(qmk_batched* h, const qmk_batched_step_args* args, void*
 int qmk_batched_embed_sum(int batch, const int64_t* codes, const void* talker_embed, int talker_rows,
                           const void* const* group_tables, int group_rows, const void* extra_bf16, int extra_stride,
                           void* out_bf16, void* stream);
+/* *counter += inc on `stream` (one thread; the frame counter of a captured frame loop).
+ * CUDA graphs: qmk_batched_step / _step_ex / _embed_sum / _counter_add only enqueue kernels on `stream` (no allocation, no
+ * synchronisation, no host-side state that a replay would miss: positions, tokens and the counter live in device memory), so a
+ * step or a whole frame may be captured with cudaStreamBeginCapture and replayed; the programmatic-launch edges are kept. */
+int qmk_batched_counter_add(uint64_t* counter, uint64_t inc, void* stream);
 /* csrc/qmk_bstep.cuh holds a PERSISTENT form of the step: one cooperative launch runs all layers, the LM head and the argmax
  * (grid barriers between phases, weights re-packed k-block-major and prefetched through a shared-memory ring by a producer
  * warp, tcgen05 / TMEM projections).  It serves the one-pass prefill below.  For decode steps it is opt-in
@@ -284,6 +291,10 @@ int qmk_batched_is_persistent(const qmk_batched* h);
 int qmk_batched_sync_status(qmk_batched* h, void* stream);
 /* Debug (QMK_BATCHED_TRACE=1): clock64 of CTA 0 entering / leaving every grid barrier of the latest persistent step. */
 int qmk_batched_trace_read(qmk_batched* h, void* stream, long long* host_out, int max_elems);
+/* Debug: timeline of the launch chain (current device).  enable != 0 arms %globaltimer stamps in the first and last CTA of every
+ * chain kernel; with host_out the records {tag = kernel id * 16 + event * 2 + (last CTA), ns} since the previous call are copied
+ * (max_records pairs of 64-bit words) and their number is returned.  enable == 0 disarms. */
+int qmk_batched_chain_trace(int enable, void* stream, unsigned long long* host_out, int max_records);
 /* Prefill of ONE utterance as a single batched pass (upstream runs the 8 prefill embeddings
  * through 8 sequential decode steps, tts_engine.py:281-282): lane i of `embeds` (bf16[n][1024], n <= batch) is position
  * position0 + i; all lanes share the caller's B = 1 cache [L][8][max_seq_len][128] and attend causally.  Writes the same KV

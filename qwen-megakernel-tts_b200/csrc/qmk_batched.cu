@@ -83,19 +83,26 @@ __global__ void kb_input(const int* token_ids, const __nv_bfloat16* embed_table,
 }
 
 // ---- O / down epilogue: split-K sum -> bf16 -> residual -> next RMSNorm ----------------------------------------------
-// grid = B, block = 256.  partial: [splits][B][1024].  hidden_out (optional, final norm only): f32[B][1024]
-__global__ void kb_resid_norm(const float* partial, int splits, int B, float* res, int residual_fp32,
+// grid = B, block = 256.  partial: [SPLITS][B][1024].  hidden_out (optional, final norm only): f32[B][1024]
+// All SPLITS partial loads of a thread are in flight together (one L2 round trip instead of SPLITS / 4: the kernel is nothing
+// but that latency), the sum keeps the split order.
+template <int SPLITS>
+__global__ void kb_resid_norm(const float* partial, int B, float* res, int residual_fp32,
                               const __nv_bfloat16* w_norm, __nv_bfloat16* xn, float* hidden_out, int* advance_positions) {
   __shared__ float s_red[8];
+  qmkb::KTrace kt;
+  kt.mark(0);
+  const int b = blockIdx.x, t = threadIdx.x;
   qmkb::pdl_wait();
   qmkb::pdl_launch_dependents();
-  const int b = blockIdx.x, t = threadIdx.x;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = 0; s < splits; ++s) {
-    const float4 p = *reinterpret_cast<const float4*>(partial + ((size_t)s * B + b) * H + t * 4);
-    acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
-  }
+  kt.mark(1);
+  float4 pp[SPLITS];
+#pragma unroll
+  for (int s = 0; s < SPLITS; ++s) pp[s] = __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)s * B + b) * H + t * 4));
   float4 r = *reinterpret_cast<const float4*>(res + (size_t)b * H + t * 4);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int s = 0; s < SPLITS; ++s) { acc.x += pp[s].x; acc.y += pp[s].y; acc.z += pp[s].z; acc.w += pp[s].w; }
   const float o[4] = {bf16_round(acc.x), bf16_round(acc.y), bf16_round(acc.z), bf16_round(acc.w)};
   float x[4] = {r.x + o[0], r.y + o[1], r.z + o[2], r.w + o[3]};
   if (!residual_fp32) {
@@ -108,86 +115,134 @@ __global__ void kb_resid_norm(const float* partial, int splits, int B, float* re
   if (hidden_out)
     *reinterpret_cast<float4*>(hidden_out + (size_t)b * H + t * 4) = make_float4(bf16_lo(n.x), bf16_hi(n.x), bf16_lo(n.y), bf16_hi(n.y));
   if (advance_positions != nullptr && t == 0) advance_positions[b] += 1;   // a step without an LM head ends here
+  kt.flush(3);
 }
 
 // ---- QKV epilogue + decode attention, one CTA per (stream, kv head) --------------------------------------------------
 // Warps 0-3 first finish the projection for this group: split-K sum -> bf16 -> per-head RMSNorm + rotate-half RoPE in
-// bf16 steps (q heads 2g, 2g+1 and k) -> q into shared memory, k / v appended to the cache row positions[b].  Then all
-// 8 warps stride over positions 0 .. pos (lane owns 4 dims), fp32 online softmax, fixed-order cross-warp merge.
-// grid = (B, 8), block = 256.  partial: [splits][B][4096] (q rows 0..2047, k 2048..3071, v 3072..4095).
-__global__ void kb_qkv_attention(const float* partial, int splits, int B, const int* positions, const __nv_bfloat16* q_norm,
+// bf16 steps (q heads 2g, 2g+1 and k) -> q, and the new k / v row, into shared memory; k / v are also appended to the cache row
+// positions[b].  Then all 8 warps stride over positions 0 .. pos (lane owns 4 dims), fp32 online softmax, fixed-order
+// cross-warp merge.  The cached rows of the first ATT_PRE rounds (positions < 8 ATT_PRE) are requested BEFORE the grid
+// dependency resolves: they were written by earlier steps, so their L2 / HBM latency overlaps the projection that precedes
+// this kernel; deeper contexts continue in batches of ATT_PRE independent row loads.
+// grid = (B, 8), block = 256.  partial: [SPLITS][B][4096] (q rows 0..2047, k 2048..3071, v 3072..4095).
+constexpr int ATT_PRE = 4;
+template <int SPLITS>
+__global__ void kb_qkv_attention(const float* partial, int B, const int* positions, const __nv_bfloat16* q_norm,
                                  const __nv_bfloat16* k_norm, const __nv_bfloat16* cos_t, const __nv_bfloat16* sin_t,
                                  __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, __nv_bfloat16* a_out, int layer, int L,
                                  int max_seq, float scale) {
   __shared__ float s_q[2][HD];
+  __shared__ float s_kv[2][HD];   // the new row: k (after norm + RoPE), v
   __shared__ float s_acc[8][2][HD];
   __shared__ float s_m[8][2], s_l[8][2];
-  qmkb::pdl_wait();
-  qmkb::pdl_launch_dependents();
+  qmkb::KTrace kt;
+  kt.mark(0);
   const int b = blockIdx.x, g = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // positions[] was last written two kernels ago at the latest (the previous step's final kernel; every kernel of the chain
+  // resolves its own dependency before it lets its successor start), so it may be read ahead of the dependency.
   int pos = positions[b];
   pos = pos < 0 ? 0 : (pos >= max_seq ? max_seq - 1 : pos);   // a stream that ran past its cache keeps rewriting the last row
   const size_t base = (((size_t)b * L + layer) * NKVH + g) * max_seq * HD;
+  uint2 kk[ATT_PRE], vv[ATT_PRE];
+#pragma unroll
+  for (int i = 0; i < ATT_PRE; ++i) {
+    const int p = warp + 8 * i;
+    if (p < pos) {
+      kk[i] = __ldcg(reinterpret_cast<const uint2*>(k_cache + base + (size_t)p * HD + lane * 4));
+      vv[i] = __ldcg(reinterpret_cast<const uint2*>(v_cache + base + (size_t)p * HD + lane * 4));
+    }
+  }
+  const __nv_bfloat16* wn = warp < 2 ? q_norm : k_norm;
+  const uint2 wn_raw = warp < 3 ? *reinterpret_cast<const uint2*>(wn + lane * 4) : make_uint2(0u, 0u);
+  const int dbase = (lane * 4) & 63;
+  const uint2 cs_raw = *reinterpret_cast<const uint2*>(cos_t + (size_t)pos * HD + dbase), sn_raw = *reinterpret_cast<const uint2*>(sin_t + (size_t)pos * HD + dbase);
+  qmkb::pdl_wait();
+  qmkb::pdl_launch_dependents();
+  kt.mark(1);
   if (warp < 4) {
     // warp 0, 1: q heads 2g, 2g+1; warp 2: k head g; warp 3: v head g
     const int row0 = warp < 2 ? (2 * g + warp) * HD : (warp == 2 ? QSZ + g * HD : QSZ + KVSZ + g * HD);
+    float4 pp[SPLITS];
+#pragma unroll
+    for (int s = 0; s < SPLITS; ++s) pp[s] = __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)s * B + b) * QKV_ROWS + row0 + lane * 4));
     float t[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int s = 0; s < splits; ++s) {
-      const float4 p = *reinterpret_cast<const float4*>(partial + ((size_t)s * B + b) * QKV_ROWS + row0 + lane * 4);
-      t[0] += p.x; t[1] += p.y; t[2] += p.z; t[3] += p.w;
-    }
+#pragma unroll
+    for (int s = 0; s < SPLITS; ++s) { t[0] += pp[s].x; t[1] += pp[s].y; t[2] += pp[s].z; t[3] += pp[s].w; }
 #pragma unroll
     for (int e = 0; e < 4; ++e) t[e] = bf16_round(t[e]);
     if (warp == 3) {
+      *reinterpret_cast<float4*>(&s_kv[1][lane * 4]) = make_float4(t[0], t[1], t[2], t[3]);
       *reinterpret_cast<uint2*>(v_cache + base + (size_t)pos * HD + lane * 4) =
           make_uint2(bf16_bits(t[0]) | (bf16_bits(t[1]) << 16), bf16_bits(t[2]) | (bf16_bits(t[3]) << 16));
     } else {
-      const __nv_bfloat16* wn = warp < 2 ? q_norm : k_norm;
       float ss = 0.f;
 #pragma unroll
       for (int e = 0; e < 4; ++e) ss = fmaf(t[e], t[e], ss);
       ss = warp_sum(ss);
       const float rms = sqrtf(ss * (1.0f / HD) + EPS);
-      const int dbase = (lane * 4) & 63;
+      const float wf[4] = {bf16_lo(wn_raw.x), bf16_hi(wn_raw.x), bf16_lo(wn_raw.y), bf16_hi(wn_raw.y)};
+      const float cf[4] = {bf16_lo(cs_raw.x), bf16_hi(cs_raw.x), bf16_lo(cs_raw.y), bf16_hi(cs_raw.y)};
+      const float sf[4] = {bf16_lo(sn_raw.x), bf16_hi(sn_raw.x), bf16_lo(sn_raw.y), bf16_hi(sn_raw.y)};
       float o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float n = bf16_round((t[e] / rms) * __bfloat162float(wn[lane * 4 + e]));
+        const float n = bf16_round((t[e] / rms) * wf[e]);
         const float other = __shfl_xor_sync(0xffffffffu, n, 16);
-        const float cs = __bfloat162float(cos_t[(size_t)pos * HD + dbase + e]), sn = __bfloat162float(sin_t[(size_t)pos * HD + dbase + e]);
-        const float x = bf16_round(n * cs), y = bf16_round(other * sn);
+        const float x = bf16_round(n * cf[e]), y = bf16_round(other * sf[e]);
         o[e] = bf16_round(lane < 16 ? x - y : x + y);
       }
       if (warp < 2) {
         *reinterpret_cast<float4*>(&s_q[warp][lane * 4]) = make_float4(o[0], o[1], o[2], o[3]);
       } else {
+        *reinterpret_cast<float4*>(&s_kv[0][lane * 4]) = make_float4(o[0], o[1], o[2], o[3]);
         *reinterpret_cast<uint2*>(k_cache + base + (size_t)pos * HD + lane * 4) =
             make_uint2(bf16_bits(o[0]) | (bf16_bits(o[1]) << 16), bf16_bits(o[2]) | (bf16_bits(o[3]) << 16));
       }
     }
   }
-  __syncthreads();   // q in shared memory; the new K / V row (global, written by this CTA) is visible to the whole CTA
+  __syncthreads();   // q and the new k / v row are in shared memory
   const int n = pos + 1;
   const float4 qa = *reinterpret_cast<const float4*>(&s_q[0][lane * 4]), qb = *reinterpret_cast<const float4*>(&s_q[1][lane * 4]);
   const float q0[4] = {qa.x, qa.y, qa.z, qa.w}, q1[4] = {qb.x, qb.y, qb.z, qb.w};
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f, acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
-  for (int p = warp; p < n; p += 8) {
-    const uint2 kk = *reinterpret_cast<const uint2*>(k_cache + base + (size_t)p * HD + lane * 4);
-    const uint2 vv = *reinterpret_cast<const uint2*>(v_cache + base + (size_t)p * HD + lane * 4);
-    const float kf[4] = {bf16_lo(kk.x), bf16_hi(kk.x), bf16_lo(kk.y), bf16_hi(kk.y)};
-    const float vf[4] = {bf16_lo(vv.x), bf16_hi(vv.x), bf16_lo(vv.y), bf16_hi(vv.y)};
-    float d0 = 0.f, d1 = 0.f;
+  for (int p0 = warp; p0 < n; p0 += 8 * ATT_PRE) {   // warp-uniform; positions in ascending order per warp, as before
+    if (p0 != warp) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { d0 = fmaf(q0[e], kf[e], d0); d1 = fmaf(q1[e], kf[e], d1); }
-    d0 = warp_sum(d0) * scale;
-    d1 = warp_sum(d1) * scale;
-    const float nm0 = fmaxf(m0, d0), nm1 = fmaxf(m1, d1);
-    const float c0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - nm0), c1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - nm1);
-    const float e0 = __expf(d0 - nm0), e1 = __expf(d1 - nm1);
-    l0 = l0 * c0 + e0; l1 = l1 * c1 + e1;
+      for (int i = 0; i < ATT_PRE; ++i) {
+        const int p = p0 + 8 * i;
+        if (p < pos) {
+          kk[i] = __ldcg(reinterpret_cast<const uint2*>(k_cache + base + (size_t)p * HD + lane * 4));
+          vv[i] = __ldcg(reinterpret_cast<const uint2*>(v_cache + base + (size_t)p * HD + lane * 4));
+        }
+      }
+    }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { acc0[e] = fmaf(e0, vf[e], acc0[e] * c0); acc1[e] = fmaf(e1, vf[e], acc1[e] * c1); }
-    m0 = nm0; m1 = nm1;
+    for (int i = 0; i < ATT_PRE; ++i) {
+      const int p = p0 + 8 * i;
+      if (p < n) {
+        float kf[4], vf[4];
+        if (p == pos) {
+          const float4 a = *reinterpret_cast<const float4*>(&s_kv[0][lane * 4]), c = *reinterpret_cast<const float4*>(&s_kv[1][lane * 4]);
+          kf[0] = a.x; kf[1] = a.y; kf[2] = a.z; kf[3] = a.w; vf[0] = c.x; vf[1] = c.y; vf[2] = c.z; vf[3] = c.w;
+        } else {
+          kf[0] = bf16_lo(kk[i].x); kf[1] = bf16_hi(kk[i].x); kf[2] = bf16_lo(kk[i].y); kf[3] = bf16_hi(kk[i].y);
+          vf[0] = bf16_lo(vv[i].x); vf[1] = bf16_hi(vv[i].x); vf[2] = bf16_lo(vv[i].y); vf[3] = bf16_hi(vv[i].y);
+        }
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { d0 = fmaf(q0[e], kf[e], d0); d1 = fmaf(q1[e], kf[e], d1); }
+        d0 = warp_sum(d0) * scale;
+        d1 = warp_sum(d1) * scale;
+        const float nm0 = fmaxf(m0, d0), nm1 = fmaxf(m1, d1);
+        const float c0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - nm0), c1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - nm1);
+        const float e0 = __expf(d0 - nm0), e1 = __expf(d1 - nm1);
+        l0 = l0 * c0 + e0; l1 = l1 * c1 + e1;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { acc0[e] = fmaf(e0, vf[e], acc0[e] * c0); acc1[e] = fmaf(e1, vf[e], acc1[e] * c1); }
+        m0 = nm0; m1 = nm1;
+      }
+    }
   }
   if (lane == 0) { s_m[warp][0] = m0; s_m[warp][1] = m1; s_l[warp][0] = l0; s_l[warp][1] = l1; }
 #pragma unroll
@@ -205,20 +260,31 @@ __global__ void kb_qkv_attention(const float* partial, int splits, int B, const 
     Ls = fmaf(s_l[w][h], f, Ls);
   }
   a_out[(size_t)b * QSZ + (2 * g + h) * HD + d] = __float2bfloat16_rn(A / Ls);
+  kt.flush(4);
 }
 
 // ---- gate/up epilogue: m = r( r(silu(r(g))) * r(u) ) -------------------------------------------------------------------
 // grid = (B, 3), block = 256; partial: [splits][B][6144] (gate rows 0..3071, up rows 3072..6143)
-__global__ void kb_gu_epilogue(const float* partial, int splits, int B, __nv_bfloat16* m_out) {
+template <int SPLITS>
+__global__ void kb_gu_epilogue(const float* partial, int B, __nv_bfloat16* m_out) {
+  qmkb::KTrace kt;
+  kt.mark(0);
   qmkb::pdl_wait();
   qmkb::pdl_launch_dependents();
+  kt.mark(1);
   const int b = blockIdx.x, j = blockIdx.y * 1024 + threadIdx.x * 4;
-  float4 g = make_float4(0.f, 0.f, 0.f, 0.f), u = g;
-  for (int s = 0; s < splits; ++s) {
+  float4 pg[SPLITS], pu[SPLITS];
+#pragma unroll
+  for (int s = 0; s < SPLITS; ++s) {
     const float* p = partial + ((size_t)s * B + b) * GU_ROWS;
-    const float4 pg = *reinterpret_cast<const float4*>(p + j), pu = *reinterpret_cast<const float4*>(p + INTER + j);
-    g.x += pg.x; g.y += pg.y; g.z += pg.z; g.w += pg.w;
-    u.x += pu.x; u.y += pu.y; u.z += pu.z; u.w += pu.w;
+    pg[s] = __ldcg(reinterpret_cast<const float4*>(p + j));
+    pu[s] = __ldcg(reinterpret_cast<const float4*>(p + INTER + j));
+  }
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f), u = g;
+#pragma unroll
+  for (int s = 0; s < SPLITS; ++s) {
+    g.x += pg[s].x; g.y += pg[s].y; g.z += pg[s].z; g.w += pg[s].w;
+    u.x += pu[s].x; u.y += pu[s].y; u.z += pu[s].z; u.w += pu[s].w;
   }
   const float gv[4] = {g.x, g.y, g.z, g.w}, uv[4] = {u.x, u.y, u.z, u.w};
   uint32_t o[4];
@@ -229,6 +295,7 @@ __global__ void kb_gu_epilogue(const float* partial, int splits, int B, __nv_bfl
     o[e] = bf16_bits(sg * bf16_round(uv[e]));
   }
   *reinterpret_cast<uint2*>(m_out + (size_t)b * INTER + j) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+  kt.flush(5);
 }
 
 // ---- LM head epilogue: bf16 logits; argmax (lowest index on ties) or temperature / top-k / multinomial (the B = 1 engine's
@@ -239,6 +306,7 @@ struct HeadSelect {
   int do_sample, top_k, group;
   float temperature;
   unsigned long long seed, counter;
+  const unsigned long long* counter_ptr;
   long long* codes_out;
   int codes_stride, codes_col;
 };
@@ -256,7 +324,13 @@ __global__ void kb_head_epilogue(const float* partial, int splits, int B, int ro
   int best_i = 0x7fffffff;
   for (int r = tid; r < rows; r += 256) {
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * B + b) * rows + r];
+    if (splits == 4) {   // the chain's head projection: four loads in flight, same summation order
+      const float p0 = __ldcg(partial + ((size_t)0 * B + b) * rows + r), p1 = __ldcg(partial + ((size_t)1 * B + b) * rows + r);
+      const float p2 = __ldcg(partial + ((size_t)2 * B + b) * rows + r), p3 = __ldcg(partial + ((size_t)3 * B + b) * rows + r);
+      acc = (((acc + p0) + p1) + p2) + p3;
+    } else {
+      for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * B + b) * rows + r];
+    }
     const float v = bf16_round(acc);
     if (sample) s_log[r] = v;
     if (v > best) { best = v; best_i = r; }
@@ -276,7 +350,8 @@ __global__ void kb_head_epilogue(const float* partial, int splits, int B, int ro
   int chosen = best_i;
   if (sample)
     chosen = qmk2::sample_token2(s_log, s_hist, s_red, tid, warp, lane, rows, sel.top_k, sel.temperature,
-                                 sel.seed + (unsigned long long)b * 0x632BE59BD9B4E019ull, sel.counter, sel.group, best, best_i);
+                                 sel.seed + (unsigned long long)b * 0x632BE59BD9B4E019ull,
+                                 sel.counter + (sel.counter_ptr != nullptr ? *sel.counter_ptr : 0ull), sel.group, best, best_i);
   if (tid == 0) {
     tokens_out[b] = chosen;
     if (sel.codes_out != nullptr) sel.codes_out[(size_t)b * sel.codes_stride + sel.codes_col] = (long long)chosen;
@@ -311,6 +386,8 @@ __global__ void kb_embed_sum(const long long* codes, const __nv_bfloat16* talker
   const uint32_t o1 = bf16_bits(e4[2] + bf16_lo(vx.y)) | (bf16_bits(e4[3] + bf16_hi(vx.y)) << 16);
   *reinterpret_cast<uint2*>(out + (size_t)b * H + t * 4) = make_uint2(o0, o1);
 }
+
+__global__ void kb_counter_add(unsigned long long* counter, unsigned long long inc) { *counter += inc; }
 
 // concatenate row blocks of two / three [rows, K] matrices into one (one-time, at model creation)
 __global__ void kb_copy_rows(const uint4* src, uint4* dst, size_t n16) {
@@ -527,7 +604,7 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 }
 static void gemm(qmk_batched* h, const CUtensorMap& mw, const CUtensorMap& mx, int M, int K, int splits, cudaStream_t st) {
   qmkb::BgemmArgs a{h->partial, M, h->B, K, splits};
-  launch_pdl(qmkb::qmk_bgemm_kernel, dim3(M / qmkb::BM, splits), dim3(128), (size_t)qmkb::SMEM_BYTES, st, mw, mx, a);
+  launch_pdl(qmkb::qmk_bgemm_kernel, dim3(M / qmkb::BM, splits), dim3(128), (size_t)qmkb::smem_bytes_for(K / splits / qmkb::BK), st, mw, mx, a);
 }
 
 // One cooperative launch of the persistent step kernel for `lanes` lanes (decode: lanes = B utterances; prefill: lanes =
@@ -594,17 +671,17 @@ static int chain_step(qmk_batched* h, const qmk_batched_step_args* a, cudaStream
              reinterpret_cast<const __nv_bfloat16*>(h->ln_in[0]), h->xn);
   for (int l = 0; l < L; ++l) {
     gemm(h, h->map_qkv[l], h->map_x1024, QKV_ROWS, H, 4, st);                       // 32 tiles x 4 K-slices
-    launch_pdl(kb_qkv_attention, dim3(B, NKVH), dim3(256), 0, st, (const float*)h->partial, 4, B, (const int*)a->positions,
+    launch_pdl(kb_qkv_attention<4>, dim3(B, NKVH), dim3(256), 0, st, (const float*)h->partial, B, (const int*)a->positions,
                reinterpret_cast<const __nv_bfloat16*>(h->qn[l]), reinterpret_cast<const __nv_bfloat16*>(h->kn[l]), cos_t, sin_t,
                kc, vc, h->abuf, l, L, h->max_seq, scale);
     gemm(h, h->map_o[l], h->map_x2048, H, QSZ, 16, st);                              // 8 tiles x 16 K-slices
-    launch_pdl(kb_resid_norm, dim3(B), dim3(256), 0, st, (const float*)h->partial, 16, B, h->res, h->residual_fp32,
+    launch_pdl(kb_resid_norm<16>, dim3(B), dim3(256), 0, st, (const float*)h->partial, B, h->res, h->residual_fp32,
                reinterpret_cast<const __nv_bfloat16*>(h->ln_post[l]), h->xn, (float*)nullptr, (int*)nullptr);
     gemm(h, h->map_gu[l], h->map_x1024, GU_ROWS, H, 4, st);                          // 48 tiles x 4 K-slices
-    launch_pdl(kb_gu_epilogue, dim3(B, 3), dim3(256), 0, st, (const float*)h->partial, 4, B, h->mbuf);
+    launch_pdl(kb_gu_epilogue<4>, dim3(B, 3), dim3(256), 0, st, (const float*)h->partial, B, h->mbuf);
     gemm(h, h->map_down[l], h->map_x3072, H, INTER, 16, st);                         // 8 tiles x 16 K-slices
     const bool last = (l == L - 1);
-    launch_pdl(kb_resid_norm, dim3(B), dim3(256), 0, st, (const float*)h->partial, 16, B, h->res, h->residual_fp32,
+    launch_pdl(kb_resid_norm<16>, dim3(B), dim3(256), 0, st, (const float*)h->partial, B, h->res, h->residual_fp32,
                reinterpret_cast<const __nv_bfloat16*>(last ? h->final_norm : h->ln_in[l + 1]), h->xn,
                last ? a->hidden_out : (float*)nullptr, (last && head_map == nullptr) ? (int*)a->positions : (int*)nullptr);
   }
@@ -613,7 +690,7 @@ static int chain_step(qmk_batched* h, const qmk_batched_step_args* a, cudaStream
     HeadSelect sel;
     sel.do_sample = (a->do_sample && a->temperature > 0.f) ? 1 : 0;
     sel.top_k = a->top_k; sel.group = a->group; sel.temperature = sel.do_sample ? a->temperature : 1.0f;
-    sel.seed = a->seed; sel.counter = a->counter;
+    sel.seed = a->seed; sel.counter = a->counter; sel.counter_ptr = reinterpret_cast<const unsigned long long*>(a->counter_ptr);
     sel.codes_out = reinterpret_cast<long long*>(a->codes_out); sel.codes_stride = a->codes_stride; sel.codes_col = a->codes_col;
     launch_pdl(kb_head_epilogue, dim3(B), dim3(256), 0, st, (const float*)h->partial, 4, B, head_rows, (int*)a->tokens_out,
                (int*)a->positions, sel);
@@ -662,6 +739,14 @@ extern "C" int qmk_batched_embed_sum(int batch, const int64_t* codes, const void
   kb_embed_sum<<<batch, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(codes), reinterpret_cast<const __nv_bfloat16*>(talker_embed),
                                                         talker_rows, gt, group_rows, reinterpret_cast<const __nv_bfloat16*>(extra_bf16),
                                                         extra_stride, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(QMK_ERR_CUDA, cudaGetErrorString(e));
+  return QMK_OK;
+}
+
+extern "C" int qmk_batched_counter_add(uint64_t* counter, uint64_t inc, void* stream) {
+  if (!counter) return fail(QMK_ERR_ARG, "qmk_batched_counter_add: null counter");
+  kb_counter_add<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(counter), (unsigned long long)inc);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(QMK_ERR_CUDA, cudaGetErrorString(e));
   return QMK_OK;
@@ -737,5 +822,33 @@ extern "C" int qmk_batched_trace_read(qmk_batched* h, void* stream, long long* h
   cudaStreamSynchronize((cudaStream_t)stream);
   const int n = std::min(max_elems, 1024);
   cudaMemcpy(host_out, h->d_trace, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost);
+  return n;
+}
+
+// Debug: timeline of the launch chain.  enable != 0 arms the stamps (the first and the last CTA of every chain kernel record
+// %globaltimer at entry, after the grid dependency, at exit; process-wide, one device); a call with host_out copies the records
+// {tag = kernel id * 16 + event * 2 + (last CTA), nanoseconds} gathered since the previous call and returns their number.
+extern "C" int qmk_batched_chain_trace(int enable, void* stream, unsigned long long* host_out, int max_records) {
+  static unsigned long long* d_buf = nullptr;
+  constexpr size_t WORDS = 1 + 2 * 16000;
+  if (enable && !d_buf) {
+    if (cudaMalloc(&d_buf, WORDS * 8) != cudaSuccess) return fail(QMK_ERR_CUDA, "qmk_batched_chain_trace: allocation failed");
+    cudaMemset(d_buf, 0, WORDS * 8);
+    cudaMemcpyToSymbol(qmkb::g_ktrace, &d_buf, sizeof(d_buf));
+  }
+  if (!d_buf) return 0;
+  cudaStreamSynchronize((cudaStream_t)stream);
+  int n = 0;
+  if (host_out && max_records > 0) {
+    unsigned long long cnt = 0;
+    cudaMemcpy(&cnt, d_buf, 8, cudaMemcpyDeviceToHost);
+    n = (int)std::min<unsigned long long>(std::min<unsigned long long>(cnt, 16000), (unsigned long long)max_records);
+    cudaMemcpy(host_out, d_buf + 1, (size_t)n * 16, cudaMemcpyDeviceToHost);
+  }
+  cudaMemset(d_buf, 0, 8);
+  if (!enable) {
+    unsigned long long* null_ptr = nullptr;
+    cudaMemcpyToSymbol(qmkb::g_ktrace, &null_ptr, sizeof(null_ptr));
+  }
   return n;
 }

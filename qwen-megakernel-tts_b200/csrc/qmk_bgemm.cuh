@@ -28,6 +28,10 @@ constexpr int TMEM_COLS = 64;  // power of two >= 32 and >= N
 constexpr int A_TILE_BYTES = BM * BK * 2;       // 16 KB
 constexpr int B_TILE_BYTES = MAX_N * BK * 2;    // 8 KB (N x 128 B used)
 constexpr int SMEM_BYTES = MAX_KB * (A_TILE_BYTES + B_TILE_BYTES) + 1024 /*alignment slack*/ + 256;
+// Shared memory a launch needs for K slices of `nkb` k-blocks.  The decode projections use slices of <= 4 k-blocks (97.25 KB):
+// two CTAs fit on an SM, so a 192-CTA grid is ONE wave and the next projection's CTAs can become resident (and pull their
+// weights) while this one's are still at work.
+__host__ __device__ constexpr int smem_bytes_for(int nkb) { return nkb * (A_TILE_BYTES + B_TILE_BYTES) + 1024 + 256; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -36,6 +40,34 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // weight TMA loads overlap with the tail of the previous kernel.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Debug timeline of the launch chain (qmk_batched_chain_trace): the first and the last CTA of every kernel read %globaltimer at
+// entry (0), after the grid dependency resolved (1), at an intermediate point (2) and at exit (3); the four values stay in
+// registers and are stored together at exit, so the stamps do not delay the work they time.  g_ktrace: [0] = next free
+// record, records of 2 words {tag = kernel id * 16 + event * 2 + (last CTA), ns} follow.
+__device__ unsigned long long* g_ktrace = nullptr;
+struct KTrace {
+  unsigned long long t[4];
+  bool on, first;
+  __device__ __forceinline__ KTrace() {
+    first = (blockIdx.x | blockIdx.y) == 0;
+    on = g_ktrace != nullptr && threadIdx.x == 0 && (first || (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1));
+    t[0] = t[1] = t[2] = t[3] = 0;
+  }
+  __device__ __forceinline__ void mark(int e) {
+    if (on) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t[e]));
+  }
+  __device__ __forceinline__ void flush(int kernel_id) {
+    if (!on) return;
+    mark(3);
+    unsigned long long* buf = g_ktrace;
+    const unsigned long long i = atomicAdd(buf, 4ull);
+    if (i + 4 <= 16000) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { buf[1 + 2 * (i + e)] = (unsigned long long)(kernel_id * 16 + e * 2 + (first ? 0 : 1)); buf[2 + 2 * (i + e)] = t[e]; }
+    }
+  }
+};
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -107,21 +139,20 @@ struct BgemmArgs {
 };
 
 // grid = (M / 128, splits), block = 128
-__global__ void __launch_bounds__(128, 1) qmk_bgemm_kernel(const __grid_constant__ CUtensorMap map_w,
+__global__ void __launch_bounds__(128, 2) qmk_bgemm_kernel(const __grid_constant__ CUtensorMap map_w,
                                                            const __grid_constant__ CUtensorMap map_x, BgemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles: 1 KB aligned
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + MAX_KB * A_TILE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + MAX_KB * (A_TILE_BYTES + B_TILE_BYTES));
-  uint64_t* done = full + MAX_KB;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM;
   const int kc = a.K / a.splits;          // K slice of this CTA
   const int k0 = blockIdx.y * kc;
   const int nkb = kc / BK;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + nkb * A_TILE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + nkb * (A_TILE_BYTES + B_TILE_BYTES));   // launch: smem_bytes_for(nkb)
+  uint64_t* done = full + MAX_KB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_KB; ++i) mbar_init(&full[i], 1);
@@ -137,6 +168,8 @@ __global__ void __launch_bounds__(128, 1) qmk_bgemm_kernel(const __grid_constant
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
   pdl_launch_dependents();
+  KTrace kt;
+  kt.mark(0);
 
   if (warp == 0 && lane == 0) {
     // ===== TMA producer: every k-block of the slice, up front.  The weight tiles do not depend on the previous
@@ -165,7 +198,9 @@ __global__ void __launch_bounds__(128, 1) qmk_bgemm_kernel(const __grid_constant
 
   // ===== epilogue: TMEM lane = row of the tile, column = stream; warp w owns lanes 32 w .. 32 w + 31 =====
   pdl_wait();   // the previous epilogue kernel has finished reading the partial buffer this kernel overwrites
+  kt.mark(1);
   mbar_wait(done, 0);
+  kt.mark(2);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int row = m0 + warp * 32 + lane;
   float* out = a.partial + (size_t)blockIdx.y * a.N * a.M;
@@ -180,6 +215,7 @@ __global__ void __launch_bounds__(128, 1) qmk_bgemm_kernel(const __grid_constant
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
+  kt.flush(1);
 }
 
 // ---- host: tensor maps through the driver entry point (no libcuda link dependency) -----------------------------

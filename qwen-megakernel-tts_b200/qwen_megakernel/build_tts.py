@@ -136,6 +136,8 @@ SIGNATURES = {
     "qmk_batched_embed_sum": (_i32, [_i32, _vp, _vp, _i32, ctypes.POINTER(_vp), _i32, _vp, _i32, _vp, _vp]),
     "qmk_batched_is_persistent": (_i32, [_vp]),
     "qmk_batched_trace_read": (_i32, [_vp, _vp, ctypes.POINTER(ctypes.c_longlong), _i32]),
+    "qmk_batched_counter_add": (_i32, [_vp, ctypes.c_uint64, _vp]),
+    "qmk_batched_chain_trace": (_i32, [_i32, _vp, ctypes.POINTER(ctypes.c_ulonglong), _i32]),
     "qmk_batched_sync_status": (_i32, [_vp, _vp]),
     "qmk_batched_prefill": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "launch_ldg_decode_direct": (None, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -172,7 +174,7 @@ class BatchedStepArgs(ctypes.Structure):
         ("positions", _vp), ("k_cache", _vp), ("v_cache", _vp), ("hidden_out", _vp), ("head", ctypes.c_int32),
         ("do_sample", ctypes.c_int32), ("top_k", ctypes.c_int32), ("group", ctypes.c_int32), ("temperature", ctypes.c_float),
         ("seed", ctypes.c_uint64), ("counter", ctypes.c_uint64), ("tokens_out", _vp), ("codes_out", _vp),
-        ("codes_stride", ctypes.c_int32), ("codes_col", ctypes.c_int32),
+        ("codes_stride", ctypes.c_int32), ("codes_col", ctypes.c_int32), ("counter_ptr", _vp),
     ]
 
 
@@ -295,7 +297,7 @@ def get_extension():
             return _ext
         path = build()
         _lib = load_library(path)
-        if _lib.qmk_abi_version() != 2:
+        if _lib.qmk_abi_version() != 3:
             raise RuntimeError("qwen_megakernel: ABI version mismatch between Python layer and libqmk_b200.so")
         _op_lib = torch.library.Library("qwen_megakernel_C", "DEF")
         _op_lib.define(DECODE_SCHEMA)

@@ -506,6 +506,19 @@ class TTSDecoder:
         return self._embed_weight
 
 
+def _capture(device, fn):
+    """Record the launches ``fn`` enqueues on the current stream into a CUDA graph (nothing executes during the capture)."""
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.device(device):
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                result = fn()
+        torch.cuda.current_stream(device).wait_stream(side)
+    return g, result
+
+
 class BatchedTTSDecoder:
     """B concurrent utterance streams (B = 16, 32, 48 or 64) decoded together; no upstream counterpart.
 
@@ -585,6 +598,27 @@ class BatchedTTSDecoder:
             raise ValueError(f"embeds must be [{self.batch}, {HIDDEN_SIZE}]")
         self._keep = e
         return self._run(None, e.data_ptr())
+
+    def step_graph(self, token_ids: torch.Tensor):
+        """``step`` replayed from a CUDA graph: the 227 launches of the chain (programmatic-launch edges included) are
+        captured once -- every per-step quantity (positions, tokens) lives in device memory -- and each later call is ONE
+        graph launch plus the copy of ``token_ids`` into the graph's input buffer.  Same results as ``step``."""
+        if self._steps >= self._max_seq:
+            raise IndexError("KV cache is full for at least one stream")
+        if not hasattr(self, "_g_tok"):
+            self._g_tok = torch.zeros(self.batch, dtype=torch.int32, device=self.device)
+            self._graph = None
+            self._graph_warm = False
+        self._g_tok.copy_(token_ids.to(self.device, torch.int32).reshape(self.batch))
+        if not self._graph_warm:                      # first call: plain launches (also the warm-up the capture needs)
+            self._graph_warm = True
+            return self.step(self._g_tok)
+        if self._graph is None:
+            self._graph, _ = _capture(self.device, lambda: self.step(self._g_tok))
+            self._steps -= 1                          # the capture only recorded the step
+        self._graph.replay()
+        self._steps += 1
+        return self._tokens, self._hidden
 
     def reset(self):
         """New utterances on every stream (O(1): rows beyond a stream's position are never read)."""
@@ -670,7 +704,7 @@ class BatchedCodePredictor:
             self._v_cache = torch.zeros_like(self._k_cache)
             self._positions = torch.zeros(B, dtype=torch.int32, device=dev)
             self._tokens = torch.zeros(B, dtype=torch.int32, device=dev)
-        self._frame_counter = 0
+            self._frame_counter = torch.zeros(1, dtype=torch.int64, device=dev)   # on the device: a captured frame draws fresh numbers per replay
 
     def __del__(self):
         try:
@@ -702,9 +736,12 @@ class BatchedCodePredictor:
             codes = torch.empty(B, NUM_CODE_GROUPS, dtype=torch.int64, device=self.device)
             codes[:, 0] = tok
             self._positions.zero_()
-            self._frame_counter += 1
+            rc = self._lib.qmk_batched_counter_add(self._frame_counter.data_ptr(), 1, _stream_ptr(self.device))   # frames count from 1
+            if rc < 0:
+                from .build_tts import NativeError
+                raise NativeError(f"qmk_batched_counter_add: {self._lib.qmk_batched_last_error().decode()} (code {rc})")
             sel = dict(do_sample=int(sample), top_k=int(top_k), temperature=float(temperature),
-                       seed=torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, counter=self._frame_counter,
+                       seed=torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, counter=0, counter_ptr=self._frame_counter.data_ptr(),
                        tokens_out=self._tokens.data_ptr(), codes_out=codes.data_ptr(), codes_stride=NUM_CODE_GROUPS)
             self._step(embeds_f32=hid.data_ptr())                                     # position 0: the talker's hidden state
             self._keep = (hid, tok, codes)
@@ -726,13 +763,17 @@ class BatchedFrameLoop:
     code-predictor frame, the 16-way embedding sum for every stream and one batched talker step -- all asynchronous on the
     device (tokens and hidden states never visit the host)."""
 
-    def __init__(self, weights: dict, batch: int, *, device=None, max_seq_len: int = 2048):
+    def __init__(self, weights: dict, batch: int, *, device=None, max_seq_len: int = 2048, graph: bool = True):
+        """``graph``: replay a frame (~915 launches) from a CUDA graph captured on the second call with the same sampling
+        settings (the first call runs the plain launches); ``codes`` is then a buffer the next frame overwrites."""
         self.talker = BatchedTTSDecoder(weights, batch, device=device, max_seq_len=max_seq_len)
         self.cp = BatchedCodePredictor(weights, batch, device=self.talker.device)
         self.device, self.batch = self.talker.device, int(batch)
         self._embed = weights["embed_weight"]
         self._tables = (ctypes.c_void_p * 15)(*[t.data_ptr() for t in self.cp.codec_embeddings])
         self._e = torch.zeros(batch, HIDDEN_SIZE, dtype=torch.bfloat16, device=self.device)
+        self._extra = torch.zeros(batch, HIDDEN_SIZE, dtype=torch.bfloat16, device=self.device)
+        self._use_graph, self._graphs, self._warm = bool(graph), {}, set()
         self.tokens = self.hidden = None
 
     def start(self, prefill_bf16: torch.Tensor, bos_token: int = CODEC_BOS):
@@ -746,6 +787,25 @@ class BatchedFrameLoop:
     def frame(self, extra_bf16: torch.Tensor, do_sample: bool = True, temperature: float = 0.9, top_k: int = 50) -> torch.Tensor:
         """One codec frame for every stream; ``extra_bf16``: bf16[B, 1024] (per-stream trailing-text / pad embedding) or
         bf16[1024] (same for all).  Returns codes int64[B, 16] (device)."""
+        if self._use_graph:
+            if self.talker._steps >= self.talker._max_seq:
+                raise IndexError("KV cache is full for at least one stream")
+            self._extra.copy_(extra_bf16.to(self.device, torch.bfloat16).expand(self.batch, HIDDEN_SIZE))
+            key = (bool(do_sample), float(temperature), int(top_k))
+            if key not in self._warm:                 # first frame with these settings: plain launches
+                self._warm.add(key)
+                return self._frame(self._extra, do_sample, temperature, top_k)
+            if key not in self._graphs:
+                self._graphs[key] = _capture(self.device, lambda: self._frame(self._extra, do_sample, temperature, top_k))
+                self.talker._steps -= 1               # the capture only recorded the frame
+            g, codes = self._graphs[key]
+            g.replay()
+            self.talker._steps += 1
+            self.tokens, self.hidden = self.talker._tokens, self.talker._hidden
+            return codes
+        return self._frame(extra_bf16, do_sample, temperature, top_k)
+
+    def _frame(self, extra_bf16, do_sample, temperature, top_k):
         from .build_tts import NativeError
         codes = self.cp.predict(self.hidden, self.tokens, self._embed, do_sample, temperature, top_k)
         extra = extra_bf16.to(self.device, torch.bfloat16).contiguous()

@@ -25,7 +25,7 @@ def test_library_builds_and_exports_header_symbols():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in qmk_b200.h but not exported"
         assert n in build_tts.SIGNATURES, f"{n} has no ctypes signature"
-    assert lib.qmk_abi_version() == 2
+    assert lib.qmk_abi_version() == 3
 
 
 def test_library_is_never_stale():

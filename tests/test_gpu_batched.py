@@ -254,3 +254,36 @@ def test_batched_frame_loop_equals_b1_loop(gpu_weights):
                 assert g >= 1 and float(torch.topk(logits[g - 1], 2).values[0] - torch.topk(logits[g - 1], 2).values[1]) <= MARGIN_RULE
                 break
             tok, hid = d1.step_with_codes(ref, cp1.codec_embeddings, extra[f, b])
+
+
+def test_graph_replay_equals_plain_launches(gpu_weights):
+    """A frame / a talker step replayed from a CUDA graph (captured from the same C-ABI calls) is bit-identical to the plain
+    launches -- sampled frames included: the frame counter lives in device memory, so every replay draws fresh numbers."""
+    from qwen_megakernel.model_tts import BatchedFrameLoop, BatchedTTSDecoder
+    from qwen_megakernel.synthetic import synthetic_inputs
+    B, S, n = 16, 64, 6
+    prefill = synthetic_inputs(7171, 2 * B).cuda().view(2, B, 1024)
+    extra = synthetic_inputs(7272, n * B).cuda().view(n, B, 1024)
+    runs = []
+    for graph in (False, True):
+        torch.manual_seed(4242)
+        loop = BatchedFrameLoop(gpu_weights, B, max_seq_len=S, graph=graph)
+        loop.start(prefill)
+        frames = [loop.frame(extra[f], do_sample=True, temperature=0.9, top_k=50).clone() for f in range(n)]
+        torch.cuda.synchronize()
+        runs.append((torch.stack(frames).cpu(), loop.tokens.clone().cpu(), loop.hidden.clone().cpu(), loop.talker.positions.clone().cpu()))
+        assert graph == bool(loop._graphs)
+    for a, b in zip(runs[0], runs[1]):
+        assert torch.equal(a, b)
+    assert len({tuple(f.flatten().tolist()) for f in runs[1][0]}) == n, "replayed frames repeat"
+    assert int(runs[1][3][0]) == 2 + 1 + n
+
+    d_plain, d_graph = BatchedTTSDecoder(gpu_weights, B, max_seq_len=S), BatchedTTSDecoder(gpu_weights, B, max_seq_len=S)
+    tok = torch.arange(B, dtype=torch.int32, device="cuda") * 7 + 3
+    tp = tg = tok
+    for _ in range(5):
+        tp, hp = d_plain.step(tp)
+        tg, hg = d_graph.step_graph(tg)
+        assert torch.equal(tp, tg) and torch.equal(hp, hg)
+        tp, tg = tp.clone(), tg.clone()
+    assert d_graph._graph is not None and d_graph._steps == 5
