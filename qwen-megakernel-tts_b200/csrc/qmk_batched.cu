@@ -34,6 +34,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// Split-K partials are staged through shared memory with cp.async: a thread's 8-16 independent 16-byte reads are then ALL in
+// flight at once (one L2 round trip).  With ordinary loads the compiler interleaves loads and dependent adds three at a time
+// -- five round trips, 1.4 us of a 2.1-us kernel (scripts/chain_trace.py) -- whatever the source order.  A thread only reads
+// back what it copied itself, so cp.async.wait_all is all the synchronisation needed.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // sum over the 256 threads of a block (8 warps); every thread gets the total
 __device__ __forceinline__ float block_sum_256(float v, float* s_red) {
   v = warp_sum(v);
@@ -83,26 +91,35 @@ __global__ void kb_input(const int* token_ids, const __nv_bfloat16* embed_table,
 }
 
 // ---- O / down epilogue: split-K sum -> bf16 -> residual -> next RMSNorm ----------------------------------------------
-// grid = B, block = 256.  partial: [SPLITS][B][1024].  hidden_out (optional, final norm only): f32[B][1024]
-// All SPLITS partial loads of a thread are in flight together (one L2 round trip instead of SPLITS / 4: the kernel is nothing
-// but that latency), the sum keeps the split order.
-template <int SPLITS>
-__global__ void kb_resid_norm(const float* partial, int B, float* res, int residual_fp32,
-                              const __nv_bfloat16* w_norm, __nv_bfloat16* xn, float* hidden_out, int* advance_positions) {
+// One CLUSTER of C CTAs per stream, 256 threads in all (thread v owns elements 4 v .. 4 v + 3).  partial: [SPLITS][B][1024].
+// hidden_out (optional, final norm only): f32[B][1024].  The kernel is nothing but the latency of its loads: all SPLITS partial
+// loads of a thread are in flight together (one L2 round trip), and the 64 KB a stream reads are spread over C SMs (one SM
+// sustains ~45 GB/s of such loads: 1.4 us for 64 KB).  The sum of squares keeps the single-CTA order: warp totals travel
+// through distributed shared memory into every CTA's s_red[8] and are added in warp order.
+template <int SPLITS, int C>
+__global__ void __launch_bounds__(256 / C) kb_resid_norm(const float* partial, int B, float* res, int residual_fp32,
+                                                         const __nv_bfloat16* w_norm, __nv_bfloat16* xn, float* hidden_out, int* advance_positions) {
   __shared__ float s_red[8];
+  __shared__ float4 s_pp[SPLITS][256 / C];
   qmkb::KTrace kt;
   kt.mark(0);
-  const int b = blockIdx.x, t = threadIdx.x;
+  unsigned rank = 0;
+  if (C > 1) {
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");   // every CTA of the cluster runs (ahead of the dependency)
+  }
+  const int b = blockIdx.x / C, t = (int)rank * (256 / C) + threadIdx.x;
   qmkb::pdl_wait();
   qmkb::pdl_launch_dependents();
   kt.mark(1);
-  float4 pp[SPLITS];
 #pragma unroll
-  for (int s = 0; s < SPLITS; ++s) pp[s] = __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)s * B + b) * H + t * 4));
+  for (int s = 0; s < SPLITS; ++s) cp_async16(&s_pp[s][threadIdx.x], partial + ((size_t)s * B + b) * H + t * 4);
   float4 r = *reinterpret_cast<const float4*>(res + (size_t)b * H + t * 4);
+  const uint2 wv = *reinterpret_cast<const uint2*>(w_norm + t * 4);
+  cp_async_wait_all();
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int s = 0; s < SPLITS; ++s) { acc.x += pp[s].x; acc.y += pp[s].y; acc.z += pp[s].z; acc.w += pp[s].w; }
+  for (int s = 0; s < SPLITS; ++s) { const float4 pv = s_pp[s][threadIdx.x]; acc.x += pv.x; acc.y += pv.y; acc.z += pv.z; acc.w += pv.w; }
   if (kt.on && acc.x == 1.2345e-30f) kt.t[0] = 0;   // (trace only) the stamp below waits for the loads
   kt.mark(2);
   const float o[4] = {bf16_round(acc.x), bf16_round(acc.y), bf16_round(acc.z), bf16_round(acc.w)};
@@ -112,7 +129,33 @@ __global__ void kb_resid_norm(const float* partial, int B, float* res, int resid
     for (int e = 0; e < 4; ++e) x[e] = bf16_round(x[e]);
   }
   *reinterpret_cast<float4*>(res + (size_t)b * H + t * 4) = make_float4(x[0], x[1], x[2], x[3]);
-  const uint2 n = rmsnorm4(x, w_norm, s_red);
+  // n = r( r(x) * rsqrt(mean(r(x)^2) + eps) * w ): same arithmetic and summation order as rmsnorm4
+  float rr[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) rr[e] = bf16_round(x[e]);
+  const float ws = warp_sum(fmaf(rr[0], rr[0], rr[1] * rr[1]) + fmaf(rr[2], rr[2], rr[3] * rr[3]));
+  if ((threadIdx.x & 31) == 0) {
+    if (C > 1) {
+      const uint32_t local = (uint32_t)__cvta_generic_to_shared(&s_red[t >> 5]);
+#pragma unroll
+      for (int peer = 0; peer < C; ++peer) {
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(peer));
+        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(ws) : "memory");
+      }
+    } else {
+      s_red[t >> 5] = ws;
+    }
+  }
+  if (C > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  else __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += s_red[w];
+  const float inv = rsqrtf(tot * (1.0f / H) + EPS);
+  const __nv_bfloat162 n01 = __floats2bfloat162_rn((rr[0] * inv) * bf16_lo(wv.x), (rr[1] * inv) * bf16_hi(wv.x));
+  const __nv_bfloat162 n23 = __floats2bfloat162_rn((rr[2] * inv) * bf16_lo(wv.y), (rr[3] * inv) * bf16_hi(wv.y));
+  const uint2 n = make_uint2(*reinterpret_cast<const uint32_t*>(&n01), *reinterpret_cast<const uint32_t*>(&n23));
   *reinterpret_cast<uint2*>(xn + (size_t)b * H + t * 4) = n;
   if (hidden_out)
     *reinterpret_cast<float4*>(hidden_out + (size_t)b * H + t * 4) = make_float4(bf16_lo(n.x), bf16_hi(n.x), bf16_lo(n.y), bf16_hi(n.y));
@@ -123,24 +166,28 @@ __global__ void kb_resid_norm(const float* partial, int B, float* res, int resid
 // ---- QKV epilogue + decode attention, one CTA per (stream, kv head) --------------------------------------------------
 // Warps 0-3 first finish the projection for this group: split-K sum -> bf16 -> per-head RMSNorm + rotate-half RoPE in
 // bf16 steps (q heads 2g, 2g+1 and k) -> q, and the new k / v row, into shared memory; k / v are also appended to the cache row
-// positions[b].  Then all 8 warps stride over positions 0 .. pos (lane owns 4 dims), fp32 online softmax, fixed-order
-// cross-warp merge.  The cached rows of the first ATT_PRE rounds (positions < 8 ATT_PRE) are requested BEFORE the grid
+// positions[b].  Then all ATT_NW warps stride over positions 0 .. pos (lane owns 4 dims), fp32 online softmax, fixed-order
+// cross-warp merge.  The cached rows of the first ATT_PRE rounds (positions < 32) are requested BEFORE the grid
 // dependency resolves: they were written by earlier steps, so their L2 / HBM latency overlaps the projection that precedes
 // this kernel; deeper contexts continue in batches of ATT_PRE independent row loads.
+// Grid shape, measured (us per B = 16 / B = 64 step, graph replay): one item per 256-thread CTA 656 / 864 (kept); four warps per
+// item with eight rows each in flight 694 / 866; two / four items per 512- / 1024-thread CTA - / 903, - / 930.  An EMPTY
+// 512 x 256 grid costs 4.8 us in a dependent chain (scripts/ubench/pdl_gap.cu), but programmatic launch hides that behind the
+// preceding projection, and fat CTAs keep the next projection's CTAs from becoming resident early.
 // grid = (B, 8), block = 256.  partial: [SPLITS][B][4096] (q rows 0..2047, k 2048..3071, v 3072..4095).
-constexpr int ATT_PRE = 4;
+constexpr int ATT_PRE = 4, ATT_NW = 8;
 template <int SPLITS>
-__global__ void kb_qkv_attention(const float* partial, int B, const int* positions, const __nv_bfloat16* q_norm,
+__global__ void __launch_bounds__(32 * ATT_NW) kb_qkv_attention(const float* partial, int B, const int* positions, const __nv_bfloat16* q_norm,
                                  const __nv_bfloat16* k_norm, const __nv_bfloat16* cos_t, const __nv_bfloat16* sin_t,
                                  __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, __nv_bfloat16* a_out, int layer, int L,
                                  int max_seq, float scale) {
   __shared__ float s_q[2][HD];
   __shared__ float s_kv[2][HD];   // the new row: k (after norm + RoPE), v
-  __shared__ float s_acc[8][2][HD];
-  __shared__ float s_m[8][2], s_l[8][2];
+  __shared__ float s_acc[ATT_NW][2][HD];
+  __shared__ float s_m[ATT_NW][2], s_l[ATT_NW][2];
   qmkb::KTrace kt;
   kt.mark(0);
-  const int b = blockIdx.x, g = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x, g = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // positions[] was last written two kernels ago at the latest (the previous step's final kernel; every kernel of the chain
   // resolves its own dependency before it lets its successor start), so it may be read ahead of the dependency.
   int pos = positions[b];
@@ -149,7 +196,7 @@ __global__ void kb_qkv_attention(const float* partial, int B, const int* positio
   uint2 kk[ATT_PRE], vv[ATT_PRE];
 #pragma unroll
   for (int i = 0; i < ATT_PRE; ++i) {
-    const int p = warp + 8 * i;
+    const int p = warp + ATT_NW * i;
     if (p < pos) {
       kk[i] = __ldcg(reinterpret_cast<const uint2*>(k_cache + base + (size_t)p * HD + lane * 4));
       vv[i] = __ldcg(reinterpret_cast<const uint2*>(v_cache + base + (size_t)p * HD + lane * 4));
@@ -209,11 +256,11 @@ __global__ void kb_qkv_attention(const float* partial, int B, const int* positio
   const float4 qa = *reinterpret_cast<const float4*>(&s_q[0][lane * 4]), qb = *reinterpret_cast<const float4*>(&s_q[1][lane * 4]);
   const float q0[4] = {qa.x, qa.y, qa.z, qa.w}, q1[4] = {qb.x, qb.y, qb.z, qb.w};
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f, acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
-  for (int p0 = warp; p0 < n; p0 += 8 * ATT_PRE) {   // warp-uniform; positions in ascending order per warp, as before
+  for (int p0 = warp; p0 < n; p0 += ATT_NW * ATT_PRE) {   // warp-uniform; positions in ascending order per warp, as before
     if (p0 != warp) {
 #pragma unroll
       for (int i = 0; i < ATT_PRE; ++i) {
-        const int p = p0 + 8 * i;
+        const int p = p0 + ATT_NW * i;
         if (p < pos) {
           kk[i] = __ldcg(reinterpret_cast<const uint2*>(k_cache + base + (size_t)p * HD + lane * 4));
           vv[i] = __ldcg(reinterpret_cast<const uint2*>(v_cache + base + (size_t)p * HD + lane * 4));
@@ -222,7 +269,7 @@ __global__ void kb_qkv_attention(const float* partial, int B, const int* positio
     }
 #pragma unroll
     for (int i = 0; i < ATT_PRE; ++i) {
-      const int p = p0 + 8 * i;
+      const int p = p0 + ATT_NW * i;
       if (p < n) {
         float kf[4], vf[4];
         if (p == pos) {
@@ -251,43 +298,47 @@ __global__ void kb_qkv_attention(const float* partial, int B, const int* positio
 #pragma unroll
   for (int e = 0; e < 4; ++e) { s_acc[warp][0][lane * 4 + e] = acc0[e]; s_acc[warp][1][lane * 4 + e] = acc1[e]; }
   __syncthreads();
-  const int h = threadIdx.x >> 7, d = threadIdx.x & 127;
-  float M = -INFINITY;
+  for (int o = tid; o < 2 * HD; o += 32 * ATT_NW) {   // warps merged in warp order
+    const int h = o >> 7, d = o & 127;
+    float M = -INFINITY;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) M = fmaxf(M, s_m[w][h]);
-  float A = 0.f, Ls = 0.f;
+    for (int w = 0; w < ATT_NW; ++w) M = fmaxf(M, s_m[w][h]);
+    float A = 0.f, Ls = 0.f;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    const float f = (s_m[w][h] == -INFINITY) ? 0.f : __expf(s_m[w][h] - M);
-    A = fmaf(s_acc[w][h][d], f, A);
-    Ls = fmaf(s_l[w][h], f, Ls);
+    for (int w = 0; w < ATT_NW; ++w) {
+      const float f = (s_m[w][h] == -INFINITY) ? 0.f : __expf(s_m[w][h] - M);
+      A = fmaf(s_acc[w][h][d], f, A);
+      Ls = fmaf(s_l[w][h], f, Ls);
+    }
+    a_out[(size_t)b * QSZ + (2 * g + h) * HD + d] = __float2bfloat16_rn(A / Ls);
   }
-  a_out[(size_t)b * QSZ + (2 * g + h) * HD + d] = __float2bfloat16_rn(A / Ls);
   kt.flush(4);
 }
 
 // ---- gate/up epilogue: m = r( r(silu(r(g))) * r(u) ) -------------------------------------------------------------------
 // grid = (B, 3), block = 256; partial: [splits][B][6144] (gate rows 0..3071, up rows 3072..6143)
 template <int SPLITS>
-__global__ void kb_gu_epilogue(const float* partial, int B, __nv_bfloat16* m_out) {
+__global__ void __launch_bounds__(256) kb_gu_epilogue(const float* partial, int B, __nv_bfloat16* m_out) {
   qmkb::KTrace kt;
   kt.mark(0);
   qmkb::pdl_wait();
   qmkb::pdl_launch_dependents();
   kt.mark(1);
   const int b = blockIdx.x, j = blockIdx.y * 1024 + threadIdx.x * 4;
-  float4 pg[SPLITS], pu[SPLITS];
+  __shared__ float4 s_pg[SPLITS][256], s_pu[SPLITS][256];
 #pragma unroll
   for (int s = 0; s < SPLITS; ++s) {
     const float* p = partial + ((size_t)s * B + b) * GU_ROWS;
-    pg[s] = __ldcg(reinterpret_cast<const float4*>(p + j));
-    pu[s] = __ldcg(reinterpret_cast<const float4*>(p + INTER + j));
+    cp_async16(&s_pg[s][threadIdx.x], p + j);
+    cp_async16(&s_pu[s][threadIdx.x], p + INTER + j);
   }
+  cp_async_wait_all();
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f), u = g;
 #pragma unroll
   for (int s = 0; s < SPLITS; ++s) {
-    g.x += pg[s].x; g.y += pg[s].y; g.z += pg[s].z; g.w += pg[s].w;
-    u.x += pu[s].x; u.y += pu[s].y; u.z += pu[s].z; u.w += pu[s].w;
+    const float4 pg = s_pg[s][threadIdx.x], pu = s_pu[s][threadIdx.x];
+    g.x += pg.x; g.y += pg.y; g.z += pg.z; g.w += pg.w;
+    u.x += pu.x; u.y += pu.y; u.z += pu.z; u.w += pu.w;
   }
   const float gv[4] = {g.x, g.y, g.z, g.w}, uv[4] = {u.x, u.y, u.z, u.w};
   uint32_t o[4];
@@ -319,24 +370,27 @@ __global__ void kb_head_epilogue(const float* partial, int splits, int B, int ro
   __shared__ float s_log[2048];
   __shared__ unsigned s_hist[512];
   __shared__ float s_red[64];
+  extern __shared__ __align__(16) float s_stage[];   // [splits][rows]: the stream's partial logits (dynamic: splits * rows * 4 bytes)
   qmkb::pdl_wait();
   qmkb::pdl_launch_dependents();
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool sample = sel.do_sample && rows <= 2048 && rows % 256 == 0;
   float best = -INFINITY;
   int best_i = 0x7fffffff;
-  for (int r = tid; r < rows; r += 256) {
-    float acc = 0.f;
-    if (splits == 4) {   // the chain's head projection: four loads in flight, same summation order
-      const float p0 = __ldcg(partial + ((size_t)0 * B + b) * rows + r), p1 = __ldcg(partial + ((size_t)1 * B + b) * rows + r);
-      const float p2 = __ldcg(partial + ((size_t)2 * B + b) * rows + r), p3 = __ldcg(partial + ((size_t)3 * B + b) * rows + r);
-      acc = (((acc + p0) + p1) + p2) + p3;
-    } else {
-      for (int s = 0; s < splits; ++s) acc += partial[((size_t)s * B + b) * rows + r];
+  for (int s = 0; s < splits; ++s)
+    for (int c = tid * 4; c < rows; c += 1024) cp_async16(s_stage + (size_t)s * rows + c, partial + ((size_t)s * B + b) * rows + c);
+  cp_async_wait_all();
+  for (int c = tid * 4; c < rows; c += 1024) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+      const float4 pv = *reinterpret_cast<const float4*>(s_stage + (size_t)s * rows + c);
+      acc.x += pv.x; acc.y += pv.y; acc.z += pv.z; acc.w += pv.w;
     }
-    const float v = bf16_round(acc);
-    if (sample) s_log[r] = v;
-    if (v > best) { best = v; best_i = r; }
+    const float v4[4] = {bf16_round(acc.x), bf16_round(acc.y), bf16_round(acc.z), bf16_round(acc.w)};
+    if (sample) *reinterpret_cast<float4*>(s_log + c) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (v4[e] > best) { best = v4[e]; best_i = c + e; }   // ascending indices per thread: the lowest index of a tie is kept
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -415,6 +469,7 @@ int fail(int code, const char* msg) {
 
 }  // namespace
 
+constexpr int MAX_HEAD_ROWS_B = 8192;   // LM-head rows the head epilogue can stage in shared memory (4 splits x rows x 4 bytes = 128 KB)
 constexpr size_t PARTIAL_ELEMS = (size_t)2 * 1024 * 1024;   // fp32 split-K partials: max splits x B x rows = 4 x 64 x 6144
 constexpr int MAX_LANES = 64;
 static size_t qmkb_hidden_offset() { return PARTIAL_ELEMS; }   // prefill: per-lane hidden states live behind the partials
@@ -466,6 +521,7 @@ extern "C" int qmk_batched_create(int device, const LDGLayerWeights* layers_host
   if (batch < 16 || batch > MAX_N || batch % 16) return fail(QMK_ERR_ARG, "qmk_batched_create: batch must be 16, 32, 48 or 64");
   if (lm_head_rows % BM || lm_head_rows <= 0) return fail(QMK_ERR_ARG, "qmk_batched_create: lm_head_rows must be a multiple of 128");
   if (num_layers < 1 || max_seq_len < 1) return fail(QMK_ERR_ARG, "qmk_batched_create: bad num_layers / max_seq_len");
+  if (lm_head_rows > MAX_HEAD_ROWS_B) return fail(QMK_ERR_ARG, "qmk_batched_create: lm_head_rows above 8192");
   if ((size_t)6 * batch * lm_head_rows > PARTIAL_ELEMS) return fail(QMK_ERR_ARG, "qmk_batched_create: lm_head_rows too large for the split-K partial buffer");
   *out = nullptr;
   int ndev = 0;
@@ -569,6 +625,7 @@ extern "C" int qmk_batched_create(int device, const LDGLayerWeights* layers_host
     if (!okp) { qmk_batched_destroy(h); return fail(QMK_ERR_CUDA, "qmk_batched_create: allocation failed (persistent kernel)"); }
   }
   if (cudaFuncSetAttribute(qmk_bgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(kb_head_epilogue, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * MAX_HEAD_ROWS_B * (int)sizeof(float)) != cudaSuccess ||
       cudaDeviceSynchronize() != cudaSuccess) {
     qmk_batched_destroy(h);
     return fail(QMK_ERR_CUDA, "qmk_batched_create: kernel setup failed");
@@ -604,6 +661,30 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cfg.numAttrs = 1;
   const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
   if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e;
+}
+template <typename... KArgs, typename... Args>
+static void launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, unsigned cluster_x, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = cluster_x; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e;
+}
+// residual + RMSNorm after an O / down projection: a cluster of 4 CTAs per stream (2 beyond 32 streams: the grid stays <= 128 CTAs)
+static void resid_norm(qmk_batched* h, cudaStream_t st, const void* w_norm, float* hidden_out, int* advance_positions) {
+  const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(w_norm);
+  if (h->B <= 32)
+    launch_pdl_cluster(kb_resid_norm<16, 4>, dim3(h->B * 4), dim3(64), 4, st, (const float*)h->partial, h->B, h->res, h->residual_fp32, w, h->xn, hidden_out, advance_positions);
+  else
+    launch_pdl_cluster(kb_resid_norm<16, 2>, dim3(h->B * 2), dim3(128), 2, st, (const float*)h->partial, h->B, h->res, h->residual_fp32, w, h->xn, hidden_out, advance_positions);
 }
 static void gemm(qmk_batched* h, const CUtensorMap& mw, const CUtensorMap& mx, int M, int K, int splits, cudaStream_t st) {
   qmkb::BgemmArgs a{h->partial, M, h->B, K, splits};
@@ -674,19 +755,17 @@ static int chain_step(qmk_batched* h, const qmk_batched_step_args* a, cudaStream
              reinterpret_cast<const __nv_bfloat16*>(h->ln_in[0]), h->xn);
   for (int l = 0; l < L; ++l) {
     gemm(h, h->map_qkv[l], h->map_x1024, QKV_ROWS, H, 4, st);                       // 32 tiles x 4 K-slices
-    launch_pdl(kb_qkv_attention<4>, dim3(B, NKVH), dim3(256), 0, st, (const float*)h->partial, B, (const int*)a->positions,
+    launch_pdl(kb_qkv_attention<4>, dim3(B, NKVH), dim3(32 * ATT_NW), 0, st, (const float*)h->partial, B, (const int*)a->positions,
                reinterpret_cast<const __nv_bfloat16*>(h->qn[l]), reinterpret_cast<const __nv_bfloat16*>(h->kn[l]), cos_t, sin_t,
                kc, vc, h->abuf, l, L, h->max_seq, scale);
     gemm(h, h->map_o[l], h->map_x2048, H, QSZ, 16, st);                              // 8 tiles x 16 K-slices
-    launch_pdl(kb_resid_norm<16>, dim3(B), dim3(256), 0, st, (const float*)h->partial, B, h->res, h->residual_fp32,
-               reinterpret_cast<const __nv_bfloat16*>(h->ln_post[l]), h->xn, (float*)nullptr, (int*)nullptr);
+    resid_norm(h, st, h->ln_post[l], nullptr, nullptr);
     gemm(h, h->map_gu[l], h->map_x1024, GU_ROWS, H, 4, st);                          // 48 tiles x 4 K-slices
     launch_pdl(kb_gu_epilogue<4>, dim3(B, 3), dim3(256), 0, st, (const float*)h->partial, B, h->mbuf);
     gemm(h, h->map_down[l], h->map_x3072, H, INTER, 16, st);                         // 8 tiles x 16 K-slices
     const bool last = (l == L - 1);
-    launch_pdl(kb_resid_norm<16>, dim3(B), dim3(256), 0, st, (const float*)h->partial, B, h->res, h->residual_fp32,
-               reinterpret_cast<const __nv_bfloat16*>(last ? h->final_norm : h->ln_in[l + 1]), h->xn,
-               last ? a->hidden_out : (float*)nullptr, (last && head_map == nullptr) ? (int*)a->positions : (int*)nullptr);
+    resid_norm(h, st, last ? h->final_norm : h->ln_in[l + 1], last ? a->hidden_out : (float*)nullptr,
+               (last && head_map == nullptr) ? (int*)a->positions : (int*)nullptr);
   }
   if (head_map != nullptr) {
     gemm(h, *head_map, h->map_x1024, head_rows, H, 4, st);
@@ -695,7 +774,7 @@ static int chain_step(qmk_batched* h, const qmk_batched_step_args* a, cudaStream
     sel.top_k = a->top_k; sel.group = a->group; sel.temperature = sel.do_sample ? a->temperature : 1.0f;
     sel.seed = a->seed; sel.counter = a->counter; sel.counter_ptr = reinterpret_cast<const unsigned long long*>(a->counter_ptr);
     sel.codes_out = reinterpret_cast<long long*>(a->codes_out); sel.codes_stride = a->codes_stride; sel.codes_col = a->codes_col;
-    launch_pdl(kb_head_epilogue, dim3(B), dim3(256), 0, st, (const float*)h->partial, 4, B, head_rows, (int*)a->tokens_out,
+    launch_pdl(kb_head_epilogue, dim3(B), dim3(256), (size_t)4 * head_rows * sizeof(float), st, (const float*)h->partial, 4, B, head_rows, (int*)a->tokens_out,
                (int*)a->positions, sel);
   }
   cudaError_t e = g_launch_err != cudaSuccess ? g_launch_err : cudaGetLastError();
@@ -706,7 +785,7 @@ static int chain_step(qmk_batched* h, const qmk_batched_step_args* a, cudaStream
 // Register a further LM head (bf16 [rows, 1024], rows % 128 == 0): returns its index (1, 2, ...; 0 is the create-time head).
 extern "C" int qmk_batched_add_head(qmk_batched* h, const void* lm_head_weight, int rows) {
   if (!h || !lm_head_weight) return fail(QMK_ERR_ARG, "qmk_batched_add_head: null argument");
-  if (rows <= 0 || rows % qmkb::BM || (size_t)6 * h->B * rows > PARTIAL_ELEMS) return fail(QMK_ERR_ARG, "qmk_batched_add_head: bad row count");
+  if (rows <= 0 || rows % qmkb::BM || rows > MAX_HEAD_ROWS_B || (size_t)6 * h->B * rows > PARTIAL_ELEMS) return fail(QMK_ERR_ARG, "qmk_batched_add_head: bad row count");
   CUtensorMap m;
   if (qmkb::make_tensor_map(&m, lm_head_weight, rows, H, qmkb::BM)) return fail(QMK_ERR_CUDA, "qmk_batched_add_head: cuTensorMapEncodeTiled failed");
   h->extra_head_maps.push_back(m);

@@ -34,11 +34,15 @@ int main() {
   const int N = 400;
   struct Cfg { const char* name; int grid, threads; size_t smem; } cfgs[] = {
       {"128 x 128, 97 KB (GEMM)", 128, 128, 97 * 1024}, {"16 x 256 (epilogue B=16)", 16, 256, 0}, {"512 x 256 (attention B=64)", 512, 256, 0},
-      {"alternating GEMM / epilogue", -1, 0, 0}};
+      {"alternating GEMM / epilogue", -1, 0, 0},
+      {"512 x 128", 512, 128, 0}, {"512 x 64", 512, 64, 0}, {"256 x 256", 256, 256, 0}, {"256 x 512", 256, 512, 0}, {"128 x 1024", 128, 1024, 0},
+      {"148 x 256", 148, 256, 0}, {"296 x 256", 296, 256, 0}, {"192 x 256", 192, 256, 0}, {"64 x 256", 64, 256, 0}, {"128 x 256", 128, 256, 0}};
+  const bool quick = getenv("PDL_GAP_QUICK") != nullptr;
   for (auto& c : cfgs) {
     for (int work : {0, 2000}) {
       for (int mode = 0; mode < 3; ++mode) {   // 0 plain, 1 PDL trigger early, 2 PDL trigger late
         for (int graph = 0; graph < 2; ++graph) {
+          if (quick && !(mode == 1 && graph == 1)) continue;
           auto issue = [&]() {
             for (int i = 0; i < N; ++i) {
               int grid = c.grid, threads = c.threads; size_t smem = c.smem;
