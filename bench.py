@@ -394,16 +394,19 @@ def time_batched(weights_gpu, dev, batch: int, steps: int = 100, warmup: int = 1
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
         for _ in range(n):
-            t, _ = step_fn(tok)
-            tok.copy_(t)
+            step_fn()
         end.record()
         torch.cuda.synchronize()
         return start.elapsed_time(end) / n
-    run(bd.step, warmup)
+    def plain():
+        t, _ = bd.step(tok)
+        tok.copy_(t)
+    run(plain, warmup)
     bd.reset()
-    ms_launches = run(bd.step, steps)                 # 227 launches issued by the host per step
+    ms_launches = run(plain, steps)                   # 227 launches issued by the host per step
     bd.reset()
-    run(bd.step_graph, max(warmup, 3))                # first call plain, second captures
+    bd.step_graph(tok)
+    run(bd.step_graph, max(warmup, 3))                # feedback form (tokens stay on the device); the second call captures
     bd.reset()
     ms = run(bd.step_graph, steps)                    # the same launches replayed from a CUDA graph
     bytes_step = TALKER_STEP_BYTES + batch * sum(TALKER_KV_BYTES_PER_POS * (p + 2) for p in range(steps)) / steps

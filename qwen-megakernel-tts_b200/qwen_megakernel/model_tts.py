@@ -599,24 +599,27 @@ class BatchedTTSDecoder:
         self._keep = e
         return self._run(None, e.data_ptr())
 
-    def step_graph(self, token_ids: torch.Tensor):
+    def step_graph(self, token_ids: Optional[torch.Tensor] = None):
         """``step`` replayed from a CUDA graph: the 227 launches of the chain (programmatic-launch edges included) are
         captured once -- every per-step quantity (positions, tokens) lives in device memory -- and each later call is ONE
-        graph launch plus the copy of ``token_ids`` into the graph's input buffer.  Same results as ``step``."""
+        graph launch.  ``token_ids`` None feeds the previous step's tokens back (no copy at all); a tensor is copied into the
+        graph's input buffer first.  Same results as ``step``."""
         if self._steps >= self._max_seq:
             raise IndexError("KV cache is full for at least one stream")
         if not hasattr(self, "_g_tok"):
             self._g_tok = torch.zeros(self.batch, dtype=torch.int32, device=self.device)
-            self._graph = None
-            self._graph_warm = False
-        self._g_tok.copy_(token_ids.to(self.device, torch.int32).reshape(self.batch))
+            self._graphs, self._graph_warm = {}, False
+        feedback = token_ids is None
+        src = self._tokens if feedback else self._g_tok
+        if not feedback:
+            self._g_tok.copy_(token_ids.to(self.device, torch.int32).reshape(self.batch))
         if not self._graph_warm:                      # first call: plain launches (also the warm-up the capture needs)
             self._graph_warm = True
-            return self.step(self._g_tok)
-        if self._graph is None:
-            self._graph, _ = _capture(self.device, lambda: self.step(self._g_tok))
+            return self.step(src)
+        if feedback not in self._graphs:
+            self._graphs[feedback], _ = _capture(self.device, lambda: self.step(src))
             self._steps -= 1                          # the capture only recorded the step
-        self._graph.replay()
+        self._graphs[feedback].replay()
         self._steps += 1
         return self._tokens, self._hidden
 

@@ -19,10 +19,11 @@ n = lib.qmk_batched_chain_trace(0, st, buf, 16000)
 rec = sorted((buf[2 * i + 1], buf[2 * i]) for i in range(n) if buf[2 * i + 1])
 names = {1: "gemm", 2: "input", 3: "resid_norm", 4: "qkv_attn", 5: "gu_epi", 6: "head"}
 ev = {0: "entry", 1: "dep ok", 2: "mma done", 3: "exit"}
+ev2 = {3: "loads ok", 4: "q ready"}    # what stamp 2 marks in the epilogue kernels
 print(f"B={B}: {n} records")
 # the middle step, layers 10..11
 t_first = rec[0][0]
 third = [r for r in rec if r[0] >= rec[len(rec) // 2][0]]
 t0 = third[0][0]
 for ns, tag in third[:120]:
-    print(f"{(ns - t0) / 1000:9.2f} us  {names.get(tag >> 4, tag >> 4):10s} {ev[(tag >> 1) & 7]:8s} {'last CTA' if tag & 1 else 'first CTA'}")
+    print(f"{(ns - t0) / 1000:9.2f} us  {names.get(tag >> 4, tag >> 4):10s} {(ev2.get(tag >> 4, ev[2]) if (tag >> 1) & 7 == 2 else ev[(tag >> 1) & 7]):8s} {'last CTA' if tag & 1 else 'first CTA'}")

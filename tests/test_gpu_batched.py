@@ -286,4 +286,9 @@ def test_graph_replay_equals_plain_launches(gpu_weights):
         tg, hg = d_graph.step_graph(tg)
         assert torch.equal(tp, tg) and torch.equal(hp, hg)
         tp, tg = tp.clone(), tg.clone()
-    assert d_graph._graph is not None and d_graph._steps == 5
+    assert d_graph._graphs and d_graph._steps == 5
+    for _ in range(3):                                # feedback form: the previous tokens are the input, no copy
+        tp, hp = d_plain.step(tp.clone())
+        tg, hg = d_graph.step_graph()
+        assert torch.equal(tp, tg) and torch.equal(hp, hg)
+    assert set(d_graph._graphs) == {False, True}
