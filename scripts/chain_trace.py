@@ -17,7 +17,7 @@ for _ in range(3): dec.step(tok)
 buf = (ctypes.c_ulonglong * 32000)()
 n = lib.qmk_batched_chain_trace(0, st, buf, 16000)
 rec = sorted((buf[2 * i + 1], buf[2 * i]) for i in range(n) if buf[2 * i + 1])
-names = {1: "gemm", 2: "input", 3: "resid_norm", 4: "qkv_attn", 5: "gu_epi", 6: "head"}
+names = {1: "gemm", 2: "input", 3: "resid_norm", 4: "qkv_attn", 5: "gu_epi", 6: "head", 7: "gu_gemm"}
 ev = {0: "entry", 1: "dep ok", 2: "mma done", 3: "exit"}
 ev2 = {3: "loads ok", 4: "q ready"}    # what stamp 2 marks in the epilogue kernels
 print(f"B={B}: {n} records")
