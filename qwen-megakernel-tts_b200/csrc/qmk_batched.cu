@@ -175,7 +175,10 @@ __global__ void __launch_bounds__(256 / C) kb_resid_norm(const float* partial, i
 // 512 x 256 grid costs 4.8 us in a dependent chain (scripts/ubench/pdl_gap.cu), but programmatic launch hides that behind the
 // preceding projection, and fat CTAs keep the next projection's CTAs from becoming resident early.
 // grid = (B, 8), block = 256.  partial: [SPLITS][B][4096] (q rows 0..2047, k 2048..3071, v 3072..4095).
-constexpr int ATT_PRE = 4, ATT_NW = 8;
+#ifndef QMK_BATT_PRE
+#define QMK_BATT_PRE 4
+#endif
+constexpr int ATT_PRE = QMK_BATT_PRE, ATT_NW = 8;
 template <int SPLITS>
 __global__ void __launch_bounds__(32 * ATT_NW) kb_qkv_attention(const float* partial, int B, const int* positions, const __nv_bfloat16* q_norm,
                                  const __nv_bfloat16* k_norm, const __nv_bfloat16* cos_t, const __nv_bfloat16* sin_t,

@@ -11,7 +11,7 @@ for B in (16, 64):
     tok = torch.arange(B, dtype=torch.int32, device="cuda") + 5
     for _ in range(5): dec.step(tok)
     torch.cuda.synchronize()
-    n = 50
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 50
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dec.reset(); a.record(); t0 = time.perf_counter()
     for _ in range(n): dec.step(tok)

@@ -140,6 +140,8 @@ def test_entry_points_reject_null_arguments_without_a_gpu():
     assert lib.qmk_batched_prefill(None, None, 1, 0, None, None, None, None, None) == -1
     assert lib.qmk_batched_add_head(None, None, 128) == -1
     assert lib.qmk_batched_embed_sum(0, None, None, 0, None, 0, None, 0, None, None) == -1
+    assert lib.qmk_batched_counter_add(None, 1, None) == -1
+    assert lib.qmk_batched_chain_trace(0, None, None, 0) == 0          # never armed: nothing to copy, no CUDA call
     assert b"null" in lib.qmk_last_error() or b"null" in lib.qmk_batched_last_error()
     assert lib.qmk_legacy_check_blob(None, 5, None) == 0
     lib.qmk_legacy_invalidate(None)                     # no cached models: a no-op

@@ -292,3 +292,26 @@ def test_graph_replay_equals_plain_launches(gpu_weights):
         tg, hg = d_graph.step_graph()
         assert torch.equal(tp, tg) and torch.equal(hp, hg)
     assert set(d_graph._graphs) == {False, True}
+
+
+def test_chain_trace_records_every_kernel_of_a_step(gpu_weights):
+    """Debug timeline (qmk_batched_chain_trace): one 5-layer step = 5 x (4 GEMMs + 4 epilogues) stamped by their first and last CTA."""
+    import ctypes
+    from qwen_megakernel.model_tts import BatchedTTSDecoder
+    dec = BatchedTTSDecoder(gpu_weights, 16, max_seq_len=64, num_layers=5)
+    tok = torch.arange(16, dtype=torch.int32, device="cuda")
+    dec.step(tok)
+    lib, st = dec._lib, torch.cuda.current_stream().cuda_stream
+    assert lib.qmk_batched_chain_trace(1, st, None, 0) == 0
+    dec.step(tok)
+    buf = (ctypes.c_ulonglong * 4096)()
+    n = lib.qmk_batched_chain_trace(0, st, buf, 2048)
+    kinds = {}
+    for i in range(n):
+        tag, ns = buf[2 * i], buf[2 * i + 1]
+        if (tag >> 1) & 7 == 3 and not tag & 1:                        # exit stamp of the first CTA: one per kernel
+            kinds[tag >> 4] = kinds.get(tag >> 4, 0) + 1
+            assert ns > 0
+    assert kinds.get(1) == 5 * 4 + 1 and kinds.get(3) == 10 and kinds.get(4) == 5 and kinds.get(5) == 5, kinds
+    dec.step(tok)                                                      # disarmed: nothing is recorded any more
+    assert lib.qmk_batched_chain_trace(0, st, buf, 2048) == 0
