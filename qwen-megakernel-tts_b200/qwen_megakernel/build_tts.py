@@ -88,12 +88,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError("qwen_megakernel: libqmk_b200.so is missing/stale and nvcc was not found")
-    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("QMK_NVCC_EXTRA", "").split() + ["-Xptxas", "-v"] * int(verbose) + [f'-DQMK_SRC_HASH="{want}"', f"-I{_INCLUDE}", f"-I{_CSRC}", "-o", LIB_PATH] + srcs
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr)
+    # Several ranks of one job may find the library stale at the same moment: one of them compiles (exclusive lock), into a
+    # temporary name that replaces the library atomically, the others wait for the lock and then find it current.
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and os.path.exists(LIB_PATH) and library_hash(LIB_PATH) == want:
+                return LIB_PATH
+            tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
+            cmd = [nvcc] + NVCC_FLAGS + os.environ.get("QMK_NVCC_EXTRA", "").split() + ["-Xptxas", "-v"] * int(verbose) + [f'-DQMK_SRC_HASH="{want}"', f"-I{_INCLUDE}", f"-I{_CSRC}", "-o", tmp] + srcs
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
+            os.replace(tmp, LIB_PATH)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
