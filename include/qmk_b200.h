@@ -299,7 +299,9 @@ int qmk_batched_chain_trace(int enable, void* stream, unsigned long long* host_o
  * through 8 sequential decode steps, tts_engine.py:281-282): lane i of `embeds` (bf16[n][1024], n <= batch) is position
  * position0 + i; all lanes share the caller's B = 1 cache [L][8][max_seq_len][128] and attend causally.  Writes the same KV
  * rows as n sequential steps; hidden_out_last (f32[1024]) / token_out_last (int32[1]) receive the last position's
- * post-norm hidden state and argmax token.  Needs the persistent kernel. */
+ * post-norm hidden state and argmax token.  Default: the launch chain with lane = position (9 kernels per layer: the QKV
+ * epilogue is split into "all lanes' K / V rows" and "causal attention"); QMK_PREFILL_PERSISTENT=1 at create time selects the
+ * persistent kernel's prefill mode (needs >= 144 SMs; slower: 1.44 vs 0.78 ms for 8 positions on B200). */
 int qmk_batched_prefill(qmk_batched* h, const void* embeds, int n, int position0, void* k_cache, void* v_cache,
                         float* hidden_out_last, int32_t* token_out_last, void* stream);
 

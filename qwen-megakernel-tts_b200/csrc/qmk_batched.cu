@@ -69,20 +69,21 @@ __device__ __forceinline__ uint2 rmsnorm4(const float (&x)[4], const __nv_bfloat
 // ---- step input: embedding row or caller vector -> fp32 residual + layer-0 input norm -------------------------------
 // grid = B, block = 256
 __global__ void kb_input(const int* token_ids, const __nv_bfloat16* embed_table, int vocab, const __nv_bfloat16* embeds,
-                         const float* embeds_f32, float* res, const __nv_bfloat16* w_in, __nv_bfloat16* xn) {
+                         const float* embeds_f32, float* res, const __nv_bfloat16* w_in, __nv_bfloat16* xn, int n_valid) {
   __shared__ float s_red[8];
   qmkb::pdl_wait();
   qmkb::pdl_launch_dependents();
   const int b = blockIdx.x, t = threadIdx.x;
+  const int bs = b < n_valid ? b : n_valid - 1;   // prefill with fewer positions than lanes: the spare lanes repeat the last one
   float x[4];
   if (embeds_f32 != nullptr) {      // fp32 vector rounded to bf16 on load (the talker's hidden state entering the code predictor)
-    const float4 v = *reinterpret_cast<const float4*>(embeds_f32 + (size_t)b * H + t * 4);
+    const float4 v = *reinterpret_cast<const float4*>(embeds_f32 + (size_t)bs * H + t * 4);
     x[0] = bf16_round(v.x); x[1] = bf16_round(v.y); x[2] = bf16_round(v.z); x[3] = bf16_round(v.w);
   } else {
-    int tok = token_ids ? token_ids[b] : -1;
+    int tok = token_ids ? token_ids[bs] : -1;
     if (tok >= vocab) tok = vocab - 1;             // device-side ids are not trusted: clamp instead of reading out of bounds
     if (tok < 0 && embeds == nullptr) tok = 0;     // sentinel without an embedding buffer
-    const __nv_bfloat16* src = tok >= 0 ? embed_table + (size_t)tok * H : embeds + (size_t)b * H;
+    const __nv_bfloat16* src = tok >= 0 ? embed_table + (size_t)tok * H : embeds + (size_t)bs * H;
     const uint2 v = *reinterpret_cast<const uint2*>(src + t * 4);
     x[0] = bf16_lo(v.x); x[1] = bf16_hi(v.x); x[2] = bf16_lo(v.y); x[3] = bf16_hi(v.y);
   }
@@ -318,6 +319,125 @@ __global__ void __launch_bounds__(32 * ATT_NW) kb_qkv_attention(const float* par
   kt.flush(4);
 }
 
+// ---- one-pass prefill through the launch chain: lane i = position p0 + i of ONE utterance, all lanes share a B = 1 cache
+//      [L][8][max_seq][128].  The QKV epilogue is split in two kernels because lane i attends to the rows the other lanes write:
+//      (1) finish: split-K sum -> bf16 -> per-head norm + RoPE at position p0 + lane; q -> qpre (fp32, bf16-exact), k / v rows -> cache;
+//      (2) causal attention of lane i over rows 0 .. p0 + i (the kernel boundary orders it after every lane's rows). --------------
+// grid = (n, 8), block = 128
+template <int SPLITS>
+__global__ void __launch_bounds__(128) kb_qkv_finish_prefill(const float* partial, int B, int p0, const __nv_bfloat16* q_norm, const __nv_bfloat16* k_norm,
+                                                             const __nv_bfloat16* cos_t, const __nv_bfloat16* sin_t, __nv_bfloat16* k_cache,
+                                                             __nv_bfloat16* v_cache, float* qpre, int layer, int max_seq) {
+  const int b = blockIdx.x, g = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pos = p0 + b;
+  const size_t base = ((size_t)layer * NKVH + g) * max_seq * HD;
+  const __nv_bfloat16* wn = warp < 2 ? q_norm : k_norm;
+  const uint2 wn_raw = warp < 3 ? *reinterpret_cast<const uint2*>(wn + lane * 4) : make_uint2(0u, 0u);
+  const int dbase = (lane * 4) & 63;
+  const uint2 cs_raw = *reinterpret_cast<const uint2*>(cos_t + (size_t)pos * HD + dbase), sn_raw = *reinterpret_cast<const uint2*>(sin_t + (size_t)pos * HD + dbase);
+  qmkb::pdl_wait();
+  qmkb::pdl_launch_dependents();
+  // warp 0, 1: q heads 2g, 2g+1; warp 2: k head g; warp 3: v head g
+  const int row0 = warp < 2 ? (2 * g + warp) * HD : (warp == 2 ? QSZ + g * HD : QSZ + KVSZ + g * HD);
+  float4 pp[SPLITS];
+#pragma unroll
+  for (int s = 0; s < SPLITS; ++s) pp[s] = __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)s * B + b) * QKV_ROWS + row0 + lane * 4));
+  float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int s = 0; s < SPLITS; ++s) { t[0] += pp[s].x; t[1] += pp[s].y; t[2] += pp[s].z; t[3] += pp[s].w; }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) t[e] = bf16_round(t[e]);
+  if (warp == 3) {
+    *reinterpret_cast<uint2*>(v_cache + base + (size_t)pos * HD + lane * 4) =
+        make_uint2(bf16_bits(t[0]) | (bf16_bits(t[1]) << 16), bf16_bits(t[2]) | (bf16_bits(t[3]) << 16));
+    return;
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) ss = fmaf(t[e], t[e], ss);
+  ss = warp_sum(ss);
+  const float rms = sqrtf(ss * (1.0f / HD) + EPS);
+  const float wf[4] = {bf16_lo(wn_raw.x), bf16_hi(wn_raw.x), bf16_lo(wn_raw.y), bf16_hi(wn_raw.y)};
+  const float cf[4] = {bf16_lo(cs_raw.x), bf16_hi(cs_raw.x), bf16_lo(cs_raw.y), bf16_hi(cs_raw.y)};
+  const float sf[4] = {bf16_lo(sn_raw.x), bf16_hi(sn_raw.x), bf16_lo(sn_raw.y), bf16_hi(sn_raw.y)};
+  float o[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float nv = bf16_round((t[e] / rms) * wf[e]);
+    const float other = __shfl_xor_sync(0xffffffffu, nv, 16);
+    const float x = bf16_round(nv * cf[e]), y = bf16_round(other * sf[e]);
+    o[e] = bf16_round(lane < 16 ? x - y : x + y);
+  }
+  if (warp < 2)
+    *reinterpret_cast<float4*>(qpre + ((size_t)b * 16 + 2 * g + warp) * HD + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  else
+    *reinterpret_cast<uint2*>(k_cache + base + (size_t)pos * HD + lane * 4) =
+        make_uint2(bf16_bits(o[0]) | (bf16_bits(o[1]) << 16), bf16_bits(o[2]) | (bf16_bits(o[3]) << 16));
+}
+// grid = (n, 8), block = 256
+__global__ void __launch_bounds__(256) kb_attention_prefill(const float* qpre, int p0, const __nv_bfloat16* k_cache, const __nv_bfloat16* v_cache,
+                                                            __nv_bfloat16* a_out, int layer, int max_seq, float scale) {
+  __shared__ float s_acc[ATT_NW][2][HD];
+  __shared__ float s_m[ATT_NW][2], s_l[ATT_NW][2];
+  const int b = blockIdx.x, g = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = p0 + b + 1;   // causal: rows 0 .. p0 + b
+  const size_t base = ((size_t)layer * NKVH + g) * max_seq * HD;
+  qmkb::pdl_wait();
+  qmkb::pdl_launch_dependents();
+  const float4 qa = __ldcg(reinterpret_cast<const float4*>(qpre + ((size_t)b * 16 + 2 * g) * HD + lane * 4));
+  const float4 qb = __ldcg(reinterpret_cast<const float4*>(qpre + ((size_t)b * 16 + 2 * g + 1) * HD + lane * 4));
+  const float q0[4] = {qa.x, qa.y, qa.z, qa.w}, q1[4] = {qb.x, qb.y, qb.z, qb.w};
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f, acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+  for (int p00 = warp; p00 < n; p00 += ATT_NW * ATT_PRE) {
+    uint2 kk[ATT_PRE], vv[ATT_PRE];
+#pragma unroll
+    for (int i = 0; i < ATT_PRE; ++i) {
+      const int p = p00 + ATT_NW * i;
+      if (p < n) {
+        kk[i] = __ldcg(reinterpret_cast<const uint2*>(k_cache + base + (size_t)p * HD + lane * 4));
+        vv[i] = __ldcg(reinterpret_cast<const uint2*>(v_cache + base + (size_t)p * HD + lane * 4));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < ATT_PRE; ++i) {
+      const int p = p00 + ATT_NW * i;
+      if (p < n) {
+        const float kf[4] = {bf16_lo(kk[i].x), bf16_hi(kk[i].x), bf16_lo(kk[i].y), bf16_hi(kk[i].y)};
+        const float vf[4] = {bf16_lo(vv[i].x), bf16_hi(vv[i].x), bf16_lo(vv[i].y), bf16_hi(vv[i].y)};
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { d0 = fmaf(q0[e], kf[e], d0); d1 = fmaf(q1[e], kf[e], d1); }
+        d0 = warp_sum(d0) * scale;
+        d1 = warp_sum(d1) * scale;
+        const float nm0 = fmaxf(m0, d0), nm1 = fmaxf(m1, d1);
+        const float c0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - nm0), c1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - nm1);
+        const float e0 = __expf(d0 - nm0), e1 = __expf(d1 - nm1);
+        l0 = l0 * c0 + e0; l1 = l1 * c1 + e1;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { acc0[e] = fmaf(e0, vf[e], acc0[e] * c0); acc1[e] = fmaf(e1, vf[e], acc1[e] * c1); }
+        m0 = nm0; m1 = nm1;
+      }
+    }
+  }
+  if (lane == 0) { s_m[warp][0] = m0; s_m[warp][1] = m1; s_l[warp][0] = l0; s_l[warp][1] = l1; }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { s_acc[warp][0][lane * 4 + e] = acc0[e]; s_acc[warp][1][lane * 4 + e] = acc1[e]; }
+  __syncthreads();
+  const int h = tid >> 7, d = tid & 127;
+  float M = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < ATT_NW; ++w) M = fmaxf(M, s_m[w][h]);
+  float A = 0.f, Ls = 0.f;
+#pragma unroll
+  for (int w = 0; w < ATT_NW; ++w) {
+    const float f = (s_m[w][h] == -INFINITY) ? 0.f : __expf(s_m[w][h] - M);
+    A = fmaf(s_acc[w][h][d], f, A);
+    Ls = fmaf(s_l[w][h], f, Ls);
+  }
+  a_out[(size_t)b * QSZ + (2 * g + h) * HD + d] = __float2bfloat16_rn(A / Ls);
+}
+__global__ void kb_lane_positions(int* pos, int p0, int B) { if (threadIdx.x < B) pos[threadIdx.x] = p0 + threadIdx.x; }
+
 // ---- gate/up epilogue: m = r( r(silu(r(g))) * r(u) ) -------------------------------------------------------------------
 // grid = (B, 3), block = 256; partial: [splits][B][6144] (gate rows 0..3071, up rows 3072..6143)
 template <int SPLITS>
@@ -508,6 +628,10 @@ struct qmk_batched {
   unsigned bar_count = 0;
   int* d_status = nullptr;
   int* d_pos0 = nullptr;                  // prefill: first position
+  int prefill_persistent = 0;            // QMK_PREFILL_PERSISTENT=1: the prefill as one persistent launch (csrc/qmk_bstep.cuh) instead of the chain
+  float* qpre = nullptr;                 // chain prefill: q of every lane, f32[B][16][128]
+  int* pos_scratch = nullptr;            // chain prefill: int[B] lane positions
+  int* tok_scratch = nullptr;            // chain prefill: int[B] argmax tokens
   int splits_od = 16;                    // K slices of the O / down projections (8 measured: 741 / 892 us per step instead of 660 / 866)
   long long* d_trace = nullptr;           // QMK_BATCHED_TRACE=1: barrier stamps of CTA 0 (debug)
   int* d_tok_scratch = nullptr;           // prefill: per-lane argmax (only the last lane's is reported)
@@ -536,6 +660,7 @@ extern "C" int qmk_batched_create(int device, const LDGLayerWeights* layers_host
   if (prop.major != 10) return fail(QMK_ERR_UNSUPPORTED, "qmk_batched_create: tcgen05 needs an sm_100 device");
   qmk_batched* h = new qmk_batched();
   h->device = device; h->L = num_layers; h->B = batch; h->max_seq = max_seq_len; h->head_rows = lm_head_rows;
+  if (const char* env = getenv("QMK_PREFILL_PERSISTENT")) h->prefill_persistent = atoi(env) != 0;
   h->residual_fp32 = residual_fp32 ? 1 : 0;
   h->final_norm = final_norm_weight; h->lm_head = lm_head_weight; h->embed = embed_weight; h->cos_t = cos_table; h->sin_t = sin_table;
   const size_t L = num_layers;
@@ -544,7 +669,9 @@ extern "C" int qmk_batched_create(int device, const LDGLayerWeights* layers_host
             cudaMalloc(&h->xn, (size_t)batch * H * 2) == cudaSuccess &&
             cudaMalloc(&h->abuf, (size_t)batch * QSZ * 2) == cudaSuccess && cudaMalloc(&h->mbuf, (size_t)batch * INTER * 2) == cudaSuccess &&
             cudaMemset(h->xn, 0, (size_t)batch * H * 2) == cudaSuccess && cudaMemset(h->abuf, 0, (size_t)batch * QSZ * 2) == cudaSuccess &&
-            cudaMemset(h->mbuf, 0, (size_t)batch * INTER * 2) == cudaSuccess;   // rows of unused lanes feed the tensor cores too: keep them finite
+            cudaMemset(h->mbuf, 0, (size_t)batch * INTER * 2) == cudaSuccess &&   // rows of unused lanes feed the tensor cores too: keep them finite
+            cudaMalloc(&h->qpre, (size_t)batch * QSZ * 4) == cudaSuccess && cudaMalloc(&h->pos_scratch, (size_t)batch * sizeof(int)) == cudaSuccess &&
+            cudaMalloc(&h->tok_scratch, (size_t)batch * sizeof(int)) == cudaSuccess;
   if (!ok) { qmk_batched_destroy(h); return fail(QMK_ERR_CUDA, "qmk_batched_create: allocation failed"); }
   for (int l = 0; l < num_layers; ++l) {
     const LDGLayerWeights& w = layers_host[l];
@@ -642,7 +769,7 @@ extern "C" void qmk_batched_destroy(qmk_batched* h) {
   if (!h) return;
   BatchedDeviceGuard guard(h->device);
   cudaDeviceSynchronize();
-  cudaFree(h->w_qkv); cudaFree(h->w_gu); cudaFree(h->res); cudaFree(h->partial);
+  cudaFree(h->w_qkv); cudaFree(h->w_gu); cudaFree(h->res); cudaFree(h->partial); cudaFree(h->qpre); cudaFree(h->pos_scratch); cudaFree(h->tok_scratch);
   cudaFree(h->xn); cudaFree(h->abuf); cudaFree(h->mbuf);
   cudaFree(h->p_qkv); cudaFree(h->p_o); cudaFree(h->p_gu); cudaFree(h->p_down); cudaFree(h->p_head); cudaFree(h->d_ptrs); cudaFree(h->qbuf); cudaFree(h->d_bar); cudaFree(h->d_status); cudaFree(h->d_pos0);
   cudaFree(h->d_tok_scratch); cudaFree(h->d_trace);
@@ -758,7 +885,7 @@ static int chain_step(qmk_batched* h, const qmk_batched_step_args* a, cudaStream
   else if (a->head > 0) { head_rows = h->extra_head_rows[a->head - 1]; head_map = &h->extra_head_maps[a->head - 1]; }
   launch_pdl(kb_input, dim3(B), dim3(256), 0, st, (const int*)a->token_ids, table, table_rows,
              reinterpret_cast<const __nv_bfloat16*>(a->embeds_bf16), (const float*)a->embeds_f32, h->res,
-             reinterpret_cast<const __nv_bfloat16*>(h->ln_in[0]), h->xn);
+             reinterpret_cast<const __nv_bfloat16*>(h->ln_in[0]), h->xn, B);
   for (int l = 0; l < L; ++l) {
     gemm(h, h->map_qkv[l], h->map_x1024, QKV_ROWS, H, 4, st);                       // 32 tiles x 4 K-slices
     launch_pdl(kb_qkv_attention<4>, dim3(B, NKVH), dim3(32 * ATT_NW), 0, st, (const float*)h->partial, B, (const int*)a->positions,
@@ -863,14 +990,62 @@ extern "C" int qmk_batched_step(qmk_batched* h, const int32_t* token_ids, const 
 // through 8 sequential decode steps, tts_engine.py:281-282): lane i is position position0 + i, all lanes share the caller's
 // B = 1 cache [L][8][max_seq][128] and attend causally.  Writes the same KV rows as n sequential steps and returns the LAST
 // position's post-norm hidden state (f32[1024]) and argmax token; n <= batch.  Needs the persistent step kernel.
+// The prefill through the launch chain (default): the decode chain with lane = position, the QKV epilogue split into "finish"
+// (all lanes' K / V rows into the shared cache) and causal attention; 9 launches per layer.
+static int chain_prefill(qmk_batched* h, const void* embeds, int n, int position0, void* k_cache, void* v_cache, float* hid_all, cudaStream_t st) {
+  const int B = h->B, L = h->L;
+  const float scale = 0.08838834764831845f;
+  __nv_bfloat16* kc = reinterpret_cast<__nv_bfloat16*>(k_cache);
+  __nv_bfloat16* vc = reinterpret_cast<__nv_bfloat16*>(v_cache);
+  const __nv_bfloat16* cos_t = reinterpret_cast<const __nv_bfloat16*>(h->cos_t);
+  const __nv_bfloat16* sin_t = reinterpret_cast<const __nv_bfloat16*>(h->sin_t);
+  g_launch_err = cudaSuccess;
+  kb_lane_positions<<<1, 64, 0, st>>>(h->pos_scratch, position0, B);
+  launch_pdl(kb_input, dim3(B), dim3(256), 0, st, (const int*)nullptr, reinterpret_cast<const __nv_bfloat16*>(h->embed), h->head_rows,
+             reinterpret_cast<const __nv_bfloat16*>(embeds), (const float*)nullptr, h->res, reinterpret_cast<const __nv_bfloat16*>(h->ln_in[0]), h->xn, n);
+  for (int l = 0; l < L; ++l) {
+    gemm(h, h->map_qkv[l], h->map_x1024, QKV_ROWS, H, 4, st);
+    launch_pdl(kb_qkv_finish_prefill<4>, dim3(n, NKVH), dim3(128), 0, st, (const float*)h->partial, B, position0,
+               reinterpret_cast<const __nv_bfloat16*>(h->qn[l]), reinterpret_cast<const __nv_bfloat16*>(h->kn[l]), cos_t, sin_t, kc, vc, h->qpre, l, h->max_seq);
+    launch_pdl(kb_attention_prefill, dim3(n, NKVH), dim3(256), 0, st, (const float*)h->qpre, position0, (const __nv_bfloat16*)kc, (const __nv_bfloat16*)vc,
+               h->abuf, l, h->max_seq, scale);
+    gemm(h, h->map_o[l], h->map_x2048, H, QSZ, h->splits_od, st);
+    resid_norm(h, st, h->ln_post[l], nullptr, nullptr);
+    gemm(h, h->map_gu[l], h->map_x1024, GU_ROWS, H, 4, st);
+    launch_pdl(kb_gu_epilogue<4>, dim3(B, 3), dim3(256), 0, st, (const float*)h->partial, B, h->mbuf);
+    gemm(h, h->map_down[l], h->map_x3072, H, INTER, h->splits_od, st);
+    const bool last = (l == L - 1);
+    resid_norm(h, st, last ? h->final_norm : h->ln_in[l + 1], last ? hid_all : (float*)nullptr, nullptr);
+  }
+  gemm(h, h->map_head, h->map_x1024, h->head_rows, H, 4, st);
+  HeadSelect sel;
+  memset(&sel, 0, sizeof(sel));
+  sel.group = -1; sel.temperature = 1.0f;
+  launch_pdl(kb_head_epilogue, dim3(B), dim3(256), (size_t)4 * h->head_rows * sizeof(float), st, (const float*)h->partial, 4, B, h->head_rows,
+             h->tok_scratch, h->pos_scratch, sel);
+  cudaError_t e = g_launch_err != cudaSuccess ? g_launch_err : cudaGetLastError();
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(QMK_ERR_CUDA, cudaGetErrorString(e)); }
+  return QMK_OK;
+}
+
 extern "C" int qmk_batched_prefill(qmk_batched* h, const void* embeds, int n, int position0, void* k_cache, void* v_cache,
                                    float* hidden_out_last, int32_t* token_out_last, void* stream) {
   if (!h || !embeds || !k_cache || !v_cache) return fail(QMK_ERR_ARG, "qmk_batched_prefill: null argument");
-  if (!h->persistent) return fail(QMK_ERR_UNSUPPORTED, "qmk_batched_prefill needs the persistent step kernel");
   if (n < 1 || n > h->B) return fail(QMK_ERR_ARG, "qmk_batched_prefill: n must be in [1, batch]");
   if (position0 < 0 || position0 + n > h->max_seq) return fail(QMK_ERR_ARG, "qmk_batched_prefill: positions exceed max_seq_len");
   cudaStream_t st = (cudaStream_t)stream;
   BatchedDeviceGuard guard(h->device);
+  if (!h->prefill_persistent) {
+    float* hid = reinterpret_cast<float*>(h->partial) + qmkb_hidden_offset();   // scratch behind the partials: [B][1024]
+    const int rc = chain_prefill(h, embeds, n, position0, k_cache, v_cache, hid, st);
+    if (rc != QMK_OK) return rc;
+    cudaError_t e = cudaSuccess;
+    if (hidden_out_last) e = cudaMemcpyAsync(hidden_out_last, hid + (size_t)(n - 1) * H, H * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess && token_out_last) e = cudaMemcpyAsync(token_out_last, h->tok_scratch + (n - 1), sizeof(int), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return fail(QMK_ERR_CUDA, cudaGetErrorString(e));
+    return QMK_OK;
+  }
+  if (!h->persistent) return fail(QMK_ERR_UNSUPPORTED, "QMK_PREFILL_PERSISTENT=1 needs the persistent step kernel");
   if (cudaMemcpyAsync(h->d_pos0, &position0, sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(QMK_ERR_CUDA, "qmk_batched_prefill: copy failed");
   float* hid_all = reinterpret_cast<float*>(h->partial) + qmkb_hidden_offset();   // scratch behind the partials: [n][1024]
   int rc = launch_persistent(h, n, 1, nullptr, embeds, h->d_pos0, k_cache, v_cache, hid_all, h->d_tok_scratch, st);

@@ -472,7 +472,8 @@ class TTSDecoder:
         """Feed n prefill embeddings (bf16[n, 1024], n <= 16) as ONE batched pass instead of n sequential
         ``step_with_embed`` calls (upstream tts_engine.py:281-282 loops; the prefill is 24.9 of its 50.5 ms time to first
         chunk, README.md:23): the projections run once for all positions on the tcgen05 tensor cores (every weight byte is
-        read once instead of n times) with causal attention, writing the same KV rows.  Returns what the LAST sequential
+        read once instead of n times) with causal attention, writing the same KV rows (the batched launch chain with lane =
+        position; ``QMK_PREFILL_PERSISTENT=1`` selects the persistent kernel's prefill mode instead).  Returns what the LAST sequential
         step would return: ``(token, hidden)``.  Standard RoPE only."""
         if self._mrope_delta is not None:
             raise NotImplementedError("prefill() implements standard RoPE; use step_with_embed with set_mrope()")
@@ -485,8 +486,6 @@ class TTSDecoder:
         if getattr(self, "_prefiller", None) is None:
             self._prefiller = BatchedTTSDecoder(self._weights, 16, device=self.device, max_seq_len=self._max_seq,
                                                 num_layers=self._num_layers)
-            if not self._prefiller.persistent:
-                raise RuntimeError("prefill() needs the persistent batched kernel (>= 144 SMs)")
         with torch.cuda.device(self.device):
             self._prefiller.prefill_into(e, self._position, self._k_cache, self._v_cache, self._norm_out, self._out_token)
         self._position += n
@@ -646,7 +645,7 @@ class BatchedTTSDecoder:
             raise NativeError(f"BatchedTTSDecoder: {self._lib.qmk_batched_last_error().decode()} (code {rc})")
 
     def prefill_into(self, embeds_bf16: torch.Tensor, position0: int, k_cache: torch.Tensor, v_cache: torch.Tensor,
-                     hidden_out: torch.Tensor, token_out: torch.Tensor) -> None:
+                     hidden_out: torch.Tensor, token_out: torch.Tensor, graph: bool = True) -> None:
         """One batched pass over n <= batch consecutive positions of ONE utterance (causal), writing the KV rows into a
         B = 1 cache ``[L, 8, S, 128]`` and the last position's hidden state / token (``qmk_batched_prefill``)."""
         from .build_tts import NativeError
@@ -656,11 +655,32 @@ class BatchedTTSDecoder:
             raise ValueError(f"prefill of {n} positions needs a batched decoder with batch >= {n}")
         if tuple(k_cache.shape) != (self._num_layers, NUM_KV_HEADS, self._max_seq, HEAD_DIM) or k_cache.shape != v_cache.shape:
             raise ValueError("prefill_into: cache must be [L, 8, max_seq_len, 128] with this decoder's max_seq_len")
-        self._keep = e
-        rc = self._lib.qmk_batched_prefill(self._handle, e.data_ptr(), n, int(position0), k_cache.data_ptr(), v_cache.data_ptr(),
-                                           hidden_out.data_ptr(), token_out.data_ptr(), _stream_ptr(self.device))
-        if rc < 0:
-            raise NativeError(f"qmk_batched_prefill: {self._lib.qmk_batched_last_error().decode()} (code {rc})")
+        # The ~255 launches of the pass are replayed from a CUDA graph from the third call with the same (n, position, buffers) on:
+        # an engine prefills every utterance at position 0 into the same cache.
+        if not hasattr(self, "_pre_e"):
+            self._pre_e = torch.zeros(self.batch, HIDDEN_SIZE, dtype=torch.bfloat16, device=self.device)
+            self._pre_graphs, self._pre_seen = {}, {}
+        self._pre_e[:n].copy_(e)
+        key = (n, int(position0), k_cache.data_ptr(), v_cache.data_ptr(), hidden_out.data_ptr(), token_out.data_ptr())
+
+        def launch():
+            rc = self._lib.qmk_batched_prefill(self._handle, self._pre_e.data_ptr(), n, int(position0), k_cache.data_ptr(), v_cache.data_ptr(),
+                                               hidden_out.data_ptr(), token_out.data_ptr(), _stream_ptr(self.device))
+            if rc < 0:
+                raise NativeError(f"qmk_batched_prefill: {self._lib.qmk_batched_last_error().decode()} (code {rc})")
+
+        if len(self._pre_seen) > 64:
+            self._pre_seen.clear()
+        seen = self._pre_seen.get(key, 0)
+        self._pre_seen[key] = seen + 1
+        if seen < 2 or not graph or os.environ.get("QMK_PREFILL_PERSISTENT", "0") not in ("", "0"):   # (the persistent form copies from host memory)
+            launch()
+            return
+        if key not in self._pre_graphs:
+            if len(self._pre_graphs) >= 8:
+                self._pre_graphs.clear()
+            self._pre_graphs[key], _ = _capture(self.device, launch)
+        self._pre_graphs[key].replay()
 
 
 class BatchedCodePredictor:

@@ -155,13 +155,14 @@ def test_batched_lanes_at_depth_equal_b1(gpu_weights, monkeypatch, position, per
             _lane_check(f"depth {position} lane {b} step 1", hid2[b], h1, int(toks2[b]), t1, gpu_weights["lm_head_weight"])
 
 
-@pytest.mark.parametrize("n,start", [(8, 0), (13, 5)])
-def test_prefill_as_one_batched_pass_equals_sequential_steps(gpu_weights, n, start):
+@pytest.mark.parametrize("n,start,persistent", [(8, 0, 0), (13, 5, 0), (1, 3, 0), (16, 40, 0), (8, 0, 1), (13, 5, 1)])
+def test_prefill_as_one_batched_pass_equals_sequential_steps(gpu_weights, monkeypatch, n, start, persistent):
     """n prefill embeddings in ONE batched pass (tcgen05 projections, causal attention over a shared cache)
     against n sequential step_with_embed calls of the B = 1 engine: same KV rows and last hidden state within the bf16
     tolerance (different accumulation order), same token up to near-ties; decoding then continues on the B = 1 engine."""
     from qwen_megakernel.model_tts import TTSDecoder
     from qwen_megakernel.synthetic import synthetic_inputs
+    monkeypatch.setenv("QMK_PREFILL_PERSISTENT", str(persistent))     # 0: the launch chain with lane = position (default); 1: the persistent kernel
     S = 64
     x = synthetic_inputs(4141, start + n + 2).cuda()
     seq = TTSDecoder(weights=gpu_weights, verbose=False, max_seq_len=S)
@@ -315,3 +316,22 @@ def test_chain_trace_records_every_kernel_of_a_step(gpu_weights):
     assert kinds.get(1) == 5 * 4 + 1 and kinds.get(3) == 10 and kinds.get(4) == 5 and kinds.get(5) == 5, kinds
     dec.step(tok)                                                      # disarmed: nothing is recorded any more
     assert lib.qmk_batched_chain_trace(0, st, buf, 2048) == 0
+
+
+def test_repeated_prefill_replays_a_graph_with_identical_results(gpu_weights):
+    """An engine prefills every utterance at position 0: from the third call on the pass is one CUDA-graph replay, bit-identical."""
+    from qwen_megakernel.model_tts import TTSDecoder
+    from qwen_megakernel.synthetic import synthetic_inputs
+    d = TTSDecoder(weights=gpu_weights, verbose=False, max_seq_len=64)
+    xs = [synthetic_inputs(5151 + i, 8).cuda() for i in range(2)]
+    ref = []
+    for x in xs:                                     # plain launches
+        d.reset()
+        t, h = d.prefill(x)
+        ref.append((int(t), h.clone(), d._k_cache[:, :, :8].clone(), d._v_cache[:, :, :8].clone()))
+    for rep in range(2):                             # third call onwards: replays
+        for x, (t0, h0, k0, v0) in zip(xs, ref):
+            d.reset()
+            t, h = d.prefill(x)
+            assert int(t) == t0 and torch.equal(h, h0) and torch.equal(d._k_cache[:, :, :8], k0) and torch.equal(d._v_cache[:, :, :8], v0)
+    assert d._prefiller._pre_graphs
