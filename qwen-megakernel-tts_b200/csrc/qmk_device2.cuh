@@ -541,38 +541,40 @@ __device__ void phase_attn2(Ctx2& c, const ModelDesc& md, int l, int position, u
           ll8_st(part + 1, __float_as_uint(Lsum), epoch);
         }
       }
-      // every CTA of the group merges the chunks of both heads in the fixed order s = 0..S-1
-      float* s_ml = c.s_part;   // [2][16] m then [2][16] l (s_part is free during the attention)
-      consumer_bar();
-      if (c.tid < 2 * S2_MAX) {
-        const int hh = c.tid >> 4, s = c.tid & 15;
-        float mm = -INFINITY, ll = 0.f;
-        if (s < it.S) {
-          const u64* ps = x_part + ((size_t)hh * S2_MAX + s) * PART_STRIDE;
-          mm = __uint_as_float(ll8_wait(c, ps, epoch));
-          ll = __uint_as_float(ll8_wait(c, ps + 1, epoch));
-        }
-        s_ml[hh * 16 + s] = mm;
-        s_ml[32 + hh * 16 + s] = ll;
-      }
-      consumer_bar();
-      float Mx = -INFINITY;
-      for (int s = 0; s < it.S; ++s) Mx = fmaxf(Mx, s_ml[h * 16 + s]);
-      float Lt = 0.f, B = 0.f;
+      // Every CTA of the group merges the chunks of both heads in the fixed order s = 0..S-1.  One L2 round trip, no
+      // barrier: a thread polls its own accumulator words of up to eight chunks together with ONE of the warp's max / sum
+      // words (lane s: max of chunk s, lane 16 + s: its sum; the warp shares them through shuffles).
+      const int ms = c.lane & 15;
+      const bool ml_valid = ms < it.S;
+      const u64* pml = x_part + ((size_t)h * S2_MAX + ms) * PART_STRIDE + (c.lane >> 4);
+      float Mx = -INFINITY, mlv = (c.lane >> 4) ? 0.f : -INFINITY, Lt = 0.f, B = 0.f;
       for (int s0 = 0; s0 < it.S; s0 += 8) {
-        u64 w[8];
+        u64 w[8], mlw = 0;
+        uint32_t spins = 0;
+        for (;;) {
+          bool all = true;
+          if (s0 == 0 && ml_valid) mlw = ll8_ld(pml);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (s0 + i < it.S) w[i] = ll8_ld(x_part + ((size_t)h * S2_MAX + s0 + i) * PART_STRIDE + 2 + d);
+          for (int i = 0; i < 8; ++i)
+            if (s0 + i < it.S) w[i] = ll8_ld(x_part + ((size_t)h * S2_MAX + s0 + i) * PART_STRIDE + 2 + d);
+          if (s0 == 0 && ml_valid) all = (uint32_t)(mlw >> 32) == epoch;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (s0 + i < it.S) all &= (uint32_t)(w[i] >> 32) == epoch;
+          if (QMK_LIKELY(all)) break;
+          if ((++spins & 63u) == 0 && check_abort(c, ST_TIMEOUT_LL, -1)) break;
+        }
+        __syncwarp();
+        if (s0 == 0) {
+          if (ml_valid) mlv = __uint_as_float((uint32_t)mlw);
+          for (int s = 0; s < it.S; ++s) Mx = fmaxf(Mx, __shfl_sync(0xffffffffu, mlv, s));
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          if (s0 + i < it.S) {
-            uint32_t v = (uint32_t)w[i];
-            if (QMK_UNLIKELY((uint32_t)(w[i] >> 32) != epoch))
-              v = ll8_wait(c, x_part + ((size_t)h * S2_MAX + s0 + i) * PART_STRIDE + 2 + d, epoch);
-            const float f = __expf(s_ml[h * 16 + s0 + i] - Mx);
-            Lt = fmaf(s_ml[32 + h * 16 + s0 + i], f, Lt);
-            B = fmaf(__uint_as_float(v), f, B);
+          if (s0 + i < it.S) {   // warp-uniform
+            const float f = __expf(__shfl_sync(0xffffffffu, mlv, s0 + i) - Mx);
+            Lt = fmaf(__shfl_sync(0xffffffffu, mlv, 16 + s0 + i), f, Lt);
+            B = fmaf(__uint_as_float((uint32_t)w[i]), f, B);
           }
         }
       }
