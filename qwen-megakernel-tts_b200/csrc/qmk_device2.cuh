@@ -245,6 +245,47 @@ __device__ __forceinline__ void mma_tiles(float (&acc)[4][4], const uint32_t (&a
 }
 
 // ---- attention ---------------------------------------------------------------------------------------------------
+// A round = ATT2_PW cached positions per warp (ATT2_ROUND per CTA) scored together: their rows are one batch of loads and their
+// 2 ATT2_PW partial dot products one transposed warp reduction.  Measured, us per talker step with 5 -> 6 positions per warp: p = 45: 323 -> 325,
+// 90: 331 -> 337, 200: 345 -> 353, 500: 386 -> 390, 1000: 432 -> 437, 1500: 463 -> 456, 2000: 497 -> 487 (one round fewer beyond 1920
+// positions): 5 is better over the headline's positions 9..509.
+#ifndef QMK_ATT_PW
+#define QMK_ATT_PW 5
+#endif
+constexpr int ATT2_PW = QMK_ATT_PW, ATT2_ROUND = NCW * ATT2_PW;
+static_assert(ATT2_PW == 5 || ATT2_PW == 6, "the transposed reduction below folds 2 x 5 or 2 x 6 values");
+struct KvRegs2 {
+  uint2 k[ATT2_PW];
+  uint2 v[ATT2_PW];
+};
+// Transposed reduction of 2 * ATT2_PW per-lane partial dot products; every lane ends up with all totals (12 reduction shuffles
+// + the broadcasts instead of 5 per value).  Halves fold 6 -> 3 -> 2 (padded) -> 1.
+__device__ __forceinline__ void warp_sum2pw_bcast(float (&v)[2 * ATT2_PW], int lane) {
+  const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0, b1 = (lane & 2) != 0;
+  float u[6];
+#pragma unroll
+  for (int k = 0; k < ATT2_PW; ++k)
+    u[k] = (b4 ? v[k + ATT2_PW] : v[k]) + __shfl_xor_sync(0xffffffffu, b4 ? v[k] : v[k + ATT2_PW], 16);
+  if (ATT2_PW == 5) u[5] = 0.f;
+  float w[4];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    w[k] = (b3 ? u[k + 3] : u[k]) + __shfl_xor_sync(0xffffffffu, b3 ? u[k] : u[k + 3], 8);
+  w[3] = 0.f;
+  float x[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    x[k] = (b2 ? w[k + 2] : w[k]) + __shfl_xor_sync(0xffffffffu, b2 ? w[k] : w[k + 2], 4);
+  float y = (b1 ? x[1] : x[0]) + __shfl_xor_sync(0xffffffffu, b1 ? x[0] : x[1], 2);
+  y += __shfl_xor_sync(0xffffffffu, y, 1);
+  // value index held by a lane: b4 * ATT2_PW + b3 * 3 + b2 * 2 + b1  (valid combinations only)
+#pragma unroll
+  for (int idx = 0; idx < 2 * ATT2_PW; ++idx) {
+    const int r = idx % ATT2_PW, hi = idx / ATT2_PW;
+    const int src = hi * 16 + (r >= 3 ? 8 : 0) + ((r % 3) >= 2 ? 4 : 0) + (((r % 3) % 2) ? 2 : 0);
+    v[idx] = __shfl_sync(0xffffffffu, y, src);
+  }
+}
 struct AttnItem2 {
   int S, p0, p1;
   bool has;
@@ -259,7 +300,7 @@ __device__ __forceinline__ AttnItem2 attn_item2(int position, int j) {
   // Up to two rounds of 40 positions every CTA of the group evaluates the whole context itself; beyond that the context
   // is split over the group, one round per CTA.  Measured per talker step: a second round +33 us, a third +25 us more,
   // the split's partial exchange and merge +57 us.
-  int S0 = n <= ATT_ROUND * ATT_SOLO_ROUNDS ? 1 : (n + ATT_ROUND - 1) / ATT_ROUND;
+  int S0 = n <= ATT2_ROUND * ATT_SOLO_ROUNDS ? 1 : (n + ATT2_ROUND - 1) / ATT2_ROUND;
   if (S0 > S2_MAX) S0 = S2_MAX;
   const int C = (n + S0 - 1) / S0;
   it.S = (n + C - 1) / C;
@@ -291,11 +332,11 @@ __device__ __forceinline__ void attn_l2_prefetch(const Ctx2& c, const ModelDesc&
     }
   }
 }
-__device__ __forceinline__ void attn_prefetch2(const Ctx2& c, const ModelDesc& p, int l, int position, const AttnItem2& it, int round, KvRegs& r) {
+__device__ __forceinline__ void attn_prefetch2(const Ctx2& c, const ModelDesc& p, int l, int position, const AttnItem2& it, int round, KvRegs2& r) {
   const size_t base = ((size_t)(l * NKVH + c.g) * p.max_seq) * HD;
 #pragma unroll
-  for (int i = 0; i < ATT_PER_WARP; ++i) {
-    const int pos = it.p0 + round * ATT_ROUND + c.warp + NCW * i;
+  for (int i = 0; i < ATT2_PW; ++i) {
+    const int pos = it.p0 + round * ATT2_ROUND + c.warp + NCW * i;
     if (pos < it.p1 && pos != position) {
       const size_t off = base + (size_t)pos * HD + c.lane * 4;
       r.k[i] = ld_strong_u2(p.k_cache + off);
@@ -308,7 +349,7 @@ __device__ __forceinline__ void attn_prefetch2(const Ctx2& c, const ModelDesc& p
 // over this CTA's positions; cross-warp merge; (long context) cross-chunk merge through group-local LL8 words.
 // Result: bf16 a[256] of the group's two q heads in c.s_a (every CTA of the group holds the same values).
 template <bool TR>
-__device__ void phase_attn2(Ctx2& c, const ModelDesc& md, int l, int position, uint32_t epoch, const AttnItem2& it, KvRegs& kv, Prod2& prod,
+__device__ void phase_attn2(Ctx2& c, const ModelDesc& md, int l, int position, uint32_t epoch, const AttnItem2& it, KvRegs2& kv, Prod2& prod,
                             int a_row, int a_khalf, int a_sw) {
   const Params& p = c.p;
   const uint32_t* x_q = reinterpret_cast<const uint32_t*>(c.xb + XB_POOL) + (size_t)c.slot_q * XP_WORDS;
@@ -360,7 +401,7 @@ __device__ void phase_attn2(Ctx2& c, const ModelDesc& md, int l, int position, u
     q1[0] = b.x; q1[1] = b.y; q1[2] = b.z; q1[3] = b.w;
   }
   const int len = it.has ? it.p1 - it.p0 : 0;
-  const int nrounds = (len + ATT_ROUND - 1) / ATT_ROUND;
+  const int nrounds = (len + ATT2_ROUND - 1) / ATT2_ROUND;
   if (position < 2 * NCW) {
     // Tiny context (every code-predictor step, the first talker steps): this warp owns positions w and w + 8 at most.
     // Straight-line version of the loop below.
@@ -408,14 +449,14 @@ __device__ void phase_attn2(Ctx2& c, const ModelDesc& md, int l, int position, u
   } else
   for (int r = 0; r < nrounds; ++r) {
     if (r > 0) attn_prefetch2(c, md, l, position, it, r, kv);   // (double-buffering the rows in registers spills: +15 us per step, measured twice)
-    float sc[10];
-    const int pos_first = it.p0 + r * ATT_ROUND + c.warp;
+    float sc[2 * ATT2_PW];
+    const int pos_first = it.p0 + r * ATT2_ROUND + c.warp;
     if (pos_first < it.p1) {  // warp-uniform
-      const int nv = min(ATT_PER_WARP, (it.p1 - pos_first + NCW - 1) / NCW);
+      const int nv = min(ATT2_PW, (it.p1 - pos_first + NCW - 1) / NCW);
 #pragma unroll
-      for (int i = 0; i < 10; ++i) sc[i] = 0.f;
+      for (int i = 0; i < 2 * ATT2_PW; ++i) sc[i] = 0.f;
 #pragma unroll
-      for (int i = 0; i < ATT_PER_WARP; ++i) {
+      for (int i = 0; i < ATT2_PW; ++i) {
         if (i >= nv) break;
         const int pos = pos_first + NCW * i;
         float kf[4];
@@ -433,26 +474,26 @@ __device__ void phase_attn2(Ctx2& c, const ModelDesc& md, int l, int position, u
           d1 = fmaf(q1[e], kf[e], d1);
         }
         sc[i] = d0;
-        sc[5 + i] = d1;
+        sc[ATT2_PW + i] = d1;
       }
       if (nv <= 2) {
-        const float v4[4] = {sc[0], sc[1], sc[5], sc[6]};
+        const float v4[4] = {sc[0], sc[1], sc[ATT2_PW], sc[ATT2_PW + 1]};
         const float tot = warp_sum4(v4, c.lane);
         sc[0] = __shfl_sync(0xffffffffu, tot, 0);
         sc[1] = __shfl_sync(0xffffffffu, tot, 8);
-        sc[5] = __shfl_sync(0xffffffffu, tot, 16);
-        sc[6] = __shfl_sync(0xffffffffu, tot, 24);
+        sc[ATT2_PW] = __shfl_sync(0xffffffffu, tot, 16);
+        sc[ATT2_PW + 1] = __shfl_sync(0xffffffffu, tot, 24);
       } else {
-        warp_sum10_bcast(sc, c.lane);
+        warp_sum2pw_bcast(sc, c.lane);
       }
       float mx0 = m0, mx1 = m1;
 #pragma unroll
-      for (int i = 0; i < ATT_PER_WARP; ++i) {
+      for (int i = 0; i < ATT2_PW; ++i) {
         if (i >= nv) break;
         sc[i] *= p.attn_scale;
-        sc[5 + i] *= p.attn_scale;
+        sc[ATT2_PW + i] *= p.attn_scale;
         mx0 = fmaxf(mx0, sc[i]);
-        mx1 = fmaxf(mx1, sc[5 + i]);
+        mx1 = fmaxf(mx1, sc[ATT2_PW + i]);
       }
       const float c0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - mx0);
       const float c1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - mx1);
@@ -460,7 +501,7 @@ __device__ void phase_attn2(Ctx2& c, const ModelDesc& md, int l, int position, u
 #pragma unroll
       for (int e = 0; e < 4; ++e) { acc0[e] *= c0; acc1[e] *= c1; }
 #pragma unroll
-      for (int i = 0; i < ATT_PER_WARP; ++i) {
+      for (int i = 0; i < ATT2_PW; ++i) {
         if (i >= nv) break;
         const int pos = pos_first + NCW * i;
         float vf[4];
@@ -471,7 +512,7 @@ __device__ void phase_attn2(Ctx2& c, const ModelDesc& md, int l, int position, u
           vf[0] = bf16_lo(kv.v[i].x); vf[1] = bf16_hi(kv.v[i].x);
           vf[2] = bf16_lo(kv.v[i].y); vf[3] = bf16_hi(kv.v[i].y);
         }
-        const float e0 = __expf(sc[i] - mx0), e1 = __expf(sc[5 + i] - mx1);
+        const float e0 = __expf(sc[i] - mx0), e1 = __expf(sc[ATT2_PW + i] - mx1);
         l0 += e0; l1 += e1;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -646,7 +687,7 @@ __device__ void consumer_loop2(Ctx2& c) {
   Prod2 prod;
   prod2_init(c, prod);
   if (c.warp >= 2) prod2_issue(c, prod, NSL);
-  KvRegs kv;
+  KvRegs2 kv;
 #define QMK2_S_CODES (reinterpret_cast<int*>(c.smem0 + S2_MISC + 128))   /* int[16]: the codes of the current frame, selected by this CTA */
   const int gi0 = c.tid * 4;
   // totals of this thread's accumulator words at the end of the previous launch
