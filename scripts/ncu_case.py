@@ -5,6 +5,8 @@ in one launch], talker steps at positions 500 and 2047 [12, 13], and (with --bat
 import os
 import sys
 
+os.environ.setdefault("QMK_AUTOTUNE", "0")   # the in-situ autotuner adds ~100 decode launches at model creation: keep the launch indices fixed
+
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "qwen-megakernel-tts_b200"))
 import torch
