@@ -267,6 +267,8 @@ typedef struct qmk_batched_step_args {
   int32_t codes_stride, codes_col;
   const uint64_t* counter_ptr;  /* optional (ABI 3): device word added to `counter` when the kernel runs -- a CUDA graph captured
                                    from these calls draws fresh numbers on every replay (qmk_batched_counter_add advances it) */
+  int32_t depth_hint;           /* optional (ABI 3): an upper bound of the streams' positions known to the host (positions live on
+                                   the device); >= 256 at B = 16 / 32 (>= 1024 at B >= 48) splits every context over 4 / 2 (2) CTAs.  0 = unknown / shallow */
 } qmk_batched_step_args;
 int qmk_batched_add_head(qmk_batched* h, const void* lm_head_weight, int rows);
 int qmk_batched_step_ex(qmk_batched* h, const qmk_batched_step_args* args, void* stream);

@@ -319,6 +319,176 @@ __global__ void __launch_bounds__(32 * ATT_NW) kb_qkv_attention(const float* par
   kt.flush(4);
 }
 
+// ---- decode attention with the context split over Z CTAs (deep contexts at B <= 32: one CTA per (stream, kv head) keeps only
+//      16 KB of rows in flight, 1.1 TB/s of KV at B = 16 and 2000 positions).  CTA z takes positions [z C, (z + 1) C) of 0 .. pos,
+//      every CTA finishes q itself (four small loads), the CTA of the last chunk also appends the new K / V row; the partial
+//      (max, sum, accumulators) of a chunk goes to global memory and the LAST CTA of the item to arrive (one atomic ticket)
+//      merges the Z partials in chunk order -- deterministic -- and writes the output.  grid = (B, 8, Z), block = 256.
+//      part: f32[B][8][Z][2][130]; tickets: u32[B][8], zero between kernels (the merging CTA resets its ticket). --------------
+constexpr int ATT_PART = 130, ATT_SPLIT_MIN = 256, ATT_SPLIT_MIN_WIDE = 1024;
+template <int SPLITS, int Z>
+__global__ void __launch_bounds__(256) kb_qkv_attention_split(const float* partial, int B, const int* positions, const __nv_bfloat16* q_norm,
+                                                              const __nv_bfloat16* k_norm, const __nv_bfloat16* cos_t, const __nv_bfloat16* sin_t,
+                                                              __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, __nv_bfloat16* a_out, float* part,
+                                                              unsigned* tickets, int layer, int L, int max_seq, float scale) {
+  __shared__ float s_q[2][HD];
+  __shared__ float s_kv[2][HD];
+  __shared__ float s_acc[ATT_NW][2][HD];
+  __shared__ float s_m[ATT_NW][2], s_l[ATT_NW][2];
+  __shared__ unsigned s_last;
+  const int b = blockIdx.x, g = blockIdx.y, z = blockIdx.z, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int pos = positions[b];
+  pos = pos < 0 ? 0 : (pos >= max_seq ? max_seq - 1 : pos);
+  const int n = pos + 1;
+  const int C = ((n + Z - 1) / Z + 7) & ~7;                  // chunk length, a multiple of the 8 warps
+  const int p_lo = z * C, p_hi = p_lo + C < n ? p_lo + C : n;   // may be empty for the trailing chunks of a short context
+  const bool owner = pos >= p_lo && pos < p_lo + C;          // the chunk that holds the new position appends the row
+  const size_t base = (((size_t)b * L + layer) * NKVH + g) * max_seq * HD;
+  uint2 kk[ATT_PRE], vv[ATT_PRE];
+#pragma unroll
+  for (int i = 0; i < ATT_PRE; ++i) {
+    const int p = p_lo + warp + ATT_NW * i;
+    if (p < p_hi && p < pos) {
+      kk[i] = __ldcg(reinterpret_cast<const uint2*>(k_cache + base + (size_t)p * HD + lane * 4));
+      vv[i] = __ldcg(reinterpret_cast<const uint2*>(v_cache + base + (size_t)p * HD + lane * 4));
+    }
+  }
+  const __nv_bfloat16* wn = warp < 2 ? q_norm : k_norm;
+  const uint2 wn_raw = warp < 3 ? *reinterpret_cast<const uint2*>(wn + lane * 4) : make_uint2(0u, 0u);
+  const int dbase = (lane * 4) & 63;
+  const uint2 cs_raw = *reinterpret_cast<const uint2*>(cos_t + (size_t)pos * HD + dbase), sn_raw = *reinterpret_cast<const uint2*>(sin_t + (size_t)pos * HD + dbase);
+  qmkb::pdl_wait();
+  qmkb::pdl_launch_dependents();
+  if (warp < 2 || (owner && warp < 4)) {
+    const int row0 = warp < 2 ? (2 * g + warp) * HD : (warp == 2 ? QSZ + g * HD : QSZ + KVSZ + g * HD);
+    float4 pp[SPLITS];
+#pragma unroll
+    for (int s = 0; s < SPLITS; ++s) pp[s] = __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)s * B + b) * QKV_ROWS + row0 + lane * 4));
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s = 0; s < SPLITS; ++s) { t[0] += pp[s].x; t[1] += pp[s].y; t[2] += pp[s].z; t[3] += pp[s].w; }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) t[e] = bf16_round(t[e]);
+    if (warp == 3) {
+      *reinterpret_cast<float4*>(&s_kv[1][lane * 4]) = make_float4(t[0], t[1], t[2], t[3]);
+      *reinterpret_cast<uint2*>(v_cache + base + (size_t)pos * HD + lane * 4) =
+          make_uint2(bf16_bits(t[0]) | (bf16_bits(t[1]) << 16), bf16_bits(t[2]) | (bf16_bits(t[3]) << 16));
+    } else {
+      float ss = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ss = fmaf(t[e], t[e], ss);
+      ss = warp_sum(ss);
+      const float rms = sqrtf(ss * (1.0f / HD) + EPS);
+      const float wf[4] = {bf16_lo(wn_raw.x), bf16_hi(wn_raw.x), bf16_lo(wn_raw.y), bf16_hi(wn_raw.y)};
+      const float cf[4] = {bf16_lo(cs_raw.x), bf16_hi(cs_raw.x), bf16_lo(cs_raw.y), bf16_hi(cs_raw.y)};
+      const float sf[4] = {bf16_lo(sn_raw.x), bf16_hi(sn_raw.x), bf16_lo(sn_raw.y), bf16_hi(sn_raw.y)};
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float nv = bf16_round((t[e] / rms) * wf[e]);
+        const float other = __shfl_xor_sync(0xffffffffu, nv, 16);
+        const float x = bf16_round(nv * cf[e]), y = bf16_round(other * sf[e]);
+        o[e] = bf16_round(lane < 16 ? x - y : x + y);
+      }
+      if (warp < 2) {
+        *reinterpret_cast<float4*>(&s_q[warp][lane * 4]) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+        *reinterpret_cast<float4*>(&s_kv[0][lane * 4]) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint2*>(k_cache + base + (size_t)pos * HD + lane * 4) =
+            make_uint2(bf16_bits(o[0]) | (bf16_bits(o[1]) << 16), bf16_bits(o[2]) | (bf16_bits(o[3]) << 16));
+      }
+    }
+  }
+  __syncthreads();
+  const float4 qa = *reinterpret_cast<const float4*>(&s_q[0][lane * 4]), qb = *reinterpret_cast<const float4*>(&s_q[1][lane * 4]);
+  const float q0[4] = {qa.x, qa.y, qa.z, qa.w}, q1[4] = {qb.x, qb.y, qb.z, qb.w};
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f, acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+  for (int p0 = p_lo + warp; p0 < p_hi; p0 += ATT_NW * ATT_PRE) {
+    if (p0 != p_lo + warp) {
+#pragma unroll
+      for (int i = 0; i < ATT_PRE; ++i) {
+        const int p = p0 + ATT_NW * i;
+        if (p < p_hi && p < pos) {
+          kk[i] = __ldcg(reinterpret_cast<const uint2*>(k_cache + base + (size_t)p * HD + lane * 4));
+          vv[i] = __ldcg(reinterpret_cast<const uint2*>(v_cache + base + (size_t)p * HD + lane * 4));
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < ATT_PRE; ++i) {
+      const int p = p0 + ATT_NW * i;
+      if (p < p_hi) {
+        float kf[4], vf[4];
+        if (p == pos) {
+          const float4 a = *reinterpret_cast<const float4*>(&s_kv[0][lane * 4]), c = *reinterpret_cast<const float4*>(&s_kv[1][lane * 4]);
+          kf[0] = a.x; kf[1] = a.y; kf[2] = a.z; kf[3] = a.w; vf[0] = c.x; vf[1] = c.y; vf[2] = c.z; vf[3] = c.w;
+        } else {
+          kf[0] = bf16_lo(kk[i].x); kf[1] = bf16_hi(kk[i].x); kf[2] = bf16_lo(kk[i].y); kf[3] = bf16_hi(kk[i].y);
+          vf[0] = bf16_lo(vv[i].x); vf[1] = bf16_hi(vv[i].x); vf[2] = bf16_lo(vv[i].y); vf[3] = bf16_hi(vv[i].y);
+        }
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { d0 = fmaf(q0[e], kf[e], d0); d1 = fmaf(q1[e], kf[e], d1); }
+        d0 = warp_sum(d0) * scale;
+        d1 = warp_sum(d1) * scale;
+        const float nm0 = fmaxf(m0, d0), nm1 = fmaxf(m1, d1);
+        const float c0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - nm0), c1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - nm1);
+        const float e0 = __expf(d0 - nm0), e1 = __expf(d1 - nm1);
+        l0 = l0 * c0 + e0; l1 = l1 * c1 + e1;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { acc0[e] = fmaf(e0, vf[e], acc0[e] * c0); acc1[e] = fmaf(e1, vf[e], acc1[e] * c1); }
+        m0 = nm0; m1 = nm1;
+      }
+    }
+  }
+  if (lane == 0) { s_m[warp][0] = m0; s_m[warp][1] = m1; s_l[warp][0] = l0; s_l[warp][1] = l1; }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { s_acc[warp][0][lane * 4 + e] = acc0[e]; s_acc[warp][1][lane * 4 + e] = acc1[e]; }
+  __syncthreads();
+  const int h = tid >> 7, d = tid & 127;
+  float M = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < ATT_NW; ++w) M = fmaxf(M, s_m[w][h]);
+  float A = 0.f, Ls = 0.f;
+#pragma unroll
+  for (int w = 0; w < ATT_NW; ++w) {
+    const float f = (s_m[w][h] == -INFINITY) ? 0.f : __expf(s_m[w][h] - M);
+    A = fmaf(s_acc[w][h][d], f, A);
+    Ls = fmaf(s_l[w][h], f, Ls);
+  }
+  // this chunk's partial -> global memory, then one ticket per CTA: the last one merges
+  float* mine = part + ((((size_t)b * NKVH + g) * Z + z) * 2 + h) * ATT_PART;
+  __stcg(mine + 2 + d, A);
+  if (d == 0) { __stcg(mine, M); __stcg(mine + 1, Ls); }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned t = atomicAdd(&tickets[b * NKVH + g], 1u);
+    s_last = (t == (unsigned)(Z - 1)) ? 1u : 0u;
+    if (t == (unsigned)(Z - 1)) tickets[b * NKVH + g] = 0u;   // every CTA of the item has drawn: ready for the next kernel
+  }
+  __syncthreads();
+  if (s_last == 0u) return;
+  __threadfence();
+  float pm[Z], pl[Z], pa[Z];
+#pragma unroll
+  for (int zz = 0; zz < Z; ++zz) {
+    const float* src = part + ((((size_t)b * NKVH + g) * Z + zz) * 2 + h) * ATT_PART;
+    pm[zz] = __ldcg(src); pl[zz] = __ldcg(src + 1); pa[zz] = __ldcg(src + 2 + d);
+  }
+  float Mx = -INFINITY;
+#pragma unroll
+  for (int zz = 0; zz < Z; ++zz) Mx = fmaxf(Mx, pm[zz]);
+  float At = 0.f, Lt = 0.f;
+#pragma unroll
+  for (int zz = 0; zz < Z; ++zz) {
+    const float f = (pm[zz] == -INFINITY) ? 0.f : __expf(pm[zz] - Mx);
+    At = fmaf(pa[zz], f, At);
+    Lt = fmaf(pl[zz], f, Lt);
+  }
+  a_out[(size_t)b * QSZ + (2 * g + h) * HD + d] = __float2bfloat16_rn(At / Lt);
+}
+
 // ---- one-pass prefill through the launch chain: lane i = position p0 + i of ONE utterance, all lanes share a B = 1 cache
 //      [L][8][max_seq][128].  The QKV epilogue is split in two kernels because lane i attends to the rows the other lanes write:
 //      (1) finish: split-K sum -> bf16 -> per-head norm + RoPE at position p0 + lane; q -> qpre (fp32, bf16-exact), k / v rows -> cache;
@@ -629,6 +799,8 @@ struct qmk_batched {
   int* d_status = nullptr;
   int* d_pos0 = nullptr;                  // prefill: first position
   int prefill_persistent = 0;            // QMK_PREFILL_PERSISTENT=1: the prefill as one persistent launch (csrc/qmk_bstep.cuh) instead of the chain
+  float* att_part = nullptr;             // split attention: f32[B][8][4][2][130] chunk partials
+  unsigned* att_tickets = nullptr;       // split attention: u32[B][8], zero between kernels
   float* qpre = nullptr;                 // chain prefill: q of every lane, f32[B][16][128]
   int* pos_scratch = nullptr;            // chain prefill: int[B] lane positions
   int* tok_scratch = nullptr;            // chain prefill: int[B] argmax tokens
@@ -671,7 +843,10 @@ extern "C" int qmk_batched_create(int device, const LDGLayerWeights* layers_host
             cudaMemset(h->xn, 0, (size_t)batch * H * 2) == cudaSuccess && cudaMemset(h->abuf, 0, (size_t)batch * QSZ * 2) == cudaSuccess &&
             cudaMemset(h->mbuf, 0, (size_t)batch * INTER * 2) == cudaSuccess &&   // rows of unused lanes feed the tensor cores too: keep them finite
             cudaMalloc(&h->qpre, (size_t)batch * QSZ * 4) == cudaSuccess && cudaMalloc(&h->pos_scratch, (size_t)batch * sizeof(int)) == cudaSuccess &&
-            cudaMalloc(&h->tok_scratch, (size_t)batch * sizeof(int)) == cudaSuccess;
+            cudaMalloc(&h->tok_scratch, (size_t)batch * sizeof(int)) == cudaSuccess &&
+            cudaMalloc(&h->att_part, (size_t)batch * NKVH * 4 * 2 * ATT_PART * sizeof(float)) == cudaSuccess &&
+            cudaMalloc(&h->att_tickets, (size_t)batch * NKVH * sizeof(unsigned)) == cudaSuccess &&
+            cudaMemset(h->att_tickets, 0, (size_t)batch * NKVH * sizeof(unsigned)) == cudaSuccess;
   if (!ok) { qmk_batched_destroy(h); return fail(QMK_ERR_CUDA, "qmk_batched_create: allocation failed"); }
   for (int l = 0; l < num_layers; ++l) {
     const LDGLayerWeights& w = layers_host[l];
@@ -769,7 +944,7 @@ extern "C" void qmk_batched_destroy(qmk_batched* h) {
   if (!h) return;
   BatchedDeviceGuard guard(h->device);
   cudaDeviceSynchronize();
-  cudaFree(h->w_qkv); cudaFree(h->w_gu); cudaFree(h->res); cudaFree(h->partial); cudaFree(h->qpre); cudaFree(h->pos_scratch); cudaFree(h->tok_scratch);
+  cudaFree(h->w_qkv); cudaFree(h->w_gu); cudaFree(h->res); cudaFree(h->partial); cudaFree(h->qpre); cudaFree(h->pos_scratch); cudaFree(h->tok_scratch); cudaFree(h->att_part); cudaFree(h->att_tickets);
   cudaFree(h->xn); cudaFree(h->abuf); cudaFree(h->mbuf);
   cudaFree(h->p_qkv); cudaFree(h->p_o); cudaFree(h->p_gu); cudaFree(h->p_down); cudaFree(h->p_head); cudaFree(h->d_ptrs); cudaFree(h->qbuf); cudaFree(h->d_bar); cudaFree(h->d_status); cudaFree(h->d_pos0);
   cudaFree(h->d_tok_scratch); cudaFree(h->d_trace);
@@ -888,9 +1063,25 @@ static int chain_step(qmk_batched* h, const qmk_batched_step_args* a, cudaStream
              reinterpret_cast<const __nv_bfloat16*>(h->ln_in[0]), h->xn, B);
   for (int l = 0; l < L; ++l) {
     gemm(h, h->map_qkv[l], h->map_x1024, QKV_ROWS, H, 4, st);                       // 32 tiles x 4 K-slices
-    launch_pdl(kb_qkv_attention<4>, dim3(B, NKVH), dim3(32 * ATT_NW), 0, st, (const float*)h->partial, B, (const int*)a->positions,
-               reinterpret_cast<const __nv_bfloat16*>(h->qn[l]), reinterpret_cast<const __nv_bfloat16*>(h->kn[l]), cos_t, sin_t,
-               kc, vc, h->abuf, l, L, h->max_seq, scale);
+    {
+      const __nv_bfloat16* qn = reinterpret_cast<const __nv_bfloat16*>(h->qn[l]);
+      const __nv_bfloat16* kn = reinterpret_cast<const __nv_bfloat16*>(h->kn[l]);
+      const float* pp = h->partial;
+      const int* pos = (const int*)a->positions;
+      // Deep contexts: the context of an item is split over several CTAs (the caller's hint; positions live on the device).
+      // Measured, ms per step at p = 500 / 1000 / 2000 with 1 / 2 / 4 / 8 CTAs per item: B = 16: 1.38 2.06 3.40 / 1.19 1.60 2.40 /
+      // 1.10 1.40 2.02 / 1.17 1.40 1.91; B = 64: 2.07 3.18 5.35 / 2.07 3.07 5.01 / 2.21 3.19 5.08 / 2.46 3.41 5.27.
+      const int zsplit = (B == 16 && a->depth_hint >= ATT_SPLIT_MIN) ? 4
+                         : ((B == 32 && a->depth_hint >= ATT_SPLIT_MIN) || (B >= 48 && a->depth_hint >= ATT_SPLIT_MIN_WIDE)) ? 2 : 1;
+      if (zsplit == 4)
+        launch_pdl(kb_qkv_attention_split<4, 4>, dim3(B, NKVH, 4), dim3(256), 0, st, pp, B, pos, qn, kn, cos_t, sin_t, kc, vc, h->abuf, h->att_part,
+                   h->att_tickets, l, L, h->max_seq, scale);
+      else if (zsplit == 2)
+        launch_pdl(kb_qkv_attention_split<4, 2>, dim3(B, NKVH, 2), dim3(256), 0, st, pp, B, pos, qn, kn, cos_t, sin_t, kc, vc, h->abuf, h->att_part,
+                   h->att_tickets, l, L, h->max_seq, scale);
+      else
+        launch_pdl(kb_qkv_attention<4>, dim3(B, NKVH), dim3(32 * ATT_NW), 0, st, pp, B, pos, qn, kn, cos_t, sin_t, kc, vc, h->abuf, l, L, h->max_seq, scale);
+    }
     gemm(h, h->map_o[l], h->map_x2048, H, QSZ, h->splits_od, st);                    // 8 tiles x 16 K-slices
     resid_norm(h, st, h->ln_post[l], nullptr, nullptr);
     gemm(h, h->map_gu[l], h->map_x1024, GU_ROWS, H, 4, st);                          // 48 tiles x 4 K-slices

@@ -188,7 +188,7 @@ class BatchedStepArgs(ctypes.Structure):
         ("positions", _vp), ("k_cache", _vp), ("v_cache", _vp), ("hidden_out", _vp), ("head", ctypes.c_int32),
         ("do_sample", ctypes.c_int32), ("top_k", ctypes.c_int32), ("group", ctypes.c_int32), ("temperature", ctypes.c_float),
         ("seed", ctypes.c_uint64), ("counter", ctypes.c_uint64), ("tokens_out", _vp), ("codes_out", _vp),
-        ("codes_stride", ctypes.c_int32), ("codes_col", ctypes.c_int32), ("counter_ptr", _vp),
+        ("codes_stride", ctypes.c_int32), ("codes_col", ctypes.c_int32), ("counter_ptr", _vp), ("depth_hint", ctypes.c_int32),
     ]
 
 

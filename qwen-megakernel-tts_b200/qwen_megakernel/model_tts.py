@@ -573,9 +573,16 @@ class BatchedTTSDecoder:
         from .build_tts import NativeError
         if self._steps >= self._max_seq:
             raise IndexError("KV cache is full for at least one stream")
-        rc = self._lib.qmk_batched_step(self._handle, token_ptr, embed_ptr, self.positions.data_ptr(),
-                                        self._k_cache.data_ptr(), self._v_cache.data_ptr(), self._hidden.data_ptr(),
-                                        self._tokens.data_ptr(), _stream_ptr(self.device))
+        if self.persistent_decode:
+            rc = self._lib.qmk_batched_step(self._handle, token_ptr, embed_ptr, self.positions.data_ptr(),
+                                            self._k_cache.data_ptr(), self._v_cache.data_ptr(), self._hidden.data_ptr(),
+                                            self._tokens.data_ptr(), _stream_ptr(self.device))
+        else:   # the launch chain, with the host's bound on the positions (deep contexts are split over several CTAs)
+            from .build_tts import BatchedStepArgs
+            a = BatchedStepArgs(token_ids=token_ptr, embeds_bf16=embed_ptr, positions=self.positions.data_ptr(),
+                                k_cache=self._k_cache.data_ptr(), v_cache=self._v_cache.data_ptr(), hidden_out=self._hidden.data_ptr(),
+                                tokens_out=self._tokens.data_ptr(), head=0, group=-1, depth_hint=self._steps)
+            rc = self._lib.qmk_batched_step_ex(self._handle, ctypes.byref(a), _stream_ptr(self.device))
         if rc < 0:
             raise NativeError(f"qmk_batched_step: {self._lib.qmk_batched_last_error().decode()} (code {rc})")
         self._steps += 1
@@ -609,16 +616,17 @@ class BatchedTTSDecoder:
             self._g_tok = torch.zeros(self.batch, dtype=torch.int32, device=self.device)
             self._graphs, self._graph_warm = {}, False
         feedback = token_ids is None
+        deep = (self._steps >= 256) + (self._steps >= 1024)   # (the captured chain switches to split attention at depth: qmk_batched_step_args.depth_hint)
         src = self._tokens if feedback else self._g_tok
         if not feedback:
             self._g_tok.copy_(token_ids.to(self.device, torch.int32).reshape(self.batch))
         if not self._graph_warm:                      # first call: plain launches (also the warm-up the capture needs)
             self._graph_warm = True
             return self.step(src)
-        if feedback not in self._graphs:
-            self._graphs[feedback], _ = _capture(self.device, lambda: self.step(src))
+        if (feedback, deep) not in self._graphs:
+            self._graphs[(feedback, deep)], _ = _capture(self.device, lambda: self.step(src))
             self._steps -= 1                          # the capture only recorded the step
-        self._graphs[feedback].replay()
+        self._graphs[(feedback, deep)].replay()
         self._steps += 1
         return self._tokens, self._hidden
 
@@ -814,7 +822,7 @@ class BatchedFrameLoop:
             if self.talker._steps >= self.talker._max_seq:
                 raise IndexError("KV cache is full for at least one stream")
             self._extra.copy_(extra_bf16.to(self.device, torch.bfloat16).expand(self.batch, HIDDEN_SIZE))
-            key = (bool(do_sample), float(temperature), int(top_k))
+            key = (bool(do_sample), float(temperature), int(top_k), (self.talker._steps >= 256) + (self.talker._steps >= 1024))
             if key not in self._warm:                 # first frame with these settings: plain launches
                 self._warm.add(key)
                 return self._frame(self._extra, do_sample, temperature, top_k)
