@@ -76,6 +76,30 @@ def test_attention_split_covers_every_position_once(position):
     assert s <= 16
 
 
+def batched_split_chunk(position: int, z: int, nz: int):
+    """kb_qkv_attention_split (csrc/qmk_batched.cu): chunk z of a context of position + 1 rows split over nz CTAs"""
+    n = position + 1
+    c = ((-(-n // nz)) + 7) & ~7
+    p_lo = z * c
+    p_hi = min(p_lo + c, n)
+    owner = p_lo <= position < p_lo + c
+    return p_lo, p_hi, owner
+
+
+@pytest.mark.parametrize("nz", [2, 4])
+@pytest.mark.parametrize("position", [0, 5, 7, 8, 255, 256, 257, 1023, 1500, 2046, 2047])
+def test_batched_attention_split_covers_every_position_once(position, nz):
+    """every position belongs to exactly one chunk, exactly one chunk appends the new row, trailing chunks may be empty"""
+    covered, owners = [], 0
+    for z in range(nz):
+        p_lo, p_hi, owner = batched_split_chunk(position, z, nz)
+        covered += list(range(p_lo, max(p_lo, p_hi)))
+        owners += owner
+        if owner:
+            assert p_lo <= position < p_hi
+    assert covered == list(range(position + 1)) and owners == 1
+
+
 def test_group_row_assignment_partitions_every_matrix():
     """QKV / gate-up rows and the O / down slabs of the 8 x 16 CTAs tile every weight matrix exactly once"""
     q, k, v, gu, o, d = set(), set(), set(), set(), set(), set()
