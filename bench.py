@@ -108,7 +108,7 @@ class ClockSampler:
             self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+                 "-lms", "200"], stdout=self.tmp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
