@@ -573,7 +573,9 @@ class BatchedTTSDecoder:
         from .build_tts import NativeError
         if self._steps >= self._max_seq:
             raise IndexError("KV cache is full for at least one stream")
-        if self.persistent_decode:
+        if getattr(self, "_pd", None) is None:
+            self._pd = self.persistent_decode         # fixed at create time (QMK_BATCHED_PERSISTENT)
+        if self._pd:
             rc = self._lib.qmk_batched_step(self._handle, token_ptr, embed_ptr, self.positions.data_ptr(),
                                             self._k_cache.data_ptr(), self._v_cache.data_ptr(), self._hidden.data_ptr(),
                                             self._tokens.data_ptr(), _stream_ptr(self.device))
