@@ -331,6 +331,33 @@ def time_prefill(loop: FrameLoop, reps: int = 5):
     return out
 
 
+def time_text_projection(weights_gpu, dev, n_tokens=(32, 128), iters: int = 50):
+    """Text side of the prefill (tts_engine.py:262-263, once per utterance): TextProjectionKernel.embed_text_ids (one chain of
+    five kernels per 64 tokens, fc1 / fc2 on tcgen05) beside upstream's four PyTorch operators (TextProjection), CUDA-event
+    ms per call with the ids already on the device."""
+    from qwen_megakernel.model_tts import TextProjection, TextProjectionKernel
+    native, glue = TextProjectionKernel(weights_gpu, device=str(dev)), TextProjection(weights_gpu, device=str(dev))
+    out = {}
+    for n in n_tokens:
+        ids = torch.randint(0, weights_gpu["text_embedding"].shape[0], (n,), device=dev)
+        for name, fn in (("native", native.embed_text_ids), ("torch_glue", glue.embed_text_ids)):
+            for _ in range(5):
+                fn(ids)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                fn(ids)
+            b.record()
+            torch.cuda.synchronize()
+            out[f"T{n}_{name}_ms"] = a.elapsed_time(b) / iters
+    out["algorithmic_bytes"] = 2 * (2048 * 2048 + 1024 * 2048 + 2048 + 1024)     # fc1 + fc2 + biases (+ 4 KB per token)
+    out["note"] = ("TextProjectionKernel.embed_text_ids (qmk_text_proj_embed: gather -> tcgen05 fc1 -> bias + SiLU -> tcgen05 fc2 -> bias, "
+                   "5 launches per 64 tokens) vs upstream's embedding / linear / silu / linear in PyTorch; launch-latency bound "
+                   "(12.6 MB of weights = 2 us at the HBM peak)")
+    return out
+
+
 def time_talker_at(loop: FrameLoop, position: int, n: int = 40, warmup: int = 5):
     """Mean duration of one talker launch with `position` cached rows (the launch is repeated at the same position: the KV rows
     it reads are whatever the cache holds, which does not change the work)."""
@@ -685,6 +712,10 @@ def main():
     }
     if batched is not None:
         line["batched"] = batched
+    try:      # last GPU leg: nothing measured above depends on it
+        line["text_projection"] = time_text_projection(w_gpu, dev)
+    except Exception as e:  # noqa: BLE001
+        line["text_projection"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if world == 1 and not args.no_cpu_baseline:
         fps, done, dt = cpu_frame_loop(w_cpu, 10_000, 1, args.cpu_budget)
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",

@@ -307,6 +307,22 @@ int qmk_batched_chain_trace(int enable, void* stream, unsigned long long* host_o
 int qmk_batched_prefill(qmk_batched* h, const void* embeds, int n, int position0, void* k_cache, void* v_cache,
                         float* hidden_out_last, int32_t* token_out_last, void* stream);
 
+/* ---- text side of the prefill ------------------------------------------------------------
+ * Replaces upstream TextProjection.embed_text_ids (model_tts.py:348-374; called once per utterance on the content tokens,
+ * tts_engine.py:262-263): out = fc2( silu( fc1( text_embedding[ids] ) ) ) with upstream's rounding points (bf16 after every
+ * operator, fp32 accumulation, bias added in fp32).  text_embedding bf16[vocab_rows][2048], fc1_weight bf16[2048][2048],
+ * fc1_bias bf16[2048], fc2_weight bf16[1024][2048], fc2_bias bf16[1024]: device pointers in the upstream [out, in] layout,
+ * read in place (the caller keeps them alive), 16-byte aligned.  Both projections run on tcgen05 (csrc/qmk_bgemm.cuh), up to
+ * 64 tokens per pass (csrc/qmk_text.cuh). */
+typedef struct qmk_text_proj qmk_text_proj;
+int qmk_text_proj_create(int device, const void* text_embedding, int vocab_rows, const void* fc1_weight, const void* fc1_bias,
+                         const void* fc2_weight, const void* fc2_bias, qmk_text_proj** out);
+/* ids: int64[n_ids] in DEVICE memory (values outside [0, vocab_rows) are clamped; upstream's F.embedding would trap);
+ * out_bf16: bf16[n_ids][1024] in device memory.  n_ids == 0 is a no-op.  Asynchronous on `stream`, only enqueues kernels
+ * (CUDA-graph capturable); calls on one handle share its staging buffers and must be ordered on one stream. */
+int qmk_text_proj_embed(qmk_text_proj* h, const int64_t* ids, int n_ids, void* out_bf16, void* stream);
+void qmk_text_proj_destroy(qmk_text_proj* h);
+
 /* ---- upstream-compatible entry point (same symbol, same argument list) ---------------------------- */
 /* The scratch arguments (g_activations .. g_mlp_intermediate, block_max_*) are accepted and ignored:
  * the engine keeps its own exchange buffers.  The first call for a given `layer_weights` blob re-packs

@@ -9,6 +9,9 @@ What it restates (upstream = jayanth-kumar-morem/qwen-megakernel-tts, paths rela
   * the PyTorch code-predictor decode   qwen_megakernel/model_tts.py:576-619 (``CodePredictor._layer_decode``)
   * the code-predictor frame loop       qwen_megakernel/model_tts.py:439-504 and :729-773
   * greedy / top-k sampling             qwen_megakernel/model_tts.py:756-764
+  * the text side of the prefill        qwen_megakernel/model_tts.py:361-374 (``TextProjection.embed_text_ids``) and
+                                        :776-864 (``build_prefill_embeddings``); pinned by tests/golden/text_projection.npz
+                                        (tests/golden/make_golden_text.py, the upstream functions themselves)
 The arithmetic lives in third-party PyTorch (``torch>=2.7`` unpinned upstream, requirements.txt:1;
 2.11.0+cu128 in this image): bf16 ``mv`` with fp32 accumulation, fp32 RMSNorm / softmax.
 
@@ -250,3 +253,38 @@ def frame_embed_sum(codes, talker_embed: torch.Tensor, cp_embeds, extra_bf16: to
     for g in range(15):
         e = e + cp_embeds[g][int(codes[g + 1])]
     return e + extra_bf16.to(BF16)
+
+
+class TextProjectionOracle:
+    """Upstream ``TextProjection.embed_text_ids`` (model_tts.py:361-374) written out in fp32 with its rounding points:
+
+        x = table[ids];  y = r(x W1^T + b1);  y = r(y / (1 + exp(-y)));  out = r(y W2^T + b2)
+
+    (``F.linear`` on bf16 accumulates in fp32, adds the bias in fp32 and rounds once; ``F.silu`` on bf16 computes in fp32
+    and rounds once.)  The matrix products are fp32 matmuls of the bf16 values, i.e. a different summation order than
+    torch's bf16 GEMM: equal up to one bf16 ulp, the tolerance of tests/test_text_projection.py."""
+
+    def __init__(self, weights: dict):
+        self.table = weights["text_embedding"]
+        self.w1, self.b1 = weights["text_proj_fc1_w"].float(), weights["text_proj_fc1_b"].float()
+        self.w2, self.b2 = weights["text_proj_fc2_w"].float(), weights["text_proj_fc2_b"].float()
+
+    @torch.no_grad()
+    def embed_text_ids(self, token_ids: torch.Tensor) -> torch.Tensor:
+        x = self.table[token_ids.long()].float()
+        y = (x @ self.w1.T + self.b1).to(BF16).float()
+        y = (y / (1.0 + torch.exp(-y))).to(BF16).float()
+        return (y @ self.w2.T + self.b2).to(BF16)
+
+
+def build_prefill_oracle(text_token_ids: torch.Tensor, text_projection, codec_embed_weight: torch.Tensor, pad, bos, eos):
+    """Upstream ``build_prefill_embeddings`` with cached pad / bos / eos embeddings (model_tts.py:803-864; the engine's
+    configuration, tts_engine.py:107-118): prefill = [3 role tokens | (pad, pad, pad, bos) + codec tags (nothink, think_bos,
+    think_eos, codec_pad) | first content token + codec_bos]; trailing = content[1:-5] + [eos].  bf16 adds."""
+    emb = text_projection.embed_text_ids(text_token_ids)
+    role, content = emb[:3], emb[3:]
+    tags = codec_embed_weight[torch.tensor([2155, 2156, 2157, 2148, 2149])]     # model_tts.py:45-53 codec control ids
+    fused = torch.cat([pad.expand(3, -1), bos], dim=0) + tags[:4]
+    prefill = torch.cat([role, fused, content[:1] + tags[4:5]], dim=0)
+    trailing = torch.cat([content[1:-5], eos], dim=0)
+    return prefill, trailing

@@ -1306,3 +1306,6 @@ extern "C" int qmk_batched_chain_trace(int enable, void* stream, unsigned long l
   }
   return n;
 }
+
+// ---- text side of the prefill: TextProjection.embed_text_ids on the same tcgen05 GEMM ----
+#include "qmk_text.cuh"

@@ -154,6 +154,9 @@ SIGNATURES = {
     "qmk_batched_chain_trace": (_i32, [_i32, _vp, ctypes.POINTER(ctypes.c_ulonglong), _i32]),
     "qmk_batched_sync_status": (_i32, [_vp, _vp]),
     "qmk_batched_prefill": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "qmk_text_proj_create": (_i32, [_i32, _vp, _i32, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
+    "qmk_text_proj_embed": (_i32, [_vp, _vp, _i32, _vp, _vp]),
+    "qmk_text_proj_destroy": (None, [_vp]),
     "launch_ldg_decode_direct": (None, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
     "qmk_legacy_configure": (_i32, [_vp, _i32, _i32]),

@@ -871,6 +871,65 @@ class TextProjection:
         return F.linear(F.silu(F.linear(x, self.fc1_w, self.fc1_b)), self.fc2_w, self.fc2_b)
 
 
+class TextProjectionKernel:
+    """``TextProjection`` on the native library (the text side of the prefill): same constructor and
+    ``embed_text_ids`` contract as upstream ``TextProjection`` (model_tts.py:348-374), evaluated by
+    ``qmk_text_proj_embed`` -- row gather, fc1 and fc2 on tcgen05 with the weights read in place, bias / SiLU / bf16
+    rounding fused into the split-K epilogues, one launch chain per 64 tokens (csrc/qmk_text.cuh).
+
+    Relates to ``TextProjection`` as upstream's ``CodePredictorKernel`` relates to its ``CodePredictor``: the PyTorch
+    class stays the reference, this one is the accelerated path and has no fallback (CUDA tensors only).
+    ``tts_engine.py:87`` constructs ``TextProjection(weights, device=...)``; the drop-in is that one name.
+    Ids outside the table are clamped on the device (upstream's ``F.embedding`` would trap).
+    """
+
+    def __init__(self, weights: dict, device: str = "cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("TextProjectionKernel needs a CUDA device (sm_100a); there is no CPU fallback")
+        dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self.text_embedding = weights["text_embedding"]
+        self.fc1_w, self.fc1_b = weights["text_proj_fc1_w"], weights["text_proj_fc1_b"]
+        self.fc2_w, self.fc2_b = weights["text_proj_fc2_w"], weights["text_proj_fc2_b"]
+        for name, t, shape in (("text_embedding", self.text_embedding, (self.text_embedding.shape[0], 2048)),
+                               ("text_proj_fc1_w", self.fc1_w, (2048, 2048)), ("text_proj_fc1_b", self.fc1_b, (2048,)),
+                               ("text_proj_fc2_w", self.fc2_w, (HIDDEN_SIZE, 2048)), ("text_proj_fc2_b", self.fc2_b, (HIDDEN_SIZE,))):
+            if not t.is_cuda or t.device != dev or t.dtype != torch.bfloat16 or not t.is_contiguous() or tuple(t.shape) != shape:
+                raise ValueError(f"TextProjectionKernel: {name} must be a contiguous bf16 tensor of shape {shape} on {dev}")
+        self._lib = _Native.lib()
+        h = ctypes.c_void_p()
+        rc = self._lib.qmk_text_proj_create(dev.index, self.text_embedding.data_ptr(), int(self.text_embedding.shape[0]),
+                                            self.fc1_w.data_ptr(), self.fc1_b.data_ptr(), self.fc2_w.data_ptr(),
+                                            self.fc2_b.data_ptr(), ctypes.byref(h))
+        if rc < 0:
+            from .build_tts import NativeError
+            raise NativeError(f"qmk_text_proj_create: {self._lib.qmk_batched_last_error().decode()} (code {rc})")
+        self._handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                self._lib.qmk_text_proj_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    @torch.no_grad()
+    def embed_text_ids(self, token_ids: torch.Tensor) -> torch.Tensor:
+        """``[seq_len]`` or ``[batch, seq_len]`` integer ids -> ``[*, HIDDEN_SIZE]`` bf16 (asynchronous on the current stream)."""
+        if token_ids.dtype not in (torch.int64, torch.int32, torch.int16, torch.uint8):
+            raise ValueError("TextProjectionKernel.embed_text_ids: token_ids must be an integer tensor")
+        ids = token_ids.to(device=self.device, dtype=torch.int64).contiguous()
+        out = torch.empty(*ids.shape, HIDDEN_SIZE, dtype=torch.bfloat16, device=self.device)
+        rc = self._lib.qmk_text_proj_embed(self._handle, ids.data_ptr(), ids.numel(), out.data_ptr(), _stream_ptr(self.device))
+        if rc < 0:
+            from .build_tts import NativeError
+            raise NativeError(f"qmk_text_proj_embed: {self._lib.qmk_batched_last_error().decode()} (code {rc})")
+        return out
+
+
 class CodePredictorKernel:
     """Code predictor (5 layers, 15 group heads) on the same kernel as the talker (``num_layers=5``).
 
