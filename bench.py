@@ -333,7 +333,7 @@ def time_prefill(loop: FrameLoop, reps: int = 5):
 
 def time_text_projection(weights_gpu, dev, n_tokens=(32, 128), iters: int = 50):
     """Text side of the prefill (tts_engine.py:262-263, once per utterance): TextProjectionKernel.embed_text_ids (one chain of
-    five kernels per 64 tokens, fc1 / fc2 on tcgen05) beside upstream's four PyTorch operators (TextProjection), CUDA-event
+    five kernels per 512 tokens, fc1 / fc2 on tcgen05) beside upstream's four PyTorch operators (TextProjection), CUDA-event
     ms per call with the ids already on the device."""
     from qwen_megakernel.model_tts import TextProjection, TextProjectionKernel
     native, glue = TextProjectionKernel(weights_gpu, device=str(dev)), TextProjection(weights_gpu, device=str(dev))
@@ -353,8 +353,38 @@ def time_text_projection(weights_gpu, dev, n_tokens=(32, 128), iters: int = 50):
             out[f"T{n}_{name}_ms"] = a.elapsed_time(b) / iters
     out["algorithmic_bytes"] = 2 * (2048 * 2048 + 1024 * 2048 + 2048 + 1024)     # fc1 + fc2 + biases (+ 4 KB per token)
     out["note"] = ("TextProjectionKernel.embed_text_ids (qmk_text_proj_embed: gather -> tcgen05 fc1 -> bias + SiLU -> tcgen05 fc2 -> bias, "
-                   "5 launches per 64 tokens) vs upstream's embedding / linear / silu / linear in PyTorch; launch-latency bound "
+                   "5 launches per 512 tokens) vs upstream's embedding / linear / silu / linear in PyTorch; launch-latency bound "
                    "(12.6 MB of weights = 2 us at the HBM peak)")
+    return out
+
+
+def time_first_frame_from_text(loop: FrameLoop, n_text: int = 24, reps: int = 6):
+    """Time to the first codec frame from TEXT IDS on the host (the part of upstream's TTFC this path covers, README.md:17-25:
+    embed build 7.2 + prefill 24.9 + first decode 3.1 + first code predictor 13.0 ms on an RTX 5090): ids H2D -> text projection
+    -> build_prefill_embeddings (cached pad / bos / eos, tts_engine.py:107-118) -> one-pass prefill with the BOS row -> predict ->
+    16 codes on the host.  Wall-clock ms (best of reps), native text projection vs the PyTorch operators."""
+    from qwen_megakernel.model_tts import TextProjection, TextProjectionKernel, build_prefill_embeddings
+    dev = loop.dev
+    rows = loop.w["text_embedding"].shape[0]
+    ids_host = torch.randint(0, rows, (3 + n_text + 5,)).pin_memory()      # 3 role ids, the content, 5 closing format ids
+    bos_row = loop.embed[CODEC_BOS:CODEC_BOS + 1]
+    out = {}
+    for name, tp in (("native", TextProjectionKernel(loop.w, device=str(dev))), ("torch_glue", TextProjection(loop.w, device=str(dev)))):
+        sp = tp.embed_text_ids(torch.arange(3, device=dev) % rows)
+        cached = {"pad": sp[0:1], "bos": sp[1:2], "eos": sp[2:3]}
+        best = 1e9
+        for _ in range(reps + 2):
+            loop.talker.reset()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            prefill, _trailing = build_prefill_embeddings(ids_host.to(dev, non_blocking=True), tp, loop.embed, device=str(dev),
+                                                         cached_tts_embeds=cached)
+            tok, hid = loop.talker.prefill(torch.cat([prefill, bos_row], dim=0))
+            codes = loop.cp.predict(hid, tok, loop.embed, do_sample=True, temperature=0.9, top_k=50)
+            codes.cpu()
+            best = min(best, (time.perf_counter() - t0) * 1e3)
+        out[f"first_frame_ms_from_text_ids_{name}"] = best
+    loop.talker.reset()
     return out
 
 
@@ -714,6 +744,7 @@ def main():
         line["batched"] = batched
     try:      # last GPU leg: nothing measured above depends on it
         line["text_projection"] = time_text_projection(w_gpu, dev)
+        line["text_projection"].update(time_first_frame_from_text(loop))
     except Exception as e:  # noqa: BLE001
         line["text_projection"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if world == 1 and not args.no_cpu_baseline:

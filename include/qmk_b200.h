@@ -312,8 +312,8 @@ int qmk_batched_prefill(qmk_batched* h, const void* embeds, int n, int position0
  * tts_engine.py:262-263): out = fc2( silu( fc1( text_embedding[ids] ) ) ) with upstream's rounding points (bf16 after every
  * operator, fp32 accumulation, bias added in fp32).  text_embedding bf16[vocab_rows][2048], fc1_weight bf16[2048][2048],
  * fc1_bias bf16[2048], fc2_weight bf16[1024][2048], fc2_bias bf16[1024]: device pointers in the upstream [out, in] layout,
- * read in place (the caller keeps them alive), 16-byte aligned.  Both projections run on tcgen05 (csrc/qmk_bgemm.cuh), up to
- * 64 tokens per pass (csrc/qmk_text.cuh). */
+ * read in place (the caller keeps them alive), 16-byte aligned.  Both projections run on tcgen05 (csrc/qmk_bgemm.cuh): one chain
+ * of five launches per 512 tokens, blocks of 64 tokens along gridDim.z (csrc/qmk_text.cuh). */
 typedef struct qmk_text_proj qmk_text_proj;
 int qmk_text_proj_create(int device, const void* text_embedding, int vocab_rows, const void* fc1_weight, const void* fc1_bias,
                          const void* fc2_weight, const void* fc2_bias, qmk_text_proj** out);

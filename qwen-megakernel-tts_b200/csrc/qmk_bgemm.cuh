@@ -7,6 +7,7 @@
 // UMMA N, so D = W_tile * X^T lives in N TMEM columns.  K is split across CTAs (split-K) because a decode GEMM has
 // only M/128 = 8 .. 48 row tiles and all 148 SMs must pull weights to saturate HBM; the partials are summed by the
 // fused epilogue kernels (qmk_batched.cu), which also apply the bf16 rounding / norm / RoPE / SwiGLU of the step.
+// gridDim.z > 1 (text projection, qmk_text.cuh): z-th block of N rows of X against the same weights, partials behind each other.
 // Warp 0 lane 0: TMA producer (all k-blocks of the slice are issued up front: <= 6 x 24 KB); warp 1 lane 0: MMA
 // issuer (tcgen05.mma, cta_group::1, kind::f16, bf16 x bf16 -> fp32); warps 0-3: epilogue (tcgen05.ld 32x32b).
 #pragma once
@@ -133,12 +134,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 
 struct BgemmArgs {
-  float* partial;   // [splits][N][M]
+  float* partial;   // [gridDim.z][splits][N][M]
   int M, N, K;      // N multiple of 16, <= 64; K multiple of 64 * splits
   int splits;
 };
 
-// grid = (M / 128, splits), block = 128
+// grid = (M / 128, splits, row blocks of X), block = 128
 __global__ void __launch_bounds__(128, 2) qmk_bgemm_kernel(const __grid_constant__ CUtensorMap map_w,
                                                            const __grid_constant__ CUtensorMap map_x, BgemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(128, 2) qmk_bgemm_kernel(const __grid_constant
       tma_load_2d(sA + kb * A_TILE_BYTES, &map_w, k0 + kb * BK, m0, &full[kb]);
     }
     pdl_wait();
-    for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sB + kb * B_TILE_BYTES, &map_x, k0 + kb * BK, 0, &full[kb]);
+    for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sB + kb * B_TILE_BYTES, &map_x, k0 + kb * BK, (int)blockIdx.z * a.N, &full[kb]);
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer =====
     const uint32_t idesc = make_instr_desc(a.N);
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(128, 2) qmk_bgemm_kernel(const __grid_constant
   kt.mark(2);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int row = m0 + warp * 32 + lane;
-  float* out = a.partial + (size_t)blockIdx.y * a.N * a.M;
+  float* out = a.partial + ((size_t)blockIdx.z * a.splits + blockIdx.y) * a.N * a.M;
   for (int n0 = 0; n0 < a.N; n0 += 16) {
     uint32_t v[16];
     tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, v);

@@ -5,12 +5,13 @@
 //     y  = bf16( silu( bf16( x fc1_w^T + fc1_b ) ) )  bf16 [T][2048]
 //     out = bf16( y fc2_w^T + fc2_b )                 bf16 [T][1024]
 //
-// Upstream issues four PyTorch operators (embedding, linear, silu, linear).  Here a chunk of up to 64 tokens is one chain of
+// Upstream issues four PyTorch operators (embedding, linear, silu, linear).  Here a pass of up to 512 tokens is one chain of
 // five kernels under programmatic dependent launch: row gather -> fc1 on tcgen05 (qmk_bgemm_kernel: UMMA M = 128 weight rows,
 // N = tokens, split-K 8 so that 128 CTAs pull the 8.4 MB of fc1) -> split-K sum + bias + SiLU -> fc2 on tcgen05 (split-K 16,
-// 128 CTAs, 4.2 MB) -> split-K sum + bias.  The weights are read in place in the upstream [out, in] layout through TMA tensor
-// maps; longer texts run chunk after chunk with fc1 / fc2 resident in L2 (12.6 MB).  Rounding points are upstream's: the
-// products accumulate in fp32, the bias is added in fp32, one rounding to bf16 per operator (F.linear, F.silu on bf16).
+// 128 CTAs, 4.2 MB) -> split-K sum + bias.  More than 64 tokens are blocks of 64 along gridDim.z of the same launches (every
+// block multiplies the same weight tiles, which come from L2 after the first).  The weights are read in place in the upstream
+// [out, in] layout through TMA tensor maps.  Rounding points are upstream's: the products accumulate in fp32, the bias is added
+// in fp32, one rounding to bf16 per operator (F.linear, F.silu on bf16).
 //
 // Included at the end of qmk_batched.cu (same translation unit: the tcgen05 GEMM, the PDL launcher and the error helpers).
 #pragma once
@@ -18,7 +19,8 @@
 namespace {
 
 constexpr int TXT_H = 2048;                 // text hidden size (fc1: 2048 -> 2048, fc2: 2048 -> 1024)
-constexpr int TXT_LANES = 64;               // tokens per chunk = the UMMA N limit
+constexpr int TXT_LANES = 64;               // tokens per block = the UMMA N limit
+constexpr int TXT_BLOCKS = 8;               // blocks per pass (512 tokens)
 constexpr int TXT_SPLITS1 = 8, TXT_SPLITS2 = 16;
 
 // grid = lanes (multiple of 16), block = 256: lane n < n_valid copies table row ids[n] (16 bytes per thread), spare lanes are
@@ -36,11 +38,13 @@ __global__ void __launch_bounds__(256) kt_gather(const long long* ids, int n_val
   x0[(size_t)n * (TXT_H / 8) + threadIdx.x] = v;
 }
 
+// partial: [blocks][splits][N][M]; token n = lane n % N of block n / N
 __device__ __forceinline__ float4 kt_split_sum(const float* partial, int splits, int N, int M, int n, int r) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* base = partial + (((size_t)(n / N) * splits) * N + n % N) * M + r;
 #pragma unroll 8
   for (int s = 0; s < splits; ++s) {
-    const float4 p = __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)s * N + n) * M + r));
+    const float4 p = __ldcg(reinterpret_cast<const float4*>(base + (size_t)s * N * M));
     acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
   }
   return acc;
@@ -49,7 +53,7 @@ __device__ __forceinline__ float kt_silu_bf16(float pre) {
   const float y = bf16_round(pre);                 // F.linear's bf16 output
   return bf16_round(y / (1.0f + expf(-y)));        // F.silu on bf16: fp32 arithmetic, one rounding
 }
-// grid = (lanes, 2), block = 256; thread = 4 consecutive fc1 rows of one token.  partial: [SPLITS1][lanes][2048].
+// grid = (lanes of all blocks, 2), block = 256; thread = 4 consecutive fc1 rows of one token.  partial: [blocks][SPLITS1][N][2048].
 __global__ void __launch_bounds__(256) kt_fc1_epilogue(const float* partial, int N, const __nv_bfloat16* bias, __nv_bfloat16* x1) {
   qmkb::pdl_launch_dependents();
   const int n = blockIdx.x, r = blockIdx.y * 1024 + threadIdx.x * 4;
@@ -61,7 +65,7 @@ __global__ void __launch_bounds__(256) kt_fc1_epilogue(const float* partial, int
   *reinterpret_cast<uint2*>(x1 + (size_t)n * TXT_H + r) =
       make_uint2(*reinterpret_cast<const uint32_t*>(&y01), *reinterpret_cast<const uint32_t*>(&y23));
 }
-// grid = valid tokens, block = 256; thread = 4 consecutive fc2 rows.  partial: [SPLITS2][lanes][1024]; out: bf16[tokens][1024].
+// grid = valid tokens, block = 256; thread = 4 consecutive fc2 rows.  partial: [blocks][SPLITS2][N][1024]; out: bf16[tokens][1024].
 __global__ void __launch_bounds__(256) kt_fc2_epilogue(const float* partial, int N, const __nv_bfloat16* bias, __nv_bfloat16* out) {
   qmkb::pdl_launch_dependents();
   const int n = blockIdx.x, r = threadIdx.x * 4;
@@ -81,8 +85,8 @@ struct qmk_text_proj {
   const void *table = nullptr, *fc1_b = nullptr, *fc2_b = nullptr;
   CUtensorMap map_w1, map_w2;
   CUtensorMap map_x0[TXT_LANES / 16], map_x1[TXT_LANES / 16];   // activations as UMMA N = 16 / 32 / 48 / 64 rows
-  __nv_bfloat16 *x0 = nullptr, *x1 = nullptr;                   // [64][2048] gathered rows / SiLU outputs
-  float* partial = nullptr;                                      // split-K partials: max(8 x 64 x 2048, 16 x 64 x 1024) floats
+  __nv_bfloat16 *x0 = nullptr, *x1 = nullptr;                   // [512][2048] gathered rows / SiLU outputs
+  float* partial = nullptr;                                      // split-K partials: 8 blocks x max(8 x 64 x 2048, 16 x 64 x 1024) floats
 };
 
 extern "C" void qmk_text_proj_destroy(qmk_text_proj* h) {
@@ -110,16 +114,16 @@ extern "C" int qmk_text_proj_create(int device, const void* text_embedding, int 
   if (prop.major != 10) return fail(QMK_ERR_UNSUPPORTED, "qmk_text_proj_create: tcgen05 needs an sm_100 device");
   qmk_text_proj* h = new qmk_text_proj();
   h->device = device; h->vocab = vocab_rows; h->table = text_embedding; h->fc1_b = fc1_bias; h->fc2_b = fc2_bias;
-  const size_t act = (size_t)TXT_LANES * TXT_H * 2;
-  const size_t part = (size_t)TXT_LANES * std::max(TXT_SPLITS1 * TXT_H, TXT_SPLITS2 * H) * sizeof(float);
+  const size_t act = (size_t)TXT_BLOCKS * TXT_LANES * TXT_H * 2;
+  const size_t part = (size_t)TXT_BLOCKS * TXT_LANES * std::max(TXT_SPLITS1 * TXT_H, TXT_SPLITS2 * H) * sizeof(float);
   bool ok = cudaMalloc(&h->x0, act) == cudaSuccess && cudaMalloc(&h->x1, act) == cudaSuccess && cudaMalloc(&h->partial, part) == cudaSuccess &&
             cudaMemset(h->x0, 0, act) == cudaSuccess && cudaMemset(h->x1, 0, act) == cudaSuccess;
   if (!ok) { qmk_text_proj_destroy(h); return fail(QMK_ERR_CUDA, "qmk_text_proj_create: allocation failed"); }
   int rc = make_tensor_map(&h->map_w1, fc1_weight, TXT_H, TXT_H, BM);
   rc |= make_tensor_map(&h->map_w2, fc2_weight, H, TXT_H, BM);
   for (int i = 0; i < TXT_LANES / 16; ++i) {
-    rc |= make_tensor_map(&h->map_x0[i], h->x0, TXT_LANES, TXT_H, 16 * (i + 1));
-    rc |= make_tensor_map(&h->map_x1[i], h->x1, TXT_LANES, TXT_H, 16 * (i + 1));
+    rc |= make_tensor_map(&h->map_x0[i], h->x0, TXT_BLOCKS * TXT_LANES, TXT_H, 16 * (i + 1));
+    rc |= make_tensor_map(&h->map_x1[i], h->x1, TXT_BLOCKS * TXT_LANES, TXT_H, 16 * (i + 1));
   }
   if (rc) { qmk_text_proj_destroy(h); return fail(QMK_ERR_CUDA, "qmk_text_proj_create: cuTensorMapEncodeTiled failed"); }
   if (cudaFuncSetAttribute(qmk_bgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
@@ -141,17 +145,19 @@ extern "C" int qmk_text_proj_embed(qmk_text_proj* h, const int64_t* ids, int n_i
   BatchedDeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   g_launch_err = cudaSuccess;
-  for (int off = 0; off < n_ids; off += TXT_LANES) {
-    const int nv = std::min(TXT_LANES, n_ids - off), N = (nv + 15) & ~15, mi = N / 16 - 1;
-    launch_pdl(kt_gather, dim3(N), dim3(256), 0, st, reinterpret_cast<const long long*>(ids) + off, nv,
+  for (int off = 0; off < n_ids; off += TXT_BLOCKS * TXT_LANES) {
+    // one pass: nb blocks of N lanes (a single block is trimmed to the next multiple of 16 tokens)
+    const int nv = std::min(TXT_BLOCKS * TXT_LANES, n_ids - off), nb = (nv + TXT_LANES - 1) / TXT_LANES;
+    const int N = nb > 1 ? TXT_LANES : (nv + 15) & ~15, mi = N / 16 - 1;
+    launch_pdl(kt_gather, dim3(nb * N), dim3(256), 0, st, reinterpret_cast<const long long*>(ids) + off, nv,
                reinterpret_cast<const uint4*>(h->table), h->vocab, reinterpret_cast<uint4*>(h->x0));
     BgemmArgs a1{h->partial, TXT_H, N, TXT_H, TXT_SPLITS1};
-    launch_pdl(qmk_bgemm_kernel, dim3(TXT_H / BM, TXT_SPLITS1), dim3(128), (size_t)smem_bytes_for(TXT_H / TXT_SPLITS1 / BK), st,
+    launch_pdl(qmk_bgemm_kernel, dim3(TXT_H / BM, TXT_SPLITS1, nb), dim3(128), (size_t)smem_bytes_for(TXT_H / TXT_SPLITS1 / BK), st,
                h->map_w1, h->map_x0[mi], a1);
-    launch_pdl(kt_fc1_epilogue, dim3(N, 2), dim3(256), 0, st, (const float*)h->partial, N,
+    launch_pdl(kt_fc1_epilogue, dim3(nb * N, 2), dim3(256), 0, st, (const float*)h->partial, N,
                reinterpret_cast<const __nv_bfloat16*>(h->fc1_b), h->x1);
     BgemmArgs a2{h->partial, H, N, TXT_H, TXT_SPLITS2};
-    launch_pdl(qmk_bgemm_kernel, dim3(H / BM, TXT_SPLITS2), dim3(128), (size_t)smem_bytes_for(TXT_H / TXT_SPLITS2 / BK), st,
+    launch_pdl(qmk_bgemm_kernel, dim3(H / BM, TXT_SPLITS2, nb), dim3(128), (size_t)smem_bytes_for(TXT_H / TXT_SPLITS2 / BK), st,
                h->map_w2, h->map_x1[mi], a2);
     launch_pdl(kt_fc2_epilogue, dim3(nv), dim3(256), 0, st, (const float*)h->partial, N,
                reinterpret_cast<const __nv_bfloat16*>(h->fc2_b), reinterpret_cast<__nv_bfloat16*>(out_bf16) + (size_t)off * H);

@@ -875,7 +875,7 @@ class TextProjectionKernel:
     """``TextProjection`` on the native library (the text side of the prefill): same constructor and
     ``embed_text_ids`` contract as upstream ``TextProjection`` (model_tts.py:348-374), evaluated by
     ``qmk_text_proj_embed`` -- row gather, fc1 and fc2 on tcgen05 with the weights read in place, bias / SiLU / bf16
-    rounding fused into the split-K epilogues, one launch chain per 64 tokens (csrc/qmk_text.cuh).
+    rounding fused into the split-K epilogues, one chain of five launches per 512 tokens (csrc/qmk_text.cuh).
 
     Relates to ``TextProjection`` as upstream's ``CodePredictorKernel`` relates to its ``CodePredictor``: the PyTorch
     class stays the reference, this one is the accelerated path and has no fallback (CUDA tensors only).

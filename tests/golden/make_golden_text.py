@@ -8,7 +8,7 @@ Run in the build container only (needs /root/reference):
 Imports, unmodified, upstream qwen_megakernel/model_tts.py (loaded by path under a private alias; its top level needs
 only math / struct / typing / torch) and records on CPU (bf16, torch as installed), for the seeded synthetic weights of
 qwen_megakernel/synthetic.py with a 512-row text table:
-  * TextProjection.embed_text_ids (model_tts.py:361-374) of 150 seeded ids (three passes of the 64-token kernel: 64 + 64 + 22);
+  * TextProjection.embed_text_ids (model_tts.py:361-374) of 150 seeded ids (three 64-token blocks of the kernel: 64 + 64 + 22);
   * build_prefill_embeddings (model_tts.py:776-864) of a 3 + 17 token utterance with cached pad / bos / eos embeddings
     (the engine's configuration, tts_engine.py:107-118): prefill [8, 1024] and trailing text [12, 1024].
 Output (committed): tests/golden/text_projection.npz; bf16 values are stored as bit patterns (uint16).

@@ -124,7 +124,7 @@ def text_kernel(text_weights):
 
 @pytest.mark.gpu
 def test_text_kernel_vs_upstream_fixture_and_oracle(text_golden, text_weights, text_kernel):
-    """150 ids = three passes of the 64-token chain (64 + 64 + 22 -> UMMA N = 64, 64, 32)."""
+    """150 ids = one pass of three 64-token blocks along gridDim.z (the last one holds 22 tokens and 42 zero rows)."""
     from oracle.tts_oracle import TextProjectionOracle
     tp, _ = text_kernel
     ids = torch.from_numpy(text_golden["ids"])
@@ -136,9 +136,9 @@ def test_text_kernel_vs_upstream_fixture_and_oracle(text_golden, text_weights, t
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n", [0, 1, 5, 16, 17, 48, 64, 65, 128, 200])
+@pytest.mark.parametrize("n", [0, 1, 5, 16, 17, 48, 64, 65, 128, 200, 512, 513, 1100])
 def test_text_kernel_ragged_lengths_vs_pytorch_on_device(text_kernel, n):
-    """Empty, single, partial-tile, exact-tile and multi-pass inputs against upstream's operators on the same GPU; rows must
+    """Empty, single, partial-tile, exact-tile, multi-block and multi-pass (> 512) inputs against upstream's operators on the same GPU; rows must
     not depend on what else is in the call (row i of a long call == the same id alone)."""
     from qwen_megakernel import model_tts as m
     tp, wg = text_kernel
