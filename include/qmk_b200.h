@@ -319,7 +319,8 @@ int qmk_text_proj_create(int device, const void* text_embedding, int vocab_rows,
                          const void* fc2_weight, const void* fc2_bias, qmk_text_proj** out);
 /* ids: int64[n_ids] in DEVICE memory (values outside [0, vocab_rows) are clamped; upstream's F.embedding would trap);
  * out_bf16: bf16[n_ids][1024] in device memory.  n_ids == 0 is a no-op.  Asynchronous on `stream`, only enqueues kernels
- * (CUDA-graph capturable); calls on one handle share its staging buffers and must be ordered on one stream. */
+ * (CUDA-graph capturable).  Calls on one handle share its staging buffers: a call on another stream than the previous call
+ * first waits for that stream (event); calls recorded into a graph are ordered by whoever replays it. */
 int qmk_text_proj_embed(qmk_text_proj* h, const int64_t* ids, int n_ids, void* out_bf16, void* stream);
 void qmk_text_proj_destroy(qmk_text_proj* h);
 

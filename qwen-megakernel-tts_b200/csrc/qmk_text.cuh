@@ -87,13 +87,37 @@ struct qmk_text_proj {
   CUtensorMap map_x0[TXT_LANES / 16], map_x1[TXT_LANES / 16];   // activations as UMMA N = 16 / 32 / 48 / 64 rows
   __nv_bfloat16 *x0 = nullptr, *x1 = nullptr;                   // [512][2048] gathered rows / SiLU outputs
   float* partial = nullptr;                                      // split-K partials: 8 blocks x max(8 x 64 x 2048, 16 x 64 x 1024) floats
+  std::mutex mu;                                                 // host-side enqueue of one call at a time
+  cudaStream_t last_stream = nullptr;                            // the staging buffers are shared: calls are ordered across streams
+  bool has_last_stream = false;
+  cudaEvent_t handover = nullptr;
 };
+
+// A call on another stream than the handle's previous call first waits for that stream (the calls share x0 / x1 / partial).
+// Calls recorded into a CUDA graph are left alone: whoever replays the graph orders it.
+static void text_order_after_previous_stream(qmk_text_proj* h, cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return; }
+  if (cs != cudaStreamCaptureStatusNone) return;
+  if (h->has_last_stream && h->last_stream != st) {
+    cudaError_t err = h->handover ? cudaSuccess : cudaEventCreateWithFlags(&h->handover, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventRecord(h->handover, h->last_stream);
+    if (err == cudaSuccess) err = cudaStreamWaitEvent(st, h->handover, 0);
+    if (err != cudaSuccess) {   // the previous stream no longer exists: its work is ordered by a device-wide wait
+      cudaGetLastError();
+      cudaDeviceSynchronize();
+    }
+  }
+  h->last_stream = st;
+  h->has_last_stream = true;
+}
 
 extern "C" void qmk_text_proj_destroy(qmk_text_proj* h) {
   if (!h) return;
   BatchedDeviceGuard guard(h->device);
   cudaDeviceSynchronize();
   cudaFree(h->x0); cudaFree(h->x1); cudaFree(h->partial);
+  if (h->handover) cudaEventDestroy(h->handover);
   delete h;
 }
 
@@ -137,13 +161,15 @@ extern "C" int qmk_text_proj_create(int device, const void* text_embedding, int 
 
 // ids: int64[n_ids] in DEVICE memory (clamped to the table); out: bf16[n_ids][1024] in device memory.  Asynchronous on `stream`;
 // only enqueues kernels (no allocation, no synchronisation), so it may be captured in a CUDA graph.  Calls on one handle share
-// its staging buffers: they must be ordered on one stream (or by events).
+// its staging buffers: a call on another stream than the previous one waits for it (event); captured calls are not ordered here.
 extern "C" int qmk_text_proj_embed(qmk_text_proj* h, const int64_t* ids, int n_ids, void* out_bf16, void* stream) {
   using namespace qmkb;
   if (!h || n_ids < 0 || (n_ids > 0 && (!ids || !out_bf16))) return fail(QMK_ERR_ARG, "qmk_text_proj_embed: bad argument");
   if (n_ids == 0) return QMK_OK;
   BatchedDeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> lock(h->mu);
+  text_order_after_previous_stream(h, st);
   g_launch_err = cudaSuccess;
   for (int off = 0; off < n_ids; off += TXT_BLOCKS * TXT_LANES) {
     // one pass: nb blocks of N lanes (a single block is trimmed to the next multiple of 16 tokens)

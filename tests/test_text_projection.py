@@ -168,12 +168,20 @@ def test_text_kernel_shapes_dtypes_and_clamping(text_kernel):
         tp.embed_text_ids(torch.zeros(3))
     with pytest.raises(ValueError):
         m.TextProjectionKernel({**wg, "text_proj_fc1_w": wg["text_proj_fc1_w"].float()}, device="cuda")
-    side = torch.cuda.Stream()                                             # another stream: ordered by the caller
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        o2 = tp.embed_text_ids(torch.arange(14).cuda())
-    side.synchronize()
-    assert torch.equal(o2, out.view(14, 1024))
+    ids14 = torch.arange(14).cuda()
+    big = torch.arange(1100).cuda() % rows
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()                     # calls alternating between two streams share the handle's staging buffers:
+    outs = []                                      # the library orders them (no wait_stream here)
+    for i in range(6):
+        if i % 2:
+            with torch.cuda.stream(side):
+                outs.append(tp.embed_text_ids(ids14))
+        else:
+            tp.embed_text_ids(big)                 # a long call on the default stream right before the side-stream call
+    torch.cuda.synchronize()
+    for o2 in outs:
+        assert torch.equal(o2, out.view(14, 1024))
 
 
 @pytest.mark.gpu
