@@ -13,3 +13,5 @@ for sample in (False, True):
     for _ in range(100): cp.predict(hid, 100, w["embed_weight"], do_sample=sample, temperature=0.9, top_k=50)
     b.record(); torch.cuda.synchronize()
     print("sampled" if sample else "greedy", round(a.elapsed_time(b) * 10, 1), "us per frame")
+codes = [cp.predict(hid, 100, w["embed_weight"], do_sample=True, temperature=0.9, top_k=50).cpu().tolist() for _ in range(3)]
+print("codes", codes)
