@@ -370,3 +370,41 @@ def test_legacy_cache_notices_a_changed_blob(gpu_weights):
     assert not torch.equal(h_a, h_b)
     blob.copy_(other)                      # same address, different model
     assert torch.equal(run(blob), h_b)
+
+
+# ---- upstream's own validator scenarios, free-running ----------------------------------------------------------------
+
+@pytest.mark.parametrize("scenario", ["bos", "pad_prefix", "embeds"])
+def test_validate_kernel_scenarios_free_running(talker, cpu_weights, scenario):
+    """validate_kernel.py:261-337, 377-400: (1) greedy decode from [CODEC_BOS]; (2) prefix [PAD, PAD, PAD, BOS] then decode;
+    (3) step(BOS) then 19 x step_with_embed(randn bf16) -- every implementation free-runs on its OWN tokens, pass = all tokens
+    equal and min cosine(hidden) > 0.99 (validate_kernel.py:414-416).  The two sequences stay comparable until the first decision
+    whose reference margin is within the 1e-2 rule; a mismatch at a larger margin is a failure."""
+    from oracle.tts_oracle import TalkerOracle, top2_margin
+    from qwen_megakernel.synthetic import synthetic_inputs
+    CODEC_PAD = 2148
+    orc = TalkerOracle(cpu_weights, max_seq=64)
+    talker.reset()
+    emb = synthetic_inputs(2024, 20)
+    if scenario == "bos":
+        forced, n = [CODEC_BOS], 30
+    elif scenario == "pad_prefix":
+        forced, n = [CODEC_PAD, CODEC_PAD, CODEC_PAD, CODEC_BOS], 24
+    else:
+        forced, n = [CODEC_BOS], 20
+    rt, rm, rh, toks, hids = [], [], [], [], []
+    t0 = t1 = None
+    for i in range(n):
+        if scenario == "embeds" and i >= 1:
+            t0, h0 = orc.step_with_embed(emb[i])
+            t1, h1 = talker.step_with_embed(emb[i].cuda())
+        else:
+            t0, h0 = orc.step(forced[i] if i < len(forced) else t0)
+            t1, h1 = talker.step(forced[i] if i < len(forced) else t1)
+        rt.append(t0); rm.append(top2_margin(orc.last_logits)); rh.append(h0)
+        toks.append(t1); hids.append(h1.cpu())
+        if t0 != t1 and scenario != "embeds":
+            break      # own tokens differ from here on: the runs are no longer the same experiment
+    rep = compare(f"cuda-vs-oracle free-running {scenario}", toks, hids, rt, rm, rh)
+    assert_parity(rep)
+    print(f"{scenario}: {rep.steps} of {n} steps in lock-step")
