@@ -474,9 +474,12 @@ class TTSDecoder:
         chunk, README.md:23): the projections run once for all positions on the tcgen05 tensor cores (every weight byte is
         read once instead of n times) with causal attention, writing the same KV rows (the batched launch chain with lane =
         position; ``QMK_PREFILL_PERSISTENT=1`` selects the persistent kernel's prefill mode instead).  Returns what the LAST sequential
-        step would return: ``(token, hidden)``.  Standard RoPE only."""
-        if self._mrope_delta is not None:
-            raise NotImplementedError("prefill() implements standard RoPE; use step_with_embed with set_mrope()")
+        step would return: ``(token, hidden)``.  M-RoPE: with the same position on all three axes (``delta == (0, 0, 0)``, what
+        text-only TTS uses) the rotation is bit-identical to standard RoPE and the pass applies as it is; different per-axis
+        offsets need ``step_with_embed``."""
+        if self._mrope_delta is not None and any(self._mrope_delta):
+            raise NotImplementedError("prefill() needs the same position on all three M-RoPE axes (delta (0, 0, 0)); "
+                                      "use step_with_embed for per-axis offsets")
         e = embeds_bf16.to(self.device, torch.bfloat16).reshape(-1, HIDDEN_SIZE)
         n = e.shape[0]
         if n < 1 or n > 16:

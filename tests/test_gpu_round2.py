@@ -314,6 +314,31 @@ def test_mrope_with_equal_axes_is_standard_rope(talker, gpu_weights):
     assert all(torch.equal(h0, h1) for (_, h0), (_, h1) in zip(a, b))
 
 
+def test_prefill_under_mrope_with_equal_axes(gpu_weights):
+    """``prefill`` (standard-RoPE launch chain) is usable after ``set_mrope`` as long as the three axes carry the same position
+    (text-only TTS): same KV rows as the M-RoPE step_with_embed calls within the bf16 tolerance; per-axis offsets are refused."""
+    from qwen_megakernel.model_tts import TTSDecoder
+    from qwen_megakernel.synthetic import synthetic_inputs
+    x = synthetic_inputs(555, 9).cuda()
+    seq = TTSDecoder(weights=gpu_weights, verbose=False, max_seq_len=64)
+    one = TTSDecoder(weights=gpu_weights, verbose=False, max_seq_len=64)
+    seq.set_mrope((24, 20, 20))
+    one.set_mrope((24, 20, 20))
+    for i in range(8):
+        t_ref, h_ref = seq.step_with_embed(x[i])
+    t, h = one.prefill(x[:8])
+    assert one.position == seq.position == 8
+    assert float((h - h_ref).abs().max() / h_ref.abs().max()) <= 2e-2
+    for a, b in ((one._k_cache, seq._k_cache), (one._v_cache, seq._v_cache)):
+        assert float((a[:, :, :8].float() - b[:, :, :8].float()).abs().max()) <= 0.07
+    t2, h2 = one.step_with_embed(x[8])                   # decoding continues under M-RoPE on the B = 1 engine
+    t2r, h2r = seq.step_with_embed(x[8])
+    assert float((h2 - h2r).abs().max() / h2r.abs().max()) <= 2e-2
+    one.set_mrope((24, 20, 20), delta=(0, 3, 5))
+    with pytest.raises(NotImplementedError):
+        one.prefill(x[:2])
+
+
 # ---- boundary hardening -------------------------------------------------------------------------------------------------------
 def test_engine_orders_launches_across_streams(talker, cp_kernel, gpu_weights):
     """All decoders of a device share one engine (exchange words, totals, epochs): launches issued on different CUDA streams
