@@ -2,7 +2,7 @@
 
 Drop-in for the model layer of jayanth-kumar-morem/qwen-megakernel-tts:
 
-    from qwen_megakernel.model_tts import TTSDecoder, CodePredictorKernel, load_tts_weights
+    from qwen_megakernel.model_tts import TTSDecoder, CodePredictorKernel, TextProjectionKernel, load_tts_weights
     from qwen_megakernel.build_tts import get_extension     # registers torch.ops.qwen_megakernel_C.decode
 
 Importing the package neither builds nor loads native code (as upstream, qwen_megakernel/__init__.py:9);
