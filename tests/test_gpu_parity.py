@@ -323,8 +323,15 @@ def test_upstream_decode_op_drop_in(gpu_weights, golden):
                                            L, S, S, 1.0 / 128 ** 0.5)       # position == max_seq_len
 
 
+@pytest.mark.parametrize("position", [4100, 8190, 8191])
+def test_attention_at_upstream_max_seq_len(gpu_weights, cpu_weights, position):
+    """MAX_SEQ_LEN = 8192 is the cache upstream's TTSDecoder allocates (model_tts.py:28, 227-231): the last rows of a full-size
+    cache (chunks of 512 positions per CTA of a group, 13 rounds each) against the oracle, and the cache-full error behind them."""
+    test_long_context_attention_vs_oracle(gpu_weights, cpu_weights, position, S=8192)
+
+
 @pytest.mark.parametrize("position", [39, 40, 59, 60, 61, 79, 80, 81, 200, 639, 641, 1079, 1081, 1500, 2047])
-def test_long_context_attention_vs_oracle(gpu_weights, cpu_weights, position):
+def test_long_context_attention_vs_oracle(gpu_weights, cpu_weights, position, S=2048):
     """Split-KV / multi-round attention: fill both KV caches with the same random rows, then decode one
     token at `position` with a 3-layer stack and compare with the oracle.  Edge cases of both kernels: the group
     kernel's second solo round (n = 41) and the switch to the 16-way split (n = 81, chunks longer than one round
@@ -332,7 +339,7 @@ def test_long_context_attention_vs_oracle(gpu_weights, cpu_weights, position):
     from oracle.tts_oracle import TalkerOracle, top2_margin
     from qwen_megakernel.model_tts import TTSDecoder
     from qwen_megakernel.synthetic import _normal_bf16, synthetic_inputs
-    L, S = 3, 2048
+    L = 3
     wc = dict(cpu_weights); wc["layer_weights"] = cpu_weights["layer_weights"][:11 * L]
     wg = dict(gpu_weights); wg["layer_weights"] = gpu_weights["layer_weights"][:11 * L]
     orc = TalkerOracle(wc, max_seq=S)
@@ -351,6 +358,9 @@ def test_long_context_attention_vs_oracle(gpu_weights, cpu_weights, position):
     # the appended KV rows must equal the oracle's (bf16, small tolerance for accumulation order)
     kd = (dec._k_cache[:, :, position].float().cpu() - orc.stack.k_cache[:, :, position].float()).abs().max()
     assert kd <= 0.07, kd
+    if position + 1 == S:      # the cache is full now: the next step must raise instead of writing out of bounds (upstream writes)
+        with pytest.raises(IndexError):
+            dec.step_with_embed(x[1].cuda())
 
 
 def test_argument_validation(talker):
