@@ -226,3 +226,34 @@ def test_text_kernel_full_size_table_and_graph_capture():
     s.synchronize()
     print("graph replay bit-equal to the plain call:", torch.equal(static_out, out.flip(0)))
     assert_text_parity("graph replay vs plain call", static_out, out.flip(0))
+
+
+# ---- CPU: the chain's index arithmetic restated -----------------------------------------------------------------------
+
+@pytest.mark.parametrize("n_ids", [1, 16, 17, 64, 65, 150, 512, 513, 1100])
+def test_text_chain_partial_layout_restated(n_ids):
+    """csrc/qmk_text.cuh + qmk_bgemm.cuh in numpy index arithmetic: a pass covers <= 512 tokens as nb blocks of N lanes (one
+    block: N = tokens rounded up to 16; several: N = 64); the GEMM CTA (row tile, K slice y, block z) writes
+    partial[((z * splits + y) * N + n) * M + row]; the epilogue of token t reads slices s = 0 .. splits - 1 at
+    ((t // N) * splits * N + t % N) * M + row + s * N * M.  Every token must read exactly the words its own block wrote, every
+    word of a pass is written once, and the passes tile the call."""
+    LANES, BLOCKS, M, SPLITS = 64, 8, 2048, 8
+    covered = 0
+    for off in range(0, n_ids, BLOCKS * LANES):
+        nv = min(BLOCKS * LANES, n_ids - off)
+        nb = (nv + LANES - 1) // LANES
+        N = LANES if nb > 1 else (nv + 15) & ~15
+        assert N % 16 == 0 and 16 <= N <= 64 and nb * N >= nv and (nb - 1) * N < nv
+        owner = {}                                     # word -> (block, slice, lane) for one row of the tile
+        for z in range(nb):
+            for y in range(SPLITS):
+                for n in range(N):
+                    w = ((z * SPLITS + y) * N + n) * M
+                    assert w not in owner
+                    owner[w] = (z, y, n)
+        assert max(owner) + M <= BLOCKS * LANES * SPLITS * M        # inside the 8-block partial buffer
+        for t in range(nv):
+            base = ((t // N) * SPLITS * N + t % N) * M
+            assert [owner[base + s * N * M] for s in range(SPLITS)] == [(t // N, s, t % N) for s in range(SPLITS)]
+        covered += nv
+    assert covered == n_ids
